@@ -1,0 +1,33 @@
+# Build everything in-tree.  The .so files are git-ignored but travel to the GPU box.
+#   make            -> product (CUDA core + C ABI), host mirror, oracle
+#   make product | host | oracle
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       := /usr/bin/g++
+PKG       := raytracer-2025_b200
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false / -ffp-contract=off: the reference is strict IEEE binary64 without contraction
+NVCCFLAGS := -ccbin /usr/bin/g++ $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-fopenmp,-O3 -Iinclude -I$(PKG)/csrc
+CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -fopenmp -Wall -Wno-unknown-pragmas -Iinclude
+
+PRODUCT_SRC := $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cpp)
+PRODUCT_HDR := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/rt2025.h include/rt2025_rng.h
+
+all: product host oracle
+
+product: $(PKG)/librt2025.so
+host: $(PKG)/librt2025_host.so
+oracle: oracle/liboracle.so
+
+$(PKG)/librt2025.so: $(PRODUCT_SRC) $(PRODUCT_HDR)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(filter %.cu %.cpp,$(PRODUCT_SRC)) -Xlinker -lgomp
+
+$(PKG)/librt2025_host.so: $(PKG)/host/host_capi.cpp $(PKG)/host/rt2025.hpp $(PKG)/host/scenes.hpp include/rt2025.h
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(PKG)/host/host_capi.cpp
+
+oracle/liboracle.so: oracle/oracle.cpp include/rt2025.h include/rt2025_rng.h
+	$(CXX) $(CXXFLAGS) -O3 -shared -o $@ oracle/oracle.cpp
+
+clean:
+	rm -f $(PKG)/librt2025.so $(PKG)/librt2025_host.so oracle/liboracle.so
+
+.PHONY: all product host oracle clean

@@ -1,0 +1,1467 @@
+// oracle.cpp — CPU restatement of the reference path tracer (caidj0/Raytracer-2025).
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py may load it.  The product (librt2025.so)
+// never links, loads or calls anything in this directory.
+//
+// The reference is a Rust crate and no Rust toolchain exists in this image or on the GPU box,
+// so the reference itself cannot be compiled (oracle/_ref does not exist).  This file restates
+// its algorithm in C++ binary64 with the reference's container semantics — recursive
+// ray_color, virtual dispatch, linear `Hittables`, median-split `BVH`, per-node divisions in the
+// slab test — operation for operation; each function cites the file:line it follows.  Compile
+// with -ffp-contract=off: rustc never contracts a*b+c into an fma.
+//
+// Pinning: the reference's own tests hold known answers only for AABB::hit (aabb.rs:213-227),
+// longest_axis/union/from_points (aabb.rs:199-253), get_sphere_uv (sphere.rs:152-169), Ray::at,
+// Vec3 algebra and quaternion rotation; tests/test_oracle_kat.py checks those through the orc_kat_*
+// entry points below.  Hits, scatter, pdfs, media, textures and the tone map have no vectors
+// in the reference: for them this oracle is "parity unpinned" (SURVEY.md §8c).
+//
+// The one deliberate difference: the reference draws from the unseeded thread RNG; here every
+// draw is an addressed Philox4x32-10 sample (include/rt2025_rng.h), which the CUDA core uses too.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "rt2025.h"
+#include "rt2025_rng.h"
+
+namespace orc {
+
+static const double PI = 3.14159265358979323846264338327950288;
+static const double INF = std::numeric_limits<double>::infinity();
+
+// ---------------------------------------------------------------- utils/vec3.rs
+struct Vec3 {
+    double e[3];
+    Vec3() : e{0, 0, 0} {}
+    Vec3(double x, double y, double z) : e{x, y, z} {}
+    explicit Vec3(const double* p) : e{p[0], p[1], p[2]} {}
+    double x() const { return e[0]; }
+    double y() const { return e[1]; }
+    double z() const { return e[2]; }
+    double operator[](int i) const { return e[i]; }
+    double& operator[](int i) { return e[i]; }
+};
+static inline Vec3 operator+(Vec3 a, Vec3 b) { return Vec3(a[0] + b[0], a[1] + b[1], a[2] + b[2]); }
+static inline Vec3 operator-(Vec3 a, Vec3 b) { return Vec3(a[0] - b[0], a[1] - b[1], a[2] - b[2]); }
+static inline Vec3 operator*(Vec3 a, Vec3 b) { return Vec3(a[0] * b[0], a[1] * b[1], a[2] * b[2]); }
+static inline Vec3 vdiv(Vec3 a, Vec3 b) { return Vec3(a[0] / b[0], a[1] / b[1], a[2] / b[2]); }  // impl_op!(Div) vec3.rs:296
+static inline Vec3 operator-(Vec3 a) { return Vec3(-a[0], -a[1], -a[2]); }
+static inline Vec3 operator*(double s, Vec3 a) { return Vec3(s * a[0], s * a[1], s * a[2]); }   // vec3.rs:140-146
+static inline Vec3 operator*(Vec3 a, double s) { return Vec3(a[0] * s, a[1] * s, a[2] * s); }   // vec3.rs:156-162
+static inline Vec3 operator/(Vec3 a, double s) { return (1.0 / s) * a; }                        // vec3.rs:222-228
+static inline double dot(Vec3 a, Vec3 b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }     // vec3.rs:107-109
+static inline Vec3 cross(Vec3 a, Vec3 b) {                                                       // vec3.rs:111-117
+    return Vec3(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
+}
+static inline double length_squared(Vec3 a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }  // vec3.rs:96-98
+static inline double length(Vec3 a) { return std::sqrt(length_squared(a)); }
+// UnitVec3::from_vec3, vec3.rs:303-310
+static inline bool unit_vector(Vec3 v, Vec3& out) {
+    Vec3 r = v / length(v);
+    out = r;
+    return std::isfinite(r[0]) && std::isfinite(r[1]) && std::isfinite(r[2]);
+}
+// Rust f64::min/max return the other operand when one is NaN
+static inline double rmin(double a, double b) { return std::isnan(a) ? b : (std::isnan(b) ? a : (a < b ? a : b)); }
+static inline double rmax(double a, double b) { return std::isnan(a) ? b : (std::isnan(b) ? a : (a > b ? a : b)); }
+
+// ---------------------------------------------------------------- utils/ray.rs
+struct Ray {
+    Vec3 orig, dir;
+    double time = 0.0;
+    Ray() {}
+    Ray(Vec3 o, Vec3 d, double t = 0.0) : orig(o), dir(d), time(t) {}
+    Vec3 at(double t) const { return orig + t * dir; }  // ray.rs:39-41
+};
+
+// ---------------------------------------------------------------- utils/interval.rs
+struct Interval {
+    double min, max;
+    Interval() : min(0), max(0) {}
+    static Interval make(double a, double b) {  // Interval::new, interval.rs:10-15
+        Interval i;
+        i.min = rmin(a, b);
+        i.max = rmax(a, b);
+        return i;
+    }
+    static Interval raw(double mn, double mx) {  // from_range / struct literal
+        Interval i;
+        i.min = mn;
+        i.max = mx;
+        return i;
+    }
+    bool contains(double x) const { return x >= min && x <= max; }  // :65-67
+    double size() const { return rmax(max - min, 0.0); }            // :42-44
+    static bool intersect(const Interval& a, const Interval& b, Interval& out) {  // :46-56
+        double mx = rmin(a.max, b.max);
+        double mn = rmax(a.min, b.min);
+        if (mn <= mx) {
+            out = raw(mn, mx);
+            return true;
+        }
+        return false;
+    }
+    static Interval union_(Interval a, Interval b) { return raw(rmin(a.min, b.min), rmax(a.max, b.max)); }  // :58-63
+};
+static const Interval UNIVERSE = Interval::raw(-INF, INF);
+
+// ---------------------------------------------------------------- aabb.rs
+struct AABB {
+    Interval x, y, z;
+    static AABB empty() { return AABB{Interval::raw(INF, -INF), Interval::raw(INF, -INF), Interval::raw(INF, -INF)}; }
+    static AABB from6(const double* b) { return AABB{Interval::raw(b[0], b[1]), Interval::raw(b[2], b[3]), Interval::raw(b[4], b[5])}; }
+    const Interval& axis_interval(int n) const { return n == 0 ? x : (n == 1 ? y : z); }
+    AABB pad_to_minimums() const {  // aabb.rs:43-51
+        const double DELTA = 0.0001;
+        auto f = [&](Interval t) {
+            if (t.size() < DELTA) {
+                double padding = DELTA / 2.0;  // Interval::expand, interval.rs:29-35
+                return Interval::raw(t.min - padding, t.max + padding);
+            }
+            return t;
+        };
+        return AABB{f(x), f(y), f(z)};
+    }
+    static AABB from_points(Vec3 a, Vec3 b) {  // aabb.rs:21-28
+        return AABB{Interval::make(a[0], b[0]), Interval::make(a[1], b[1]), Interval::make(a[2], b[2])}.pad_to_minimums();
+    }
+    // aabb.rs:62-78: one division per axis per call, NaN-suppressing Interval::new, try_fold intersect
+    bool hit(const Ray& r, Interval ray_t) const {
+        Interval acc = ray_t;
+        for (int axis = 0; axis < 3; axis++) {
+            const Interval& ax = axis_interval(axis);
+            double adinv = 1.0 / r.dir[axis];
+            double t0 = (ax.min - r.orig[axis]) * adinv;
+            double t1 = (ax.max - r.orig[axis]) * adinv;
+            Interval slab = Interval::make(t0, t1);
+            Interval next;
+            if (!Interval::intersect(acc, slab, next)) return false;
+            acc = next;
+        }
+        return true;
+    }
+    int longest_axis() const {  // aabb.rs:80-92
+        double lx = x.size(), ly = y.size(), lz = z.size();
+        if (lx > ly) return lx > lz ? 0 : 2;
+        return ly > lz ? 1 : 2;
+    }
+    static AABB union_(AABB a, AABB b) {  // aabb.rs:94-100
+        return AABB{Interval::union_(a.x, b.x), Interval::union_(a.y, b.y), Interval::union_(a.z, b.z)};
+    }
+};
+
+// ---------------------------------------------------------------- utils/quaternion.rs
+struct Quaternion {
+    double w, x, y, z;
+    Quaternion conjugate() const { return Quaternion{w, -x, -y, -z}; }  // :84-91
+    Quaternion mul(const Quaternion& r) const {                         // :94-104
+        return Quaternion{w * r.w - x * r.x - y * r.y - z * r.z, w * r.x + x * r.w + y * r.z - z * r.y,
+                          w * r.y - x * r.z + y * r.w + z * r.x, w * r.z + x * r.y - y * r.x + z * r.w};
+    }
+    Vec3 rotate_vector(Vec3 v) const {  // :72-82
+        Quaternion qv{0.0, v[0], v[1], v[2]};
+        Quaternion r = mul(qv).mul(conjugate());
+        return Vec3(r.x, r.y, r.z);
+    }
+    static Quaternion from_axis_angle(Vec3 axis, double deg) {  // :39-51
+        double half = (deg * (PI / 180.0)) * 0.5;
+        double s = std::sin(half), c = std::cos(half);
+        Vec3 a;
+        unit_vector(axis, a);
+        return Quaternion{c, a[0] * s, a[1] * s, a[2] * s};
+    }
+};
+
+// ---------------------------------------------------------------- utils/onb.rs
+struct ONB {
+    Vec3 axis[3];
+    bool ok = true;
+    ONB() {}
+    explicit ONB(Vec3 n) {  // onb.rs:8-22
+        Vec3 a = std::fabs(n.x()) > 0.9 ? Vec3(0.0, 1.0, 0.0) : Vec3(1.0, 0.0, 0.0);
+        Vec3 u;
+        ok = unit_vector(cross(n, a), u);
+        Vec3 w = cross(u, n);
+        axis[0] = u, axis[1] = n, axis[2] = w;
+    }
+    Vec3 onb_to_world(Vec3 v) const { return v[0] * axis[0] + v[1] * axis[1] + v[2] * axis[2]; }  // :34-38
+};
+
+// ---------------------------------------------------------------- Philox4x32-10 (rt2025_rng.h)
+struct Rand2 {
+    double a, b;
+};
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)RT_PHILOX_M0 * c[0];
+        uint64_t p1 = (uint64_t)RT_PHILOX_M1 * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0, c[1] = n1, c[2] = n2, c[3] = n3;
+        k0 += RT_PHILOX_W0;
+        k1 += RT_PHILOX_W1;
+    }
+}
+static inline Rand2 philox_pair(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t segment, uint32_t slot) {
+    uint32_t c[4] = {pixel, sample, segment, slot};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    Rand2 r;
+    r.a = (double)(((uint64_t)(c[0] >> 5) << 26) | (uint64_t)(c[1] >> 6)) * 0x1.0p-53;
+    r.b = (double)(((uint64_t)(c[2] >> 5) << 26) | (uint64_t)(c[3] >> 6)) * 0x1.0p-53;
+    return r;
+}
+
+// The per-path sampling context: stands in for the thread-local RNG of utils/random.rs.
+struct PathCtx {
+    uint64_t seed = 0;
+    uint32_t pixel = 0, sample = 0, segment = 0;
+    bool media_enabled = true;  // orc_closest_hit leaves media out (they are stochastic)
+    Rand2 draw(uint32_t slot) const { return philox_pair(seed, pixel, sample, segment, slot); }
+};
+
+// ---------------------------------------------------------------- sampling helpers, vec3.rs
+static inline Vec3 random_unit_vector(double r1, double r2) {  // vec3.rs:313-322
+    double x = std::cos(2.0 * PI * r1) * 2.0 * std::sqrt(r2 * (1.0 - r2));
+    double y = std::sin(2.0 * PI * r1) * 2.0 * std::sqrt(r2 * (1.0 - r2));
+    double z = 1.0 - 2.0 * r2;
+    return Vec3(x, y, z);
+}
+static inline Vec3 random_cosine_direction(double r1, double r2) {  // vec3.rs:333-343
+    double phi = 2.0 * PI * r1;
+    double x = std::sin(phi) * std::sqrt(r2);
+    double y = std::sqrt(1.0 - r2);
+    double z = std::cos(phi) * std::sqrt(r2);
+    return Vec3(x, y, z);
+}
+static inline Vec3 reflect(Vec3 v, Vec3 n) { return v - 2.0 * dot(v, n) * n; }  // vec3.rs:71-73
+static inline bool refract(Vec3 uv, Vec3 n, double relative_eta, Vec3& out) {  // vec3.rs:345-354
+    double cos_theta = rmin(dot(-uv, n), 1.0);
+    Vec3 out_perp = relative_eta * (uv + cos_theta * n);
+    double out_parallel_length = std::sqrt(1.0 - length_squared(out_perp));
+    if (std::isnan(out_parallel_length)) return false;
+    Vec3 out_parallel = -out_parallel_length * n;
+    out = out_perp + out_parallel;
+    return true;
+}
+
+// ---------------------------------------------------------------- texture.rs
+struct Scene;
+struct Texture {
+    virtual ~Texture() {}
+    virtual Vec3 value(double u, double v, Vec3 p) const = 0;
+};
+struct SolidColor : Texture {  // texture.rs:32-36
+    Vec3 albedo;
+    Vec3 value(double, double, Vec3) const override { return albedo; }
+};
+struct CheckerTexture : Texture {  // texture.rs:59-73
+    double inv_scale;
+    const Texture *even, *odd;
+    static int32_t as_i32(double x) {  // Rust `as i32` saturates, NaN -> 0
+        if (std::isnan(x)) return 0;
+        if (x >= 2147483647.0) return INT32_MAX;
+        if (x <= -2147483648.0) return INT32_MIN;
+        return (int32_t)x;
+    }
+    Vec3 value(double u, double v, Vec3 p) const override {
+        int32_t xi = as_i32(std::floor(inv_scale * p.x()));
+        int32_t yi = as_i32(std::floor(inv_scale * p.y()));
+        int32_t zi = as_i32(std::floor(inv_scale * p.z()));
+        int32_t sum = (int32_t)((uint32_t)xi + (uint32_t)yi + (uint32_t)zi);  // release-mode wrap
+        bool is_even = sum % 2 == 0;
+        return is_even ? even->value(u, v, p) : odd->value(u, v, p);
+    }
+};
+struct ImageTexture : Texture {  // texture.rs:81-174, utils/image.rs:55-82
+    uint32_t width = 0, height = 0;
+    const float* texels = nullptr;  // RGBA32F
+    bool linear = false, interp = false;
+    static float srgb_to_linear(float x) {  // palette Srgb::into_linear<f32> (crate not vendored)
+        if (x <= 0.04045f) return (float)(1.0 / 12.92) * x;
+        return std::pow(std::fma(x, (float)(1.0 / 1.055), (float)(0.055 / 1.055)), 2.4f);
+    }
+    void pixel_data(uint32_t x, uint32_t y, float out[4]) const {  // image.rs:63-82
+        x = std::min(x, width - 1);
+        y = std::min(y, height - 1);
+        const float* p = texels + ((size_t)y * width + x) * 4;
+        if (linear) {
+            for (int i = 0; i < 4; i++) out[i] = p[i];
+        } else {
+            for (int i = 0; i < 3; i++) out[i] = srgb_to_linear(p[i]);
+            out[3] = p[3];
+        }
+    }
+    static double abs_fract(double x) { return x - std::floor(x); }  // texture.rs:161-163
+    static uint32_t as_u32(double x) {
+        if (!(x > 0.0)) return 0;
+        if (x >= 4294967295.0) return 0xFFFFFFFFu;
+        return (uint32_t)x;
+    }
+    void get_pixel(double u, double v, float out[4]) const {
+        u = abs_fract(u);
+        v = 1.0 - abs_fract(v);
+        if (!interp) {  // texture.rs:111-119
+            uint32_t i = as_u32(u * (double)width), j = as_u32(v * (double)height);
+            pixel_data(i, j, out);
+            return;
+        }
+        // texture.rs:121-151
+        double x = u * (double)width - 0.5, y = v * (double)height - 0.5;
+        uint32_t x0 = as_u32(rmax(std::floor(x), 0.0)), y0 = as_u32(rmax(std::floor(y), 0.0));
+        uint32_t x1 = std::min(x0 + 1, width - 1), y1 = std::min(y0 + 1, height - 1);
+        double dx = x - (double)x0, dy = y - (double)y0;
+        float p00[4], p10[4], p01[4], p11[4];
+        pixel_data(x0, y0, p00), pixel_data(x1, y0, p10), pixel_data(x0, y1, p01), pixel_data(x1, y1, p11);
+        for (int i = 0; i < 4; i++) {
+            float v0 = p00[i] * (1.0f - (float)dx) + p10[i] * ((float)dx);
+            float v1 = p01[i] * (1.0f - (float)dx) + p11[i] * ((float)dx);
+            out[i] = v0 * (1.0f - (float)dy) + v1 * ((float)dy);
+        }
+    }
+    Vec3 value(double u, double v, Vec3) const override {  // texture.rs:166-174
+        if (height == 0) return Vec3(0.0, 1.0, 1.0);
+        float px[4];
+        get_pixel(u, v, px);
+        return Vec3((double)px[0], (double)px[1], (double)px[2]);
+    }
+    double alpha(double u, double v) const {  // texture.rs:102-109
+        if (height == 0) return 1.0;
+        float px[4];
+        get_pixel(u, v, px);
+        return (double)px[3];
+    }
+};
+struct NoiseTexture : Texture {  // texture.rs:191-196, utils/perlin.rs:40-89
+    const rt_perlin* tab;
+    double scale;
+    double noise(Vec3 p) const {
+        int64_t ijk[3];
+        double uvw[3];
+        for (int a = 0; a < 3; a++) {
+            double fl = std::floor(p[a]);
+            ijk[a] = std::isnan(fl) ? 0 : (fl >= 9.2e18 ? INT64_MAX : (fl <= -9.2e18 ? INT64_MIN : (int64_t)fl));
+            uvw[a] = p[a] - fl;
+        }
+        Vec3 c[2][2][2];
+        for (int di = 0; di < 2; di++)
+            for (int dj = 0; dj < 2; dj++)
+                for (int dk = 0; dk < 2; dk++) {
+                    uint32_t idx = tab->perm_x[(uint64_t)(ijk[0] + di) & 255] ^ tab->perm_y[(uint64_t)(ijk[1] + dj) & 255] ^
+                                   tab->perm_z[(uint64_t)(ijk[2] + dk) & 255];
+                    c[di][dj][dk] = Vec3(tab->randvec[idx]);
+                }
+        // perlin_interp, perlin.rs:73-89
+        double u = uvw[0], v = uvw[1], w = uvw[2];
+        double uu = u * u * (3.0 - 2.0 * u), vv = v * v * (3.0 - 2.0 * v), ww = w * w * (3.0 - 2.0 * w);
+        double accum = 0.0;
+        for (int i = 0; i < 2; i++)
+            for (int j = 0; j < 2; j++)
+                for (int k = 0; k < 2; k++) {
+                    Vec3 weight_v(u - (double)i, v - (double)j, w - (double)k);
+                    accum += ((double)i * uu + (double)(1 - i) * (1.0 - uu)) * ((double)j * vv + (double)(1 - j) * (1.0 - vv)) *
+                             ((double)k * ww + (double)(1 - k) * (1.0 - ww)) * dot(c[i][j][k], weight_v);
+                }
+        return accum;
+    }
+    double turb(Vec3 p, int depth) const {  // perlin.rs:61-71
+        double accum = 0.0, weight = 1.0;
+        Vec3 temp_p = p;
+        for (int i = 0; i < depth; i++) {
+            accum = accum + weight * noise(temp_p);
+            temp_p = 2.0 * temp_p;
+            weight = 0.5 * weight;
+        }
+        return std::fabs(accum);
+    }
+    Vec3 value(double, double, Vec3 p) const override {
+        return Vec3(0.5, 0.5, 0.5) * (1.0 + std::sin(scale * p.z() + 10.0 * turb(p, 7)));
+    }
+};
+struct GradientTexture : Texture {  // RT_TEX_GRADIENT_Y (rt2025.h): the book-1 sky
+    Vec3 c0, c1;
+    Vec3 value(double, double, Vec3 p) const override {
+        double a = 0.5 * (p.y() + 1.0);
+        return (1.0 - a) * c0 + a * c1;
+    }
+};
+
+// ---------------------------------------------------------------- hit.rs
+struct Material;
+struct HitRecord {
+    Vec3 p, normal;
+    const Material* mat = nullptr;
+    double t = 0, u = 0, v = 0;
+    bool front_face = false;
+    uint32_t prim_id = RT_NONE, inst_id = RT_NONE;
+    static HitRecord make(Vec3 p, Vec3 normal, const Material* mat, double t, double u, double v, const Ray& r_in) {  // hit.rs:24-43
+        HitRecord h;
+        h.front_face = dot(r_in.dir, normal) < 0.0;
+        h.p = p;
+        h.normal = h.front_face ? normal : -normal;
+        h.mat = mat;
+        h.t = t, h.u = u, h.v = v;
+        return h;
+    }
+};
+
+// ---------------------------------------------------------------- material.rs / pdf.rs
+enum ScatterKind { SCATTER_NONE, SCATTER_COSINE, SCATTER_SPHERE, SCATTER_RAY };
+struct ScatterRecord {
+    ScatterKind kind = SCATTER_NONE;
+    Vec3 attenuation;
+    ONB uvw;
+    Ray ray;
+    bool error = false;  // an unwrap()/expect() of the reference would have panicked
+};
+struct Material {
+    virtual ~Material() {}
+    virtual ScatterRecord scatter(const Ray&, const HitRecord&, const PathCtx&, uint32_t /*mix level*/) const { return ScatterRecord(); }
+    virtual Vec3 emitted(const Ray&, const HitRecord&) const { return Vec3(0, 0, 0); }
+};
+static ScatterRecord cosine_record(Vec3 albedo, Vec3 normal) {  // CosinePDF::new, pdf.rs:41-48
+    ScatterRecord s;
+    s.kind = SCATTER_COSINE;
+    s.attenuation = albedo;
+    s.uvw = ONB(normal);
+    s.error = !s.uvw.ok;
+    return s;
+}
+struct EmptyMaterial : Material {  // material.rs:38-47
+    ScatterRecord scatter(const Ray&, const HitRecord& rec, const PathCtx&, uint32_t) const override {
+        return cosine_record(Vec3(0.75, 0.75, 0.75), rec.normal);
+    }
+};
+struct Lambertian : Material {  // material.rs:59-66
+    const Texture* texture;
+    ScatterRecord scatter(const Ray&, const HitRecord& rec, const PathCtx&, uint32_t) const override {
+        return cosine_record(texture->value(rec.u, rec.v, rec.p), rec.normal);
+    }
+};
+struct Metal : Material {  // material.rs:82-95
+    Vec3 albedo;
+    double fuzz;
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx& ctx, uint32_t) const override {
+        ScatterRecord s;
+        Vec3 ud;
+        if (!unit_vector(r_in.dir, ud)) return s;  // `?` -> None
+        Vec3 raw_reflected = reflect(ud, rec.normal);
+        Vec3 ur;
+        if (!unit_vector(raw_reflected, ur)) return s;
+        Rand2 xi = ctx.draw(RT_SLOT_MATERIAL);
+        Vec3 reflected = ur + (fuzz * random_unit_vector(xi.a, xi.b));
+        s.kind = SCATTER_RAY;
+        s.attenuation = albedo;
+        s.ray = Ray(rec.p, reflected, r_in.time);
+        return s;
+    }
+};
+struct Dielectric : Material {  // material.rs:110-144
+    const Texture* attenuation;
+    double refraction_index;
+    static double reflectance(double cosine, double ri) {  // :110-114
+        double r0 = (1.0 - ri) / (1.0 + ri);
+        double r0_squared = r0 * r0;
+        double x = 1.0 - cosine;
+        double x2 = x * x;
+        double x5 = x * (x2 * x2);  // powi(5)
+        return r0_squared + (1.0 - r0_squared) * x5;
+    }
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx& ctx, uint32_t) const override {
+        ScatterRecord s;
+        double ri = rec.front_face ? 1.0 / refraction_index : refraction_index;
+        Vec3 unit_direction;
+        if (!unit_vector(r_in.dir, unit_direction)) {
+            s.error = true;
+            return s;
+        }
+        double cos_theta = rmin(dot(-unit_direction, rec.normal), 1.0);
+        double sin_theta = std::sqrt(1.0 - cos_theta * cos_theta);
+        bool cannot_refract = ri * sin_theta > 1.0;
+        Vec3 direction;
+        if (cannot_refract || reflectance(cos_theta, ri) > ctx.draw(RT_SLOT_MATERIAL).a) {
+            direction = reflect(unit_direction, rec.normal);
+        } else if (!refract(unit_direction, rec.normal, ri, direction)) {
+            s.error = true;  // .unwrap() on None
+            return s;
+        }
+        s.kind = SCATTER_RAY;
+        s.attenuation = attenuation->value(rec.u, rec.v, rec.p);
+        s.ray = Ray(rec.p, direction, r_in.time);
+        return s;
+    }
+};
+struct DiffuseLight : Material {  // material.rs:170-186
+    const Texture* texture;
+    const Material* material = nullptr;
+    Vec3 emitted(const Ray& ray, const HitRecord& rec) const override {
+        Vec3 self_emit = texture->value(rec.u, rec.v, rec.p);
+        Vec3 mat_emit = material ? material->emitted(ray, rec) : Vec3(0, 0, 0);
+        return self_emit + mat_emit;
+    }
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx& ctx, uint32_t lvl) const override {
+        return material ? material->scatter(r_in, rec, ctx, lvl) : ScatterRecord();
+    }
+};
+struct Isotropic : Material {  // material.rs:198-207
+    const Texture* texture;
+    ScatterRecord scatter(const Ray&, const HitRecord& rec, const PathCtx&, uint32_t) const override {
+        ScatterRecord s;
+        s.kind = SCATTER_SPHERE;
+        s.attenuation = texture->value(rec.u, rec.v, rec.p);
+        return s;
+    }
+};
+struct Transparent : Material {  // material.rs:211-218
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx&, uint32_t) const override {
+        ScatterRecord s;
+        s.kind = SCATTER_RAY;
+        s.attenuation = Vec3(1, 1, 1);
+        s.ray = Ray(rec.p, r_in.dir, r_in.time);
+        return s;
+    }
+};
+struct Mix : Material {  // material.rs:249-267
+    const Material *mat1, *mat2;
+    double ratio;
+    const ImageTexture* alpha = nullptr;
+    double get_ratio(const HitRecord& rec) const { return alpha ? alpha->alpha(rec.u, rec.v) : ratio; }
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx& ctx, uint32_t lvl) const override {
+        double r = get_ratio(rec);
+        if (ctx.draw(RT_SLOT_MIX + 256u * lvl).a > r) return mat1->scatter(r_in, rec, ctx, lvl + 1);
+        return mat2->scatter(r_in, rec, ctx, lvl + 1);
+    }
+    Vec3 emitted(const Ray& r_in, const HitRecord& rec) const override {
+        double r = get_ratio(rec);
+        return mat1->emitted(r_in, rec) * (1.0 - r) + mat2->emitted(r_in, rec) * r;
+    }
+};
+struct Portal : Material {  // material/portal.rs:14-31
+    Vec3 attenuation, offset;
+    Quaternion q;
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx&, uint32_t) const override {
+        ScatterRecord s;
+        s.kind = SCATTER_RAY;
+        s.attenuation = attenuation;
+        s.ray = Ray(rec.p + offset, q.rotate_vector(r_in.dir), r_in.time);
+        return s;
+    }
+};
+
+// PDF::value for the two material pdfs — pdf.rs:22-29, 51-57
+static bool pdf_value(const ScatterRecord& s, Vec3 direction, Vec3& brdf, double& pdf) {
+    if (s.kind == SCATTER_SPHERE) {
+        pdf = 1.0 / (4.0 * PI);
+        brdf = s.attenuation / (4.0 * PI);
+        return true;
+    }
+    Vec3 ud;
+    if (!unit_vector(direction, ud)) return false;  // .unwrap()
+    double cosine_theta = dot(ud, s.uvw.axis[1]);
+    pdf = rmax(0.0, cosine_theta / PI);
+    brdf = s.attenuation * rmax(cosine_theta, 0.0) / PI;
+    return true;
+}
+static Vec3 pdf_generate(const ScatterRecord& s, double r1, double r2) {  // pdf.rs:31-33, 59-63
+    if (s.kind == SCATTER_SPHERE) return random_unit_vector(r1, r2);
+    return s.uvw.onb_to_world(random_cosine_direction(r1, r2));
+}
+
+// ---------------------------------------------------------------- Hittable and its implementors
+struct LightSample {
+    uint32_t leaf;  // chosen light leaf (global depth-first index)
+    double r1, r2;
+    bool error = false;
+};
+struct Hittable {
+    AABB bbox;
+    uint32_t id = RT_NONE;
+    uint32_t first_leaf = 0, n_leaves = 0;  // light-leaf range when part of a lights tree
+    virtual ~Hittable() {}
+    virtual bool hit(const Ray& r, const Interval& interval, const PathCtx& ctx, HitRecord& rec) const = 0;
+    virtual double pdf_value(Vec3 /*origin*/, Vec3 /*direction*/) const { return std::nan(""); }  // unimplemented!()
+    virtual Vec3 random(Vec3 /*origin*/, LightSample& ls) const {
+        ls.error = true;
+        return Vec3(1, 0, 0);
+    }
+    virtual bool can_be_light() const { return false; }
+    virtual void count_leaves(uint32_t& next) {
+        first_leaf = next;
+        n_leaves = 1;
+        next += 1;
+    }
+};
+
+struct Sphere : Hittable {  // shapes/sphere.rs
+    Vec3 center, center_vec;
+    double radius;
+    const Material* mat;
+    bool can_be_light() const override { return true; }
+    static void get_sphere_uv(Vec3 p, double& u, double& v) {  // :53-61
+        double theta = std::acos(-p.y());
+        double phi = std::atan2(-p.z(), p.x()) + PI;
+        u = phi / (2.0 * PI);
+        v = theta / PI;
+    }
+    bool hit(const Ray& r, const Interval& interval, const PathCtx&, HitRecord& rec) const override {  // :77-108
+        Vec3 current_center = center + r.time * center_vec;
+        Vec3 oc = current_center - r.orig;
+        double a = length_squared(r.dir);
+        double h = dot(r.dir, oc);
+        double c = length_squared(oc) - radius * radius;
+        double discriminant = h * h - a * c;
+        if (discriminant < 0.0) return false;
+        double sqrtd = std::sqrt(discriminant);
+        double root = (h - sqrtd) / a;
+        if (!interval.contains(root)) {
+            root = (h + sqrtd) / a;
+            if (!interval.contains(root)) return false;
+        }
+        Vec3 p = r.at(root);
+        Vec3 outward_normal = (p - current_center) / radius;
+        double u, v;
+        get_sphere_uv(outward_normal, u, v);
+        rec = HitRecord::make(p, outward_normal, mat, root, u, v, r);
+        rec.prim_id = id;
+        return true;
+    }
+    double pdf_value(Vec3 origin, Vec3 direction) const override {  // :114-132
+        HitRecord rec;
+        PathCtx none;
+        if (!hit(Ray(origin, direction), Interval::make(1e-8, INF), none, rec)) return 0.0;
+        double dist_squared = length_squared((center + 0.0 * center_vec) - origin);
+        double cos_theta_max = std::sqrt(1.0 - radius * radius / dist_squared);
+        if (std::isnan(cos_theta_max)) return 1.0 / (4.0 * PI);
+        double solid_angle = 2.0 * PI * (1.0 - cos_theta_max);
+        return 1.0 / solid_angle;
+    }
+    Vec3 random(Vec3 origin, LightSample& ls) const override {  // :134-144, :63-73
+        Vec3 direction = (center + 0.0 * center_vec) - origin;
+        double distance_squared = length_squared(direction);
+        Vec3 ud;
+        if (!unit_vector(direction, ud)) ls.error = true;
+        ONB uvw(ud);
+        if (!uvw.ok) ls.error = true;
+        double r1 = ls.r1, r2 = ls.r2;
+        double y = 1.0 + r2 * (std::sqrt(1.0 - radius * radius / distance_squared) - 1.0);
+        double phi = 2.0 * PI * r1;
+        double x = std::cos(phi) * std::sqrt(1.0 - y * y);
+        double z = std::sin(phi) * std::sqrt(1.0 - y * y);
+        Vec3 out;
+        if (!unit_vector(uvw.onb_to_world(Vec3(x, y, z)), out)) ls.error = true;
+        return out;
+    }
+};
+
+struct PlanarShape : Hittable {  // shapes/quad.rs, shapes/triangle.rs
+    bool triangle;
+    Vec3 anchor, u, v, w, normal;
+    double parm_d, area;
+    const Material* mat;
+    bool can_be_light() const override { return true; }
+    bool is_interior(double a, double b) const {  // quad.rs:60-68, triangle.rs:56-65
+        const Interval unit = Interval::raw(0.0, 1.0);
+        if (triangle) return unit.contains(a) && unit.contains(b) && unit.contains(a + b);
+        return unit.contains(a) && unit.contains(b);
+    }
+    bool hit(const Ray& r, const Interval& interval, const PathCtx&, HitRecord& rec) const override {  // quad.rs:71-102
+        double denom = dot(normal, r.dir);
+        if (std::fabs(denom) < 1e-8) return false;
+        double t = (parm_d - dot(normal, r.orig)) / denom;
+        if (!interval.contains(t)) return false;
+        Vec3 intersection = r.at(t);
+        Vec3 hp = intersection - anchor;
+        double alpha = dot(w, cross(hp, v));
+        double beta = dot(w, cross(u, hp));
+        if (!is_interior(alpha, beta)) return false;
+        rec = HitRecord::make(intersection, normal, mat, t, alpha, beta, r);
+        rec.prim_id = id;
+        return true;
+    }
+    double pdf_value(Vec3 origin, Vec3 direction) const override {  // quad.rs:108-120
+        HitRecord rec;
+        PathCtx none;
+        if (!hit(Ray(origin, direction), Interval::make(1e-8, INF), none, rec)) return 0.0;
+        double distance_squared = rec.t * rec.t * length_squared(direction);
+        double cosine = std::fabs(dot(direction, rec.normal) / length(direction));
+        return distance_squared / (cosine * area);
+    }
+    Vec3 random(Vec3 origin, LightSample& ls) const override {  // quad.rs:122-125, triangle.rs:115-128
+        double ul = ls.r1, vl = ls.r2;
+        if (triangle && ul + vl > 1.0) {
+            double nu = 1.0 - vl, nv = 1.0 - ul;
+            ul = nu, vl = nv;
+        }
+        Vec3 p = anchor + (ul * u) + (vl * v);
+        Vec3 out;
+        if (!unit_vector(p - origin, out)) ls.error = true;
+        return out;
+    }
+};
+
+struct Hittables : Hittable {  // hits.rs
+    std::vector<Hittable*> objects;
+    bool can_be_light() const override { return true; }
+    bool hit(const Ray& r, const Interval& interval, const PathCtx& ctx, HitRecord& rec) const override {  // :39-46
+        bool any = false;
+        HitRecord tmp;
+        for (auto* o : objects) {
+            if (o->hit(r, interval, ctx, tmp)) {
+                if (!any || tmp.t < rec.t) rec = tmp;  // min_by keeps the first of equal minima
+                any = true;
+            }
+        }
+        return any;
+    }
+    double pdf_value(Vec3 origin, Vec3 direction) const override {  // :52-67
+        double sum = 0.0;
+        for (auto* o : objects) sum += o->pdf_value(origin, direction);
+        return sum / (double)objects.size();
+    }
+    Vec3 random(Vec3 origin, LightSample& ls) const override {  // :69-75 — child that owns the chosen leaf
+        for (auto* o : objects)
+            if (ls.leaf >= o->first_leaf && ls.leaf < o->first_leaf + o->n_leaves) return o->random(origin, ls);
+        ls.error = true;  // "The collection of objects is empty!"
+        return Vec3(1, 0, 0);
+    }
+    void count_leaves(uint32_t& next) override {
+        first_leaf = next;
+        for (auto* o : objects) o->count_leaves(next);
+        n_leaves = next - first_leaf;
+    }
+};
+
+struct BVHNode : Hittable {  // bvh.rs
+    Hittable *left = nullptr, *right = nullptr;
+    bool hit(const Ray& r, const Interval& interval, const PathCtx& ctx, HitRecord& rec) const override {  // :57-85
+        if (!bbox.hit(r, interval)) return false;
+        bool hit_left = false, hit_right = false;
+        HitRecord rec_left, rec_right;
+        double closest_so_far = interval.max;
+        if (left && left->hit(r, interval, ctx, rec_left)) {
+            closest_so_far = rec_left.t;
+            hit_left = true;
+        }
+        if (right) {
+            Interval right_interval = Interval::make(interval.min, closest_so_far);
+            if (right->hit(r, right_interval, ctx, rec_right)) hit_right = true;
+        }
+        if (hit_right) {
+            rec = rec_right;
+            return true;
+        }
+        if (hit_left) {
+            rec = rec_left;
+            return true;
+        }
+        return false;
+    }
+};
+
+struct Transform : Hittable {  // shapes.rs:23-133
+    Hittable* object;
+    Vec3 offset, scale;
+    Quaternion q;
+    bool can_be_light() const override { return object->can_be_light(); }
+    Vec3 transform(Vec3 v) const { return q.rotate_vector(v * scale) + offset; }                 // :74-78
+    Vec3 detransform(Vec3 v) const { return vdiv(q.conjugate().rotate_vector(v - offset), scale); }  // :80-84
+    bool hit(const Ray& r, const Interval& interval, const PathCtx& ctx, HitRecord& rec) const override {  // :88-111
+        Vec3 to = r.at(1.0);
+        Vec3 local_origin = detransform(r.orig);
+        Vec3 local_to = detransform(to);
+        Ray local_ray(local_origin, local_to - local_origin, r.time);
+        if (!object->hit(local_ray, interval, ctx, rec)) return false;
+        rec.p = transform(rec.p);
+        Vec3 n;
+        unit_vector(q.rotate_vector(vdiv(rec.normal, scale)), n);
+        rec.normal = n;
+        if (rec.inst_id == RT_NONE) rec.inst_id = id;
+        return true;
+    }
+    double pdf_value(Vec3 origin, Vec3 direction) const override {  // :117-123
+        Vec3 local_origin = detransform(origin);
+        Vec3 local_to = detransform(origin + direction);
+        return object->pdf_value(local_origin, local_to - local_origin);
+    }
+    Vec3 random(Vec3 origin, LightSample& ls) const override {  // :125-132
+        Vec3 local_origin = detransform(origin);
+        Vec3 local_dir = object->random(local_origin, ls);
+        Vec3 world_to = transform(local_origin + local_dir);
+        Vec3 out;
+        if (!unit_vector(world_to - origin, out)) ls.error = true;
+        return out;
+    }
+    void count_leaves(uint32_t& next) override {
+        first_leaf = next;
+        object->count_leaves(next);
+        n_leaves = next - first_leaf;
+    }
+};
+
+struct ConstantMedium : Hittable {  // volume.rs
+    Hittable* boundary;
+    double neg_inv_density;
+    const Material* phase;
+    uint32_t medium_index;
+    bool hit(const Ray& r, const Interval& interval, const PathCtx& ctx, HitRecord& rec) const override {  // :37-73
+        if (!ctx.media_enabled) return false;
+        HitRecord rec1, rec2;
+        if (!boundary->hit(r, UNIVERSE, ctx, rec1)) return false;
+        if (!boundary->hit(r, Interval::make(rec1.t + 0.0001, INF), ctx, rec2)) return false;
+        if (rec1.t < interval.min) rec1.t = interval.min;  // clamp_min_assign
+        if (rec2.t > interval.max) rec2.t = interval.max;  // clamp_max_assign
+        if (rec1.t >= rec2.t) return false;
+        if (rec1.t < 0.0) rec1.t = 0.0;
+        double ray_length = length(r.dir);
+        double distance_inside_boundary = (rec2.t - rec1.t) * ray_length;
+        double hit_distance = neg_inv_density * std::log(ctx.draw(RT_SLOT_MEDIUM0 + medium_index).a);
+        if (hit_distance > distance_inside_boundary) return false;
+        double t = rec1.t + hit_distance / ray_length;
+        Vec3 p = r.at(t);
+        rec = HitRecord::make(p, Vec3(1.0, 0.0, 0.0), phase, t, 0.0, 0.0, r);
+        rec.prim_id = id;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------- scene assembly from rt_scene_desc
+struct LightLeaf {
+    double weight, cdf;
+};
+struct Scene {
+    std::vector<std::unique_ptr<Texture>> textures;
+    std::vector<std::unique_ptr<Material>> materials;
+    std::vector<std::unique_ptr<Hittable>> owned;  // every node incl. BVH internals
+    std::vector<Hittable*> by_object;               // desc object index -> node
+    std::vector<rt_perlin> perlins;
+    std::vector<float> texels;
+    Hittable* world = nullptr;
+    Hittable* lights = nullptr;
+    std::vector<LightLeaf> light_leaves;
+    std::vector<uint32_t> ranks;  // per desc object; RT_NONE for containers
+    // flattened leaves for brute force: leaf + chain of transforms (outermost first)
+    struct Leaf {
+        Hittable* prim;
+        std::vector<const Transform*> chain;
+    };
+    std::vector<Leaf> leaves;
+    std::string error;
+};
+
+static uint64_t total_order_key(double x) {  // f64::total_cmp, bvh.rs:52
+    uint64_t b;
+    std::memcpy(&b, &x, 8);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// BVH::from_vec, bvh.rs:16-46
+static Hittable* build_bvh(Scene& sc, std::vector<Hittable*> objects) {
+    auto* node = new BVHNode();
+    sc.owned.emplace_back(node);
+    AABB bbox = AABB::empty();
+    for (auto* o : objects) bbox = AABB::union_(bbox, o->bbox);
+    node->bbox = bbox;
+    int axis = bbox.longest_axis();
+    size_t len = objects.size();
+    if (len == 1) {
+        node->left = objects[0];
+    } else if (len == 2) {
+        node->left = objects[0];
+        node->right = objects[1];
+    } else {
+        std::stable_sort(objects.begin(), objects.end(), [axis](const Hittable* a, const Hittable* b) {
+            return total_order_key(a->bbox.axis_interval(axis).min) < total_order_key(b->bbox.axis_interval(axis).min);
+        });
+        size_t mid = len / 2;
+        std::vector<Hittable*> left_vec(objects.begin(), objects.begin() + mid), right_vec(objects.begin() + mid, objects.end());
+        node->left = build_bvh(sc, std::move(left_vec));
+        node->right = build_bvh(sc, std::move(right_vec));
+    }
+    return node;
+}
+
+static Hittable* build_object(Scene& sc, const rt_scene_desc& d, uint32_t idx) {
+    if (idx >= d.n_objects) {
+        sc.error = "object index out of range";
+        return nullptr;
+    }
+    const rt_object& o = d.objects[idx];
+    Hittable* h = nullptr;
+    auto kids = [&](std::vector<Hittable*>& out) {
+        for (uint32_t k = 0; k < o.child_count; k++) {
+            Hittable* c = build_object(sc, d, d.children[o.first_child + k]);
+            if (!c) return false;
+            out.push_back(c);
+        }
+        return true;
+    };
+    switch (o.kind) {
+        case RT_OBJ_SPHERE: {
+            auto* s = new Sphere();
+            const rt_sphere& p = d.spheres[o.data];
+            s->center = Vec3(p.center), s->center_vec = Vec3(p.center_vec), s->radius = p.radius;
+            s->mat = sc.materials[o.material].get();
+            h = s;
+            break;
+        }
+        case RT_OBJ_QUAD:
+        case RT_OBJ_TRIANGLE: {
+            auto* q = new PlanarShape();
+            const rt_planar& p = d.planars[o.data];
+            q->triangle = o.kind == RT_OBJ_TRIANGLE;
+            q->anchor = Vec3(p.anchor), q->u = Vec3(p.u), q->v = Vec3(p.v), q->w = Vec3(p.w), q->normal = Vec3(p.normal);
+            q->parm_d = p.parm_d, q->area = p.area;
+            q->mat = sc.materials[o.material].get();
+            h = q;
+            break;
+        }
+        case RT_OBJ_LIST: {
+            auto* l = new Hittables();
+            if (!kids(l->objects)) {
+                delete l;
+                return nullptr;
+            }
+            h = l;
+            break;
+        }
+        case RT_OBJ_BVH: {
+            std::vector<Hittable*> v;
+            if (!kids(v)) return nullptr;
+            if (v.empty()) {
+                sc.error = "BVH node must contain at least one object";
+                return nullptr;
+            }
+            h = build_bvh(sc, v);  // already owned
+            h->id = idx;
+            sc.by_object[idx] = h;
+            return h;
+        }
+        case RT_OBJ_TRANSFORM: {
+            auto* t = new Transform();
+            const rt_transform& p = d.transforms[o.data];
+            t->offset = Vec3(p.offset), t->scale = Vec3(p.scale);
+            t->q = Quaternion{p.quat[0], p.quat[1], p.quat[2], p.quat[3]};
+            t->object = build_object(sc, d, d.children[o.first_child]);
+            if (!t->object) {
+                delete t;
+                return nullptr;
+            }
+            h = t;
+            break;
+        }
+        case RT_OBJ_MEDIUM: {
+            auto* m = new ConstantMedium();
+            m->neg_inv_density = d.media[o.data].neg_inv_density;
+            m->medium_index = o.data;
+            m->phase = sc.materials[o.material].get();
+            m->boundary = build_object(sc, d, d.children[o.first_child]);
+            if (!m->boundary) {
+                delete m;
+                return nullptr;
+            }
+            h = m;
+            break;
+        }
+        default:
+            sc.error = "unknown object kind";
+            return nullptr;
+    }
+    h->bbox = AABB::from6(o.bbox);
+    h->id = idx;
+    sc.owned.emplace_back(h);
+    sc.by_object[idx] = h;
+    return h;
+}
+
+// Appendix B of SURVEY.md: depth-first, list children in order, BVH right before left.
+static void assign_ranks(Scene& sc, Hittable* h, uint32_t& next, std::vector<const Transform*>& chain) {
+    if (auto* l = dynamic_cast<Hittables*>(h)) {
+        for (auto* o : l->objects) assign_ranks(sc, o, next, chain);
+    } else if (auto* b = dynamic_cast<BVHNode*>(h)) {
+        if (b->right) assign_ranks(sc, b->right, next, chain);
+        if (b->left) assign_ranks(sc, b->left, next, chain);
+    } else if (auto* t = dynamic_cast<Transform*>(h)) {
+        chain.push_back(t);
+        assign_ranks(sc, t->object, next, chain);
+        chain.pop_back();
+    } else if (dynamic_cast<ConstantMedium*>(h)) {
+        sc.ranks[h->id] = next++;  // the medium competes as one candidate; its boundary is private
+    } else {
+        sc.ranks[h->id] = next++;
+        sc.leaves.push_back(Scene::Leaf{h, chain});
+    }
+}
+
+static void light_weights(Hittable* h, double w, std::vector<LightLeaf>& out) {
+    if (auto* l = dynamic_cast<Hittables*>(h)) {
+        for (auto* o : l->objects) light_weights(o, w / (double)l->objects.size(), out);
+    } else if (auto* t = dynamic_cast<Transform*>(h)) {
+        light_weights(t->object, w, out);
+    } else {
+        out.push_back(LightLeaf{w, 0.0});
+    }
+}
+
+static Scene* scene_from_desc(const rt_scene_desc* d, std::string& err) {
+    auto sc = std::make_unique<Scene>();
+    if (!d || d->version != RT_ABI_VERSION) {
+        err = "bad descriptor version";
+        return nullptr;
+    }
+    sc->perlins.assign(d->perlins, d->perlins + d->n_perlins);
+    sc->texels.assign(d->texels, d->texels + d->n_texels);
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const rt_texture& t = d->textures[i];
+        Texture* out = nullptr;
+        switch (t.kind) {
+            case RT_TEX_SOLID: {
+                auto* s = new SolidColor();
+                s->albedo = Vec3(t.color);
+                out = s;
+                break;
+            }
+            case RT_TEX_CHECKER: {
+                auto* c = new CheckerTexture();
+                c->inv_scale = t.scale;
+                if (t.a >= i || t.b >= i) {
+                    err = "checker child texture must precede it";
+                    delete c;
+                    return nullptr;
+                }
+                c->even = sc->textures[t.a].get(), c->odd = sc->textures[t.b].get();
+                out = c;
+                break;
+            }
+            case RT_TEX_IMAGE: {
+                auto* im = new ImageTexture();
+                if (t.a != RT_NONE) {
+                    const rt_image& ri = d->images[t.a];
+                    im->width = ri.width, im->height = ri.height;
+                    im->texels = sc->texels.data() + ri.texel_offset;
+                    im->linear = (ri.flags & RT_IMG_LINEAR) != 0;
+                    im->interp = (ri.flags & RT_IMG_INTERP) != 0;
+                }
+                out = im;
+                break;
+            }
+            case RT_TEX_NOISE: {
+                auto* n = new NoiseTexture();
+                n->tab = &sc->perlins[t.a];
+                n->scale = t.scale;
+                out = n;
+                break;
+            }
+            case RT_TEX_GRADIENT_Y: {
+                auto* g = new GradientTexture();
+                g->c0 = Vec3(t.color), g->c1 = Vec3(t.color2);
+                out = g;
+                break;
+            }
+            default:
+                err = "unknown texture kind";
+                return nullptr;
+        }
+        sc->textures.emplace_back(out);
+    }
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const rt_material& m = d->materials[i];
+        Material* out = nullptr;
+        auto tex = [&](uint32_t t) -> const Texture* { return t == RT_NONE ? nullptr : sc->textures[t].get(); };
+        auto inner = [&](uint32_t k) -> const Material* { return (k == RT_NONE || k >= i) ? nullptr : sc->materials[k].get(); };
+        switch (m.kind) {
+            case RT_MAT_EMPTY: out = new EmptyMaterial(); break;
+            case RT_MAT_LAMBERTIAN: { auto* x = new Lambertian(); x->texture = tex(m.tex); out = x; break; }
+            case RT_MAT_METAL: { auto* x = new Metal(); x->albedo = Vec3(m.color); x->fuzz = m.param; out = x; break; }
+            case RT_MAT_DIELECTRIC: { auto* x = new Dielectric(); x->attenuation = tex(m.tex); x->refraction_index = m.param; out = x; break; }
+            case RT_MAT_DIFFUSE_LIGHT: { auto* x = new DiffuseLight(); x->texture = tex(m.tex); x->material = inner(m.inner); out = x; break; }
+            case RT_MAT_ISOTROPIC: { auto* x = new Isotropic(); x->texture = tex(m.tex); out = x; break; }
+            case RT_MAT_TRANSPARENT: out = new Transparent(); break;
+            case RT_MAT_MIX: {
+                auto* x = new Mix();
+                x->mat1 = inner(m.inner), x->mat2 = inner(m.inner2), x->ratio = m.param;
+                x->alpha = m.tex == RT_NONE ? nullptr : dynamic_cast<const ImageTexture*>(tex(m.tex));
+                if (!x->mat1 || !x->mat2) { err = "Mix children must precede it"; delete x; return nullptr; }
+                out = x;
+                break;
+            }
+            case RT_MAT_PORTAL: {
+                auto* x = new Portal();
+                x->attenuation = Vec3(m.color), x->offset = Vec3(m.v);
+                x->q = Quaternion{m.v[3], m.v[4], m.v[5], m.v[6]};
+                out = x;
+                break;
+            }
+            default: err = "unknown material kind"; return nullptr;
+        }
+        sc->materials.emplace_back(out);
+    }
+    sc->by_object.assign(d->n_objects, nullptr);
+    sc->ranks.assign(d->n_objects, RT_NONE);
+    sc->world = build_object(*sc, *d, d->world_root);
+    if (!sc->world) {
+        err = sc->error;
+        return nullptr;
+    }
+    if (d->lights_root != RT_NONE) {
+        sc->lights = build_object(*sc, *d, d->lights_root);
+        if (!sc->lights) {
+            err = sc->error;
+            return nullptr;
+        }
+        if (!sc->lights->can_be_light()) {
+            err = "lights contains a BVH or ConstantMedium: pdf_value/random are unimplemented!() (hit.rs:51-59)";
+            return nullptr;
+        }
+        uint32_t next = 0;
+        sc->lights->count_leaves(next);
+        light_weights(sc->lights, 1.0, sc->light_leaves);
+        double acc = 0.0;
+        for (auto& l : sc->light_leaves) {
+            acc += l.weight;
+            l.cdf = acc;
+        }
+    }
+    uint32_t next = 0;
+    std::vector<const Transform*> chain;
+    assign_ranks(*sc, sc->world, next, chain);
+    return sc.release();
+}
+
+// ---------------------------------------------------------------- camera.rs
+struct RenderCounters {
+    uint64_t paths = 0, segments = 0, errors = 0;
+};
+
+// shapes/environment.rs:14-24
+static Vec3 background_value(const Scene& sc, const rt_camera& cam, const Ray& ray, bool& error) {
+    Vec3 p;
+    if (!unit_vector(ray.dir, p)) {
+        error = true;
+        return Vec3(0, 0, 0);
+    }
+    double theta = std::acos(-p.y());
+    double phi = PI - std::atan2(-p.z(), p.x());
+    double u = phi / (2.0 * PI);
+    double v = theta / PI;
+    return sc.textures[cam.background_tex]->value(u, v, p);
+}
+
+// Camera::ray_color, camera.rs:275-325.  `error` is set where the reference would panic.
+static Vec3 ray_color(const Scene& sc, const rt_camera& cam, const Ray& r, uint32_t depth, PathCtx& ctx, RenderCounters& cnt, bool& error) {
+    if (depth == 0) return Vec3(0, 0, 0);
+    ctx.segment = cam.max_depth - depth;
+    cnt.segments++;
+    HitRecord rec;
+    if (!sc.world->hit(r, Interval::raw(1e-8, INF), ctx, rec)) return background_value(sc, cam, r, error);
+
+    Vec3 color_from_emission = rec.mat->emitted(r, rec);
+    ScatterRecord srec = rec.mat->scatter(r, rec, ctx, 0);
+    if (srec.error) {
+        error = true;
+        return Vec3(0, 0, 0);
+    }
+    if (srec.kind == SCATTER_NONE) return color_from_emission;
+
+    Vec3 color_from_scatter;
+    if (srec.kind == SCATTER_RAY) {
+        Vec3 L = ray_color(sc, cam, srec.ray, depth - 1, ctx, cnt, error);
+        color_from_scatter = srec.attenuation * L;
+    } else {
+        // MixturePDF over (material pdf, HittablePDF(lights)) — camera.rs:297-304, pdf.rs:66-120
+        Rand2 pick = ctx.draw(RT_SLOT_MIXTURE);
+        Rand2 dirxi = ctx.draw(RT_SLOT_DIRECTION);
+        Vec3 generate_vec;
+        if (sc.lights) {
+            if (pick.a < 0.5) {
+                generate_vec = pdf_generate(srec, dirxi.a, dirxi.b);
+            } else {
+                LightSample ls;
+                ls.leaf = (uint32_t)sc.light_leaves.size() - 1;
+                for (uint32_t i = 0; i < sc.light_leaves.size(); i++)
+                    if (pick.b < sc.light_leaves[i].cdf) {
+                        ls.leaf = i;
+                        break;
+                    }
+                ls.r1 = dirxi.a, ls.r2 = dirxi.b;
+                generate_vec = sc.lights->random(rec.p, ls);
+                if (ls.error) {
+                    error = true;
+                    return Vec3(0, 0, 0);
+                }
+            }
+        } else {
+            generate_vec = pdf_generate(srec, dirxi.a, dirxi.b);
+        }
+        Ray scattered(rec.p, generate_vec, r.time);
+        Vec3 albedo_x_pscatter;
+        double value0;
+        if (!pdf_value(srec, scattered.dir, albedo_x_pscatter, value0)) {
+            error = true;
+            return Vec3(0, 0, 0);
+        }
+        double pdf_val = value0;
+        if (sc.lights) {
+            double value1 = sc.lights->pdf_value(rec.p, scattered.dir);
+            if (std::isnan(value1)) error = true;                 // hits.rs:64 assert
+            if (value0 == 0.0 && value1 == 0.0) error = true;     // pdf.rs:105-109 panic
+            pdf_val = value0 * 0.5 + value1 * 0.5;
+        }
+        if (pdf_val == 0.0) error = true;  // camera.rs:309
+        if (error) return Vec3(0, 0, 0);
+        Vec3 sample_color = ray_color(sc, cam, scattered, depth - 1, ctx, cnt, error);
+        color_from_scatter = (albedo_x_pscatter * sample_color) / pdf_val;
+    }
+    Vec3 ret = color_from_emission + color_from_scatter;
+    if (std::isnan(ret[0]) || std::isnan(ret[1]) || std::isnan(ret[2])) error = true;  // camera.rs:323
+    return ret;
+}
+
+// Camera::get_ray, camera.rs:247-273
+static Ray get_ray(const rt_camera& cam, uint32_t i, uint32_t j, uint32_t s_i, uint32_t s_j, PathCtx& ctx) {
+    ctx.segment = 0;
+    Rand2 jit = ctx.draw(RT_SLOT_CAM_JITTER);
+    double px = (((double)s_i + jit.a) * cam.recip_sqrt_spp) - 0.5;
+    double py = (((double)s_j + jit.b) * cam.recip_sqrt_spp) - 0.5;
+    Vec3 pixel_sample = Vec3(cam.pixel00_loc) + (((double)i + px) * Vec3(cam.pixel_delta_u)) + (((double)j + py) * Vec3(cam.pixel_delta_v));
+    Vec3 ray_origin;
+    if (cam.defocus_angle_in_degrees <= 0.0) {
+        ray_origin = Vec3(cam.center);
+    } else {  // defocus_disk_sample + random_in_unit_disk (vec3.rs:63-69)
+        Rand2 d = ctx.draw(RT_SLOT_CAM_DISK);
+        double theta = (2.0 * PI) * d.a;
+        double rr = std::sqrt(d.b);
+        double p0 = rr * std::cos(theta), p1 = rr * std::sin(theta);
+        ray_origin = Vec3(cam.center) + (p0 * Vec3(cam.defocus_disk_u)) + (p1 * Vec3(cam.defocus_disk_v));
+    }
+    Vec3 ray_direction = pixel_sample - ray_origin;
+    double ray_time = ctx.draw(RT_SLOT_CAM_TIME).a;
+    return Ray(ray_origin, ray_direction, ray_time);
+}
+
+// utils/color.rs:14-36
+static void to_rgb(Vec3 c, uint32_t toon_map, uint8_t out[3]) {
+    if (toon_map == 1) {
+        const double A = 2.51, C = 2.43;
+        const Vec3 B(0.03, 0.03, 0.03), D(0.59, 0.59, 0.59), E(0.14, 0.14, 0.14);
+        Vec3 m = vdiv(c * (A * c + B), c * (C * c + D) + E);
+        for (int k = 0; k < 3; k++) c[k] = m[k] < 0.0 ? 0.0 : (m[k] > 1.0 ? 1.0 : m[k]);
+    }
+    for (int k = 0; k < 3; k++) {
+        // palette Srgb::from_linear (crate not vendored): the standard piecewise sRGB curve, then
+        // round to 8 bits.  palette's f32->u8 fast path may differ by 1 LSB at rounding boundaries.
+        double x = c[k];
+        double enc = x <= 0.0031308 ? 12.92 * x : 1.055 * std::pow(x, 1.0 / 2.4) - 0.055;
+        if (!(enc > 0.0)) enc = 0.0;
+        if (enc > 1.0) enc = 1.0;
+        out[k] = (uint8_t)std::lround(enc * 255.0);
+    }
+}
+
+}  // namespace orc
+
+// =====================================================================================
+// C entry points (ctypes)
+// =====================================================================================
+using namespace orc;
+
+extern "C" {
+
+static thread_local std::string g_orc_err;
+const char* orc_last_error() { return g_orc_err.c_str(); }
+
+void* orc_scene_create(const rt_scene_desc* d) {
+    std::string err;
+    Scene* s = scene_from_desc(d, err);
+    if (!s) g_orc_err = err;
+    return s;
+}
+void orc_scene_destroy(void* s) { delete (Scene*)s; }
+
+int orc_get_ranks(const void* s, uint32_t* ranks, uint32_t n) {
+    const Scene* sc = (const Scene*)s;
+    if (n != sc->ranks.size()) return -1;
+    std::copy(sc->ranks.begin(), sc->ranks.end(), ranks);
+    return 0;
+}
+
+// mode 0: the reference's container semantics (world.hit, media left out)
+// mode 1: brute force over every leaf shape with the full interval; exact ties -> lower rank
+int orc_closest_hit(const void* s, const rt_ray* rays, uint64_t n, double t_min, double t_max, int mode, rt_hit* out) {
+    const Scene* sc = (const Scene*)s;
+    Interval iv = Interval::raw(t_min, t_max);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t k = 0; k < (int64_t)n; k++) {
+        Ray r(Vec3(rays[k].origin), Vec3(rays[k].direction), rays[k].time);
+        PathCtx ctx;
+        ctx.media_enabled = false;
+        HitRecord best;
+        bool any = false;
+        if (mode == 0) {
+            any = sc->world->hit(r, iv, ctx, best);
+        } else {
+            uint32_t best_rank = RT_NONE;
+            for (const auto& leaf : sc->leaves) {
+                Ray lr = r;
+                for (const Transform* t : leaf.chain) {  // Transform::hit entry, outermost first
+                    Vec3 lo = t->detransform(lr.orig), lt = t->detransform(lr.at(1.0));
+                    lr = Ray(lo, lt - lo, lr.time);
+                }
+                HitRecord rec;
+                if (!leaf.prim->hit(lr, iv, ctx, rec)) continue;
+                uint32_t rank = sc->ranks[leaf.prim->id];
+                if (!any || rec.t < best.t || (rec.t == best.t && rank < best_rank)) {
+                    best = rec;
+                    best_rank = rank;
+                    best.inst_id = leaf.chain.empty() ? RT_NONE : leaf.chain.back()->id;
+                    any = true;
+                }
+            }
+        }
+        rt_hit h;
+        h.t = any ? best.t : INF;
+        h.prim_id = any ? best.prim_id : RT_NONE;
+        h.inst_id = any ? best.inst_id : RT_NONE;
+        h.u = any ? (float)best.u : 0.0f;
+        h.v = any ? (float)best.v : 0.0f;
+        out[k] = h;
+    }
+    return 0;
+}
+
+// The pixel loop of Camera::render (camera.rs:179-197): accum receives sum*pixel_sample_scale
+// per pixel (f64, W*H*3) for the requested partition / stratum range (see rt_render_opts).
+int orc_render(const void* s, const rt_camera* cam, const rt_render_opts* opts, double* accum, rt_stats* stats, int threads) {
+    const Scene* sc = (const Scene*)s;
+    const uint32_t W = cam->image_width, H = cam->image_height, S = cam->sqrt_spp;
+    uint32_t part_count = opts->part_count ? opts->part_count : 1, part_index = opts->part_index;
+    uint32_t s_begin = opts->sample_begin, s_end = opts->sample_end;
+    if (s_begin == 0 && s_end == 0) s_end = S * S;
+    const uint32_t tiles_x = (W + 7) / 8;
+    uint64_t paths = 0, segments = 0, errors = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : paths, segments, errors)
+    for (int64_t pix = 0; pix < (int64_t)W * H; pix++) {
+        uint32_t i = (uint32_t)(pix % W), j = (uint32_t)(pix / W);
+        uint32_t tile = (j / 8) * tiles_x + (i / 8);
+        Vec3 pixel_color(0, 0, 0);
+        if (tile % part_count == part_index) {
+            RenderCounters cnt;
+            for (uint32_t sidx = s_begin; sidx < s_end; sidx++) {
+                uint32_t s_i = sidx / S, s_j = sidx % S;
+                PathCtx ctx;
+                ctx.seed = opts->seed, ctx.pixel = (uint32_t)pix, ctx.sample = sidx;
+                Ray r = get_ray(*cam, i, j, s_i, s_j, ctx);
+                bool error = false;
+                Vec3 c = ray_color(*sc, *cam, r, cam->max_depth, ctx, cnt, error);
+                cnt.paths++;
+                if (error) {
+                    cnt.errors++;  // the reference would have aborted; the sample is dropped
+                    continue;
+                }
+                pixel_color = pixel_color + c;
+            }
+            paths += cnt.paths, segments += cnt.segments, errors += cnt.errors;
+        }
+        Vec3 scaled = pixel_color * cam->pixel_sample_scale;
+        accum[pix * 3 + 0] = scaled[0], accum[pix * 3 + 1] = scaled[1], accum[pix * 3 + 2] = scaled[2];
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->paths = paths, stats->segments = segments, stats->errors = errors;
+    }
+    return 0;
+}
+
+int orc_tonemap(const double* accum, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb) {
+    for (uint64_t i = 0; i < n_pixels; i++) to_rgb(Vec3(accum + 3 * i), toon_map, rgb + 3 * i);
+    return 0;
+}
+
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// ---- known-answer hooks for the vectors the reference's own unit tests hold ----------------
+int orc_kat_aabb_hit(const double* a, const double* b, const double* o, const double* d, double tmin, double tmax) {
+    return AABB::from_points(Vec3(a), Vec3(b)).hit(Ray(Vec3(o), Vec3(d)), Interval::make(tmin, tmax)) ? 1 : 0;
+}
+int orc_kat_aabb_longest_axis(const double* a, const double* b) { return AABB::from_points(Vec3(a), Vec3(b)).longest_axis(); }
+void orc_kat_aabb_from_points(const double* a, const double* b, double* out6) {
+    AABB x = AABB::from_points(Vec3(a), Vec3(b));
+    out6[0] = x.x.min, out6[1] = x.x.max, out6[2] = x.y.min, out6[3] = x.y.max, out6[4] = x.z.min, out6[5] = x.z.max;
+}
+void orc_kat_aabb_union(const double* a6, const double* b6, double* out6) {
+    AABB x = AABB::union_(AABB::from6(a6), AABB::from6(b6));
+    out6[0] = x.x.min, out6[1] = x.x.max, out6[2] = x.y.min, out6[3] = x.y.max, out6[4] = x.z.min, out6[5] = x.z.max;
+}
+void orc_kat_sphere_uv(const double* p, double* uv) { Sphere::get_sphere_uv(Vec3(p), uv[0], uv[1]); }
+void orc_kat_ray_at(const double* o, const double* d, double t, double* out) {
+    Vec3 p = Ray(Vec3(o), Vec3(d)).at(t);
+    out[0] = p[0], out[1] = p[1], out[2] = p[2];
+}
+void orc_kat_vec3(const double* a, const double* b, double s, double* out) {
+    // out: add(3) sub(3) mul_scalar(3) div_scalar(3) dot(1) cross(3) length(1) unit(3)
+    Vec3 A(a), B(b);
+    Vec3 r;
+    r = A + B; out[0] = r[0], out[1] = r[1], out[2] = r[2];
+    r = A - B; out[3] = r[0], out[4] = r[1], out[5] = r[2];
+    r = A * s; out[6] = r[0], out[7] = r[1], out[8] = r[2];
+    r = A / s; out[9] = r[0], out[10] = r[1], out[11] = r[2];
+    out[12] = dot(A, B);
+    r = cross(A, B); out[13] = r[0], out[14] = r[1], out[15] = r[2];
+    out[16] = length(A);
+    unit_vector(A, r); out[17] = r[0], out[18] = r[1], out[19] = r[2];
+}
+void orc_kat_quat_axis_angle_rotate(const double* axis, double deg, const double* v, double* out) {
+    Vec3 r = Quaternion::from_axis_angle(Vec3(axis), deg).rotate_vector(Vec3(v));
+    out[0] = r[0], out[1] = r[1], out[2] = r[2];
+}
+void orc_kat_quat_mul(const double* a_wxyz, const double* b_wxyz, double* out) {
+    Quaternion r = Quaternion{a_wxyz[0], a_wxyz[1], a_wxyz[2], a_wxyz[3]}.mul(Quaternion{b_wxyz[0], b_wxyz[1], b_wxyz[2], b_wxyz[3]});
+    out[0] = r.w, out[1] = r.x, out[2] = r.y, out[3] = r.z;
+}
+void orc_kat_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    philox4x32_10(c, key[0], key[1]);
+    for (int i = 0; i < 4; i++) out[i] = c[i];
+}
+void orc_kat_draw(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t segment, uint32_t slot, double* ab) {
+    Rand2 r = philox_pair(seed, pixel, sample, segment, slot);
+    ab[0] = r.a, ab[1] = r.b;
+}
+// texture / environment lookups on a built scene (used to cross-check the device textures)
+void orc_texture_value(const void* s, uint32_t tex, double u, double v, const double* p, double* out) {
+    Vec3 c = ((const Scene*)s)->textures[tex]->value(u, v, Vec3(p));
+    out[0] = c[0], out[1] = c[1], out[2] = c[2];
+}
+void orc_camera_ray(const rt_camera* cam, uint64_t seed, uint32_t i, uint32_t j, uint32_t sidx, rt_ray* out) {
+    PathCtx ctx;
+    ctx.seed = seed, ctx.pixel = j * cam->image_width + i, ctx.sample = sidx;
+    Ray r = get_ray(*cam, i, j, sidx / cam->sqrt_spp, sidx % cam->sqrt_spp, ctx);
+    for (int k = 0; k < 3; k++) out->origin[k] = r.orig[k], out->direction[k] = r.dir[k];
+    out->time = r.time;
+}
+
+}  // extern "C"

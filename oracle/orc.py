@@ -1,0 +1,120 @@
+"""ctypes bindings for the CPU oracle (oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: import this from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py — never from the product package.
+"""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+_spec = importlib.util.spec_from_file_location("rt2025", os.path.join(ROOT, "raytracer-2025_b200", "rt2025.py"))
+rt = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(rt)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", ROOT, "oracle"])
+        L = C.CDLL(path)
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.c_void_p]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_get_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_tonemap.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+        D = C.POINTER(C.c_double)
+        L.orc_kat_aabb_hit.argtypes = [D, D, D, D, C.c_double, C.c_double]
+        L.orc_kat_aabb_longest_axis.argtypes = [D, D]
+        L.orc_kat_aabb_from_points.argtypes = [D, D, D]
+        L.orc_kat_aabb_union.argtypes = [D, D, D]
+        L.orc_kat_sphere_uv.argtypes = [D, D]
+        L.orc_kat_ray_at.argtypes = [D, D, C.c_double, D]
+        L.orc_kat_vec3.argtypes = [D, D, C.c_double, D]
+        L.orc_kat_quat_axis_angle_rotate.argtypes = [D, C.c_double, D, D]
+        L.orc_kat_quat_mul.argtypes = [D, D, D]
+        U = C.POINTER(C.c_uint32)
+        L.orc_kat_philox.argtypes = [U, U, U]
+        L.orc_kat_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, D]
+        L.orc_texture_value.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, D, D]
+        L.orc_camera_ray.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def d(*v):
+    return (C.c_double * len(v))(*[float(x) for x in v])
+
+
+class OracleScene:
+    def __init__(self, host_scene):
+        self.L = lib()
+        self.host = host_scene
+        self.h = self.L.orc_scene_create(C.cast(host_scene.desc, C.c_void_p))
+        if not self.h:
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_scene_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def ranks(self):
+        n = self.host.desc.contents.n_objects
+        out = np.empty(n, dtype=np.uint32)
+        assert self.L.orc_get_ranks(self.h, out.ctypes.data, n) == 0
+        return out
+
+    def closest_hit(self, rays, t_min=1e-8, t_max=float("inf"), mode=0):
+        """mode 0: reference container semantics; mode 1: brute force over all leaves."""
+        rays = np.ascontiguousarray(rays, dtype=rt.rt_ray_dtype)
+        out = np.empty(len(rays), dtype=rt.rt_hit_dtype)
+        self.L.orc_closest_hit(self.h, rays.ctypes.data, len(rays), t_min, t_max, mode, out.ctypes.data)
+        return out
+
+    def render(self, camera=None, seed=1, part_index=0, part_count=1, sample_begin=0, sample_end=0, threads=0):
+        cam = camera if camera is not None else self.host.camera
+        o = rt.rt_render_opts()
+        o.struct_size = C.sizeof(rt.rt_render_opts)
+        o.seed, o.accum_type = seed, rt.RT_ACCUM_F64
+        o.part_index, o.part_count, o.sample_begin, o.sample_end = part_index, part_count, sample_begin, sample_end
+        img = np.zeros((cam.image_height, cam.image_width, 3), dtype=np.float64)
+        st = rt.rt_stats()
+        self.L.orc_render(self.h, C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st), threads)
+        return img, st
+
+    def texture_value(self, tex, u, v, p):
+        out = (C.c_double * 3)()
+        self.L.orc_texture_value(self.h, tex, u, v, d(*p), out)
+        return np.array(out)
+
+
+def camera_rays(camera, seed, pixels_ij, sample):
+    """Camera::get_ray for a list of (i, j) pixels at one sample index."""
+    L = lib()
+    out = np.zeros(len(pixels_ij), dtype=rt.rt_ray_dtype)
+    for k, (i, j) in enumerate(pixels_ij):
+        L.orc_camera_ray(C.byref(camera), seed, int(i), int(j), int(sample), out[k:k + 1].ctypes.data)
+    return out
+
+
+def tonemap(accum, toon_map=0):
+    a = np.ascontiguousarray(accum, dtype=np.float64)
+    out = np.empty(a.shape, dtype=np.uint8)
+    lib().orc_tonemap(a.ctypes.data, a.size // 3, toon_map, out.ctypes.data)
+    return out
