@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — paths/sec on the book-2 final scene (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA core
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+One "step" = one full render of the 800x800 frame at 1000 spp (961 effective, depth 40) =
+615,040,000 paths.  With N > 1 (torchrun, one rank per GPU) the frame is cut into interleaved
+8x8 pixel tiles, rank r renders tiles with tile_index % N == r, and one NCCL reduce(sum) of the
+float framebuffer reassembles it on rank 0: total work is fixed, so scaling is "strong".
+
+Keys beyond the base contract: `roofline` (dominant kernel = extend), `cpu_baseline` (the oracle on
+this box's host cores, bounded sample), `e2e` (flatten + upload + render + read-back + 8-bit encode
+per step, i.e. what Camera::render does), `clocks`, `gpu_launches`.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("rt2025", os.path.join(ROOT, "raytracer-2025_b200", "rt2025.py"))
+rt = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(rt)
+
+SCENE = ("book2_final", 7, [800, 1000, 40])  # name, scene seed, [width, spp, max_depth]
+RENDER_SEED = 2025
+# algorithmic HBM bytes of the dominant kernel (extend) per unit (= one path segment), DESIGN.md §5:
+# slot index in (4) + ray record read (4 x 16) + hit word written (16) + queue append (4)
+EXTEND_BYTES_PER_SEGMENT = 4 + 64 + 16 + 4
+
+
+def partition_for_rank(rank, world):
+    """rt_render_opts.part_index / part_count of a rank: interleaved 8x8 tiles, tile % world == rank."""
+    return rank, max(1, world)
+
+
+def reduce_framebuffer_and_paths(fb, paths, dst=0):
+    """The single collective of the multi-GPU path: sum the float framebuffers on `dst` (partitions
+    are disjoint, so the sum is also the gather) and total the path counts."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(fb, dst=dst, op=dist.ReduceOp.SUM)
+        t = torch.tensor([int(paths)], dtype=torch.int64, device=fb.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+    return int(paths)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (NVML, 100 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(host_scene, target_seconds=12.0):
+    """The C++ restatement of the reference (oracle/) on this box's host cores, on a bounded sample:
+    the same frame and camera, strata [0, k) of the 961."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    osc = orc.OracleScene(host_scene)
+    cores = orc.lib().orc_num_threads()
+    t0 = time.perf_counter()
+    _, st = osc.render(seed=RENDER_SEED, sample_begin=0, sample_end=1)
+    dt1 = time.perf_counter() - t0
+    k = int(max(1, min(16, target_seconds / max(dt1, 1e-3))))
+    t0 = time.perf_counter()
+    _, st = osc.render(seed=RENDER_SEED, sample_begin=0, sample_end=k)
+    dt = time.perf_counter() - t0
+    return {"value": st.paths / dt, "unit": "paths/s", "cores": cores, "kind": "port",
+            "sample": f"strata [0,{k}) of 961 over the full 800x800 frame: {st.paths} paths in {dt:.2f} s, "
+                      f"{st.segments / st.paths:.2f} segments/path",
+            "note": "C++ restatement of the reference algorithm (recursive, virtual dispatch, median BVH); "
+                    "the Rust crate itself cannot be built here (no rustc/cargo)"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the oracle port timed on host cores; rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    name, seed, params = SCENE
+    hs = rt.named_scene(name, seed=seed, params=params)
+    osc = orc.OracleScene(hs)
+    cores = orc.lib().orc_num_threads()
+    strata = 2  # per step: 800*800*2 = 1.28 M paths
+    for _ in range(args.warmup):
+        osc.render(seed=RENDER_SEED, sample_begin=0, sample_end=strata)
+    t0 = time.perf_counter()
+    paths = 0
+    for k in range(args.steps):
+        _, st = osc.render(seed=RENDER_SEED, sample_begin=(k * strata) % 960, sample_end=(k * strata) % 960 + strata)
+        paths += st.paths
+    dt = time.perf_counter() - t0
+    v = paths / dt
+    sample = f"{strata} strata of 961 per step over the full 800x800 frame ({paths // max(1, args.steps)} paths/step)"
+    print(json.dumps({
+        "impl": "reference", "metric": "paths_per_sec", "value": v, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "book2_final 800x800 spp=1000 (961 effective) depth=40", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "paths/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp", type=int, default=1000, help="samples_per_pixel field (default = the config's 1000)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    name, seed, params = SCENE
+    params = [params[0], args.spp, params[2]]
+    hs = rt.named_scene(name, seed=seed, params=params)
+    cam = hs.camera
+    W, H = cam.image_width, cam.image_height
+    scene = rt.Scene(hs, device=local_rank)
+    info = scene.info()
+    part_index, part_count = partition_for_rank(rank, world)
+    fb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(flags=rt.RT_OPT_STAGE_TIMES):
+        flush.zero_()
+        st = scene.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32,
+                                 part_index=part_index, part_count=part_count, flags=flags)
+        total = reduce_framebuffer_and_paths(fb, st.paths, dst=0)
+        return st, total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    paths = segs = launches = iters = 0
+    ms_extend = ms_shade = ms_gen = 0.0
+    for _ in range(args.steps):
+        st, total = step()
+        paths += total
+        segs += st.segments
+        launches += st.kernel_launches + 1  # + the L2 flush fill
+        iters += st.iterations
+        ms_extend += st.ms_extend
+        ms_shade += st.ms_shade
+        ms_gen += st.ms_raygen
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    extra = torch.tensor([segs, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(extra, op=dist.ReduceOp.SUM)
+    ms_total = float(ms.item())
+    value = paths / (ms_total * 1e-3)
+
+    # ---- e2e: what Camera::render does per call: flatten/upload the scene, render, reduce, read the
+    # frame back to the host, 8-bit encode.  Host buffers in, host image out.
+    d = hs.desc.contents
+    h2d = (d.n_objects * 72 + d.n_children * 4 + d.n_spheres * 64 + d.n_planars * 144 + d.n_transforms * 80 + d.n_media * 16 +
+           d.n_materials * 120 + d.n_textures * 80 + d.n_perlins * 9216 + d.n_texels * 4)
+    d2h = W * H * 3 * 4 + W * H * 3
+    host_fb = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_paths = 0
+    for _ in range(args.steps):
+        sc2 = rt.Scene(hs, device=local_rank)  # rt_scene_create: compile + BVH build + H2D of the scene
+        st = sc2.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32,
+                               part_index=part_index, part_count=part_count)
+        e2e_paths += reduce_framebuffer_and_paths(fb, st.paths, dst=0)
+        if rank == 0:
+            host_fb.copy_(fb, non_blocking=False)  # D2H of the frame
+            rgb = rt.tonemap(host_fb.numpy(), cam.toon_map)  # Color::to_rgb -> RgbImage bytes
+            assert rgb.shape == (H, W, 3)
+        sc2.close()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_paths / float(e2e_t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        n_ext_launches = max(1, iters)
+        seg_rank0 = segs
+        ext_bytes_per_launch = seg_rank0 * EXTEND_BYTES_PER_SEGMENT / n_ext_launches
+        ext_ms_per_launch = ms_extend / n_ext_launches
+        achieved = ext_bytes_per_launch / (ext_ms_per_launch * 1e-3) / 1e9 if ext_ms_per_launch > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": "paths_per_sec", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"book2_final {W}x{H} spp={args.spp} ({cam.sqrt_spp ** 2} effective) depth={cam.max_depth}",
+                       "scene_seed": seed, "prims": info.n_prims, "bvh_nodes": info.n_nodes, "media": info.n_media,
+                       "paths_per_step": paths // max(1, args.steps), "segments_per_path": float(extra[0].item()) / max(1, paths),
+                       "parallelism": f"tiles{world}" if world > 1 else "single",
+                       "l2": "flushed between steps (256 MiB fill); path-state working set 256 MiB > 126 MB L2, the 0.7 MB scene is cache-resident by design"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "includes": "rt_scene_create (flatten+SAH build+upload), render, reduce, frame D2H, 8-bit encode"},
+            "gpu_launches": int(extra[1].item()),
+            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_segment": EXTEND_BYTES_PER_SEGMENT, "segments_per_launch": seg_rank0 / n_ext_launches,
+                         "ms_per_launch": ext_ms_per_launch,
+                         "stage_ms_per_step": {"generate": ms_gen / args.steps, "extend": ms_extend / args.steps, "shade": ms_shade / args.steps},
+                         "note": "configs 1-3 keep the scene in L1/L2: the binding limit is SM issue rate under divergence, "
+                                 "not HBM (SURVEY.md §8d); see profiles/ for issue utilisation"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(hs)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

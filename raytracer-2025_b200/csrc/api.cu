@@ -1,0 +1,486 @@
+// api.cu — the extern "C" boundary (include/rt2025.h): scene upload, the wavefront driver loop,
+// closest-hit batches, tone mapping.  No C++ exception leaves this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "compile.h"
+#include "kernels.h"
+#include "rt2025.h"
+
+using namespace rt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            throw CudaFail{std::string(#call) + ": " + cudaGetErrorString(e_)};                               \
+        }                                                                                                     \
+    } while (0)
+
+struct CudaFail {
+    std::string what;
+};
+
+template <class T>
+T* upload(const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    T* d = nullptr;
+    CU(cudaMalloc(&d, v.size() * sizeof(T)));
+    CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+struct Workspace {  // wavefront buffers, cached on the scene between renders
+    WavefrontState W{};
+    uint32_t capacity = 0;
+    uint64_t n_pixels_alloc = 0;
+    Counters* h_counters = nullptr;  // pinned
+    std::vector<cudaEvent_t> events;  // stage-timing pool: 4 per iteration, read back after the render
+    cudaEvent_t event(size_t i) {
+        while (events.size() <= i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            events.push_back(e);
+        }
+        return events[i];
+    }
+    void release() {
+        for (auto e : events) cudaEventDestroy(e);
+        events.clear();
+        cudaFree(W.rec);
+        cudaFree(W.q_extend);
+        cudaFree(W.q_free);
+        for (auto& q : W.q_shade) cudaFree(q);
+        cudaFree(W.pixel_list);
+        cudaFree(W.accum);
+        cudaFree(W.counters);
+        if (h_counters) cudaFreeHost(h_counters);
+        *this = Workspace();
+    }
+};
+
+}  // namespace
+
+struct rt_scene {
+    int device = 0;
+    int sm_count = 148;
+    SceneView view{};
+    std::vector<void*> allocs;
+    std::vector<uint32_t> ranks;
+    rt_scene_info info{};
+    uint32_t lights_flat = 1;
+    Workspace ws;
+    std::mutex mu;  // one render at a time per handle
+    int extend_blocks_per_sm = 4, shade_blocks_per_sm = 4;
+};
+
+namespace {
+
+int check_device(int requested, int& device, int& sm_count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_err(RT_ERR_NO_DEVICE, "no CUDA device available: librt2025 has no CPU path");
+    }
+    if (requested >= 0) {
+        if (requested >= n) return set_err(RT_ERR_INVALID, "device ordinal out of range");
+        if (cudaSetDevice(requested) != cudaSuccess) return set_err(RT_ERR_CUDA, "cudaSetDevice failed");
+    }
+    cudaGetDevice(&device);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return set_err(RT_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (p.major != 10)
+        return set_err(RT_ERR_NO_DEVICE, std::string("built for sm_100a only; device is sm_") + std::to_string(p.major) + std::to_string(p.minor));
+    sm_count = p.multiProcessorCount;
+    return RT_OK;
+}
+
+template <class T>
+T* track(rt_scene* s, T* p) {
+    if (p) s->allocs.push_back((void*)p);
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err.c_str(); }
+uint32_t rt_abi_version(void) { return RT_ABI_VERSION; }
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_scene** out) {
+    if (!desc || !out) return set_err(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    rt_scene* s = nullptr;
+    try {
+        CompiledScene cs;
+        std::string err;
+        uint32_t flags = opts ? opts->flags : 0;
+        int rc = compile_scene(*desc, flags, cs, err);
+        if (rc != RT_OK) return set_err(rc, err);
+        int device = 0, sms = 0;
+        rc = check_device(opts ? opts->device : -1, device, sms);
+        if (rc != RT_OK) return rc;
+        s = new rt_scene();
+        s->device = device;
+        s->sm_count = sms;
+        SceneView& v = s->view;
+        v.nodes = track(s, upload(cs.nodes));
+        v.geom = track(s, upload(cs.geom));
+        v.meta = track(s, upload(cs.meta));
+        v.xforms = track(s, upload(cs.xforms));
+        v.materials = track(s, upload(cs.materials));
+        v.textures = track(s, upload(cs.textures));
+        v.images = track(s, upload(cs.images));
+        v.texels = track(s, upload(cs.texels));
+        v.perlins = track(s, upload(cs.perlins));
+        v.media = track(s, upload(cs.media));
+        v.lights = track(s, upload(cs.lights));
+        v.world_root = cs.world_root;
+        v.n_media = (uint32_t)cs.media.size();
+        v.n_lights = (uint32_t)cs.lights.size();
+        v.n_prims = (uint32_t)cs.geom.size();
+        s->ranks = cs.ranks;
+        // lights is "flat" when every leaf has the same weight 1/n (a single-level list)
+        s->lights_flat = 1;
+        for (auto& l : cs.lights)
+            if (l.weight != 1.0 / (double)cs.lights.size()) s->lights_flat = 0;
+        rt_scene_info& i = s->info;
+        i.n_prims = v.n_prims, i.n_spheres = cs.n_spheres, i.n_planars = cs.n_planars, i.n_nodes = (uint32_t)cs.nodes.size();
+        i.n_media = v.n_media, i.n_lights = v.n_lights, i.n_materials = (uint32_t)cs.materials.size(), i.n_textures = (uint32_t)cs.textures.size();
+        i.bvh_depth = cs.bvh_depth;
+        i.device_bytes = cs.nodes.size() * sizeof(Node) + cs.geom.size() * sizeof(PrimGeom) + cs.meta.size() * sizeof(PrimMeta) +
+                         cs.texels.size() * sizeof(float4) + cs.perlins.size() * sizeof(Perlin);
+        kernel_occupancy(&s->extend_blocks_per_sm, &s->shade_blocks_per_sm);
+        if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;
+        if (s->shade_blocks_per_sm < 1) s->shade_blocks_per_sm = 1;
+        CU(cudaDeviceSynchronize());
+        *out = s;
+        return RT_OK;
+    } catch (const CudaFail& f) {
+        if (s) rt_scene_destroy(s);
+        return set_err(RT_ERR_CUDA, f.what);
+    } catch (const std::bad_alloc&) {
+        if (s) rt_scene_destroy(s);
+        return set_err(RT_ERR_OOM, "out of host memory");
+    } catch (...) {
+        if (s) rt_scene_destroy(s);
+        return set_err(RT_ERR_INVALID, "unexpected failure in rt_scene_create");
+    }
+}
+
+int rt_scene_destroy(rt_scene* s) {
+    if (!s) return RT_OK;
+    cudaSetDevice(s->device);
+    for (void* p : s->allocs) cudaFree(p);
+    s->ws.release();
+    delete s;
+    return RT_OK;
+}
+
+int rt_scene_get_info(const rt_scene* s, rt_scene_info* info) {
+    if (!s || !info) return set_err(RT_ERR_INVALID, "null argument");
+    *info = s->info;
+    return RT_OK;
+}
+
+int rt_scene_get_ranks(const rt_scene* s, uint32_t* ranks, uint32_t n) {
+    if (!s || !ranks) return set_err(RT_ERR_INVALID, "null argument");
+    if (n != s->ranks.size()) return set_err(RT_ERR_INVALID, "n_objects mismatch");
+    std::copy(s->ranks.begin(), s->ranks.end(), ranks);
+    return RT_OK;
+}
+
+int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, double t_min, double t_max, uint32_t flags,
+                          rt_hit* d_out, void* stream, rt_stats* stats) {
+    if (!s || (n && (!d_rays || !d_out))) return set_err(RT_ERR_INVALID, "null argument");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return RT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d_cnt = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = RT_OK;
+    try {
+        CU(cudaSetDevice(s->device));
+        const bool count = (flags & RT_OPT_COUNT) != 0;
+        if (count) {
+            CU(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
+        }
+        int grid = s->sm_count * s->extend_blocks_per_sm;
+        uint64_t need = (n + EXTEND_BLOCK - 1) / EXTEND_BLOCK;
+        if ((uint64_t)grid > need) grid = (int)need;
+        if (stats) {
+            CU(cudaEventCreate(&e0));
+            CU(cudaEventCreate(&e1));
+            CU(cudaEventRecord(e0, st));
+        }
+        launch_closest_hit(s->view, d_rays, n, t_min, t_max, count, d_out, d_cnt, grid, st);
+        CU(cudaGetLastError());
+        if (stats) {
+            CU(cudaEventRecord(e1, st));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            stats->ms_total = ms;
+            stats->ms_extend = ms;
+            stats->segments = n;
+            stats->kernel_launches = 1;
+            if (count) {
+                unsigned long long h[2];
+                CU(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+                stats->node_visits = h[0], stats->prim_tests = h[1];
+            }
+        }
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (d_cnt) cudaFree(d_cnt);
+    return rc;
+}
+
+int rt_closest_hit(const rt_scene* s, const rt_ray* rays, uint64_t n, double t_min, double t_max, uint32_t flags, rt_hit* out,
+                   rt_stats* stats) {
+    if (!s || (n && (!rays || !out))) return set_err(RT_ERR_INVALID, "null argument");
+    if (n == 0) {
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        return RT_OK;
+    }
+    rt_ray* d_rays = nullptr;
+    rt_hit* d_out = nullptr;
+    int rc = RT_OK;
+    try {
+        CU(cudaSetDevice(s->device));
+        CU(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
+        CU(cudaMalloc(&d_out, n * sizeof(rt_hit)));
+        CU(cudaMemcpy(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice));
+        rc = rt_closest_hit_device(s, d_rays, n, t_min, t_max, flags, d_out, nullptr, stats);
+        if (rc == RT_OK) {
+            CU(cudaDeviceSynchronize());
+            CU(cudaMemcpy(out, d_out, n * sizeof(rt_hit), cudaMemcpyDeviceToHost));
+        }
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    cudaFree(d_rays);
+    cudaFree(d_out);
+    return rc;
+}
+
+static uint64_t count_partition_pixels(uint32_t W, uint32_t H, uint32_t part_index, uint32_t part_count) {
+    uint32_t tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
+    uint64_t n = 0;
+    for (uint32_t ty = 0; ty < tiles_y; ty++)
+        for (uint32_t tx = 0; tx < tiles_x; tx++) {
+            uint32_t tile = ty * tiles_x + tx;
+            if (tile % part_count != part_index) continue;
+            uint32_t w = std::min(8u, W - tx * 8), h = std::min(8u, H - ty * 8);
+            n += (uint64_t)w * h;
+        }
+    return n;
+}
+
+int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_opts* opts, void* d_accum, void* stream, rt_stats* stats) {
+    if (!cs || !cam || !d_accum) return set_err(RT_ERR_INVALID, "null argument");
+    rt_scene* s = const_cast<rt_scene*>(cs);
+    rt_render_opts o{};
+    if (opts) {
+        if (opts->struct_size != sizeof(rt_render_opts)) return set_err(RT_ERR_VERSION, "rt_render_opts.struct_size mismatch");
+        o = *opts;
+    }
+    if (cam->image_width == 0 || cam->image_height == 0 || cam->sqrt_spp == 0)
+        return set_err(RT_ERR_INVALID, "camera has an empty image or zero samples");
+    if (cam->background_tex >= s->info.n_textures) return set_err(RT_ERR_INVALID, "camera.background_tex out of range");
+    const uint32_t part_count = o.part_count ? o.part_count : 1;
+    if (o.part_index >= part_count) return set_err(RT_ERR_INVALID, "part_index >= part_count");
+    uint32_t s_begin = o.sample_begin, s_end = o.sample_end;
+    const uint32_t spp = cam->sqrt_spp * cam->sqrt_spp;
+    if (s_begin == 0 && s_end == 0) s_end = spp;
+    if (s_begin > s_end || s_end > spp) return set_err(RT_ERR_INVALID, "bad sample range");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+
+    std::lock_guard<std::mutex> lock(s->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n_px_img = (uint64_t)cam->image_width * cam->image_height;
+    const uint64_t n_pixels = count_partition_pixels(cam->image_width, cam->image_height, o.part_index, part_count);
+    const uint64_t total_paths = n_pixels * (uint64_t)(s_end - s_begin);
+    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 21);
+    capacity = std::max(capacity, 1024u);
+    cudaEvent_t ev[8] = {nullptr};
+    int rc = RT_OK;
+    try {
+        CU(cudaSetDevice(s->device));
+        Workspace& ws = s->ws;
+        if (ws.capacity != capacity || ws.n_pixels_alloc < n_px_img) {
+            ws.release();
+            WavefrontState& W = ws.W;
+            CU(cudaMalloc(&W.rec, (size_t)capacity * sizeof(PathRec)));
+            CU(cudaMalloc(&W.q_extend, (size_t)capacity * 4));
+            CU(cudaMalloc(&W.q_free, (size_t)capacity * 4));
+            for (auto& q : W.q_shade) CU(cudaMalloc(&q, (size_t)capacity * 4));
+            CU(cudaMalloc(&W.pixel_list, n_px_img * 4));
+            CU(cudaMalloc(&W.accum, n_px_img * 3 * sizeof(double)));
+            CU(cudaMalloc(&W.counters, sizeof(Counters)));
+            CU(cudaMallocHost(&ws.h_counters, sizeof(Counters)));
+            ws.capacity = capacity;
+            ws.n_pixels_alloc = n_px_img;
+        }
+        WavefrontState W = ws.W;
+        W.capacity = capacity;
+        W.n_pixels = (uint32_t)n_pixels;
+        W.total_paths = total_paths;
+        RenderParams P{};
+        P.cam = *cam;
+        P.seed = o.seed;
+        P.sample_begin = s_begin;
+        P.part_index = o.part_index, P.part_count = part_count;
+        P.lights_flat = s->lights_flat;
+        P.bin_by_class = (o.reserved[0] & 1u) ? 0u : 1u;  // reserved[0] bit 0: disable material binning (A/B evidence)
+
+        const bool count = (o.flags & RT_OPT_COUNT) != 0, stage = (o.flags & RT_OPT_STAGE_TIMES) != 0;
+        const int grid_e = s->sm_count * s->extend_blocks_per_sm, grid_s = s->sm_count * s->shade_blocks_per_sm;
+        const int grid_g = s->sm_count * 4;
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(ev[0], st));
+        Counters init{};
+        init.n_free = capacity;
+        CU(cudaMemcpyAsync(W.counters, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(W.accum, 0, n_px_img * 3 * sizeof(double), st));
+        uint64_t launches = 2;
+        double ms_gen = 0, ms_ext = 0, ms_shd = 0;
+        if (total_paths > 0) {
+            launch_init(W, P, grid_g, st);
+            launches += 2;
+            const int burst = 8;  // iterations between host checks of the counters
+            size_t iters = 0;
+            while (true) {
+                for (int b = 0; b < burst; b++, iters++) {
+                    // stage times: events are only recorded here and read after the render, so the
+                    // measurement does not add a host synchronisation to the timed region
+                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 0), st));
+                    launch_generate(P, W, grid_g, st);
+                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 1), st));
+                    launch_extend(s->view, P, W, count, grid_e, st);
+                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 2), st));
+                    launch_shade(s->view, P, W, grid_s, st);
+                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 3), st));
+                    launches += 6;
+                }
+                CU(cudaMemcpyAsync(ws.h_counters, W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                CU(cudaGetLastError());
+                if (ws.h_counters->next_path >= total_paths && ws.h_counters->n_extend == 0) break;
+            }
+            if (stage) {
+                for (size_t i = 0; i < iters; i++) {
+                    float a, b, c;
+                    CU(cudaEventElapsedTime(&a, ws.events[4 * i], ws.events[4 * i + 1]));
+                    CU(cudaEventElapsedTime(&b, ws.events[4 * i + 1], ws.events[4 * i + 2]));
+                    CU(cudaEventElapsedTime(&c, ws.events[4 * i + 2], ws.events[4 * i + 3]));
+                    ms_gen += a, ms_ext += b, ms_shd += c;
+                }
+            }
+        }
+        launch_finalize(W.accum, n_px_img * 3, cam->pixel_sample_scale, d_accum, o.accum_type == RT_ACCUM_F64, grid_g, st);
+        launches += 1;
+        CU(cudaEventRecord(ev[1], st));
+        CU(cudaEventSynchronize(ev[1]));
+        CU(cudaGetLastError());
+        if (stats) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+            const Counters& c = *ws.h_counters;
+            stats->paths = total_paths;
+            stats->segments = total_paths ? c.segments : 0;
+            stats->node_visits = total_paths ? c.node_visits : 0;
+            stats->prim_tests = total_paths ? c.prim_tests : 0;
+            stats->errors = total_paths ? c.errors : 0;
+            stats->iterations = total_paths ? c.iterations : 0;
+            stats->kernel_launches = launches;
+            stats->ms_total = ms;
+            stats->ms_raygen = ms_gen, stats->ms_extend = ms_ext, stats->ms_shade = ms_shd;
+            stats->ms_other = stage ? ms - ms_gen - ms_ext - ms_shd : 0.0;
+        }
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    return rc;
+}
+
+int rt_render(const rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, void* accum, rt_stats* stats) {
+    if (!s || !cam || !accum) return set_err(RT_ERR_INVALID, "null argument");
+    const size_t elem = (opts && opts->accum_type == RT_ACCUM_F64) ? 8 : 4;
+    const size_t bytes = (size_t)cam->image_width * cam->image_height * 3 * elem;
+    void* d = nullptr;
+    int rc = RT_OK;
+    try {
+        CU(cudaSetDevice(s->device));
+        CU(cudaMalloc(&d, bytes));
+        rc = rt_render_device(s, cam, opts, d, nullptr, stats);
+        if (rc == RT_OK) CU(cudaMemcpy(accum, d, bytes, cudaMemcpyDeviceToHost));
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int rt_tonemap(const void* accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb) {
+    if (!accum || !rgb) return set_err(RT_ERR_INVALID, "null argument");
+    int device, sms;
+    int rc = check_device(-1, device, sms);
+    if (rc != RT_OK) return rc;
+    const size_t elem = accum_type == RT_ACCUM_F64 ? 8 : 4;
+    void* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    int* d_flag = nullptr;
+    try {
+        CU(cudaMalloc(&d_in, n_pixels * 3 * elem));
+        CU(cudaMalloc(&d_out, n_pixels * 3));
+        CU(cudaMalloc(&d_flag, sizeof(int)));
+        CU(cudaMemset(d_flag, 0, sizeof(int)));
+        CU(cudaMemcpy(d_in, accum, n_pixels * 3 * elem, cudaMemcpyHostToDevice));
+        launch_tonemap(d_in, accum_type == RT_ACCUM_F64, n_pixels, toon_map, d_out, d_flag, nullptr);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(rgb, d_out, n_pixels * 3, cudaMemcpyDeviceToHost));
+        int flag = 0;
+        CU(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) rc = set_err(RT_ERR_INVALID, "NaN radiance in the image (utils/color.rs:28 asserts)");
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_flag);
+    return rc;
+}
+
+}  // extern "C"

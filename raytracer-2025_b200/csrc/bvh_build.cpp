@@ -1,0 +1,177 @@
+// bvh_build.cpp — binned-SAH BVH2 builder (host, OpenMP tasks).
+//
+// The reference's BVH is a median split on the longest axis (bvh.rs:16-46); only its
+// *semantics* (closest hit, tie order) are kept — the tie order is carried by per-primitive
+// ranks, so the acceleration structure is free to be a surface-area-heuristic tree laid out
+// for the GPU: 64-byte nodes that hold both children's boxes.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+#include "compile.h"
+
+namespace rt {
+
+namespace {
+
+struct Ctx {
+    const BuildBox* boxes;
+    uint32_t* idx;
+    Node* nodes;
+    std::atomic<uint32_t>* node_count;
+    std::atomic<uint32_t>* max_depth;
+    uint32_t base;
+};
+
+struct Box3 {
+    float lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; a++) lo[a] = INFINITY, hi[a] = -INFINITY;
+    }
+    void grow(const float* l, const float* h) {
+        for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], l[a]), hi[a] = std::max(hi[a], h[a]);
+    }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0.f) || !(dy >= 0.f) || !(dz >= 0.f)) return 0.f;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+constexpr int NBINS = 16;
+constexpr float C_TRAV = 1.0f, C_PRIM = 2.0f;
+constexpr uint32_t LEAF_TARGET = 4;  // SAH may stop at <= this many primitives
+constexpr uint32_t TASK_MIN = 8192;
+
+inline float centroid(const BuildBox& b, int a) { return 0.5f * (b.lo[a] + b.hi[a]); }
+
+uint32_t make_leaf(const Ctx& c, uint32_t begin, uint32_t end) {
+    return LEAF_FLAG | ((c.base + begin) << 3) | (end - begin - 1);
+}
+
+// returns the child reference for [begin,end) and its bounds
+uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth, Box3& bounds) {
+    const uint32_t n = end - begin;
+    bounds.reset();
+    Box3 cb;
+    cb.reset();
+    for (uint32_t i = begin; i < end; i++) {
+        const BuildBox& b = c.boxes[c.idx[i]];
+        bounds.grow(b.lo, b.hi);
+        float ce[3] = {centroid(b, 0), centroid(b, 1), centroid(b, 2)};
+        cb.grow(ce, ce);
+    }
+    uint32_t d = c.max_depth->load(std::memory_order_relaxed);
+    while (depth > d && !c.max_depth->compare_exchange_weak(d, depth)) {
+    }
+    if (n == 1) return make_leaf(c, begin, end);
+
+    uint32_t mid = 0;
+    bool have_split = false;
+    if (depth < 32) {
+        float best_cost = INFINITY;
+        int best_axis = -1, best_bin = -1;
+        for (int a = 0; a < 3; a++) {
+            float ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0.f)) continue;
+            float scale = NBINS / ext;
+            uint32_t cnt[NBINS] = {0};
+            Box3 bb[NBINS];
+            for (auto& x : bb) x.reset();
+            for (uint32_t i = begin; i < end; i++) {
+                const BuildBox& b = c.boxes[c.idx[i]];
+                int k = std::min(NBINS - 1, std::max(0, (int)((centroid(b, a) - cb.lo[a]) * scale)));
+                cnt[k]++;
+                bb[k].grow(b.lo, b.hi);
+            }
+            float right_area[NBINS];
+            uint32_t right_cnt[NBINS];
+            Box3 acc;
+            acc.reset();
+            uint32_t ac = 0;
+            for (int k = NBINS - 1; k > 0; k--) {
+                acc.grow(bb[k].lo, bb[k].hi);
+                ac += cnt[k];
+                right_area[k] = acc.half_area();
+                right_cnt[k] = ac;
+            }
+            acc.reset();
+            ac = 0;
+            for (int k = 0; k < NBINS - 1; k++) {
+                acc.grow(bb[k].lo, bb[k].hi);
+                ac += cnt[k];
+                if (ac == 0 || right_cnt[k + 1] == 0) continue;
+                float cost = acc.half_area() * ac + right_area[k + 1] * right_cnt[k + 1];
+                if (cost < best_cost) best_cost = cost, best_axis = a, best_bin = k;
+            }
+        }
+        if (best_axis >= 0) {
+            float area = bounds.half_area();
+            float split_cost = C_TRAV + (area > 0.f ? best_cost / area : (float)n) * C_PRIM;
+            float leaf_cost = (float)n * C_PRIM;
+            if (n <= LEAF_TARGET && leaf_cost <= split_cost) return make_leaf(c, begin, end);
+            float ext = cb.hi[best_axis] - cb.lo[best_axis];
+            float scale = NBINS / ext, lo = cb.lo[best_axis];
+            uint32_t* p = std::partition(c.idx + begin, c.idx + end, [&](uint32_t i) {
+                int k = std::min(NBINS - 1, std::max(0, (int)((centroid(c.boxes[i], best_axis) - lo) * scale)));
+                return k <= best_bin;
+            });
+            mid = (uint32_t)(p - c.idx);
+            have_split = mid > begin && mid < end;
+        }
+    }
+    if (!have_split) {
+        if (n <= MAX_LEAF_PRIMS && depth < 32) return make_leaf(c, begin, end);
+        // identical centroids or depth guard: object median on the widest centroid axis
+        int a = 0;
+        for (int k = 1; k < 3; k++)
+            if (cb.hi[k] - cb.lo[k] > cb.hi[a] - cb.lo[a]) a = k;
+        mid = begin + n / 2;
+        std::nth_element(c.idx + begin, c.idx + mid, c.idx + end,
+                         [&](uint32_t x, uint32_t y) { return centroid(c.boxes[x], a) < centroid(c.boxes[y], a); });
+    }
+
+    uint32_t me = c.node_count->fetch_add(1);
+    Box3 bl, br;
+    uint32_t cl, cr;
+    if (n >= TASK_MIN) {
+#pragma omp task shared(bl, cl) firstprivate(begin, mid, depth)
+        cl = build_range(c, begin, mid, depth + 1, bl);
+        cr = build_range(c, mid, end, depth + 1, br);
+#pragma omp taskwait
+    } else {
+        cl = build_range(c, begin, mid, depth + 1, bl);
+        cr = build_range(c, mid, end, depth + 1, br);
+    }
+    Node& nd = c.nodes[me];
+    for (int a = 0; a < 3; a++) nd.lo0[a] = bl.lo[a], nd.hi0[a] = bl.hi[a], nd.lo1[a] = br.lo[a], nd.hi1[a] = br.hi[a];
+    nd.child0 = cl;
+    nd.child1 = cr;
+    nd.pad0 = nd.pad1 = 0;
+    return me;
+}
+
+}  // namespace
+
+uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes,
+                   std::vector<uint32_t>& order, uint32_t& depth_out) {
+    const uint32_t n = (uint32_t)boxes.size();
+    order.resize(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    if (n == 0) return INVALID_REF;
+    const uint32_t node_base = (uint32_t)nodes.size();
+    nodes.resize(node_base + (n > 1 ? n - 1 : 0));
+    std::atomic<uint32_t> count{node_base}, depth{0};
+    Ctx c{boxes.data(), order.data(), nodes.data(), &count, &depth, first_prim_base};
+    Box3 b;
+    uint32_t root = 0;
+#pragma omp parallel
+#pragma omp single
+    root = build_range(c, 0, n, 1, b);
+    nodes.resize(count.load());
+    depth_out = std::max(depth_out, depth.load());
+    return root;
+}
+
+}  // namespace rt

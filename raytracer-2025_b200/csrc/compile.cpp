@@ -1,0 +1,568 @@
+// compile.cpp — rt_scene_desc -> CompiledScene.
+//
+//   1. validate every index of the description;
+//   2. copy materials / textures (image texels are sRGB-decoded once here instead of per fetch,
+//      utils/image.rs:75-81);
+//   3. walk the object graph depth first.  The walk order IS the reference's tie order
+//      (SURVEY.md appendix B): `Hittables` children in insertion order (Iterator::min_by keeps the
+//      first minimum, hits.rs:42), `BVH` right subtree before left (bvh.rs:78-84) with the tree
+//      shape of BVH::from_vec (bvh.rs:16-46) recomputed from the objects' bounding boxes;
+//   4. bake every Transform chain into the primitives below it (Transform::hit keeps t and the
+//      surface coordinates, shapes.rs:93-111), split media boundaries into their own groups;
+//   5. flatten the lights tree into leaves with their selection probability;
+//   6. build one SAH BVH per group and store primitives in leaf order.
+#include "compile.h"
+
+#include <vector_functions.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace rt {
+
+namespace {
+
+struct V3 {
+    double x, y, z;
+};
+inline V3 v3(const double* p) { return V3{p[0], p[1], p[2]}; }
+inline V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(double s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+struct Affine {
+    double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double b[3] = {0, 0, 0};
+    bool identity = true;
+    uint32_t inst_object = RT_NONE;
+    mutable uint32_t xform_slot = 0xFFFFFFFEu;  // index in CompiledScene::xforms once emitted
+    V3 point(V3 p) const {
+        return V3{A[0] * p.x + A[1] * p.y + A[2] * p.z + b[0], A[3] * p.x + A[4] * p.y + A[5] * p.z + b[1],
+                  A[6] * p.x + A[7] * p.y + A[8] * p.z + b[2]};
+    }
+    V3 vec(V3 p) const {
+        return V3{A[0] * p.x + A[1] * p.y + A[2] * p.z, A[3] * p.x + A[4] * p.y + A[5] * p.z,
+                  A[6] * p.x + A[7] * p.y + A[8] * p.z};
+    }
+    double det() const {
+        return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    }
+    bool inverse(double inv[9]) const {
+        double d = det();
+        if (d == 0.0 || !std::isfinite(d)) return false;
+        double r = 1.0 / d;
+        inv[0] = (A[4] * A[8] - A[5] * A[7]) * r;
+        inv[1] = (A[2] * A[7] - A[1] * A[8]) * r;
+        inv[2] = (A[1] * A[5] - A[2] * A[4]) * r;
+        inv[3] = (A[5] * A[6] - A[3] * A[8]) * r;
+        inv[4] = (A[0] * A[8] - A[2] * A[6]) * r;
+        inv[5] = (A[2] * A[3] - A[0] * A[5]) * r;
+        inv[6] = (A[3] * A[7] - A[4] * A[6]) * r;
+        inv[7] = (A[1] * A[6] - A[0] * A[7]) * r;
+        inv[8] = (A[0] * A[4] - A[1] * A[3]) * r;
+        return true;
+    }
+};
+
+// Transform::transform (shapes.rs:74-78) as a matrix: x -> q * (x .* scale) * conj(q) + offset
+Affine affine_of(const rt_transform& t, uint32_t object) {
+    const double w = t.quat[0], x = t.quat[1], y = t.quat[2], z = t.quat[3];
+    // columns of the rotation = images of the basis vectors under the Hamilton sandwich product;
+    // the quaternion is not renormalised (neither is it in quaternion.rs:72-82)
+    double R[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z),           2 * (x * z + w * y),
+                   2 * (x * y + w * z),           w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                   2 * (x * z - w * y),           2 * (y * z + w * x),           w * w - x * x - y * y + z * z};
+    Affine a;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) a.A[r * 3 + c] = R[r * 3 + c] * t.scale[c];
+    for (int k = 0; k < 3; k++) a.b[k] = t.offset[k];
+    a.identity = false;
+    a.inst_object = object;
+    return a;
+}
+// outer(inner(x))
+Affine compose(const Affine& outer, const Affine& inner) {
+    if (outer.identity) return inner;
+    Affine r;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += outer.A[i * 3 + k] * inner.A[k * 3 + j];
+            r.A[i * 3 + j] = s;
+        }
+    V3 b = outer.point(V3{inner.b[0], inner.b[1], inner.b[2]});
+    r.b[0] = b.x, r.b[1] = b.y, r.b[2] = b.z;
+    r.identity = false;
+    r.inst_object = inner.inst_object;  // innermost Transform
+    return r;
+}
+
+struct FlatPrim {
+    PrimGeom g;
+    PrimMeta m;
+    double lo[3], hi[3];
+};
+
+float round_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+float round_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+uint64_t total_order_key(double x) {  // f64::total_cmp (bvh.rs:52)
+    uint64_t b;
+    std::memcpy(&b, &x, 8);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+uint32_t shade_class_of(const rt_scene_desc& d, const rt_material& m) {
+    switch (m.kind) {
+        case RT_MAT_EMPTY: return SC_DIFFUSE;
+        case RT_MAT_LAMBERTIAN: return d.textures[m.tex].kind == RT_TEX_SOLID ? SC_DIFFUSE : SC_TEXTURED;
+        case RT_MAT_METAL: return SC_METAL;
+        case RT_MAT_DIELECTRIC: return SC_DIELECTRIC;
+        case RT_MAT_DIFFUSE_LIGHT: return m.inner == RT_NONE ? SC_EMISSIVE : SC_OTHER;
+        case RT_MAT_ISOTROPIC: return SC_ISOTROPIC;
+        default: return SC_OTHER;
+    }
+}
+
+float srgb_to_linear(float x) {  // palette Srgb::into_linear<f32>, applied per fetch by image.rs:80
+    if (x <= 0.04045f) return (float)(1.0 / 12.92) * x;
+    return std::pow(std::fma(x, (float)(1.0 / 1.055), (float)(0.055 / 1.055)), 2.4f);
+}
+
+struct Compiler {
+    const rt_scene_desc& d;
+    uint32_t flags;
+    CompiledScene& out;
+    std::string& err;
+    std::vector<std::vector<FlatPrim>> groups;  // 0 = world surfaces, 1+m = boundary of media[m]
+    std::vector<uint32_t> group_of_medium;
+    uint32_t next_rank = 0;
+    int status = RT_OK;
+
+    bool fail(int code, const std::string& msg) {
+        if (status == RT_OK) status = code, err = msg;
+        return false;
+    }
+
+    bool validate() {
+        if (d.version != RT_ABI_VERSION) return fail(RT_ERR_VERSION, "rt_scene_desc.version mismatch");
+        if (d.struct_size != sizeof(rt_scene_desc)) return fail(RT_ERR_VERSION, "rt_scene_desc.struct_size mismatch");
+        if (d.world_root >= d.n_objects) return fail(RT_ERR_INVALID, "world_root out of range");
+        if (d.lights_root != RT_NONE && d.lights_root >= d.n_objects) return fail(RT_ERR_INVALID, "lights_root out of range");
+        auto need = [&](const void* p, uint64_t n, const char* what) {
+            if (n && !p) return fail(RT_ERR_INVALID, std::string(what) + " is null");
+            return true;
+        };
+        if (!need(d.objects, d.n_objects, "objects") || !need(d.children, d.n_children, "children") ||
+            !need(d.spheres, d.n_spheres, "spheres") || !need(d.planars, d.n_planars, "planars") ||
+            !need(d.transforms, d.n_transforms, "transforms") || !need(d.media, d.n_media, "media") ||
+            !need(d.materials, d.n_materials, "materials") || !need(d.textures, d.n_textures, "textures") ||
+            !need(d.images, d.n_images, "images") || !need(d.texels, d.n_texels, "texels") ||
+            !need(d.perlins, d.n_perlins, "perlins"))
+            return false;
+        for (uint32_t i = 0; i < d.n_textures; i++) {
+            const rt_texture& t = d.textures[i];
+            switch (t.kind) {
+                case RT_TEX_SOLID:
+                case RT_TEX_GRADIENT_Y: break;
+                case RT_TEX_CHECKER:
+                    if (t.a >= i || t.b >= i) return fail(RT_ERR_INVALID, "checker children must precede the checker");
+                    break;
+                case RT_TEX_IMAGE:
+                    if (t.a != RT_NONE) {
+                        if (t.a >= d.n_images) return fail(RT_ERR_INVALID, "image index out of range");
+                        const rt_image& im = d.images[t.a];
+                        if (im.texel_offset + (uint64_t)im.width * im.height * 4 > d.n_texels)
+                            return fail(RT_ERR_INVALID, "image texels out of range");
+                    }
+                    break;
+                case RT_TEX_NOISE:
+                    if (t.a >= d.n_perlins) return fail(RT_ERR_INVALID, "perlin index out of range");
+                    break;
+                default: return fail(RT_ERR_INVALID, "unknown texture kind");
+            }
+        }
+        for (uint32_t i = 0; i < d.n_materials; i++) {
+            const rt_material& m = d.materials[i];
+            auto tex_ok = [&](bool required) { return m.tex < d.n_textures || (!required && m.tex == RT_NONE); };
+            switch (m.kind) {
+                case RT_MAT_EMPTY:
+                case RT_MAT_METAL:
+                case RT_MAT_TRANSPARENT:
+                case RT_MAT_PORTAL: break;
+                case RT_MAT_LAMBERTIAN:
+                case RT_MAT_DIELECTRIC:
+                case RT_MAT_ISOTROPIC:
+                    if (!tex_ok(true)) return fail(RT_ERR_INVALID, "material texture out of range");
+                    break;
+                case RT_MAT_DIFFUSE_LIGHT:
+                    if (!tex_ok(true)) return fail(RT_ERR_INVALID, "material texture out of range");
+                    if (m.inner != RT_NONE && m.inner >= i) return fail(RT_ERR_INVALID, "inner material must precede its wrapper");
+                    break;
+                case RT_MAT_MIX:
+                    if (m.inner >= i || m.inner2 >= i) return fail(RT_ERR_INVALID, "Mix children must precede it");
+                    if (!tex_ok(false)) return fail(RT_ERR_INVALID, "material texture out of range");
+                    if (m.tex != RT_NONE && d.textures[m.tex].kind != RT_TEX_IMAGE)
+                        return fail(RT_ERR_INVALID, "Mix ratio texture must be an image");
+                    break;
+                default: return fail(RT_ERR_INVALID, "unknown material kind");
+            }
+        }
+        std::vector<uint8_t> seen(d.n_objects, 0);
+        for (uint32_t i = 0; i < d.n_objects; i++) {
+            const rt_object& o = d.objects[i];
+            if ((uint64_t)o.first_child + o.child_count > d.n_children) return fail(RT_ERR_INVALID, "children range out of bounds");
+            switch (o.kind) {
+                case RT_OBJ_SPHERE:
+                    if (o.data >= d.n_spheres || o.material >= d.n_materials) return fail(RT_ERR_INVALID, "sphere payload/material out of range");
+                    break;
+                case RT_OBJ_QUAD:
+                case RT_OBJ_TRIANGLE:
+                    if (o.data >= d.n_planars || o.material >= d.n_materials) return fail(RT_ERR_INVALID, "planar payload/material out of range");
+                    break;
+                case RT_OBJ_LIST: break;
+                case RT_OBJ_BVH:
+                    if (o.child_count == 0) return fail(RT_ERR_INVALID, "BVH node must contain at least one object");
+                    break;
+                case RT_OBJ_TRANSFORM:
+                    if (o.data >= d.n_transforms || o.child_count != 1) return fail(RT_ERR_INVALID, "bad Transform");
+                    break;
+                case RT_OBJ_MEDIUM:
+                    if (o.data >= d.n_media || o.child_count != 1 || o.material >= d.n_materials) return fail(RT_ERR_INVALID, "bad ConstantMedium");
+                    break;
+                default: return fail(RT_ERR_INVALID, "unknown object kind");
+            }
+            for (uint32_t k = 0; k < o.child_count; k++) {
+                uint32_t c = d.children[o.first_child + k];
+                if (c >= d.n_objects) return fail(RT_ERR_INVALID, "child index out of range");
+                if (c >= i) return fail(RT_ERR_INVALID, "children must precede their parent (the graph is a tree emitted bottom-up)");
+            }
+        }
+        (void)seen;
+        return true;
+    }
+
+    void copy_tables() {
+        out.textures.resize(d.n_textures);
+        for (uint32_t i = 0; i < d.n_textures; i++) {
+            const rt_texture& s = d.textures[i];
+            Texture t{};
+            t.kind = s.kind, t.a = s.a, t.b = s.b;
+            for (int k = 0; k < 3; k++) t.color[k] = s.color[k], t.color2[k] = s.color2[k];
+            t.scale = s.scale;
+            out.textures[i] = t;
+        }
+        out.materials.resize(d.n_materials);
+        for (uint32_t i = 0; i < d.n_materials; i++) {
+            const rt_material& s = d.materials[i];
+            Material m{};
+            m.kind = s.kind, m.tex = s.tex, m.inner = s.inner, m.inner2 = s.inner2;
+            for (int k = 0; k < 3; k++) m.color[k] = s.color[k];
+            m.param = s.param;
+            for (int k = 0; k < 8; k++) m.v[k] = s.v[k];
+            m.shade_class = shade_class_of(d, s);
+            // does shading this material read the surface coordinates (image / checker lookups)?
+            auto tex_uv = [&](uint32_t t) { return t != RT_NONE && (d.textures[t].kind == RT_TEX_IMAGE || d.textures[t].kind == RT_TEX_CHECKER); };
+            m.needs_uv = tex_uv(s.tex) ? 1u : 0u;
+            if (s.inner != RT_NONE && s.inner < i) m.needs_uv |= out.materials[s.inner].needs_uv;
+            if (s.inner2 != RT_NONE && s.inner2 < i) m.needs_uv |= out.materials[s.inner2].needs_uv;
+            out.materials[i] = m;
+        }
+        out.images.resize(d.n_images);
+        out.texels.resize(d.n_texels / 4);
+        for (uint32_t i = 0; i < d.n_images; i++) {
+            const rt_image& s = d.images[i];
+            Image im{};
+            im.width = s.width, im.height = s.height, im.flags = s.flags;
+            im.texel_offset = s.texel_offset / 4;
+            out.images[i] = im;
+            const float* p = d.texels + s.texel_offset;
+            for (uint64_t k = 0; k < (uint64_t)s.width * s.height; k++) {
+                float4 t;
+                if (s.flags & RT_IMG_LINEAR)
+                    t = make_float4(p[4 * k], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]);
+                else
+                    t = make_float4(srgb_to_linear(p[4 * k]), srgb_to_linear(p[4 * k + 1]), srgb_to_linear(p[4 * k + 2]), p[4 * k + 3]);
+                out.texels[im.texel_offset + k] = t;
+            }
+        }
+        out.perlins.resize(d.n_perlins);
+        for (uint32_t i = 0; i < d.n_perlins; i++) std::memcpy(&out.perlins[i], &d.perlins[i], sizeof(Perlin));
+        static_assert(sizeof(Perlin) == sizeof(rt_perlin), "perlin layout");
+    }
+
+    uint32_t xform_index(const Affine& a) {
+        if (a.identity) return RT_NONE;
+        if (a.xform_slot != 0xFFFFFFFEu) return a.xform_slot;
+        Xform x{};
+        std::memcpy(x.A, a.A, sizeof(x.A));
+        std::memcpy(x.b, a.b, sizeof(x.b));
+        if (!a.inverse(x.Ainv)) {
+            fail(RT_ERR_UNSUPPORTED, "singular Transform (zero scale)");
+            return RT_NONE;
+        }
+        x.inst_object = a.inst_object;
+        out.xforms.push_back(x);
+        a.xform_slot = (uint32_t)out.xforms.size() - 1;
+        return a.xform_slot;
+    }
+
+    // geometry of a leaf shape after applying the chain; `local` keeps it untransformed (lights)
+    bool bake(uint32_t obj, const Affine& a, bool local, PrimGeom& g, uint32_t& kind, double lo[3], double hi[3], double* area_out) {
+        const rt_object& o = d.objects[obj];
+        std::memset(&g, 0, sizeof(g));
+        const bool ident = a.identity || local;
+        if (o.kind == RT_OBJ_SPHERE) {
+            const rt_sphere& s = d.spheres[o.data];
+            V3 c = v3(s.center), cv = v3(s.center_vec);
+            double r = s.radius;
+            if (!ident) {
+                // a sphere stays a sphere only under a similarity: A^T A = k I
+                double k = a.A[0] * a.A[0] + a.A[3] * a.A[3] + a.A[6] * a.A[6];
+                double tol = 1e-12 * k;
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) {
+                        double s2 = a.A[i] * a.A[j] + a.A[3 + i] * a.A[3 + j] + a.A[6 + i] * a.A[6 + j];
+                        if (std::fabs(s2 - (i == j ? k : 0.0)) > tol)
+                            return fail(RT_ERR_UNSUPPORTED, "Sphere under a non-uniform scale (an ellipsoid) is not supported yet");
+                    }
+                c = a.point(c);
+                cv = a.vec(cv);
+                r = r * std::sqrt(k);
+            }
+            g.d[0] = c.x, g.d[1] = c.y, g.d[2] = c.z, g.d[3] = cv.x, g.d[4] = cv.y, g.d[5] = cv.z, g.d[6] = r;
+            kind = PRIM_SPHERE;
+            V3 c1 = c + cv;
+            double cc[2][3] = {{c.x, c.y, c.z}, {c1.x, c1.y, c1.z}};
+            for (int k = 0; k < 3; k++) lo[k] = std::min(cc[0][k], cc[1][k]) - r, hi[k] = std::max(cc[0][k], cc[1][k]) + r;
+            if (area_out) *area_out = 0.0;
+            return true;
+        }
+        const rt_planar& p = d.planars[o.data];
+        const bool tri = o.kind == RT_OBJ_TRIANGLE;
+        kind = tri ? PRIM_TRIANGLE : PRIM_QUAD;
+        V3 q = v3(p.anchor), u = v3(p.u), v = v3(p.v), n = v3(p.normal), w = v3(p.w);
+        double D = p.parm_d, area = p.area;
+        if (!ident) {
+            q = a.point(q), u = a.vec(u), v = a.vec(v);
+            // re-derive exactly like Quad::new (quad.rs:31-49)
+            V3 nn = cross(u, v);
+            double len = std::sqrt(dot(nn, nn));
+            n = (1.0 / len) * nn;
+            if (!std::isfinite(n.x) || !std::isfinite(n.y) || !std::isfinite(n.z))
+                return fail(RT_ERR_UNSUPPORTED, "a Transform flattens a quad/triangle to zero area");
+            w = (1.0 / dot(nn, nn)) * nn;
+            area = tri ? len / 2.0 : len;
+            if (a.det() < 0.0) n = V3{-n.x, -n.y, -n.z};  // keep the side the inverse-transpose normal faces (shapes.rs:104-108)
+            D = dot(n, q);
+        }
+        double* e = g.d;
+        e[0] = q.x, e[1] = q.y, e[2] = q.z, e[3] = u.x, e[4] = u.y, e[5] = u.z, e[6] = v.x, e[7] = v.y, e[8] = v.z;
+        e[9] = n.x, e[10] = n.y, e[11] = n.z, e[12] = D, e[13] = w.x, e[14] = w.y, e[15] = w.z;
+        V3 pts[4] = {q, q + u, q + v, q + u + v};
+        int np = tri ? 3 : 4;
+        for (int k = 0; k < 3; k++) lo[k] = INFINITY, hi[k] = -INFINITY;
+        for (int i = 0; i < np; i++) {
+            double c[3] = {pts[i].x, pts[i].y, pts[i].z};
+            for (int k = 0; k < 3; k++) lo[k] = std::min(lo[k], c[k]), hi[k] = std::max(hi[k], c[k]);
+        }
+        if (area_out) *area_out = area;
+        return true;
+    }
+
+    // order in which BVH::from_vec + BVH::hit would prefer the children on a tie: right before left
+    void bvh_visit_order(std::vector<uint32_t> objs, std::vector<uint32_t>& order) {
+        size_t len = objs.size();
+        if (len == 1) {
+            order.push_back(objs[0]);
+            return;
+        }
+        if (len == 2) {
+            order.push_back(objs[1]);
+            order.push_back(objs[0]);
+            return;
+        }
+        double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t o : objs) {
+            const double* b = d.objects[o].bbox;
+            for (int k = 0; k < 3; k++) mn[k] = std::fmin(mn[k], b[2 * k]), mx[k] = std::fmax(mx[k], b[2 * k + 1]);
+        }
+        double s[3];
+        for (int k = 0; k < 3; k++) s[k] = std::fmax(mx[k] - mn[k], 0.0);
+        int axis = s[0] > s[1] ? (s[0] > s[2] ? 0 : 2) : (s[1] > s[2] ? 1 : 2);  // aabb.rs:80-92
+        std::stable_sort(objs.begin(), objs.end(), [&](uint32_t x, uint32_t y) {
+            return total_order_key(d.objects[x].bbox[2 * axis]) < total_order_key(d.objects[y].bbox[2 * axis]);
+        });
+        size_t mid = len / 2;
+        std::vector<uint32_t> left(objs.begin(), objs.begin() + mid), right(objs.begin() + mid, objs.end());
+        objs.clear();
+        objs.shrink_to_fit();
+        bvh_visit_order(std::move(right), order);
+        bvh_visit_order(std::move(left), order);
+    }
+
+    // depth-first walk in tie order; group = which primitive set receives the leaves
+    void walk(uint32_t obj, const Affine& chain, uint32_t group, bool in_medium) {
+        if (status != RT_OK) return;
+        const rt_object& o = d.objects[obj];
+        switch (o.kind) {
+            case RT_OBJ_SPHERE:
+            case RT_OBJ_QUAD:
+            case RT_OBJ_TRIANGLE: {
+                FlatPrim fp;
+                uint32_t kind;
+                if (!bake(obj, chain, false, fp.g, kind, fp.lo, fp.hi, nullptr)) return;
+                fp.m.kind_mat = (kind << 30) | o.material;
+                fp.m.object = obj;
+                fp.m.rank = in_medium ? 0 : next_rank++;
+                if (!in_medium) out.ranks[obj] = fp.m.rank;
+                // the chain is kept for rt_hit.inst_id and for sphere u,v (computed from the local normal)
+                fp.m.xform = xform_index(chain);
+                groups[group].push_back(fp);
+                if (kind == PRIM_SPHERE) out.n_spheres++; else out.n_planars++;
+                break;
+            }
+            case RT_OBJ_LIST:
+                for (uint32_t k = 0; k < o.child_count; k++) walk(d.children[o.first_child + k], chain, group, in_medium);
+                break;
+            case RT_OBJ_BVH: {
+                std::vector<uint32_t> kids(d.children + o.first_child, d.children + o.first_child + o.child_count);
+                std::vector<uint32_t> order;
+                if ((flags & RT_BUILD_NO_REF_RANKS) || in_medium)
+                    order = kids;
+                else
+                    bvh_visit_order(std::move(kids), order);
+                for (uint32_t c : order) walk(c, chain, group, in_medium);
+                break;
+            }
+            case RT_OBJ_TRANSFORM: {
+                Affine a = compose(chain, affine_of(d.transforms[o.data], obj));
+                walk(d.children[o.first_child], a, group, in_medium);
+                break;
+            }
+            case RT_OBJ_MEDIUM: {
+                if (in_medium) {
+                    fail(RT_ERR_UNSUPPORTED, "a ConstantMedium inside the boundary of another medium is not supported");
+                    return;
+                }
+                Medium m{};
+                m.material = o.material;
+                m.object = obj;
+                m.rank = next_rank++;
+                out.ranks[obj] = m.rank;
+                m.neg_inv_density = d.media[o.data].neg_inv_density;
+                m.medium_index = o.data;
+                m.has_xform = chain.identity ? 0 : 1;
+                double inv[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                if (!chain.identity && !chain.inverse(inv)) {
+                    fail(RT_ERR_UNSUPPORTED, "singular Transform above a ConstantMedium");
+                    return;
+                }
+                std::memcpy(m.Ainv, inv, sizeof(inv));
+                groups.emplace_back();
+                uint32_t g = (uint32_t)groups.size() - 1;
+                group_of_medium.push_back(g);
+                out.media.push_back(m);
+                walk(d.children[o.first_child], chain, g, true);
+                break;
+            }
+        }
+    }
+
+    void walk_lights(uint32_t obj, const Affine& chain, double weight) {
+        if (status != RT_OK) return;
+        const rt_object& o = d.objects[obj];
+        switch (o.kind) {
+            case RT_OBJ_SPHERE:
+            case RT_OBJ_QUAD:
+            case RT_OBJ_TRIANGLE: {
+                Light l{};
+                double lo[3], hi[3];
+                if (!bake(obj, chain, true, l.g, l.kind, lo, hi, &l.area)) return;
+                l.xform = xform_index(chain);
+                l.weight = weight;
+                out.lights.push_back(l);
+                break;
+            }
+            case RT_OBJ_LIST:
+                if (o.child_count == 0) {
+                    fail(RT_ERR_INVALID, "The collection of objects is empty! (lights, hits.rs:73)");
+                    return;
+                }
+                for (uint32_t k = 0; k < o.child_count; k++)
+                    walk_lights(d.children[o.first_child + k], chain, weight / (double)o.child_count);
+                break;
+            case RT_OBJ_TRANSFORM:
+                walk_lights(d.children[o.first_child], compose(chain, affine_of(d.transforms[o.data], obj)), weight);
+                break;
+            default:
+                fail(RT_ERR_UNSUPPORTED, "lights may not contain a BVH or ConstantMedium: pdf_value/random are unimplemented!() there (hit.rs:51-59)");
+        }
+    }
+
+    int run() {
+        if (!validate()) return status;
+        copy_tables();
+        out.ranks.assign(d.n_objects, RT_NONE);
+        groups.emplace_back();
+        walk(d.world_root, Affine(), 0, false);
+        if (status != RT_OK) return status;
+        if (d.lights_root != RT_NONE) {
+            walk_lights(d.lights_root, Affine(), 1.0);
+            if (status != RT_OK) return status;
+            double acc = 0.0;
+            for (auto& l : out.lights) {
+                acc += l.weight;
+                l.cdf = acc;
+            }
+        }
+        uint64_t total = 0;
+        for (auto& g : groups) total += g.size();
+        if (total >= (1ull << 28)) {
+            fail(RT_ERR_UNSUPPORTED, "more than 2^28 primitives");
+            return status;
+        }
+        out.geom.resize(total);
+        out.meta.resize(total);
+        uint32_t base = 0;
+        std::vector<uint32_t> roots;
+        for (auto& g : groups) {
+            std::vector<BuildBox> boxes(g.size());
+            for (size_t i = 0; i < g.size(); i++)
+                for (int k = 0; k < 3; k++) boxes[i].lo[k] = round_down(g[i].lo[k]), boxes[i].hi[k] = round_up(g[i].hi[k]);
+            std::vector<uint32_t> order;
+            uint32_t root = build_bvh(boxes, base, out.nodes, order, out.bvh_depth);
+            for (size_t i = 0; i < g.size(); i++) {
+                out.geom[base + i] = g[order[i]].g;
+                out.meta[base + i] = g[order[i]].m;
+            }
+            roots.push_back(root);
+            base += (uint32_t)g.size();
+            std::vector<FlatPrim>().swap(g);
+        }
+        out.world_root = roots[0];
+        for (size_t m = 0; m < out.media.size(); m++) out.media[m].root = roots[group_of_medium[m]];
+        return RT_OK;
+    }
+};
+
+}  // namespace
+
+int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err) {
+    Compiler c{d, flags, out, err};
+    return c.run();
+}
+
+}  // namespace rt

@@ -1,0 +1,44 @@
+// compile.h — host-side "scene compiler": rt_scene_desc (reference-shaped object graph)
+// -> flat device arrays (scene_types.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include <vector_types.h>
+
+#include "rt2025.h"
+#include "scene_types.h"
+
+namespace rt {
+
+struct CompiledScene {
+    std::vector<Node> nodes;
+    std::vector<PrimGeom> geom;
+    std::vector<PrimMeta> meta;
+    std::vector<Xform> xforms;
+    std::vector<Material> materials;
+    std::vector<Texture> textures;
+    std::vector<Image> images;
+    std::vector<float4> texels;
+    std::vector<Perlin> perlins;
+    std::vector<Medium> media;
+    std::vector<Light> lights;
+    std::vector<uint32_t> ranks;  // per desc object, RT_NONE for containers
+    uint32_t world_root = INVALID_REF;
+    uint32_t bvh_depth = 0;
+    uint32_t n_spheres = 0, n_planars = 0;
+};
+
+// returns RT_OK or a negative rt_status and fills err
+int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err);
+
+// Binned-SAH BVH2 over conservative binary32 boxes.  `order` receives the leaf order (a
+// permutation of 0..n-1); nodes are appended to `nodes`; leaf references point at
+// first_prim_base + position in `order`.  Returns the root child reference.
+struct BuildBox {
+    float lo[3], hi[3];
+};
+uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes,
+                   std::vector<uint32_t>& order, uint32_t& depth_out);
+
+}  // namespace rt

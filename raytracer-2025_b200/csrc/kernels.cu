@@ -1,0 +1,575 @@
+// kernels.cu — the wavefront path tracer and the closest-hit batch kernel (sm_100a).
+//
+// Pipeline per iteration (all queues and counters live in HBM; no host round trip is needed to
+// size a launch — kernels are persistent grid-stride loops that read the counts themselves):
+//
+//   generate : refill free path slots with camera rays      (Camera::get_ray, camera.rs:247-273)
+//   extend   : closest surface hit + constant-medium sampling (world.hit, camera.rs:286)
+//              -> appends the slot to the shade queue of its material class
+//   shade    : emitted + scatter + mixture-pdf light sampling (camera.rs:290-321)
+//              -> survivors go back to the extend queue, finished slots to the free queue
+//
+// A path lives in one 128-byte record for its whole life; only 4-byte slot indices move between
+// queues.  Radiance is accumulated with binary64 atomics into a per-pixel framebuffer.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "shade.cuh"
+
+namespace rt {
+
+// ------------------------------------------------------------------------------------------
+// closest-hit batch kernel (rt_closest_hit)
+// ------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(EXTEND_BLOCK) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint64_t n, double tmin,
+                                                              double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
+    __shared__ uint32_t s_stack[TRAVERSAL_STACK * EXTEND_BLOCK];
+    uint32_t* stack = s_stack + threadIdx.x;
+    TraceCounters cnt{0, 0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double* rp = reinterpret_cast<const double*>(rays + i);
+        RayD r;
+        r.o = D3{rp[0], rp[1], rp[2]};
+        r.d = D3{rp[3], rp[4], rp[5]};
+        r.time = rp[6];
+        double t;
+        uint32_t prim;
+        rt_hit h;
+        if (closest_hit<COUNT, true>(sv, sv.world_root, r, tmin, tmax, stack, EXTEND_BLOCK, t, prim, &cnt)) {
+            HitInfo hi;
+            surface_hit_info(sv, prim, t, r, true, hi);
+            const PrimMeta m = sv.meta[prim];
+            h.t = t;
+            h.prim_id = m.object;
+            h.inst_id = m.xform == RT_NONE ? RT_NONE : sv.xforms[m.xform].inst_object;
+            h.u = (float)hi.u, h.v = (float)hi.v;
+        } else {
+            h.t = INFINITY;
+            h.prim_id = RT_NONE, h.inst_id = RT_NONE;
+            h.u = 0.f, h.v = 0.f;
+        }
+        out[i] = h;
+    }
+    if (COUNT) {
+        atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
+        atomicAdd(&counters[1], (unsigned long long)cnt.prims);
+    }
+}
+
+void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint64_t n, double tmin, double tmax, bool count, rt_hit* d_out,
+                        unsigned long long* d_counters, int grid, cudaStream_t stream) {
+    if (count)
+        k_closest_hit<true><<<grid, EXTEND_BLOCK, 0, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
+    else
+        k_closest_hit<false><<<grid, EXTEND_BLOCK, 0, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
+}
+
+// ------------------------------------------------------------------------------------------
+// wavefront state
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_ray(const PathRec* __restrict__ rec, RayD& r) {
+    const double2* p = reinterpret_cast<const double2*>(rec);
+    double2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+    r.o = D3{a0.x, a0.y, a1.x};
+    r.d = D3{a1.y, a2.x, a2.y};
+    r.time = a3.x;
+}
+
+// warp-aggregated append of `slot` to the queue selected by `q` (lanes with q < 0 do not append)
+__device__ __forceinline__ void queue_append(uint32_t* const* queues, uint32_t* counts, int q, uint32_t slot) {
+    unsigned active = __activemask();
+    unsigned peers = __match_any_sync(active, q);
+    if (q >= 0) {
+        int leader = __ffs(peers) - 1;
+        int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&counts[q], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        uint32_t off = __popc(peers & ((1u << lane) - 1));
+        queues[q][base + off] = slot;
+    }
+}
+
+__global__ void k_init_free(uint32_t* q_free, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) q_free[i] = i;
+}
+
+// pixel list of this partition: 8x8 tiles dealt round-robin (rt_render_opts.part_index/part_count)
+__global__ void k_pixel_list(uint32_t W, uint32_t H, uint32_t part_index, uint32_t part_count, uint32_t* list, uint32_t* count) {
+    uint32_t tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
+    uint32_t n_tiles = tiles_x * tiles_y;
+    // one warp handles one tile = 64 pixels, two per lane; order inside the list is tile-major
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    uint32_t n_warps = gridDim.x * blockDim.x / 32;
+    for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+        if (tile % part_count != part_index) continue;
+        uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+        // positions in the list are claimed with one atomic per tile (order only affects scheduling)
+        uint32_t valid = 0;
+        uint32_t px[2], ok[2];
+        for (int k = 0; k < 2; k++) {
+            uint32_t p = lane + 32 * k;
+            uint32_t x = tx * 8 + (p & 7), y = ty * 8 + (p >> 3);
+            ok[k] = x < W && y < H;
+            px[k] = y * W + x;
+            valid += ok[k];
+        }
+        uint32_t total = valid;
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(count, total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        // exclusive prefix of `valid` over lanes
+        uint32_t incl = valid;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        uint32_t pos = base + incl - valid;
+        for (int k = 0; k < 2; k++)
+            if (ok[k]) list[pos++] = px[k];
+    }
+}
+
+// Camera::get_ray, camera.rs:247-273
+__global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState W) {
+    const uint64_t remaining = W.total_paths - W.counters->next_path;
+    const uint32_t n_free = W.counters->n_free;
+    const uint32_t n_new = (uint32_t)(remaining < (uint64_t)n_free ? remaining : (uint64_t)n_free);
+    const uint32_t extend_base = W.counters->n_extend;
+    const uint64_t first = W.counters->next_path;
+    const rt_camera& cam = P.cam;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
+        uint32_t slot = W.q_free[n_free - 1 - j];
+        uint64_t g = first + j;
+        uint32_t sidx = P.sample_begin + (uint32_t)(g / W.n_pixels);
+        uint32_t pixel = W.pixel_list[g % W.n_pixels];
+        uint32_t i = pixel % cam.image_width, jj = pixel / cam.image_width;
+        uint32_t s_i = sidx / cam.sqrt_spp, s_j = sidx % cam.sqrt_spp;
+        Rand2 jit = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_JITTER);
+        double px = (((double)s_i + jit.a) * cam.recip_sqrt_spp) - 0.5;
+        double py = (((double)s_j + jit.b) * cam.recip_sqrt_spp) - 0.5;
+        D3 pixel_sample = ld3(cam.pixel00_loc) + (((double)i + px) * ld3(cam.pixel_delta_u)) + (((double)jj + py) * ld3(cam.pixel_delta_v));
+        D3 origin;
+        if (cam.defocus_angle_in_degrees <= 0.0) {
+            origin = ld3(cam.center);
+        } else {  // defocus_disk_sample, vec3.rs:63-69
+            Rand2 dk = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_DISK);
+            double theta = (2.0 * RT_PI) * dk.a;
+            double rr = sqrt(dk.b);
+            double s, c;
+            sincos(theta, &s, &c);
+            double p0 = rr * c, p1 = rr * s;
+            origin = ld3(cam.center) + (p0 * ld3(cam.defocus_disk_u)) + (p1 * ld3(cam.defocus_disk_v));
+        }
+        D3 dir = pixel_sample - origin;
+        double time = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_TIME).a;
+        double2* rp = reinterpret_cast<double2*>(W.rec + slot);
+        rp[0] = make_double2(origin.x, origin.y);
+        rp[1] = make_double2(origin.z, dir.x);
+        rp[2] = make_double2(dir.y, dir.z);
+        rp[3] = make_double2(time, 1.0);
+        rp[4] = make_double2(1.0, 1.0);
+        reinterpret_cast<uint4*>(rp)[5] = make_uint4(pixel, sidx, 0u, 0u);
+        W.q_extend[extend_base + j] = slot;
+    }
+}
+
+// single-thread bookkeeping between the stages
+__global__ void k_step(WavefrontState W, int phase) {
+    Counters* c = W.counters;
+    if (phase == 0) {  // after generate
+        uint64_t remaining = W.total_paths - c->next_path;
+        uint32_t n_new = (uint32_t)(remaining < (uint64_t)c->n_free ? remaining : (uint64_t)c->n_free);
+        c->next_path += n_new;
+        c->n_free -= n_new;
+        c->n_extend += n_new;
+        c->segments += c->n_extend;
+        c->iterations += (c->n_extend > 0);
+    } else if (phase == 1) {  // after extend
+        c->n_extend = 0;
+    } else {  // after shade
+        for (int k = 0; k < SC_COUNT; k++) c->n_shade[k] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// extend
+// ------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(EXTEND_BLOCK) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
+    __shared__ uint32_t s_stack[TRAVERSAL_STACK * EXTEND_BLOCK];
+    uint32_t* stack = s_stack + threadIdx.x;
+    TraceCounters cnt{0, 0};
+    const uint32_t n = W.counters->n_extend;
+    // whole warps iterate together so the aggregated append sees a converged warp
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        int q = -1;
+        uint32_t slot = 0;
+        if (j < n) {
+            slot = W.q_extend[j];
+            PathRec* rec = W.rec + slot;
+            RayD r;
+            load_ray(rec, r);
+            const uint4 ids = reinterpret_cast<const uint4*>(rec)[5];
+            double t = INFINITY;
+            uint32_t prim = 0xFFFFFFFFu;
+            uint32_t kind = HIT_MISS, rank = 0xFFFFFFFFu;
+            if (closest_hit<COUNT, true>(sv, sv.world_root, r, 1e-8, INFINITY, stack, EXTEND_BLOCK, t, prim, &cnt)) {
+                kind = HIT_SURFACE;
+                rank = sv.meta[prim].rank;
+            }
+            // ConstantMedium::hit for every medium, volume.rs:37-73
+            for (uint32_t m = 0; m < sv.n_media; m++) {
+                const Medium& med = sv.media[m];
+                double t1, t2;
+                uint32_t bp;
+                if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, stack, EXTEND_BLOCK, t1, bp, &cnt)) continue;
+                if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, stack, EXTEND_BLOCK, t2, bp, &cnt)) continue;
+                if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
+                if (t1 >= t2) continue;
+                if (t1 < 0.0) t1 = 0.0;
+                D3 dl = med.has_xform ? mul33(med.Ainv, r.d) : r.d;
+                double ray_length = length(dl);
+                double distance_inside_boundary = (t2 - t1) * ray_length;
+                double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
+                double hit_distance = med.neg_inv_density * log(xi);
+                if (hit_distance > distance_inside_boundary) continue;
+                double tm = t1 + hit_distance / ray_length;
+                // the medium competes with the other children of its container like any hit
+                if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
+                    t = tm;
+                    prim = m;
+                    kind = HIT_MEDIUM;
+                    rank = med.rank;
+                }
+            }
+            reinterpret_cast<double2*>(rec)[6] = make_double2(t, __hiloint2double((int)kind, (int)prim));
+            if (kind == HIT_MISS)
+                q = SC_MISS;
+            else if (kind == HIT_MEDIUM)
+                q = (int)sv.materials[sv.media[prim].material].shade_class;
+            else
+                q = (int)sv.materials[sv.meta[prim].kind_mat & 0x3FFFFFFFu].shade_class;
+            if (!P.bin_by_class) q = q == SC_MISS ? SC_MISS : SC_DIFFUSE;
+        }
+        queue_append(W.q_shade, W.counters->n_shade, q, slot);
+    }
+    if (COUNT) {
+        atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
+        atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// shade
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void contribute(const RenderParams& P, const WavefrontState& W, uint32_t pixel, D3 c) {
+    if (isnan(c.x) || isnan(c.y) || isnan(c.z)) {  // camera.rs:323 would panic
+        atomicAdd(&W.counters->errors, 1ull);
+        return;
+    }
+    double* a = W.accum + (size_t)pixel * 3;
+    if (c.x != 0.0) atomicAdd(a + 0, c.x);
+    if (c.y != 0.0) atomicAdd(a + 1, c.y);
+    if (c.z != 0.0) atomicAdd(a + 2, c.z);
+}
+
+__global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParams P, WavefrontState W) {
+    // concatenated view over the class queues
+    uint32_t start[SC_COUNT + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int k = 0; k < SC_COUNT; k++) start[k + 1] = start[k] + W.counters->n_shade[k];
+    const uint32_t n = start[SC_COUNT];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    uint32_t* const out_queues[2] = {W.q_extend, W.q_free};
+    uint32_t* out_counts = &W.counters->n_extend;  // n_extend, n_free are adjacent
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        int q = -1;
+        uint32_t slot = 0;
+        if (j < n) {
+            int cls = 0;
+#pragma unroll
+            for (int k = 1; k < SC_COUNT; k++) cls += (j >= start[k]);
+            slot = W.q_shade[cls][j - start[cls]];
+            PathRec* rec = W.rec + slot;
+            RayD r;
+            load_ray(rec, r);
+            const double2* rp = reinterpret_cast<const double2*>(rec);
+            D3 beta = D3{rp[3].y, rp[4].x, rp[4].y};
+            const uint4 ids = reinterpret_cast<const uint4*>(rec)[5];
+            const uint32_t pixel = ids.x, sidx = ids.y, segment = ids.z;
+            const double t = rp[6].x;
+            const uint32_t kind = (uint32_t)__double2hiint(rp[6].y), prim = (uint32_t)__double2loint(rp[6].y);
+            bool alive = false, error = false;
+            RayD nr = r;
+            D3 nbeta = beta;
+
+            if (kind == HIT_MISS) {
+                D3 bg;
+                if (background_value(sv, P.cam.background_tex, r.d, bg))
+                    contribute(P, W, pixel, beta * bg);
+                else
+                    error = true;
+            } else {
+                HitInfo h;
+                if (kind == HIT_MEDIUM) {  // volume.rs:66-72
+                    h.p = r.o + t * r.d;
+                    D3 nrm = D3{1.0, 0.0, 0.0};
+                    h.front_face = dot(r.d, nrm) < 0.0;
+                    h.normal = h.front_face ? nrm : -nrm;
+                    h.u = 0.0, h.v = 0.0;
+                    h.material = sv.media[prim].material;
+                } else {
+                    uint32_t mat = sv.meta[prim].kind_mat & 0x3FFFFFFFu;
+                    surface_hit_info(sv, prim, t, r, sv.materials[mat].needs_uv != 0, h);
+                }
+                // emitted (camera.rs:290) — only light-carrying materials can return non-black
+                uint32_t mat = h.material;
+                uint32_t mk = sv.materials[mat].kind;
+                if (mk == RT_MAT_DIFFUSE_LIGHT || mk == RT_MAT_MIX) {
+                    D3 e = material_emitted(sv, mat, h);
+                    contribute(P, W, pixel, beta * e);
+                }
+                // resolve DiffuseLight wrappers and Mix picks down to the scattering material
+                uint32_t level = 0;
+                while (mat != RT_NONE) {
+                    const Material& M = sv.materials[mat];
+                    if (M.kind == RT_MAT_DIFFUSE_LIGHT)
+                        mat = M.inner;
+                    else if (M.kind == RT_MAT_MIX) {  // material.rs:249-257
+                        double ratio = M.tex == RT_NONE ? M.param
+                                                        : (sv.textures[M.tex].a == RT_NONE ? 1.0 : (double)image_get_pixel(sv, sv.textures[M.tex].a, h.u, h.v).w);
+                        double xi = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_MIX + 256u * level).a;
+                        mat = xi > ratio ? M.inner : M.inner2;
+                        level++;
+                    } else
+                        break;
+                }
+                if (mat != RT_NONE) {
+                    const Material& M = sv.materials[mat];
+                    nr.o = h.p;
+                    switch (M.kind) {
+                        case RT_MAT_METAL: {  // material.rs:82-95
+                            D3 ud, ur;
+                            if (unit_vector(r.d, ud) && unit_vector(reflect(ud, h.normal), ur)) {
+                                Rand2 xi = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_MATERIAL);
+                                nr.d = ur + (M.param * random_unit_vector(xi.a, xi.b));
+                                nbeta = beta * ld3(M.color);
+                                alive = true;
+                            }
+                            break;
+                        }
+                        case RT_MAT_DIELECTRIC: {  // material.rs:117-144
+                            double ri = h.front_face ? 1.0 / M.param : M.param;
+                            D3 ud;
+                            if (!unit_vector(r.d, ud)) {
+                                error = true;
+                                break;
+                            }
+                            double cos_theta = rmin(dot(-ud, h.normal), 1.0);
+                            double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+                            bool cannot_refract = ri * sin_theta > 1.0;
+                            double r0 = (1.0 - ri) / (1.0 + ri);
+                            double r0s = r0 * r0;
+                            double x = 1.0 - cos_theta;
+                            double x2 = x * x;
+                            double reflectance = r0s + (1.0 - r0s) * (x * (x2 * x2));
+                            D3 dir;
+                            if (cannot_refract || reflectance > philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_MATERIAL).a) {
+                                dir = reflect(ud, h.normal);
+                            } else if (!refract(ud, h.normal, ri, dir)) {
+                                error = true;
+                                break;
+                            }
+                            nr.d = dir;
+                            nbeta = beta * texture_value(sv, M.tex, h.u, h.v, h.p);
+                            alive = true;
+                            break;
+                        }
+                        case RT_MAT_TRANSPARENT:  // material.rs:211-218
+                            alive = true;
+                            break;
+                        case RT_MAT_PORTAL: {  // material/portal.rs:21-30
+                            nr.o = h.p + ld3(M.v);
+                            // quaternion sandwich product, quaternion.rs:72-104
+                            double qw = M.v[3], qx = M.v[4], qy = M.v[5], qz = M.v[6];
+                            double aw = qw * 0.0 - qx * r.d.x - qy * r.d.y - qz * r.d.z;
+                            double ax = qw * r.d.x + qx * 0.0 + qy * r.d.z - qz * r.d.y;
+                            double ay = qw * r.d.y - qx * r.d.z + qy * 0.0 + qz * r.d.x;
+                            double az = qw * r.d.z + qx * r.d.y - qy * r.d.x + qz * 0.0;
+                            double cx = -qx, cy = -qy, cz = -qz;
+                            nr.d.x = aw * cx + ax * qw + ay * cz - az * cy;
+                            nr.d.y = aw * cy - ax * cz + ay * qw + az * cx;
+                            nr.d.z = aw * cz + ax * cy - ay * cx + az * qw;
+                            nbeta = beta * ld3(M.color);
+                            alive = true;
+                            break;
+                        }
+                        case RT_MAT_EMPTY:
+                        case RT_MAT_LAMBERTIAN:
+                        case RT_MAT_ISOTROPIC: {
+                            // ScatterRecord::PDF branch, camera.rs:297-312
+                            const bool iso = M.kind == RT_MAT_ISOTROPIC;
+                            D3 albedo = M.kind == RT_MAT_EMPTY ? D3{0.75, 0.75, 0.75} : texture_value(sv, M.tex, h.u, h.v, h.p);
+                            ONB uvw;
+                            if (!iso && !make_onb(h.normal, uvw)) {
+                                error = true;
+                                break;
+                            }
+                            Rand2 pick = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_MIXTURE);
+                            Rand2 dx = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_DIRECTION);
+                            D3 gen;
+                            const bool have_lights = sv.n_lights > 0;
+                            if (have_lights && !(pick.a < 0.5)) {
+                                if (!lights_random(sv, h.p, pick.b, dx.a, dx.b, gen)) {
+                                    error = true;
+                                    break;
+                                }
+                            } else {
+                                gen = iso ? random_unit_vector(dx.a, dx.b) : onb_to_world(uvw, random_cosine_direction(dx.a, dx.b));
+                            }
+                            // PDF::value, pdf.rs:22-29, 51-57
+                            D3 axp;
+                            double value0;
+                            if (iso) {
+                                value0 = 1.0 / (4.0 * RT_PI);
+                                axp = albedo / (4.0 * RT_PI);
+                            } else {
+                                D3 ud;
+                                if (!unit_vector(gen, ud)) {
+                                    error = true;
+                                    break;
+                                }
+                                double cosine_theta = dot(ud, uvw.v);
+                                value0 = rmax(0.0, cosine_theta / RT_PI);
+                                axp = albedo * rmax(cosine_theta, 0.0) / RT_PI;
+                            }
+                            double pdf_val = value0;
+                            if (have_lights) {
+                                double value1 = lights_pdf_value(sv, P.lights_flat, h.p, gen);
+                                if (isnan(value1) || (value0 == 0.0 && value1 == 0.0)) {  // hits.rs:64, pdf.rs:105-109
+                                    error = true;
+                                    break;
+                                }
+                                pdf_val = value0 * 0.5 + value1 * 0.5;
+                            }
+                            if (pdf_val == 0.0) {  // camera.rs:309
+                                error = true;
+                                break;
+                            }
+                            nr.d = gen;
+                            nbeta = beta * (axp / pdf_val);
+                            alive = true;
+                            break;
+                        }
+                        default: break;
+                    }
+                }
+            }
+            if (error) {
+                atomicAdd(&W.counters->errors, 1ull);
+                alive = false;
+            }
+            // a zero throughput can never contribute again; depth == 0 returns black (camera.rs:282)
+            if (alive && (segment + 1 >= P.cam.max_depth || (nbeta.x == 0.0 && nbeta.y == 0.0 && nbeta.z == 0.0))) alive = false;
+            if (alive) {
+                double2* wp = reinterpret_cast<double2*>(rec);
+                wp[0] = make_double2(nr.o.x, nr.o.y);
+                wp[1] = make_double2(nr.o.z, nr.d.x);
+                wp[2] = make_double2(nr.d.y, nr.d.z);
+                wp[3] = make_double2(nr.time, nbeta.x);
+                wp[4] = make_double2(nbeta.y, nbeta.z);
+                reinterpret_cast<uint4*>(wp)[5] = make_uint4(pixel, sidx, segment + 1, 0u);
+            }
+            q = alive ? 0 : 1;
+        }
+        queue_append(out_queues, out_counts, q, slot);
+    }
+}
+
+__global__ void k_finalize(const double* __restrict__ accum, uint64_t n, double scale, void* out, int out_f64) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double v = accum[i] * scale;
+        if (out_f64)
+            reinterpret_cast<double*>(out)[i] = v;
+        else
+            reinterpret_cast<float*>(out)[i] = (float)v;
+    }
+}
+
+
+// Color::to_rgb, utils/color.rs:14-36: optional ACES fit, then linear -> sRGB 8 bit.  palette's
+// encoder is not vendored with the reference; this is the standard piecewise curve rounded to
+// nearest (palette's f32 fast path may differ by one code at rounding boundaries).
+__global__ void k_tonemap(const void* __restrict__ accum, int f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* __restrict__ rgb, int* error_flag) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += (uint64_t)gridDim.x * blockDim.x) {
+        D3 c;
+        if (f64) {
+            const double* a = reinterpret_cast<const double*>(accum) + 3 * i;
+            c = D3{a[0], a[1], a[2]};
+        } else {
+            const float* a = reinterpret_cast<const float*>(accum) + 3 * i;
+            c = D3{(double)a[0], (double)a[1], (double)a[2]};
+        }
+        if (isnan(c.x) || isnan(c.y) || isnan(c.z)) *error_flag = 1;  // color.rs:28 assert
+        if (toon_map == 1) {  // aces_tonemap, color.rs:14-25
+            const double A = 2.51, C = 2.43;
+            const D3 B = D3{0.03, 0.03, 0.03}, Dd = D3{0.59, 0.59, 0.59}, E = D3{0.14, 0.14, 0.14};
+            D3 num = c * (A * c + B), den = c * (C * c + Dd) + E;
+            D3 m = D3{num.x / den.x, num.y / den.y, num.z / den.z};
+            c = D3{fmin(fmax(m.x, 0.0), 1.0), fmin(fmax(m.y, 0.0), 1.0), fmin(fmax(m.z, 0.0), 1.0)};
+        }
+        double v[3] = {c.x, c.y, c.z};
+        for (int k = 0; k < 3; k++) {
+            double x = v[k];
+            double enc = x <= 0.0031308 ? 12.92 * x : 1.055 * pow(x, 1.0 / 2.4) - 0.055;
+            if (!(enc > 0.0)) enc = 0.0;
+            if (enc > 1.0) enc = 1.0;
+            rgb[3 * i + k] = (uint8_t)llrint(floor(enc * 255.0 + 0.5));
+        }
+    }
+}
+void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb, int* error_flag, cudaStream_t s) {
+    int grid = (int)((n_pixels + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    k_tonemap<<<grid, 256, 0, s>>>(accum, f64 ? 1 : 0, n_pixels, toon_map, rgb, error_flag);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s) {
+    k_init_free<<<grid, 256, 0, s>>>(W.q_free, W.capacity);
+    k_pixel_list<<<grid, 256, 0, s>>>(P.cam.image_width, P.cam.image_height, P.part_index, P.part_count, W.pixel_list, &W.counters->n_pixels);
+}
+void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
+    k_generate<<<grid, 256, 0, s>>>(P, W);
+    k_step<<<1, 1, 0, s>>>(W, 0);
+}
+void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, cudaStream_t s) {
+    if (count)
+        k_extend<true><<<grid, EXTEND_BLOCK, 0, s>>>(sv, P, W);
+    else
+        k_extend<false><<<grid, EXTEND_BLOCK, 0, s>>>(sv, P, W);
+    k_step<<<1, 1, 0, s>>>(W, 1);
+}
+void launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
+    k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sv, P, W);
+    k_step<<<1, 1, 0, s>>>(W, 2);
+}
+void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s) {
+    k_finalize<<<grid, 256, 0, s>>>(accum, n, scale, out, out_f64 ? 1 : 0);
+}
+
+void kernel_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false>, EXTEND_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade, SHADE_BLOCK, 0);
+}
+
+}  // namespace rt

@@ -1,0 +1,126 @@
+// scene_types.h — device-resident scene layout shared by the host compile step and the kernels.
+//
+// HBM layout (everything 16-byte aligned, read-only during a render):
+//   nodes[]   64 B  BVH2 node holding BOTH children's boxes as conservative binary32 bounds and
+//                   two child references; one node visit = 4 x LDG.128 and two slab tests.
+//   geom[]   128 B  one primitive in BVH leaf order, binary64, the very numbers of the reference's
+//                   structs (sphere.rs:17-22, quad.rs:18-29): sphere = centre(3) centre_vec(3)
+//                   radius; quad/triangle = anchor(3) u(3) v(3) normal(3) D w(3).
+//   meta[]    16 B  kind|material, object id (rt_hit.prim_id), tie rank, uv-frame / instance id.
+// Transforms are baked into the primitives at compile time (t is preserved by Transform::hit,
+// shapes.rs:93-101), so traversal is single level.
+#pragma once
+#include <stdint.h>
+
+namespace rt {
+
+constexpr uint32_t LEAF_FLAG = 0x80000000u;
+constexpr uint32_t INVALID_REF = 0x7FFFFFFFu;  // empty child / empty group
+constexpr int MAX_LEAF_PRIMS = 8;
+constexpr int TRAVERSAL_STACK = 64;
+
+// child reference: interior -> node index; leaf -> LEAF_FLAG | first_prim << 3 | (count - 1)
+struct alignas(16) Node {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    uint32_t child0, child1;
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(Node) == 64, "node must be 64 bytes");
+
+enum PrimKind : uint32_t { PRIM_SPHERE = 0, PRIM_QUAD = 1, PRIM_TRIANGLE = 2 };
+
+struct alignas(16) PrimGeom {
+    double d[16];
+};
+static_assert(sizeof(PrimGeom) == 128, "primitive record must be 128 bytes");
+
+struct alignas(16) PrimMeta {
+    uint32_t kind_mat;  // kind in bits 30..31, material index in bits 0..29
+    uint32_t rank;      // lower rank wins an exact t tie (hits.rs:42, bvh.rs:78-84)
+    uint32_t object;    // index of the leaf shape in rt_scene_desc.objects
+    uint32_t xform;     // index into xforms[] (baked Transform chain) or RT_NONE
+};
+
+// A baked chain of Transforms: x_world = A x_local + b ; x_local = Ainv (x_world - b)
+struct Xform {
+    double A[9];
+    double b[3];
+    double Ainv[9];
+    uint32_t inst_object;  // object id of the innermost Transform (rt_hit.inst_id)
+    uint32_t pad;
+};
+
+struct Material {
+    uint32_t kind, tex, inner, inner2;
+    double color[3];
+    double param;
+    double v[8];
+    uint32_t shade_class, needs_uv;
+};
+
+struct Texture {
+    uint32_t kind, a, b, pad;
+    double color[3];
+    double color2[3];
+    double scale;
+};
+
+struct Image {
+    uint32_t width, height, flags, pad;
+    uint64_t texel_offset;  // in float4 texels
+};
+
+struct Perlin {
+    double randvec[256][3];
+    uint32_t perm_x[256], perm_y[256], perm_z[256];
+};
+
+struct Medium {
+    uint32_t root;      // boundary group root reference
+    uint32_t material;  // its Isotropic
+    uint32_t object;    // object id of the ConstantMedium
+    uint32_t rank;
+    double neg_inv_density;
+    double Ainv[9];     // linear part of world->local above the medium (ray_length is local, volume.rs:55)
+    uint32_t has_xform, medium_index;
+};
+
+// One leaf of the lights tree (hits.rs:52-75), geometry in the local space of its Transform chain
+struct Light {
+    PrimGeom g;
+    uint32_t kind;
+    uint32_t xform;  // RT_NONE or index into xforms[]
+    double weight, cdf, area;
+};
+
+// shade work classes used to bin hits (extend -> shade queues)
+enum ShadeClass : uint32_t {
+    SC_MISS = 0,      // background lookup, path ends
+    SC_DIFFUSE = 1,   // cosine pdf with a solid albedo (Lambertian / EmptyMaterial)
+    SC_TEXTURED = 2,  // cosine pdf with checker / image / noise albedo
+    SC_ISOTROPIC = 3,
+    SC_METAL = 4,
+    SC_DIELECTRIC = 5,
+    SC_EMISSIVE = 6,  // DiffuseLight without inner material: path ends
+    SC_OTHER = 7,     // Mix, Portal, Transparent, DiffuseLight with inner
+    SC_COUNT = 8
+};
+
+struct SceneView {
+    const Node* nodes;
+    const PrimGeom* geom;
+    const PrimMeta* meta;
+    const Xform* xforms;
+    const Material* materials;
+    const Texture* textures;
+    const Image* images;
+    const float4* texels;
+    const Perlin* perlins;
+    const Medium* media;
+    const Light* lights;
+    uint32_t world_root;
+    uint32_t n_media, n_lights, n_prims;
+};
+
+}  // namespace rt

@@ -1,0 +1,280 @@
+"""GPU parity tests: the CUDA core (through the C ABI) against the oracle and the committed
+golden fixtures.  Integer outputs (primitive / instance ids) must be bit-exact; hit distances
+within 1e-9 relative (the north star allows 1e-5); same-seed images within 1e-6 relative for all
+but a vanishing fraction of pixels (a path whose branch flips on a last-bit libm difference)."""
+import os
+
+import numpy as np
+import pytest
+
+from scenes_util import compare_hits, random_graph_scene, random_rays
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+NAMED = {
+    "book2_final": ("book2_final", 7, [32, 4, 12]),
+    "cornell_glass": ("cornell_glass", 7, [32, 4, 12]),
+    "book1_final": ("book1_final", 7, [48, 4, 12]),
+}
+
+
+def golden_scene(rt, name):
+    if name == "random_graph":
+        return random_graph_scene(rt, 11, n_prims=72, with_media=True, width=32, spp=4, depth=8)
+    n, seed, params = NAMED[name]
+    return rt.named_scene(n, seed=seed, params=params)
+
+
+def image_close(img, ref, frac_bad=2e-3, rel=1e-6):
+    diff = np.abs(img - ref)
+    bad = (diff > rel * (1 + np.abs(ref))).any(axis=2)
+    assert bad.mean() <= frac_bad, f"{int(bad.sum())}/{bad.size} pixels differ (max {diff.max():.3e})"
+    assert abs(img.mean() - ref.mean()) <= 1e-3 * ref.mean() + 1e-9
+
+
+@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph"])
+def test_closest_hit_matches_golden(gpu, rt, name):
+    fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sc = rt.Scene(golden_scene(rt, name))
+    got, st = sc.closest_hit(fx["rays"])
+    compare_hits(rt, got, fx["hits"])
+    assert st.kernel_launches == 1
+
+
+@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph"])
+def test_render_matches_golden_image(gpu, rt, name):
+    fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sc = rt.Scene(golden_scene(rt, name))
+    img, st = sc.render(seed=int(fx["render_seed"]))
+    assert st.paths == int(fx["paths"])
+    assert abs(int(st.errors) - int(fx["errors"])) <= 2
+    image_close(img, fx["image"], frac_bad=5e-3)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_closest_hit_matches_oracle_on_random_graphs(gpu, rt, orc, seed):
+    hs = random_graph_scene(rt, seed, n_prims=120)
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    assert np.array_equal(sc.ranks(), osc.ranks())
+    rng = np.random.default_rng(seed)
+    o, d, t = random_rays(rng, 30000)
+    rays = rt.make_rays(o, d, t)
+    got, _ = sc.closest_hit(rays)
+    compare_hits(rt, got, osc.closest_hit(rays, mode=0))
+    # a finite interval and a shifted t_min
+    got, _ = sc.closest_hit(rays, t_min=0.5, t_max=7.0)
+    compare_hits(rt, got, osc.closest_hit(rays, t_min=0.5, t_max=7.0, mode=0))
+
+
+def test_untransformed_hits_are_bit_exact(gpu, rt, orc):
+    # primitives outside any Transform are intersected with the reference's own arithmetic
+    hs = random_graph_scene(rt, 5, n_prims=150, with_transforms=False)
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    rng = np.random.default_rng(5)
+    o, d, t = random_rays(rng, 30000)
+    rays = rt.make_rays(o, d, t)
+    got, _ = sc.closest_hit(rays)
+    want = osc.closest_hit(rays, mode=0)
+    assert np.array_equal(got["prim_id"], want["prim_id"])
+    assert np.array_equal(got["t"], want["t"])
+
+
+def test_tie_rules(gpu, rt, orc):
+    # hits.rs:42 first child wins; bvh.rs:78-84 right child wins; both through the rank order
+    for container, winner in (("list", 0), ("bvh", 1)):
+        b = rt.Builder(1)
+        m = b.empty()
+        q = [b.quad([-1, -1, 0], [2, 0, 0], [0, 2, 0], m) for _ in range(2)]
+        inner = b.list(q) if container == "list" else b.list([b.bvh(q)])
+        hs = b.finish(inner)
+        rays = rt.make_rays([[0.2, 0.3, 5], [0.9, -0.9, 2]], [[0, 0, -1], [0, 0, -1]])
+        got, _ = rt.Scene(hs).closest_hit(rays)
+        assert got["prim_id"].tolist() == [winner, winner]
+        assert got["t"].tolist() == [5.0, 2.0]
+    # five overlapping coplanar quads in a BVH: the median split decides (see the oracle test)
+    b = rt.Builder(1)
+    m = b.empty()
+    xs = [3.0, 0.0, 4.0, 1.0, 2.0]
+    hs = b.finish(b.list([b.bvh([b.quad([x, -1, 0], [10, 0, 0], [0, 2, 0], m) for x in xs])]))
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    rng = np.random.default_rng(0)
+    o = np.column_stack([rng.uniform(-1, 15, 2000), rng.uniform(-1.5, 1.5, 2000), np.full(2000, 5.0)])
+    rays = rt.make_rays(o, np.tile([0, 0, -1.0], (2000, 1)))
+    got, _ = sc.closest_hit(rays)
+    compare_hits(rt, got, osc.closest_hit(rays, mode=0))
+    assert len(set(got["prim_id"].tolist())) >= 5
+
+
+def test_edge_cases(gpu, rt, orc):
+    # empty world
+    b = rt.Builder(1)
+    hs = b.finish(b.list([]), width=8, spp=1, background=b.solid(0.25, 0.5, 1.0))
+    sc = rt.Scene(hs)
+    got, _ = sc.closest_hit(rt.make_rays([[0, 0, 0]], [[0, 0, 1]]))
+    assert got["prim_id"][0] == rt.RT_NONE and np.isinf(got["t"][0])
+    img, st = sc.render(seed=1)
+    assert np.array_equal(img, np.broadcast_to([0.25, 0.5, 1.0], img.shape)) and st.segments == st.paths
+    # zero rays
+    got, _ = sc.closest_hit(np.zeros(0, dtype=rt.rt_ray_dtype))
+    assert len(got) == 0
+    # axis-parallel, zero-component and degenerate directions; NaN origin never hits
+    b = rt.Builder(1)
+    m = b.empty()
+    hs = b.finish(b.list([b.bvh([b.sphere([0, 0, 0], 1.0, m), b.quad([-1, -1, -3], [2, 0, 0], [0, 2, 0], m),
+                                 b.triangle([-1, -1, 3], [2, 0, 0], [0, 2, 0], m), b.sphere([4, 0, 0], 0.5, m)])]))
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    o = [[0, 0, 5], [0, 0, 5], [-5, 0, 0], [0, 0, 0], [0, 0, 5], [float("nan"), 0, 5], [0.25, 0.25, -10], [0, 0, 5]]
+    d = [[0, 0, -1], [0, 0, 1], [1, 0, 0], [0, 1, 0], [0, 0, 0], [0, 0, -1], [0, 0, 1e-30], [0, 0, -1e300]]
+    rays = rt.make_rays(o, d)
+    got, _ = sc.closest_hit(rays)
+    want = osc.closest_hit(rays, mode=0)
+    assert np.array_equal(got["prim_id"], want["prim_id"])
+    hit = want["prim_id"] != rt.RT_NONE
+    assert np.array_equal(got["t"][hit], want["t"][hit])
+
+
+def test_moving_sphere_and_time(gpu, rt, orc):
+    b = rt.Builder(1)
+    hs = b.finish(b.list([b.sphere_moving([0, 0, 0], [4, 0, 0], 1.0, b.empty())]))
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    rng = np.random.default_rng(2)
+    o = np.column_stack([rng.uniform(-2, 6, 4000), rng.uniform(-1.5, 1.5, 4000), np.full(4000, 6.0)])
+    rays = rt.make_rays(o, np.tile([0, 0, -1.0], (4000, 1)), rng.uniform(0, 1, 4000))
+    got, _ = sc.closest_hit(rays)
+    want = osc.closest_hit(rays, mode=0)
+    assert np.array_equal(got["prim_id"], want["prim_id"]) and np.array_equal(got["t"], want["t"])
+    assert (want["prim_id"] == 0).sum() > 300
+
+
+@pytest.mark.parametrize("name,seed,params", [("book2_final", 3, [64, 9, 40]), ("cornell_glass", 3, [64, 9, 50]),
+                                              ("book1_final", 3, [96, 9, 50])])
+def test_same_seed_image_matches_oracle(gpu, rt, orc, name, seed, params):
+    hs = rt.named_scene(name, seed=seed, params=params)
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    img, st = sc.render(seed=17)
+    ref, ost = osc.render(seed=17)
+    assert st.paths == ost.paths and st.errors == ost.errors
+    image_close(img, ref)
+
+
+def test_materials_textures_and_lights_vs_oracle(gpu, rt, orc):
+    # every material / texture / light kind of configs 1-3 plus Mix, Transparent, Portal, checker,
+    # image (nearest + bilinear), triangle and transformed lights
+    rng = np.random.default_rng(7)
+    b = rt.Builder(3)
+    tex_img = b.image(rng.uniform(0, 1, (16, 8, 4)).astype(np.float32))
+    tex_raw = b.image(rng.uniform(0, 1, (5, 7, 4)).astype(np.float32), raw=True)
+    white = b.lambertian(b.solid(0.8, 0.8, 0.8))
+    mats = [
+        b.lambertian(tex_img), b.lambertian(tex_raw), b.lambertian(b.checker(0.5, b.solid(1, 1, 1), tex_img)),
+        b.lambertian(b.noise(2.0)), b.metal([0.9, 0.8, 0.7], 0.3), b.dielectric(b.solid(0.9, 1.0, 0.9), 1.33),
+        b.mix(white, b.metal([1, 1, 1], 0.0), 0.4), b.transparent(),
+        b.portal([0.9, 0.9, 1.0], [0.0, 0.0, -6.0], b.quat_axis_angle([0, 1, 0], 20.0)),
+        b.diffuse_light(b.solid(0.5, 0.4, 0.3), inner=white), b.isotropic(b.solid(0.5, 0.5, 0.9)),
+    ]
+    objs = []
+    for k, m in enumerate(mats):
+        x, y = (k % 4) * 2.2 - 3.3, (k // 4) * 2.2 - 2.0
+        objs.append(b.sphere([x, y, 0], 1.0, m) if k % 2 == 0 else b.quad([x - 0.9, y - 0.9, 0], [1.8, 0, 0], [0, 1.8, 0], m))
+    floor = b.quad([-8, -3.2, -8], [16, 0, 0], [0, 0, 16], white)
+    light = b.diffuse_light(b.solid(10, 10, 10))
+    q = b.quat_axis_angle([1, 0, 0], 25.0)
+    l1 = b.transform(b.quad([-1, 0, -1], [2, 0, 0], [0, 0, 2], light), offset=[0, 6, 2], quat=q, scale=[1.5, 1.5, 1.5])
+    l2 = b.triangle([3, 5, -1], [2, 0, 0], [0, 0, 2], light)
+    world = b.list([b.bvh(objs), floor, l1, l2])
+    e = b.empty()
+    lights = b.list([b.transform(b.quad([-1, 0, -1], [2, 0, 0], [0, 0, 2], e), offset=[0, 6, 2], quat=q, scale=[1.5, 1.5, 1.5]),
+                     b.list([b.triangle([3, 5, -1], [2, 0, 0], [0, 0, 2], e), b.sphere([-3.3, -2.0, 0], 1.0, e)])])
+    hs = b.finish(world, lights, width=48, spp=16, max_depth=10, vfov=50, look_from=(0, 1, 12), look_at=(0, 0, 0),
+                  background=b.gradient([1, 1, 1], [0.5, 0.7, 1.0]), defocus_angle=0.8, focus_dist=12.0)
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    img, st = sc.render(seed=23)
+    ref, ost = osc.render(seed=23)
+    assert st.paths == ost.paths
+    assert abs(int(st.errors) - int(ost.errors)) <= 2
+    image_close(img, ref, frac_bad=5e-3)
+
+
+def test_media_including_transformed_boundaries(gpu, rt, orc):
+    b = rt.Builder(4)
+    white = b.lambertian(b.solid(0.7, 0.7, 0.7))
+    floor = b.quad([-8, -2, -8], [16, 0, 0], [0, 0, 16], white)
+    light = b.quad([-2, 6, -2], [4, 0, 0], [0, 0, 4], b.diffuse_light(b.solid(9, 9, 9)))
+    fog_box = b.transform(b.box([-1, -1, -1], [1, 1, 1], b.empty()), offset=[-2, 0, 0], quat=b.quat_axis_angle([0, 1, 0], 30.0))
+    m1 = b.medium(fog_box, 0.9, b.solid(0.9, 0.9, 0.9))
+    m2 = b.transform(b.medium(b.sphere([0, 0, 0], 1.0, b.empty()), 1.5, b.solid(0.2, 0.3, 0.9)), offset=[2, 0, 0], scale=[1.5, 1.5, 1.5])
+    m3 = b.medium(b.sphere([0, 0, 0], 30.0, b.empty()), 0.01, b.solid(1, 1, 1))
+    world = b.list([floor, light, m1, m2, m3, b.sphere([0, 0, -3], 1.0, b.dielectric(b.solid(1, 1, 1), 1.5))])
+    lights = b.list([b.quad([-2, 6, -2], [4, 0, 0], [0, 0, 4], b.empty())])
+    hs = b.finish(world, lights, width=48, spp=16, max_depth=12, vfov=45, look_from=(0, 2, 10), look_at=(0, 0, 0))
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    assert sc.info().n_media == 3
+    img, st = sc.render(seed=5)
+    ref, ost = osc.render(seed=5)
+    assert st.paths == ost.paths and st.errors == ost.errors
+    image_close(img, ref, frac_bad=5e-3)
+
+
+def test_partitions_sample_ranges_and_capacity(gpu, rt):
+    # multi-GPU decomposition (rt_render_opts.part_*) and stratum ranges must add up to the whole,
+    # and the answer must not depend on how many paths are in flight
+    hs = rt.named_scene("book2_final", seed=5, params=[72, 9, 20])
+    sc = rt.Scene(hs)
+    whole, st = sc.render(seed=3)
+    parts = [sc.render(seed=3, part_index=k, part_count=3)[0] for k in range(3)]
+    nz = [(p != 0).any(axis=2) for p in parts]
+    assert not (nz[0] & nz[1]).any() and not (nz[1] & nz[2]).any()
+    assert np.allclose(sum(parts), whole, rtol=1e-12, atol=1e-14)
+    halves = sc.render(seed=3, sample_begin=0, sample_end=5)[0] + sc.render(seed=3, sample_begin=5, sample_end=9)[0]
+    assert np.allclose(halves, whole, rtol=1e-12, atol=1e-14)
+    small, st2 = sc.render(seed=3, max_paths_in_flight=4096)
+    assert np.allclose(small, whole, rtol=1e-12, atol=1e-14)
+    assert st2.paths == st.paths and st2.segments == st.segments and st2.iterations > st.iterations
+    f32, _ = sc.render(seed=3, accum_type=rt.RT_ACCUM_F32)
+    assert f32.dtype == np.float32 and np.allclose(f32, whole, rtol=1e-6, atol=1e-7)
+    other, _ = sc.render(seed=4)
+    assert not np.allclose(other, whole)
+
+
+def test_binning_does_not_change_the_image(gpu, rt):
+    import ctypes as C
+    hs = rt.named_scene("book2_final", seed=5, params=[64, 4, 20])
+    sc = rt.Scene(hs)
+    a, _ = sc.render(seed=3)
+    o = sc.render_opts(seed=3)
+    o.reserved[0] = 1  # material binning off
+    img = np.zeros_like(a)
+    st = rt.rt_stats()
+    assert sc.L.rt_render(sc.h, C.byref(hs.camera), C.byref(o), img.ctypes.data, C.byref(st)) == 0
+    assert np.allclose(img, a, rtol=1e-12, atol=1e-14)
+
+
+def test_tonemap_matches_oracle(gpu, rt, orc):
+    rng = np.random.default_rng(1)
+    img = rng.gamma(0.7, 0.8, (40, 50, 3))
+    img[0, 0] = [0, 1, 0.0031308]
+    for toon in (0, 1):
+        got = rt.tonemap(img, toon)
+        want = orc.tonemap(img, toon)
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1  # pow() last-bit differences only
+        assert (got != want).mean() < 1e-3
+    with pytest.raises(rt.RtError):
+        bad = img.copy()
+        bad[3, 3, 1] = np.nan
+        rt.tonemap(bad)
+
+
+def test_full_size_properties_book2(gpu, rt):
+    """Config 2 at BASELINE.json's full resolution (one stratum per pixel-sample block): properties
+    that do not need the oracle — energy is finite and non-negative, the light is seen, stats add up."""
+    hs = rt.named_scene("book2_final", seed=7, params=[800, 1000, 40])
+    sc = rt.Scene(hs)
+    img, st = sc.render(seed=1, sample_begin=0, sample_end=16, accum_type=rt.RT_ACCUM_F32)
+    assert st.paths == 800 * 800 * 16 and st.errors == 0
+    assert np.isfinite(img).all() and (img >= 0).all()
+    full_scale = 961 / 16  # accum holds sum * pixel_sample_scale
+    mean = img.mean() * full_scale
+    assert 0.2 < mean < 1.0
+    assert img.max() * full_scale > 5.0  # the 7,7,7 light quad is visible
+    assert 3.0 < st.segments / st.paths < 6.0

@@ -1,0 +1,166 @@
+"""Behaviour of the oracle that the reference defines structurally: container tie rules,
+interval semantics, media, partition additivity, and estimator consistency."""
+import math
+
+import numpy as np
+import pytest
+
+from scenes_util import random_graph_scene, random_rays
+
+
+def one_ray(rt, o, d, t=0.0):
+    return rt.make_rays([o], [d], [t])
+
+
+def test_reference_vs_brute_force_agree(rt, orc):
+    # mode 0 walks the containers like the reference; mode 1 tests every leaf: same winner
+    for seed in range(4):
+        hs = random_graph_scene(rt, seed, n_prims=90)
+        osc = orc.OracleScene(hs)
+        rng = np.random.default_rng(seed)
+        o, d, t = random_rays(rng, 4000)
+        rays = rt.make_rays(o, d, t)
+        a, b = osc.closest_hit(rays, mode=0), osc.closest_hit(rays, mode=1)
+        assert np.array_equal(a["prim_id"], b["prim_id"])
+        assert np.array_equal(a["inst_id"], b["inst_id"])
+        assert np.array_equal(a["t"], b["t"])
+        assert (a["prim_id"] != rt.RT_NONE).sum() > 500
+
+
+def test_list_keeps_first_of_equal_hits(rt, orc):
+    # src/hits.rs:39-46: Iterator::min_by returns the first minimum
+    b = rt.Builder(1)
+    m = b.empty()
+    q1 = b.quad([-1, -1, 0], [2, 0, 0], [0, 2, 0], m)
+    q2 = b.quad([-1, -1, 0], [2, 0, 0], [0, 2, 0], m)
+    hs = b.finish(b.list([q1, q2]))
+    osc = orc.OracleScene(hs)
+    h = osc.closest_hit(one_ray(rt, [0.2, 0.3, 5], [0, 0, -1]))
+    assert h["prim_id"][0] == 0 and h["t"][0] == 5.0
+    assert list(osc.ranks()[:2]) == [0, 1]
+    assert osc.closest_hit(one_ray(rt, [0.2, 0.3, 5], [0, 0, -1]), mode=1)["prim_id"][0] == 0
+
+
+def test_bvh_keeps_right_child_on_a_tie(rt, orc):
+    # src/bvh.rs:70-84: the right interval is [min, t_left] inclusive and hit_right.or(hit_left)
+    b = rt.Builder(1)
+    m = b.empty()
+    q1 = b.quad([-1, -1, 0], [2, 0, 0], [0, 2, 0], m)
+    q2 = b.quad([-1, -1, 0], [2, 0, 0], [0, 2, 0], m)
+    hs = b.finish(b.list([b.bvh([q1, q2])]))
+    osc = orc.OracleScene(hs)
+    assert osc.closest_hit(one_ray(rt, [0.2, 0.3, 5], [0, 0, -1]))["prim_id"][0] == 1
+    assert list(osc.ranks()[:2]) == [1, 0]
+    assert osc.closest_hit(one_ray(rt, [0.2, 0.3, 5], [0, 0, -1]), mode=1)["prim_id"][0] == 1
+
+
+def test_bvh_median_split_order(rt, orc):
+    # 5 coincident-in-t quads spread along x: BVH::from_vec sorts by box min on the longest axis,
+    # splits at len/2 and prefers the right subtree -> the largest-x quad wins everywhere they overlap
+    b = rt.Builder(1)
+    m = b.empty()
+    xs = [3.0, 0.0, 4.0, 1.0, 2.0]
+    quads = [b.quad([x, -1, 0], [10, 0, 0], [0, 2, 0], m) for x in xs]
+    hs = b.finish(b.list([b.bvh(quads)]))
+    osc = orc.OracleScene(hs)
+    h = osc.closest_hit(one_ray(rt, [6.0, 0.0, 5], [0, 0, -1]))
+    assert h["prim_id"][0] == 2  # the quad anchored at x = 4
+    ranks = osc.ranks()[:5]
+    order = [int(np.argsort(ranks)[k]) for k in range(5)]
+    assert [xs[i] for i in order] == [4.0, 3.0, 2.0, 1.0, 0.0]
+
+
+def test_interval_is_inclusive(rt, orc):
+    # src/utils/interval.rs:65-67
+    b = rt.Builder(1)
+    q = b.quad([-1, -1, 0], [2, 0, 0], [0, 2, 0], b.empty())
+    hs = b.finish(b.list([q]))
+    osc = orc.OracleScene(hs)
+    r = one_ray(rt, [0, 0, 5], [0, 0, -1])
+    assert osc.closest_hit(r, t_min=5.0, t_max=5.0)["prim_id"][0] == 0
+    assert osc.closest_hit(r, t_min=0.0, t_max=4.999)["prim_id"][0] == rt.RT_NONE
+    # |denom| < 1e-8 is a miss (quad.rs:77-79)
+    assert osc.closest_hit(one_ray(rt, [0, 0, 5], [1, 0, -1e-9]))["prim_id"][0] == rt.RT_NONE
+    # alpha, beta in [0,1] inclusive: the corner itself hits
+    assert osc.closest_hit(one_ray(rt, [1, 1, 5], [0, 0, -1]))["prim_id"][0] == 0
+
+
+def test_sphere_second_root_and_transform_keeps_t(rt, orc):
+    b = rt.Builder(1)
+    s = b.sphere([0, 0, 0], 1.0, b.empty())
+    t = b.transform(b.sphere([0, 0, 0], 1.0, b.empty()), offset=[5, 0, 0], scale=[2, 2, 2])
+    hs = b.finish(b.list([s, t]))
+    osc = orc.OracleScene(hs)
+    # from inside: the first root is negative, the second is taken (sphere.rs:97-103)
+    h = osc.closest_hit(one_ray(rt, [0, 0, 0], [0, 0, 2.0]))
+    assert h["prim_id"][0] == 0 and h["t"][0] == 0.5
+    # the scaled, translated sphere has radius 2 around (5,0,0); t is in units of the world ray
+    h = osc.closest_hit(one_ray(rt, [5, 0, 10], [0, 0, -4.0]))
+    assert h["prim_id"][0] == 1 and h["inst_id"][0] == 2 and h["t"][0] == pytest.approx(2.0, rel=1e-15)
+
+
+def test_medium_free_flight_statistics(rt, orc):
+    # volume.rs:55-64: P(scatter) = 1 - exp(-density * length inside)
+    b = rt.Builder(1)
+    med = b.medium(b.sphere([0, 0, 0], 1.0, b.empty()), 0.7, b.solid(1, 1, 1))
+    bg = b.solid(1, 1, 1)
+    hs = b.finish(b.list([med]), width=1, spp=40000, max_depth=1, vfov=1e-6, look_from=(0, 0, 5), look_at=(0, 0, 0), background=bg)
+    osc = orc.OracleScene(hs)
+    img, st = osc.render(seed=5)
+    # max_depth = 1: a scattered path returns black (depth 0), an unscattered one sees the white sky
+    p_through = img[0, 0, 0]
+    assert abs(p_through - math.exp(-0.7 * 2.0)) < 4 * math.sqrt(0.25 / 40000)
+    assert st.errors == 0
+
+
+def test_partitions_and_sample_ranges_add_up(rt, orc):
+    hs = random_graph_scene(rt, 3, n_prims=40, with_media=True, width=20, spp=9, depth=5)
+    osc = orc.OracleScene(hs)
+    whole, st = osc.render(seed=9)
+    parts = sum(osc.render(seed=9, part_index=k, part_count=3)[0] for k in range(3))
+    assert np.array_equal(whole, parts)  # disjoint pixels: exact
+    halves = osc.render(seed=9, sample_begin=0, sample_end=4)[0] + osc.render(seed=9, sample_begin=4, sample_end=9)[0]
+    assert np.allclose(whole, halves, rtol=1e-13, atol=1e-15)
+    assert st.paths == 20 * 20 * 9
+
+
+def test_light_sampling_is_unbiased(rt, orc):
+    # the mixture pdf (camera.rs:297-312) must not change the expectation: lights=None vs lights
+    def scene(with_lights):
+        b = rt.Builder(2)
+        white = b.lambertian(b.solid(0.7, 0.7, 0.7))
+        light = b.diffuse_light(b.solid(8, 8, 8))
+        floor = b.quad([-5, -1, -5], [10, 0, 0], [0, 0, 10], white)
+        lq = b.quad([-1, 3, -1], [2, 0, 0], [0, 0, 2], light)
+        ball = b.sphere([0, 0, 0], 1.0, white)
+        world = b.list([floor, lq, ball])
+        lights = b.list([b.quad([-1, 3, -1], [2, 0, 0], [0, 0, 2], b.empty())]) if with_lights else rt.RT_NONE
+        return b.finish(world, lights, width=8, spp=2500, max_depth=6, vfov=40, look_from=(0, 2, 9), look_at=(0, 0, 0))
+    a, sa = orc.OracleScene(scene(True)).render(seed=4)
+    c, sc = orc.OracleScene(scene(False)).render(seed=4)
+    assert sa.errors == 0 and sc.errors == 0
+    assert abs(a.mean() - c.mean()) < 0.05 * c.mean()
+
+
+def test_same_seed_same_image_and_thread_independence(rt, orc):
+    hs = random_graph_scene(rt, 5, n_prims=30, width=16, spp=4)
+    osc = orc.OracleScene(hs)
+    a = osc.render(seed=1, threads=1)[0]
+    b = osc.render(seed=1, threads=4)[0]
+    c = osc.render(seed=2, threads=4)[0]
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, c)
+
+
+def test_tonemap_curve(orc):
+    # utils/color.rs:27-36 with the standard sRGB encode: 0 -> 0, 1 -> 255, 0.5 -> 188, 0.0031308*12.92 knee
+    img = np.array([[[0.0, 1.0, 0.5], [2.0, -1.0, 0.2140411], [0.0031308, 0.001, 0.18]]])
+    out = orc.tonemap(img)
+    assert out[0, 0].tolist() == [0, 255, 188]
+    assert out[0, 1].tolist() == [255, 0, 127]
+    assert out[0, 2].tolist() == [10, 3, 118]
+    aces = orc.tonemap(np.array([[[1.0, 0.18, 10.0]]]), toon_map=1)
+    x = np.array([1.0, 0.18, 10.0])
+    m = np.clip(x * (2.51 * x + 0.03) / (x * (2.43 * x + 0.59) + 0.14), 0, 1)
+    enc = np.where(m <= 0.0031308, 12.92 * m, 1.055 * m ** (1 / 2.4) - 0.055)
+    assert aces[0, 0].tolist() == np.round(enc * 255).astype(int).tolist()
