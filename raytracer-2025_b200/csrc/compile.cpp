@@ -7,8 +7,9 @@
 //      (SURVEY.md appendix B): `Hittables` children in insertion order (Iterator::min_by keeps the
 //      first minimum, hits.rs:42), `BVH` right subtree before left (bvh.rs:78-84) with the tree
 //      shape of BVH::from_vec (bvh.rs:16-46) recomputed from the objects' bounding boxes;
-//   4. bake every Transform chain into the primitives below it (Transform::hit keeps t and the
-//      surface coordinates, shapes.rs:93-111), split media boundaries into their own groups;
+//   4. keep primitives below a Transform in its local space (the device takes rays there with the
+//      reference's own arithmetic, shapes.rs:74-101) but bound them in WORLD space for the single
+//      level BVH; split media boundaries into their own groups;
 //   5. flatten the lights tree into leaves with their selection probability;
 //   6. build one SAH BVH per group and store primitives in leaf order.
 #include "compile.h"
@@ -39,7 +40,7 @@ struct Affine {
     double b[3] = {0, 0, 0};
     bool identity = true;
     uint32_t inst_object = RT_NONE;
-    mutable uint32_t xform_slot = 0xFFFFFFFEu;  // index in CompiledScene::xforms once emitted
+    uint32_t xform = RT_NONE;  // index in CompiledScene::xforms of the innermost Transform
     V3 point(V3 p) const {
         return V3{A[0] * p.x + A[1] * p.y + A[2] * p.z + b[0], A[3] * p.x + A[4] * p.y + A[5] * p.z + b[1],
                   A[6] * p.x + A[7] * p.y + A[8] * p.z + b[2]};
@@ -303,82 +304,92 @@ struct Compiler {
         static_assert(sizeof(Perlin) == sizeof(rt_perlin), "perlin layout");
     }
 
-    uint32_t xform_index(const Affine& a) {
-        if (a.identity) return RT_NONE;
-        if (a.xform_slot != 0xFFFFFFFEu) return a.xform_slot;
+    // register one Transform below `parent` and return the affine image of the whole chain
+    bool push_xform(const rt_transform& t, uint32_t object, const Affine& parent, Affine& out_chain) {
         Xform x{};
-        std::memcpy(x.A, a.A, sizeof(x.A));
-        std::memcpy(x.b, a.b, sizeof(x.b));
-        if (!a.inverse(x.Ainv)) {
-            fail(RT_ERR_UNSUPPORTED, "singular Transform (zero scale)");
-            return RT_NONE;
+        for (int k = 0; k < 3; k++) x.offset[k] = t.offset[k], x.scale[k] = t.scale[k];
+        for (int k = 0; k < 4; k++) x.quat[k] = t.quat[k];
+        x.inst_object = object;
+        uint32_t self = (uint32_t)out.xforms.size();
+        x.n_chain = 0;
+        if (parent.xform != RT_NONE) {
+            const Xform& px = out.xforms[parent.xform];
+            for (uint32_t k = 0; k < px.n_chain; k++) x.chain[x.n_chain++] = px.chain[k];
         }
-        x.inst_object = a.inst_object;
+        if (x.n_chain >= MAX_XFORM_CHAIN) return fail(RT_ERR_UNSUPPORTED, "more than 4 nested Transforms");
+        x.chain[x.n_chain++] = self;
         out.xforms.push_back(x);
-        a.xform_slot = (uint32_t)out.xforms.size() - 1;
-        return a.xform_slot;
+        out_chain = compose(parent, affine_of(t, object));
+        out_chain.xform = self;
+        double inv[9];
+        if (!out_chain.inverse(inv)) return fail(RT_ERR_UNSUPPORTED, "singular Transform (zero scale)");
+        return true;
     }
 
-    // geometry of a leaf shape after applying the chain; `local` keeps it untransformed (lights)
-    bool bake(uint32_t obj, const Affine& a, bool local, PrimGeom& g, uint32_t& kind, double lo[3], double hi[3], double* area_out) {
+    // Local geometry of a leaf shape (verbatim from the description) and its WORLD-space bounds
+    // under the affine image of the Transform chain.
+    bool leaf(uint32_t obj, const Affine& a, PrimGeom& g, uint32_t& kind, double lo[3], double hi[3], double* area_out) {
         const rt_object& o = d.objects[obj];
         std::memset(&g, 0, sizeof(g));
-        const bool ident = a.identity || local;
+        V3 pts[8];
+        int np = 0;
+        double pad_r = 0.0;
         if (o.kind == RT_OBJ_SPHERE) {
             const rt_sphere& s = d.spheres[o.data];
             V3 c = v3(s.center), cv = v3(s.center_vec);
             double r = s.radius;
-            if (!ident) {
-                // a sphere stays a sphere only under a similarity: A^T A = k I
-                double k = a.A[0] * a.A[0] + a.A[3] * a.A[3] + a.A[6] * a.A[6];
-                double tol = 1e-12 * k;
-                for (int i = 0; i < 3; i++)
-                    for (int j = 0; j < 3; j++) {
-                        double s2 = a.A[i] * a.A[j] + a.A[3 + i] * a.A[3 + j] + a.A[6 + i] * a.A[6 + j];
-                        if (std::fabs(s2 - (i == j ? k : 0.0)) > tol)
-                            return fail(RT_ERR_UNSUPPORTED, "Sphere under a non-uniform scale (an ellipsoid) is not supported yet");
-                    }
-                c = a.point(c);
-                cv = a.vec(cv);
-                r = r * std::sqrt(k);
-            }
             g.d[0] = c.x, g.d[1] = c.y, g.d[2] = c.z, g.d[3] = cv.x, g.d[4] = cv.y, g.d[5] = cv.z, g.d[6] = r;
             kind = PRIM_SPHERE;
-            V3 c1 = c + cv;
-            double cc[2][3] = {{c.x, c.y, c.z}, {c1.x, c1.y, c1.z}};
-            for (int k = 0; k < 3; k++) lo[k] = std::min(cc[0][k], cc[1][k]) - r, hi[k] = std::max(cc[0][k], cc[1][k]) + r;
             if (area_out) *area_out = 0.0;
-            return true;
+            V3 c1 = c + cv;  // centre at time 1 (sphere.rs:35-51 bounds time in [0,1])
+            bool similarity = true;
+            double k = 1.0;
+            if (!a.identity) {
+                k = a.A[0] * a.A[0] + a.A[3] * a.A[3] + a.A[6] * a.A[6];
+                for (int i = 0; i < 3 && similarity; i++)
+                    for (int j = 0; j < 3; j++) {
+                        double s2 = a.A[i] * a.A[j] + a.A[3 + i] * a.A[3 + j] + a.A[6 + i] * a.A[6 + j];
+                        if (std::fabs(s2 - (i == j ? k : 0.0)) > 1e-9 * k) similarity = false;
+                    }
+            }
+            if (similarity) {  // still a sphere in world space: tight box around the moving centre
+                pts[np++] = a.identity ? c : a.point(c);
+                pts[np++] = a.identity ? c1 : a.point(c1);
+                pad_r = r * std::sqrt(k) * (1.0 + 1e-9);
+            } else {  // an ellipsoid: box of the transformed corners of the local box (like shapes.rs:49-72)
+                double mn[3], mx[3];
+                double cc[2][3] = {{c.x, c.y, c.z}, {c1.x, c1.y, c1.z}};
+                for (int q = 0; q < 3; q++) mn[q] = std::min(cc[0][q], cc[1][q]) - r, mx[q] = std::max(cc[0][q], cc[1][q]) + r;
+                for (int m = 0; m < 8; m++) pts[np++] = a.point(V3{(m & 4) ? mx[0] : mn[0], (m & 2) ? mx[1] : mn[1], (m & 1) ? mx[2] : mn[2]});
+            }
+        } else {
+            const rt_planar& p = d.planars[o.data];
+            const bool tri = o.kind == RT_OBJ_TRIANGLE;
+            kind = tri ? PRIM_TRIANGLE : PRIM_QUAD;
+            V3 q = v3(p.anchor), u = v3(p.u), v = v3(p.v);
+            double* e = g.d;
+            e[0] = q.x, e[1] = q.y, e[2] = q.z, e[3] = u.x, e[4] = u.y, e[5] = u.z, e[6] = v.x, e[7] = v.y, e[8] = v.z;
+            e[9] = p.normal[0], e[10] = p.normal[1], e[11] = p.normal[2], e[12] = p.parm_d;
+            e[13] = p.w[0], e[14] = p.w[1], e[15] = p.w[2];
+            if (area_out) *area_out = p.area;
+            V3 corner[4] = {q, q + u, q + v, q + u + v};
+            for (int i = 0; i < (tri ? 3 : 4); i++) pts[np++] = a.identity ? corner[i] : a.point(corner[i]);
         }
-        const rt_planar& p = d.planars[o.data];
-        const bool tri = o.kind == RT_OBJ_TRIANGLE;
-        kind = tri ? PRIM_TRIANGLE : PRIM_QUAD;
-        V3 q = v3(p.anchor), u = v3(p.u), v = v3(p.v), n = v3(p.normal), w = v3(p.w);
-        double D = p.parm_d, area = p.area;
-        if (!ident) {
-            q = a.point(q), u = a.vec(u), v = a.vec(v);
-            // re-derive exactly like Quad::new (quad.rs:31-49)
-            V3 nn = cross(u, v);
-            double len = std::sqrt(dot(nn, nn));
-            n = (1.0 / len) * nn;
-            if (!std::isfinite(n.x) || !std::isfinite(n.y) || !std::isfinite(n.z))
-                return fail(RT_ERR_UNSUPPORTED, "a Transform flattens a quad/triangle to zero area");
-            w = (1.0 / dot(nn, nn)) * nn;
-            area = tri ? len / 2.0 : len;
-            if (a.det() < 0.0) n = V3{-n.x, -n.y, -n.z};  // keep the side the inverse-transpose normal faces (shapes.rs:104-108)
-            D = dot(n, q);
-        }
-        double* e = g.d;
-        e[0] = q.x, e[1] = q.y, e[2] = q.z, e[3] = u.x, e[4] = u.y, e[5] = u.z, e[6] = v.x, e[7] = v.y, e[8] = v.z;
-        e[9] = n.x, e[10] = n.y, e[11] = n.z, e[12] = D, e[13] = w.x, e[14] = w.y, e[15] = w.z;
-        V3 pts[4] = {q, q + u, q + v, q + u + v};
-        int np = tri ? 3 : 4;
         for (int k = 0; k < 3; k++) lo[k] = INFINITY, hi[k] = -INFINITY;
         for (int i = 0; i < np; i++) {
             double c[3] = {pts[i].x, pts[i].y, pts[i].z};
-            for (int k = 0; k < 3; k++) lo[k] = std::min(lo[k], c[k]), hi[k] = std::max(hi[k], c[k]);
+            for (int k = 0; k < 3; k++) lo[k] = std::min(lo[k], c[k] - pad_r), hi[k] = std::max(hi[k], c[k] + pad_r);
         }
-        if (area_out) *area_out = area;
+        if (!a.identity) {
+            // the device transforms with quaternion products, this bound with a matrix: cover the
+            // last-bit disagreement between the two before the outward rounding to binary32
+            for (int k = 0; k < 3; k++) {
+                double m = 1e-12 * (std::fabs(lo[k]) + std::fabs(hi[k]) + (hi[k] - lo[k]));
+                lo[k] -= m, hi[k] += m;
+            }
+        }
+        for (int k = 0; k < 3; k++)
+            if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) return fail(RT_ERR_INVALID, "primitive with non-finite bounds");
         return true;
     }
 
@@ -423,13 +434,12 @@ struct Compiler {
             case RT_OBJ_TRIANGLE: {
                 FlatPrim fp;
                 uint32_t kind;
-                if (!bake(obj, chain, false, fp.g, kind, fp.lo, fp.hi, nullptr)) return;
+                if (!leaf(obj, chain, fp.g, kind, fp.lo, fp.hi, nullptr)) return;
                 fp.m.kind_mat = (kind << 30) | o.material;
                 fp.m.object = obj;
                 fp.m.rank = in_medium ? 0 : next_rank++;
                 if (!in_medium) out.ranks[obj] = fp.m.rank;
-                // the chain is kept for rt_hit.inst_id and for sphere u,v (computed from the local normal)
-                fp.m.xform = xform_index(chain);
+                fp.m.xform = chain.xform;
                 groups[group].push_back(fp);
                 if (kind == PRIM_SPHERE) out.n_spheres++; else out.n_planars++;
                 break;
@@ -448,7 +458,8 @@ struct Compiler {
                 break;
             }
             case RT_OBJ_TRANSFORM: {
-                Affine a = compose(chain, affine_of(d.transforms[o.data], obj));
+                Affine a;
+                if (!push_xform(d.transforms[o.data], obj, chain, a)) return;
                 walk(d.children[o.first_child], a, group, in_medium);
                 break;
             }
@@ -464,13 +475,7 @@ struct Compiler {
                 out.ranks[obj] = m.rank;
                 m.neg_inv_density = d.media[o.data].neg_inv_density;
                 m.medium_index = o.data;
-                m.has_xform = chain.identity ? 0 : 1;
-                double inv[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-                if (!chain.identity && !chain.inverse(inv)) {
-                    fail(RT_ERR_UNSUPPORTED, "singular Transform above a ConstantMedium");
-                    return;
-                }
-                std::memcpy(m.Ainv, inv, sizeof(inv));
+                m.xform = chain.xform;
                 groups.emplace_back();
                 uint32_t g = (uint32_t)groups.size() - 1;
                 group_of_medium.push_back(g);
@@ -490,8 +495,8 @@ struct Compiler {
             case RT_OBJ_TRIANGLE: {
                 Light l{};
                 double lo[3], hi[3];
-                if (!bake(obj, chain, true, l.g, l.kind, lo, hi, &l.area)) return;
-                l.xform = xform_index(chain);
+                if (!leaf(obj, chain, l.g, l.kind, lo, hi, &l.area)) return;
+                l.xform = chain.xform;
                 l.weight = weight;
                 out.lights.push_back(l);
                 break;
@@ -504,9 +509,12 @@ struct Compiler {
                 for (uint32_t k = 0; k < o.child_count; k++)
                     walk_lights(d.children[o.first_child + k], chain, weight / (double)o.child_count);
                 break;
-            case RT_OBJ_TRANSFORM:
-                walk_lights(d.children[o.first_child], compose(chain, affine_of(d.transforms[o.data], obj)), weight);
+            case RT_OBJ_TRANSFORM: {
+                Affine a;
+                if (!push_xform(d.transforms[o.data], obj, chain, a)) return;
+                walk_lights(d.children[o.first_child], a, weight);
                 break;
+            }
             default:
                 fail(RT_ERR_UNSUPPORTED, "lights may not contain a BVH or ConstantMedium: pdf_value/random are unimplemented!() there (hit.rs:51-59)");
         }

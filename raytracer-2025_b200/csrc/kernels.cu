@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK) k_extend(SceneView sv, RenderPar
                 if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
                 if (t1 >= t2) continue;
                 if (t1 < 0.0) t1 = 0.0;
-                D3 dl = med.has_xform ? mul33(med.Ainv, r.d) : r.d;
+                D3 dl = med.xform == RT_NONE ? r.d : ray_to_local(sv, med.xform, r).d;
                 double ray_length = length(dl);
                 double distance_inside_boundary = (t2 - t1) * ray_length;
                 double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
@@ -317,17 +317,22 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
                     error = true;
             } else {
                 HitInfo h;
-                if (kind == HIT_MEDIUM) {  // volume.rs:66-72
-                    h.p = r.o + t * r.d;
+                bool hit_ok = true;
+                if (kind == HIT_MEDIUM) {  // volume.rs:66-72, in the medium's local space
+                    const Medium& med = sv.media[prim];
+                    const RayD lr = med.xform == RT_NONE ? r : ray_to_local(sv, med.xform, r);
+                    h.p = lr.o + t * lr.d;
                     D3 nrm = D3{1.0, 0.0, 0.0};
-                    h.front_face = dot(r.d, nrm) < 0.0;
+                    h.front_face = dot(lr.d, nrm) < 0.0;
                     h.normal = h.front_face ? nrm : -nrm;
                     h.u = 0.0, h.v = 0.0;
-                    h.material = sv.media[prim].material;
+                    h.material = med.material;
+                    if (med.xform != RT_NONE) hit_ok = hit_to_world(sv, med.xform, h);
                 } else {
                     uint32_t mat = sv.meta[prim].kind_mat & 0x3FFFFFFFu;
-                    surface_hit_info(sv, prim, t, r, sv.materials[mat].needs_uv != 0, h);
+                    hit_ok = surface_hit_info(sv, prim, t, r, sv.materials[mat].needs_uv != 0, h);
                 }
+                if (!hit_ok) error = true;
                 // emitted (camera.rs:290) — only light-carrying materials can return non-black
                 uint32_t mat = h.material;
                 uint32_t mk = sv.materials[mat].kind;

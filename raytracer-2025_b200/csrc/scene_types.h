@@ -5,10 +5,11 @@
 //                   two child references; one node visit = 4 x LDG.128 and two slab tests.
 //   geom[]   128 B  one primitive in BVH leaf order, binary64, the very numbers of the reference's
 //                   structs (sphere.rs:17-22, quad.rs:18-29): sphere = centre(3) centre_vec(3)
-//                   radius; quad/triangle = anchor(3) u(3) v(3) normal(3) D w(3).
-//   meta[]    16 B  kind|material, object id (rt_hit.prim_id), tie rank, uv-frame / instance id.
-// Transforms are baked into the primitives at compile time (t is preserved by Transform::hit,
-// shapes.rs:93-101), so traversal is single level.
+//                   radius; quad/triangle = anchor(3) u(3) v(3) normal(3) D w(3).  Primitives
+//                   below a Transform are stored in that Transform's local space.
+//   meta[]    16 B  kind|material, tie rank, object id (rt_hit.prim_id), Transform chain id.
+// The BVH is single level over WORLD-space boxes; a leaf primitive that sits below a Transform
+// is intersected with the ray taken to its local space (t is preserved, shapes.rs:93-101).
 #pragma once
 #include <stdint.h>
 
@@ -39,16 +40,20 @@ struct alignas(16) PrimMeta {
     uint32_t kind_mat;  // kind in bits 30..31, material index in bits 0..29
     uint32_t rank;      // lower rank wins an exact t tie (hits.rs:42, bvh.rs:78-84)
     uint32_t object;    // index of the leaf shape in rt_scene_desc.objects
-    uint32_t xform;     // index into xforms[] (baked Transform chain) or RT_NONE
+    uint32_t xform;     // index into xforms[] (innermost enclosing Transform) or RT_NONE
 };
 
-// A baked chain of Transforms: x_world = A x_local + b ; x_local = Ainv (x_world - b)
+// One `Transform` (shapes.rs:23-29) plus the chain of Transforms above it.  Primitives below a
+// Transform keep their LOCAL geometry; rays are taken to local space with the reference's own
+// quaternion arithmetic (shapes.rs:74-101), so t, u, v and the tie behaviour are the reference's.
+constexpr int MAX_XFORM_CHAIN = 4;
 struct Xform {
-    double A[9];
-    double b[3];
-    double Ainv[9];
-    uint32_t inst_object;  // object id of the innermost Transform (rt_hit.inst_id)
-    uint32_t pad;
+    double offset[3];
+    double quat[4];  // w x y z
+    double scale[3];
+    uint32_t chain[MAX_XFORM_CHAIN];  // xform indices from the outermost Transform down to this one
+    uint32_t n_chain;
+    uint32_t inst_object;  // object id of this Transform (rt_hit.inst_id of the primitives directly below)
 };
 
 struct Material {
@@ -82,8 +87,8 @@ struct Medium {
     uint32_t object;    // object id of the ConstantMedium
     uint32_t rank;
     double neg_inv_density;
-    double Ainv[9];     // linear part of world->local above the medium (ray_length is local, volume.rs:55)
-    uint32_t has_xform, medium_index;
+    uint32_t xform;     // Transform chain above the medium (ray_length is local, volume.rs:55) or RT_NONE
+    uint32_t medium_index;
 };
 
 // One leaf of the lights tree (hits.rs:52-75), geometry in the local space of its Transform chain

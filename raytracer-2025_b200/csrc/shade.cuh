@@ -129,12 +129,27 @@ struct HitInfo {
     uint32_t material;
 };
 
+// Transform::hit exit (shapes.rs:103-108) for every Transform of the chain, innermost first
+__device__ inline bool hit_to_world(const SceneView& sv, uint32_t xform, HitInfo& h) {
+    const Xform* x = sv.xforms + xform;
+    const uint32_t n = __ldg(&x->n_chain);
+    bool ok = true;
+    for (uint32_t k = n; k-- > 0;) {
+        XformParams p = load_xform(sv.xforms + __ldg(&x->chain[k]));
+        h.p = xf_transform(p, h.p);
+        D3 ns = D3{h.normal.x / p.scale.x, h.normal.y / p.scale.y, h.normal.z / p.scale.z};
+        ok = unit_vector(qrotate(p.q, ns), h.normal) && ok;  // .expect("The transformed normal can't be normalized!")
+    }
+    return ok;
+}
+
 // Rebuild the HitRecord of a surface hit from (prim, t): the same arithmetic the intersection ran.
-__device__ inline void surface_hit_info(const SceneView& sv, uint32_t prim, double t, const RayD& r, bool want_uv, HitInfo& h) {
+__device__ inline bool surface_hit_info(const SceneView& sv, uint32_t prim, double t, const RayD& world_ray, bool want_uv, HitInfo& h) {
     const PrimMeta m = sv.meta[prim];
     const uint32_t kind = m.kind_mat >> 30;
     h.material = m.kind_mat & 0x3FFFFFFFu;
     const double* g = sv.geom[prim].d;
+    const RayD r = m.xform == RT_NONE ? world_ray : ray_to_local(sv, m.xform, world_ray);
     D3 outward;
     h.p = r.o + t * r.d;  // Ray::at
     h.u = 0.0, h.v = 0.0;
@@ -143,14 +158,7 @@ __device__ inline void surface_hit_info(const SceneView& sv, uint32_t prim, doub
         double radius = g[6];
         D3 current_center = center + r.time * cvec;
         outward = (h.p - current_center) / radius;
-        if (want_uv) {
-            D3 local_n = outward;
-            if (m.xform != RT_NONE) {  // the reference computes u,v in the Transform's local space (shapes.rs:100)
-                D3 l = mul33(sv.xforms[m.xform].Ainv, h.p - current_center);
-                unit_vector(l, local_n);
-            }
-            sphere_uv(local_n, h.u, h.v);
-        }
+        if (want_uv) sphere_uv(outward, h.u, h.v);
     } else {
         Planar pl;
         load_planar(g, pl);
@@ -159,19 +167,23 @@ __device__ inline void surface_hit_info(const SceneView& sv, uint32_t prim, doub
         h.u = dot(pl.w, cross(hp, pl.v));
         h.v = dot(pl.w, cross(pl.u, hp));
     }
-    h.front_face = dot(r.d, outward) < 0.0;
+    h.front_face = dot(r.d, outward) < 0.0;  // HitRecord::new, hit.rs:33-36 (in local space)
     h.normal = h.front_face ? outward : -outward;
+    if (m.xform != RT_NONE) return hit_to_world(sv, m.xform, h);
+    return true;
 }
 
 // ---- lights: Hittables::pdf_value / random over the flattened leaves (hits.rs:52-75) -----------
 __device__ inline double light_leaf_pdf(const SceneView& sv, const Light& l, D3 origin, D3 direction) {
-    if (l.xform != RT_NONE) {  // Transform::pdf_value, shapes.rs:117-123
-        const Xform& x = sv.xforms[l.xform];
-        D3 b = ld3(x.b);
-        D3 lo = mul33(x.Ainv, origin - b);
-        D3 lt = mul33(x.Ainv, (origin + direction) - b);
-        origin = lo;
-        direction = lt - lo;
+    if (l.xform != RT_NONE) {  // Transform::pdf_value, shapes.rs:117-123, outermost Transform first
+        const Xform* x = sv.xforms + l.xform;
+        for (uint32_t k = 0; k < x->n_chain; k++) {
+            XformParams p = load_xform(sv.xforms + x->chain[k]);
+            D3 lo = xf_detransform(p, origin);
+            D3 lt = xf_detransform(p, origin + direction);
+            origin = lo;
+            direction = lt - lo;
+        }
     }
     RayD r{origin, direction, 0.0};
     const double* g = l.g.d;
@@ -207,18 +219,9 @@ __device__ inline double lights_pdf_value(const SceneView& sv, uint32_t lights_f
     return sum;
 }
 
-__device__ inline bool lights_random(const SceneView& sv, D3 origin, double pick, double r1, double r2, D3& out) {
-    uint32_t leaf = sv.n_lights - 1;
-    for (uint32_t i = 0; i < sv.n_lights; i++)
-        if (pick < sv.lights[i].cdf) {
-            leaf = i;
-            break;
-        }
-    const Light& l = sv.lights[leaf];
-    D3 world_origin = origin;
-    if (l.xform != RT_NONE) origin = mul33(sv.xforms[l.xform].Ainv, origin - ld3(sv.xforms[l.xform].b));
+// leaf.random(origin) in the leaf's own space
+__device__ inline bool light_leaf_random(const Light& l, D3 origin, double r1, double r2, D3& dir) {
     const double* g = l.g.d;
-    D3 dir;
     bool ok = true;
     if (l.kind == PRIM_SPHERE) {  // sphere.rs:134-144, 63-73
         D3 center = ld3(g);
@@ -245,10 +248,30 @@ __device__ inline bool lights_random(const SceneView& sv, D3 origin, double pick
         D3 p = ld3(g) + (ul * ld3(g + 3)) + (vl * ld3(g + 6));
         ok = unit_vector(p - origin, dir);
     }
-    if (l.xform != RT_NONE) {  // Transform::random, shapes.rs:125-132
-        const Xform& x = sv.xforms[l.xform];
-        D3 world_to = mul33(x.A, origin + dir) + ld3(x.b);
-        ok = unit_vector(world_to - world_origin, dir) && ok;
+    return ok;
+}
+
+__device__ inline bool lights_random(const SceneView& sv, D3 origin, double pick, double r1, double r2, D3& out) {
+    uint32_t leaf = sv.n_lights - 1;
+    for (uint32_t i = 0; i < sv.n_lights; i++)
+        if (pick < sv.lights[i].cdf) {
+            leaf = i;
+            break;
+        }
+    const Light& l = sv.lights[leaf];
+    if (l.xform == RT_NONE) return light_leaf_random(l, origin, r1, r2, out);
+    // Transform::random nested through the chain (shapes.rs:125-132): origins go down, directions come up
+    const Xform* x = sv.xforms + l.xform;
+    const uint32_t n = x->n_chain;
+    D3 origins[MAX_XFORM_CHAIN + 1];
+    origins[0] = origin;
+    for (uint32_t k = 0; k < n; k++) origins[k + 1] = xf_detransform(load_xform(sv.xforms + x->chain[k]), origins[k]);
+    D3 dir;
+    bool ok = light_leaf_random(l, origins[n], r1, r2, dir);
+    for (uint32_t k = n; k-- > 0;) {
+        XformParams p = load_xform(sv.xforms + x->chain[k]);
+        D3 world_to = xf_transform(p, origins[k + 1] + dir);
+        ok = unit_vector(world_to - origins[k], dir) && ok;
     }
     out = dir;
     return ok;

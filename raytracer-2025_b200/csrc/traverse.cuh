@@ -17,6 +17,56 @@ struct RayD {
     double time;
 };
 
+// ---- Transform (shapes.rs:74-101) with the reference's quaternion arithmetic -------------------
+struct Quat {
+    double w, x, y, z;
+};
+__device__ __forceinline__ Quat qmul(Quat a, Quat b) {  // quaternion.rs:94-104
+    return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+                a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w};
+}
+__device__ __forceinline__ D3 qrotate(Quat q, D3 v) {  // quaternion.rs:72-82: q * (0,v) * conj(q)
+    Quat r = qmul(qmul(q, Quat{0.0, v.x, v.y, v.z}), Quat{q.w, -q.x, -q.y, -q.z});
+    return D3{r.x, r.y, r.z};
+}
+struct XformParams {
+    D3 offset, scale;
+    Quat q;
+};
+__device__ __forceinline__ XformParams load_xform(const Xform* __restrict__ x) {
+    XformParams p;
+    p.offset = D3{__ldg(&x->offset[0]), __ldg(&x->offset[1]), __ldg(&x->offset[2])};
+    p.q = Quat{__ldg(&x->quat[0]), __ldg(&x->quat[1]), __ldg(&x->quat[2]), __ldg(&x->quat[3])};
+    p.scale = D3{__ldg(&x->scale[0]), __ldg(&x->scale[1]), __ldg(&x->scale[2])};
+    return p;
+}
+__device__ __forceinline__ D3 xf_transform(const XformParams& p, D3 v) { return qrotate(p.q, v * p.scale) + p.offset; }  // shapes.rs:74-78
+__device__ __forceinline__ D3 xf_detransform(const XformParams& p, D3 v) {                                           // shapes.rs:80-84
+    D3 r = qrotate(Quat{p.q.w, -p.q.x, -p.q.y, -p.q.z}, v - p.offset);
+    return D3{r.x / p.scale.x, r.y / p.scale.y, r.z / p.scale.z};
+}
+// Transform::hit entry (shapes.rs:93-101) through the whole chain, outermost first: t is preserved
+__device__ __noinline__ RayD ray_to_local(const SceneView& sv, uint32_t xform, RayD r) {
+    const Xform* x = sv.xforms + xform;
+    const uint32_t n = __ldg(&x->n_chain);
+    for (uint32_t k = 0; k < n; k++) {
+        XformParams p = load_xform(sv.xforms + __ldg(&x->chain[k]));
+        D3 to = r.o + 1.0 * r.d;  // r.at(1.0)
+        D3 lo = xf_detransform(p, r.o);
+        D3 lt = xf_detransform(p, to);
+        r.o = lo;
+        r.d = lt - lo;
+    }
+    return r;
+}
+// point / direction versions for Transform::pdf_value and ::random (shapes.rs:117-132)
+__device__ __forceinline__ D3 point_to_local(const SceneView& sv, uint32_t xform, D3 v) {
+    const Xform* x = sv.xforms + xform;
+    const uint32_t n = __ldg(&x->n_chain);
+    for (uint32_t k = 0; k < n; k++) v = xf_detransform(load_xform(sv.xforms + __ldg(&x->chain[k])), v);
+    return v;
+}
+
 // binary32 image of the ray for the slab test: t = fma(plane, idf, noidf)
 struct RayF {
     float idx, idy, idz;     // 1/d, clamped to +-1e30
@@ -25,18 +75,25 @@ struct RayF {
 };
 
 __device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
-    auto inv = [](double d) {
+    // An axis whose 1/d overflows binary32 range (d == 0, denormal, NaN) takes no part in culling:
+    // its error bound is infinite, so its slab is (-inf, +inf).  Conservative, and only rays exactly
+    // parallel to an axis plane pay for it.
+    auto inv = [](double d, bool& clamped) {
         double i = 1.0 / d;
-        if (!(fabs(i) <= 1e30)) i = copysign(1e30, d);
+        clamped = !(fabs(i) <= 1e30);
+        if (clamped) i = copysign(1e30, d);
         return (float)i;
     };
-    f.idx = inv(r.d.x), f.idy = inv(r.d.y), f.idz = inv(r.d.z);
+    bool cx, cy, cz;
+    f.idx = inv(r.d.x, cx), f.idy = inv(r.d.y, cy), f.idz = inv(r.d.z, cz);
     f.nox = (float)(-r.o.x * (double)f.idx);
     f.noy = (float)(-r.o.y * (double)f.idy);
     f.noz = (float)(-r.o.z * (double)f.idz);
     // |t_computed - t_exact| <= (|t| + |o*idf|) * 2^-24 ; the |t| part is applied as a relative slack
     const float k = 1.0f / 4194304.0f;  // 2^-22
-    f.ex = fabsf(f.nox) * k, f.ey = fabsf(f.noy) * k, f.ez = fabsf(f.noz) * k;
+    f.ex = cx ? INFINITY : fabsf(f.nox) * k;
+    f.ey = cy ? INFINITY : fabsf(f.noy) * k;
+    f.ez = cz ? INFINITY : fabsf(f.noz) * k;
 }
 
 // returns true when the box may intersect the ray within [tmin_f, tmax_f]; tnear for ordering
@@ -152,16 +209,22 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
     uint32_t prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu;
     int sp = 0;
     uint32_t cur = root;
+    uint32_t cached_xform = 0xFFFFFFFFu;  // RT_NONE: the world ray itself
+    RayD lr = r;                          // the ray in the local space of cached_xform
     while (true) {
         if (cur & LEAF_FLAG) {
             uint32_t first = (cur & ~LEAF_FLAG) >> 3, count = (cur & 7u) + 1;
             for (uint32_t i = 0; i < count; i++) {
                 uint32_t pi = first + i;
-                const uint2 km = __ldg(reinterpret_cast<const uint2*>(&sv.meta[pi]));  // kind_mat, rank
+                const uint4 km = __ldg(reinterpret_cast<const uint4*>(&sv.meta[pi]));  // kind_mat, rank, object, xform
                 const uint32_t kind = km.x >> 30;
+                if (km.w != cached_xform) {
+                    lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
+                    cached_xform = km.w;
+                }
                 const double* g = sv.geom[pi].d;
                 double t;
-                bool hit = kind == PRIM_SPHERE ? sphere_hit(g, r, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, r, tmin, tbest, t);
+                bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, tbest, t);
                 if (COUNT) cnt->prims++;
                 if (hit) {
                     // t <= tbest here; an exact tie keeps the lower rank

@@ -77,8 +77,9 @@ def scene_rays(rt, orc, hs, n, seed):
     return prim
 
 
-def compare_hits(rt, got, want, rel=1e-9):
-    """IDs bit-exact, t within `rel` relative (the north star allows 1e-5)."""
+def compare_hits(rt, got, want, rel=0.0):
+    """IDs bit-exact; t bit-exact by default (the north star allows 1e-5 relative): every primitive,
+    transformed or not, is intersected with the reference's own binary64 arithmetic."""
     assert np.array_equal(got["prim_id"], want["prim_id"]), \
         f"{int((got['prim_id'] != want['prim_id']).sum())} primitive id mismatches"
     assert np.array_equal(got["inst_id"], want["inst_id"])
@@ -86,6 +87,7 @@ def compare_hits(rt, got, want, rel=1e-9):
     if hit.any():
         err = np.abs(got["t"][hit] - want["t"][hit]) / np.abs(want["t"][hit])
         assert err.max() <= rel, f"t relative error {err.max():.3e}"
-        assert np.abs(got["u"][hit] - want["u"][hit]).max() < 1e-5
-        assert np.abs(got["v"][hit] - want["v"][hit]).max() < 1e-5
+        # u, v go through acos/atan2 for spheres: libm last-bit differences only
+        assert np.abs(got["u"][hit] - want["u"][hit]).max() < 1e-6
+        assert np.abs(got["v"][hit] - want["v"][hit]).max() < 1e-6
     assert np.all(np.isinf(got["t"][~hit]))

@@ -82,12 +82,20 @@ def test_description_is_validated_before_any_device_work(rt):
 
 
 def test_unsupported_constructs_are_reported(rt):
-    # a Sphere under a non-uniform scale is an ellipsoid: not expressible yet -> RT_ERR_UNSUPPORTED
+    # more than 4 nested Transforms exceed the device's chain table -> RT_ERR_UNSUPPORTED
     b = rt.Builder(1)
-    t = b.transform(b.sphere([0, 0, 0], 1.0, b.empty()), scale=[1, 2, 1])
+    t = b.sphere([0, 0, 0], 1.0, b.empty())
+    for k in range(5):
+        t = b.transform(t, offset=[1, 0, 0])
     hs = b.finish(b.list([t]))
     rc, h, msg = _create(rt, hs.desc.contents)
-    assert rc == -2 and "ellipsoid" in msg
+    assert rc == -2 and "nested" in msg
+    # a zero scale cannot be inverted
+    b = rt.Builder(1)
+    t = b.transform(b.sphere([0, 0, 0], 1.0, b.empty()), scale=[1, 0, 1])
+    hs = b.finish(b.list([t]))
+    rc, h, msg = _create(rt, hs.desc.contents)
+    assert rc == -2 and "singular" in msg
     # lights containing a BVH: pdf_value/random are unimplemented!() in the reference (hit.rs:51-59)
     b = rt.Builder(1)
     s = b.sphere([0, 0, 0], 1.0, b.empty())

@@ -1,6 +1,6 @@
 """GPU parity tests: the CUDA core (through the C ABI) against the oracle and the committed
 golden fixtures.  Integer outputs (primitive / instance ids) must be bit-exact; hit distances
-within 1e-9 relative (the north star allows 1e-5); same-seed images within 1e-6 relative for all
+bit-exact (the north star allows 1e-5 relative); same-seed images within 1e-6 relative for all
 but a vanishing fraction of pixels (a path whose branch flips on a last-bit libm difference)."""
 import os
 
@@ -48,7 +48,9 @@ def test_render_matches_golden_image(gpu, rt, name):
     sc = rt.Scene(golden_scene(rt, name))
     img, st = sc.render(seed=int(fx["render_seed"]))
     assert st.paths == int(fx["paths"])
-    assert abs(int(st.errors) - int(fx["errors"])) <= 2
+    # an error marks a sample on which the reference would panic; the device stops a path whose
+    # throughput is exactly zero, so it can only meet fewer of them than the full recursion
+    assert int(st.errors) <= int(fx["errors"])
     image_close(img, fx["image"], frac_bad=5e-3)
 
 
@@ -67,9 +69,31 @@ def test_closest_hit_matches_oracle_on_random_graphs(gpu, rt, orc, seed):
     compare_hits(rt, got, osc.closest_hit(rays, t_min=0.5, t_max=7.0, mode=0))
 
 
-def test_untransformed_hits_are_bit_exact(gpu, rt, orc):
-    # primitives outside any Transform are intersected with the reference's own arithmetic
-    hs = random_graph_scene(rt, 5, n_prims=150, with_transforms=False)
+def test_ellipsoids_and_nested_transforms(gpu, rt, orc):
+    # a Sphere under a non-uniform scale is an ellipsoid (shapes.rs:74-84); Transforms nest
+    b = rt.Builder(9)
+    m = b.empty()
+    e1 = b.transform(b.sphere([0, 0, 0], 1.0, m), offset=[-2, 0, 0], quat=b.quat_axis_angle([0, 0, 1], 30.0), scale=[2.0, 0.5, 1.0])
+    inner = b.transform(b.bvh([b.sphere([0, 0, 0], 0.7, m), b.quad([-1, -1, 1], [2, 0, 0], [0, 2, 0], m),
+                               b.triangle([0, 1, -1], [1, 0, 0], [0, 1, 1], m)]), offset=[0.5, 0, 0], scale=[1, 2, 1])
+    e2 = b.transform(b.list([inner, b.sphere_moving([0, -2, 0], [1, -2, 0], 0.5, m)]), offset=[2.5, 0.5, 0],
+                     quat=b.quat_axis_angle([1, 1, 0], 50.0), scale=[0.8, 0.8, 1.6])
+    e3 = b.transform(b.sphere([0, 0, 0], 1.0, m), offset=[0, 3, 0], scale=[-1.0, 1.0, 1.5])  # a mirroring scale
+    hs = b.finish(b.list([e1, e2, e3]))
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    rng = np.random.default_rng(4)
+    o, d, t = random_rays(rng, 40000, extent=5.0)
+    rays = rt.make_rays(o, d, t)
+    got, _ = sc.closest_hit(rays)
+    want = osc.closest_hit(rays, mode=0)
+    compare_hits(rt, got, want)
+    assert (want["prim_id"] != rt.RT_NONE).sum() > 2000
+    assert len(set(want["inst_id"].tolist())) >= 4
+
+
+def test_hits_are_bit_exact(gpu, rt, orc):
+    # every primitive is intersected with the reference's own arithmetic: t is bit-identical
+    hs = random_graph_scene(rt, 5, n_prims=150)
     sc, osc = rt.Scene(hs), orc.OracleScene(hs)
     rng = np.random.default_rng(5)
     o, d, t = random_rays(rng, 30000)
@@ -185,14 +209,14 @@ def test_materials_textures_and_lights_vs_oracle(gpu, rt, orc):
     world = b.list([b.bvh(objs), floor, l1, l2])
     e = b.empty()
     lights = b.list([b.transform(b.quad([-1, 0, -1], [2, 0, 0], [0, 0, 2], e), offset=[0, 6, 2], quat=q, scale=[1.5, 1.5, 1.5]),
-                     b.list([b.triangle([3, 5, -1], [2, 0, 0], [0, 0, 2], e), b.sphere([-3.3, -2.0, 0], 1.0, e)])])
+                     b.list([b.triangle([3, 5, -1], [2, 0, 0], [0, 0, 2], e), b.sphere([-3.3, 0.2, 0], 1.0, e)])])  # the metal ball
     hs = b.finish(world, lights, width=48, spp=16, max_depth=10, vfov=50, look_from=(0, 1, 12), look_at=(0, 0, 0),
                   background=b.gradient([1, 1, 1], [0.5, 0.7, 1.0]), defocus_angle=0.8, focus_dist=12.0)
     sc, osc = rt.Scene(hs), orc.OracleScene(hs)
     img, st = sc.render(seed=23)
     ref, ost = osc.render(seed=23)
     assert st.paths == ost.paths
-    assert abs(int(st.errors) - int(ost.errors)) <= 2
+    assert int(st.errors) <= int(ost.errors)
     image_close(img, ref, frac_bad=5e-3)
 
 
