@@ -6,7 +6,9 @@ CXX       := /usr/bin/g++
 PKG       := raytracer-2025_b200
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false / -ffp-contract=off: the reference is strict IEEE binary64 without contraction
-NVCCFLAGS := -ccbin /usr/bin/g++ $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-fopenmp,-O3 -Iinclude -I$(PKG)/csrc
+EXTRA     ?=
+LIBNAME   ?= librt2025.so
+NVCCFLAGS := $(EXTRA) -ccbin /usr/bin/g++ $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-fopenmp,-O3 -Iinclude -I$(PKG)/csrc
 CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -fopenmp -Wall -Wno-unknown-pragmas -Iinclude
 
 PRODUCT_SRC := $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cpp)
@@ -14,11 +16,11 @@ PRODUCT_HDR := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include
 
 all: product host oracle
 
-product: $(PKG)/librt2025.so
+product: $(PKG)/$(LIBNAME)
 host: $(PKG)/librt2025_host.so
 oracle: oracle/liboracle.so
 
-$(PKG)/librt2025.so: $(PRODUCT_SRC) $(PRODUCT_HDR)
+$(PKG)/$(LIBNAME): $(PRODUCT_SRC) $(PRODUCT_HDR)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(filter %.cu %.cpp,$(PRODUCT_SRC)) -Xlinker -lgomp
 
 $(PKG)/librt2025_host.so: $(PKG)/host/host_capi.cpp $(PKG)/host/rt2025.hpp $(PKG)/host/scenes.hpp include/rt2025.h

@@ -29,8 +29,8 @@ _spec.loader.exec_module(rt)
 SCENE = ("book2_final", 7, [800, 1000, 40])  # name, scene seed, [width, spp, max_depth]
 RENDER_SEED = 2025
 # algorithmic HBM bytes of the dominant kernel (extend) per unit (= one path segment), DESIGN.md §5:
-# slot index in (4) + ray record read (4 x 16) + hit word written (16) + queue append (4)
-EXTEND_BYTES_PER_SEGMENT = 4 + 64 + 16 + 4
+# ray stream record read (64) + hit stream record written (16)
+EXTEND_BYTES_PER_SEGMENT = 64 + 16
 
 
 def partition_for_rank(rank, world):
@@ -207,7 +207,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     paths = segs = launches = iters = 0
-    ms_extend = ms_shade = ms_gen = 0.0
+    ms_extend = ms_shade = ms_gen = ms_media = 0.0
     for _ in range(args.steps):
         st, total = step()
         paths += total
@@ -217,6 +217,7 @@ def main():
         ms_extend += st.ms_extend
         ms_shade += st.ms_shade
         ms_gen += st.ms_raygen
+        ms_media += st.ms_other
     e1.record()
     barrier()
     sampler.stop_flag = True
@@ -289,7 +290,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_segment": EXTEND_BYTES_PER_SEGMENT, "segments_per_launch": seg_rank0 / n_ext_launches,
                          "ms_per_launch": ext_ms_per_launch,
-                         "stage_ms_per_step": {"generate": ms_gen / args.steps, "extend": ms_extend / args.steps, "shade": ms_shade / args.steps},
+                         "stage_ms_per_step": {"generate": ms_gen / args.steps, "extend": ms_extend / args.steps,
+                                               "media_bin": ms_media / args.steps, "shade": ms_shade / args.steps},
                          "note": "configs 1-3 keep the scene in L1/L2: the binding limit is SM issue rate under divergence, "
                                  "not HBM (SURVEY.md §8d); see profiles/ for issue utilisation"},
         }

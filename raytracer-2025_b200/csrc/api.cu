@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -62,9 +63,8 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
     void release() {
         for (auto e : events) cudaEventDestroy(e);
         events.clear();
-        cudaFree(W.rec);
-        cudaFree(W.q_extend);
-        cudaFree(W.q_free);
+        for (int k = 0; k < 2; k++) cudaFree(W.ray_q[k]), cudaFree(W.state_q[k]);
+        cudaFree(W.hit_q);
         for (auto& q : W.q_shade) cudaFree(q);
         cudaFree(W.pixel_list);
         cudaFree(W.accum);
@@ -76,6 +76,19 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
 
 }  // namespace
 
+// One wavefront workspace per device, shared by all scenes of the process (a render holds its lock):
+// re-creating a scene (what Camera::render does on every call) must not re-allocate half a gigabyte.
+namespace {
+struct DeviceWorkspace {
+    std::mutex mu;
+    Workspace ws;
+};
+DeviceWorkspace& device_workspace(int device) {
+    static DeviceWorkspace pool[64];
+    return pool[device & 63];
+}
+}  // namespace
+
 struct rt_scene {
     int device = 0;
     int sm_count = 148;
@@ -84,9 +97,10 @@ struct rt_scene {
     std::vector<uint32_t> ranks;
     rt_scene_info info{};
     uint32_t lights_flat = 1;
-    Workspace ws;
-    std::mutex mu;  // one render at a time per handle
+    uint32_t class_mask = 0;     // shade classes the scene's materials can produce
+    bool generic_media = false;  // some ConstantMedium boundary is not a single Sphere
     int extend_blocks_per_sm = 4, shade_blocks_per_sm = 4;
+    size_t stack_bytes = 0;  // dynamic shared memory of the traversal kernels: cached nodes + stacks
 };
 
 namespace {
@@ -165,6 +179,8 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.n_lights = (uint32_t)cs.lights.size();
         v.n_prims = (uint32_t)cs.geom.size();
         s->ranks = cs.ranks;
+        for (auto& m : cs.media) s->generic_media |= m.single_sphere == RT_NONE;
+        for (auto& m : cs.materials) s->class_mask |= 1u << m.shade_class;
         // lights is "flat" when every leaf has the same weight 1/n (a single-level list)
         s->lights_flat = 1;
         for (auto& l : cs.lights)
@@ -175,7 +191,19 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         i.bvh_depth = cs.bvh_depth;
         i.device_bytes = cs.nodes.size() * sizeof(Node) + cs.geom.size() * sizeof(PrimGeom) + cs.meta.size() * sizeof(PrimMeta) +
                          cs.texels.size() * sizeof(float4) + cs.perlins.size() * sizeof(Perlin);
-        kernel_occupancy(&s->extend_blocks_per_sm, &s->shade_blocks_per_sm);
+        // shared memory of the traversal kernels: per-thread stacks sized by this scene's tree depth,
+        // the rest (up to 227 KB) holds the breadth-first top of the BVH
+        v.n_nodes = (uint32_t)cs.nodes.size();
+        v.stack_entries = std::min<uint32_t>(cs.bvh_depth + 2, TRAVERSAL_STACK);
+        const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t);
+        // when several CTAs share an SM each gets its share of the 227 KB
+        const size_t room = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024 - stack_bytes;
+        size_t cache_bytes = room;
+        if (const char* e = getenv("RT2025_SMEM_NODES_KB")) cache_bytes = std::min<size_t>(room, (size_t)atol(e) * 1024);  // tuning knob
+        v.n_cached_nodes = (uint32_t)std::min<size_t>(cs.nodes.size(), cache_bytes / sizeof(Node));
+        s->stack_bytes = stack_bytes + (size_t)v.n_cached_nodes * sizeof(Node);
+        if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm) != 0)
+            throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
         if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;
         if (s->shade_blocks_per_sm < 1) s->shade_blocks_per_sm = 1;
         CU(cudaDeviceSynchronize());
@@ -197,7 +225,6 @@ int rt_scene_destroy(rt_scene* s) {
     if (!s) return RT_OK;
     cudaSetDevice(s->device);
     for (void* p : s->allocs) cudaFree(p);
-    s->ws.release();
     delete s;
     return RT_OK;
 }
@@ -220,6 +247,7 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
     if (!s || (n && (!d_rays || !d_out))) return set_err(RT_ERR_INVALID, "null argument");
     if (stats) std::memset(stats, 0, sizeof(*stats));
     if (n == 0) return RT_OK;
+    if (n > 0xFFFFFFF0ull) return set_err(RT_ERR_INVALID, "more than 2^32 rays in one batch");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* d_cnt = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -239,7 +267,7 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
             CU(cudaEventCreate(&e1));
             CU(cudaEventRecord(e0, st));
         }
-        launch_closest_hit(s->view, d_rays, n, t_min, t_max, count, d_out, d_cnt, grid, st);
+        launch_closest_hit(s->view, d_rays, (uint32_t)n, t_min, t_max, count, d_out, d_cnt, grid, s->stack_bytes, st);
         CU(cudaGetLastError());
         if (stats) {
             CU(cudaEventRecord(e1, st));
@@ -325,31 +353,41 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     if (s_begin > s_end || s_end > spp) return set_err(RT_ERR_INVALID, "bad sample range");
     if (stats) std::memset(stats, 0, sizeof(*stats));
 
-    std::lock_guard<std::mutex> lock(s->mu);
+    DeviceWorkspace& dws = device_workspace(s->device);
+    std::lock_guard<std::mutex> lock(dws.mu);
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n_px_img = (uint64_t)cam->image_width * cam->image_height;
     const uint64_t n_pixels = count_partition_pixels(cam->image_width, cam->image_height, o.part_index, part_count);
     const uint64_t total_paths = n_pixels * (uint64_t)(s_end - s_begin);
-    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 21);
+    // paths in flight: large enough that the ~10 launches of an iteration are amortised over millions of
+    // segments (profiles/README.md: 2^21 -> 2^24 is +23 %), never more than the job needs
+    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 24);
+    capacity = (uint32_t)std::min<uint64_t>(capacity, ((total_paths + 1023) / 1024) * 1024);
     capacity = std::max(capacity, 1024u);
     cudaEvent_t ev[8] = {nullptr};
     int rc = RT_OK;
     try {
         CU(cudaSetDevice(s->device));
-        Workspace& ws = s->ws;
-        if (ws.capacity != capacity || ws.n_pixels_alloc < n_px_img) {
+        Workspace& ws = dws.ws;
+        if (ws.capacity < capacity || ws.n_pixels_alloc < n_px_img) {  // grow-only
+            const uint32_t keep_cap = std::max(ws.capacity, capacity);
+            const uint64_t keep_px = std::max<uint64_t>(ws.n_pixels_alloc, n_px_img);
             ws.release();
+            const uint32_t capacity_alloc = keep_cap;
+            const uint64_t n_px_alloc = keep_px;
             WavefrontState& W = ws.W;
-            CU(cudaMalloc(&W.rec, (size_t)capacity * sizeof(PathRec)));
-            CU(cudaMalloc(&W.q_extend, (size_t)capacity * 4));
-            CU(cudaMalloc(&W.q_free, (size_t)capacity * 4));
-            for (auto& q : W.q_shade) CU(cudaMalloc(&q, (size_t)capacity * 4));
-            CU(cudaMalloc(&W.pixel_list, n_px_img * 4));
-            CU(cudaMalloc(&W.accum, n_px_img * 3 * sizeof(double)));
+            for (int k = 0; k < 2; k++) {
+                CU(cudaMalloc(&W.ray_q[k], (size_t)capacity_alloc * sizeof(RayRec)));
+                CU(cudaMalloc(&W.state_q[k], (size_t)capacity_alloc * sizeof(StateRec)));
+            }
+            CU(cudaMalloc(&W.hit_q, (size_t)capacity_alloc * sizeof(HitRec)));
+            for (auto& q : W.q_shade) CU(cudaMalloc(&q, (size_t)capacity_alloc * 4));
+            CU(cudaMalloc(&W.pixel_list, n_px_alloc * 4));
+            CU(cudaMalloc(&W.accum, n_px_alloc * 3 * sizeof(double)));
             CU(cudaMalloc(&W.counters, sizeof(Counters)));
             CU(cudaMallocHost(&ws.h_counters, sizeof(Counters)));
-            ws.capacity = capacity;
-            ws.n_pixels_alloc = n_px_img;
+            ws.capacity = capacity_alloc;
+            ws.n_pixels_alloc = n_px_alloc;
         }
         WavefrontState W = ws.W;
         W.capacity = capacity;
@@ -366,44 +404,47 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         const bool count = (o.flags & RT_OPT_COUNT) != 0, stage = (o.flags & RT_OPT_STAGE_TIMES) != 0;
         const int grid_e = s->sm_count * s->extend_blocks_per_sm, grid_s = s->sm_count * s->shade_blocks_per_sm;
         const int grid_g = s->sm_count * 4;
+        const int grid_m = s->sm_count * 8;
         for (auto& e : ev) CU(cudaEventCreate(&e));
         CU(cudaEventRecord(ev[0], st));
         Counters init{};
-        init.n_free = capacity;
         CU(cudaMemcpyAsync(W.counters, &init, sizeof(init), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(W.accum, 0, n_px_img * 3 * sizeof(double), st));
         uint64_t launches = 2;
-        double ms_gen = 0, ms_ext = 0, ms_shd = 0;
+        double ms_gen = 0, ms_ext = 0, ms_med = 0, ms_shd = 0;
         if (total_paths > 0) {
             launch_init(W, P, grid_g, st);
-            launches += 2;
+            launches += 1;
             const int burst = 8;  // iterations between host checks of the counters
             size_t iters = 0;
             while (true) {
                 for (int b = 0; b < burst; b++, iters++) {
+                    W.parity = (uint32_t)(iters & 1);
                     // stage times: events are only recorded here and read after the render, so the
                     // measurement does not add a host synchronisation to the timed region
-                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 0), st));
+                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 0), st));
                     launch_generate(P, W, grid_g, st);
-                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 1), st));
-                    launch_extend(s->view, P, W, count, grid_e, st);
-                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 2), st));
-                    launch_shade(s->view, P, W, grid_s, st);
-                    if (stage) CU(cudaEventRecord(ws.event(4 * iters + 3), st));
-                    launches += 6;
+                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 1), st));
+                    launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
+                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 2), st));
+                    launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st);
+                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 3), st));
+                    launches += 4 + launch_shade(s->view, P, W, s->class_mask, grid_s, st);  // generate, k_step, extend, media_bin + shade
+                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 4), st));
                 }
                 CU(cudaMemcpyAsync(ws.h_counters, W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
                 CU(cudaGetLastError());
-                if (ws.h_counters->next_path >= total_paths && ws.h_counters->n_extend == 0) break;
+                if (ws.h_counters->next_path >= total_paths && ws.h_counters->n_extend[0] == 0 && ws.h_counters->n_extend[1] == 0) break;
             }
             if (stage) {
                 for (size_t i = 0; i < iters; i++) {
-                    float a, b, c;
-                    CU(cudaEventElapsedTime(&a, ws.events[4 * i], ws.events[4 * i + 1]));
-                    CU(cudaEventElapsedTime(&b, ws.events[4 * i + 1], ws.events[4 * i + 2]));
-                    CU(cudaEventElapsedTime(&c, ws.events[4 * i + 2], ws.events[4 * i + 3]));
-                    ms_gen += a, ms_ext += b, ms_shd += c;
+                    float a, b, c, d;
+                    CU(cudaEventElapsedTime(&a, ws.events[5 * i], ws.events[5 * i + 1]));
+                    CU(cudaEventElapsedTime(&b, ws.events[5 * i + 1], ws.events[5 * i + 2]));
+                    CU(cudaEventElapsedTime(&c, ws.events[5 * i + 2], ws.events[5 * i + 3]));
+                    CU(cudaEventElapsedTime(&d, ws.events[5 * i + 3], ws.events[5 * i + 4]));
+                    ms_gen += a, ms_ext += b, ms_med += c, ms_shd += d;
                 }
             }
         }
@@ -425,7 +466,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
             stats->kernel_launches = launches;
             stats->ms_total = ms;
             stats->ms_raygen = ms_gen, stats->ms_extend = ms_ext, stats->ms_shade = ms_shd;
-            stats->ms_other = stage ? ms - ms_gen - ms_ext - ms_shd : 0.0;
+            stats->ms_other = ms_med;  // the media + binning kernel
         }
     } catch (const CudaFail& f) {
         rc = set_err(RT_ERR_CUDA, f.what);

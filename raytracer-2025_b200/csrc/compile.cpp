@@ -560,8 +560,48 @@ struct Compiler {
             base += (uint32_t)g.size();
             std::vector<FlatPrim>().swap(g);
         }
+        // Renumber the nodes breadth first from the world root (then the media groups): any prefix of
+        // the array is then the top of the tree, which the kernels stage in shared memory.
+        {
+            const size_t n = out.nodes.size();
+            std::vector<uint32_t> order;
+            order.reserve(n);
+            std::vector<uint32_t> new_index(n, 0xFFFFFFFFu);
+            for (uint32_t root : roots) {
+                if (root == INVALID_REF || (root & LEAF_FLAG)) continue;
+                size_t head = order.size();
+                new_index[root] = (uint32_t)order.size();
+                order.push_back(root);
+                while (head < order.size()) {
+                    const Node& nd = out.nodes[order[head++]];
+                    for (uint32_t c : {nd.child0, nd.child1})
+                        if (!(c & LEAF_FLAG) && c != INVALID_REF) {
+                            new_index[c] = (uint32_t)order.size();
+                            order.push_back(c);
+                        }
+                }
+            }
+            std::vector<Node> sorted(order.size());
+            for (size_t i = 0; i < order.size(); i++) {
+                Node nd = out.nodes[order[i]];
+                if (!(nd.child0 & LEAF_FLAG) && nd.child0 != INVALID_REF) nd.child0 = new_index[nd.child0];
+                if (!(nd.child1 & LEAF_FLAG) && nd.child1 != INVALID_REF) nd.child1 = new_index[nd.child1];
+                sorted[i] = nd;
+            }
+            out.nodes.swap(sorted);
+            for (uint32_t& root : roots)
+                if (root != INVALID_REF && !(root & LEAF_FLAG)) root = new_index[root];
+        }
         out.world_root = roots[0];
-        for (size_t m = 0; m < out.media.size(); m++) out.media[m].root = roots[group_of_medium[m]];
+        for (size_t m = 0; m < out.media.size(); m++) {
+            Medium& med = out.media[m];
+            med.root = roots[group_of_medium[m]];
+            med.single_sphere = RT_NONE;
+            if ((med.root & LEAF_FLAG) && med.root != INVALID_REF && (med.root & 7u) == 0) {
+                uint32_t pi = (med.root & ~LEAF_FLAG) >> 3;
+                if ((out.meta[pi].kind_mat >> 30) == PRIM_SPHERE) med.single_sphere = pi;
+            }
+        }
         return RT_OK;
     }
 };

@@ -4,13 +4,14 @@
 // size a launch — kernels are persistent grid-stride loops that read the counts themselves):
 //
 //   generate : refill free path slots with camera rays      (Camera::get_ray, camera.rs:247-273)
-//   extend   : closest surface hit + constant-medium sampling (world.hit, camera.rs:286)
-//              -> appends the slot to the shade queue of its material class
+//   extend   : closest surface hit, persistent warp-refill traversal (world.hit, camera.rs:286)
+//   media_bin: constant-medium sampling (volume.rs:37-73) against that hit, then the append of the
+//              queue position to the shade queue of the winner's material class
 //   shade    : emitted + scatter + mixture-pdf light sampling (camera.rs:290-321)
-//              -> survivors go back to the extend queue, finished slots to the free queue
+//              -> survivors are appended to the other copy of the ray/state streams
 //
-// A path lives in one 128-byte record for its whole life; only 4-byte slot indices move between
-// queues.  Radiance is accumulated with binary64 atomics into a per-pixel framebuffer.
+// Paths flow through dense, position-indexed streams (kernels.h); terminated paths simply are not
+// re-appended.  Radiance is accumulated with binary64 atomics into a per-pixel framebuffer.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,22 +23,26 @@ namespace rt {
 // ------------------------------------------------------------------------------------------
 // closest-hit batch kernel (rt_closest_hit)
 // ------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(EXTEND_BLOCK) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint64_t n, double tmin,
-                                                              double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
-    __shared__ uint32_t s_stack[TRAVERSAL_STACK * EXTEND_BLOCK];
-    uint32_t* stack = s_stack + threadIdx.x;
-    TraceCounters cnt{0, 0};
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
+    const SceneView& sv;
+    const rt_ray* __restrict__ rays;
+    rt_hit* __restrict__ out;
+    double tmin, tmax;
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r, double& t0, double& t1) const {
         const double* rp = reinterpret_cast<const double*>(rays + i);
-        RayD r;
         r.o = D3{rp[0], rp[1], rp[2]};
         r.d = D3{rp[3], rp[4], rp[5]};
         r.time = rp[6];
-        double t;
-        uint32_t prim;
+        t0 = tmin, t1 = tmax;
+        return true;
+    }
+    __device__ __forceinline__ void prefetch(uint32_t i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + i)); }
+    __device__ __forceinline__ void store(uint32_t i, bool hit, double t, uint32_t prim) const {
         rt_hit h;
-        if (closest_hit<COUNT, true>(sv, sv.world_root, r, tmin, tmax, stack, EXTEND_BLOCK, t, prim, &cnt)) {
+        if (hit) {
+            RayD r;
+            double a, b;
+            load(i, r, a, b);
             HitInfo hi;
             surface_hit_info(sv, prim, t, r, true, hi);
             const PrimMeta m = sv.meta[prim];
@@ -52,48 +57,72 @@ __global__ void __launch_bounds__(EXTEND_BLOCK) k_closest_hit(SceneView sv, cons
         }
         out[i] = h;
     }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint32_t n, double tmin,
+                                                                 double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
+    extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
+    __shared__ uint32_t s_cursor;
+    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes) + threadIdx.x;
+    if (threadIdx.x == 0) s_cursor = 0;
+    stage_nodes(sv, s_mem);
+    TraceCounters cnt{0, 0};
+    RayArrayIO io{sv, rays, out, tmin, tmax};
+    trace_persistent<COUNT, true>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
         atomicAdd(&counters[1], (unsigned long long)cnt.prims);
     }
 }
 
-void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint64_t n, double tmin, double tmax, bool count, rt_hit* d_out,
-                        unsigned long long* d_counters, int grid, cudaStream_t stream) {
+void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
+                        unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
     if (count)
-        k_closest_hit<true><<<grid, EXTEND_BLOCK, 0, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
+        k_closest_hit<true><<<grid, EXTEND_BLOCK, stack_bytes, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
     else
-        k_closest_hit<false><<<grid, EXTEND_BLOCK, 0, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
+        k_closest_hit<false><<<grid, EXTEND_BLOCK, stack_bytes, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
 }
 
 // ------------------------------------------------------------------------------------------
 // wavefront state
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_ray(const PathRec* __restrict__ rec, RayD& r) {
+__device__ __forceinline__ void load_ray(const RayRec* __restrict__ rec, RayD& r) {
     const double2* p = reinterpret_cast<const double2*>(rec);
     double2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
     r.o = D3{a0.x, a0.y, a1.x};
     r.d = D3{a1.y, a2.x, a2.y};
     r.time = a3.x;
 }
+__device__ __forceinline__ void store_ray(RayRec* __restrict__ rec, const RayD& r) {
+    double2* p = reinterpret_cast<double2*>(rec);
+    p[0] = make_double2(r.o.x, r.o.y);
+    p[1] = make_double2(r.o.z, r.d.x);
+    p[2] = make_double2(r.d.y, r.d.z);
+    p[3] = make_double2(r.time, 0.0);
+}
+__device__ __forceinline__ void store_state(StateRec* __restrict__ rec, D3 beta, uint32_t pixel, uint32_t sample, uint32_t segment) {
+    double2* p = reinterpret_cast<double2*>(rec);
+    p[0] = make_double2(beta.x, beta.y);
+    p[1] = make_double2(beta.z, 0.0);
+    reinterpret_cast<uint4*>(p)[2] = make_uint4(pixel, sample, segment, 0u);
+}
 
-// warp-aggregated append of `slot` to the queue selected by `q` (lanes with q < 0 do not append)
-__device__ __forceinline__ void queue_append(uint32_t* const* queues, uint32_t* counts, int q, uint32_t slot) {
+// warp-aggregated reservation of one entry in queue `q` (lanes with q < 0 reserve nothing);
+// returns the reserved position
+__device__ __forceinline__ uint32_t queue_reserve(uint32_t* counts, int q) {
     unsigned active = __activemask();
     unsigned peers = __match_any_sync(active, q);
+    uint32_t pos = 0;
     if (q >= 0) {
         int leader = __ffs(peers) - 1;
         int lane = threadIdx.x & 31;
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(&counts[q], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
-        uint32_t off = __popc(peers & ((1u << lane) - 1));
-        queues[q][base + off] = slot;
+        pos = base + __popc(peers & ((1u << lane) - 1));
     }
-}
-
-__global__ void k_init_free(uint32_t* q_free, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) q_free[i] = i;
+    return pos;
 }
 
 // pixel list of this partition: 8x8 tiles dealt round-robin (rt_render_opts.part_index/part_count)
@@ -133,16 +162,15 @@ __global__ void k_pixel_list(uint32_t W, uint32_t H, uint32_t part_index, uint32
     }
 }
 
-// Camera::get_ray, camera.rs:247-273
+// Camera::get_ray, camera.rs:247-273: tops the current ray stream up to capacity with camera rays
 __global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState W) {
     const uint64_t remaining = W.total_paths - W.counters->next_path;
-    const uint32_t n_free = W.counters->n_free;
-    const uint32_t n_new = (uint32_t)(remaining < (uint64_t)n_free ? remaining : (uint64_t)n_free);
-    const uint32_t extend_base = W.counters->n_extend;
+    const uint32_t extend_base = W.counters->n_extend[W.parity];
+    const uint32_t room = W.capacity - extend_base;
+    const uint32_t n_new = (uint32_t)(remaining < (uint64_t)room ? remaining : (uint64_t)room);
     const uint64_t first = W.counters->next_path;
     const rt_camera& cam = P.cam;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
-        uint32_t slot = W.q_free[n_free - 1 - j];
         uint64_t g = first + j;
         uint32_t sidx = P.sample_begin + (uint32_t)(g / W.n_pixels);
         uint32_t pixel = W.pixel_list[g % W.n_pixels];
@@ -152,9 +180,9 @@ __global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState
         double px = (((double)s_i + jit.a) * cam.recip_sqrt_spp) - 0.5;
         double py = (((double)s_j + jit.b) * cam.recip_sqrt_spp) - 0.5;
         D3 pixel_sample = ld3(cam.pixel00_loc) + (((double)i + px) * ld3(cam.pixel_delta_u)) + (((double)jj + py) * ld3(cam.pixel_delta_v));
-        D3 origin;
+        RayD r;
         if (cam.defocus_angle_in_degrees <= 0.0) {
-            origin = ld3(cam.center);
+            r.o = ld3(cam.center);
         } else {  // defocus_disk_sample, vec3.rs:63-69
             Rand2 dk = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_DISK);
             double theta = (2.0 * RT_PI) * dk.a;
@@ -162,18 +190,12 @@ __global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState
             double s, c;
             sincos(theta, &s, &c);
             double p0 = rr * c, p1 = rr * s;
-            origin = ld3(cam.center) + (p0 * ld3(cam.defocus_disk_u)) + (p1 * ld3(cam.defocus_disk_v));
+            r.o = ld3(cam.center) + (p0 * ld3(cam.defocus_disk_u)) + (p1 * ld3(cam.defocus_disk_v));
         }
-        D3 dir = pixel_sample - origin;
-        double time = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_TIME).a;
-        double2* rp = reinterpret_cast<double2*>(W.rec + slot);
-        rp[0] = make_double2(origin.x, origin.y);
-        rp[1] = make_double2(origin.z, dir.x);
-        rp[2] = make_double2(dir.y, dir.z);
-        rp[3] = make_double2(time, 1.0);
-        rp[4] = make_double2(1.0, 1.0);
-        reinterpret_cast<uint4*>(rp)[5] = make_uint4(pixel, sidx, 0u, 0u);
-        W.q_extend[extend_base + j] = slot;
+        r.d = pixel_sample - r.o;
+        r.time = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_TIME).a;
+        store_ray(W.ray_q[W.parity] + extend_base + j, r);
+        store_state(W.state_q[W.parity] + extend_base + j, D3{1.0, 1.0, 1.0}, pixel, sidx, 0u);
     }
 }
 
@@ -182,15 +204,14 @@ __global__ void k_step(WavefrontState W, int phase) {
     Counters* c = W.counters;
     if (phase == 0) {  // after generate
         uint64_t remaining = W.total_paths - c->next_path;
-        uint32_t n_new = (uint32_t)(remaining < (uint64_t)c->n_free ? remaining : (uint64_t)c->n_free);
+        uint32_t room = W.capacity - c->n_extend[W.parity];
+        uint32_t n_new = (uint32_t)(remaining < (uint64_t)room ? remaining : (uint64_t)room);
         c->next_path += n_new;
-        c->n_free -= n_new;
-        c->n_extend += n_new;
-        c->segments += c->n_extend;
-        c->iterations += (c->n_extend > 0);
-    } else if (phase == 1) {  // after extend
-        c->n_extend = 0;
-    } else {  // after shade
+        c->n_extend[W.parity] += n_new;
+        c->segments += c->n_extend[W.parity];
+        c->iterations += (c->n_extend[W.parity] > 0);
+    } else if (phase == 2) {  // after shade: the current stream is consumed
+        c->n_extend[W.parity] = 0;
         for (int k = 0; k < SC_COUNT; k++) c->n_shade[k] = 0;
     }
 }
@@ -198,56 +219,102 @@ __global__ void k_step(WavefrontState W, int phase) {
 // ------------------------------------------------------------------------------------------
 // extend
 // ------------------------------------------------------------------------------------------
+struct PathIO {  // k_extend: rays come from the current ray stream, hits go to the hit stream
+    const RayRec* __restrict__ rays;
+    HitRec* __restrict__ hits;
+    __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t0, double& t1) const {
+        load_ray(rays + j, r);
+        t0 = 1e-8, t1 = INFINITY;  // camera.rs:286
+        return true;
+    }
+    __device__ __forceinline__ void prefetch(uint32_t j) const {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + j));
+    }
+    __device__ __forceinline__ void store(uint32_t j, bool hit, double t, uint32_t prim) const {
+        *reinterpret_cast<double2*>(hits + j) =
+            make_double2(hit ? t : INFINITY, __hiloint2double((int)prim, (int)(hit ? HIT_SURFACE : HIT_MISS)));
+    }
+};
+
+// closest surface hit of every path in the extend queue (world.hit without the media, camera.rs:286)
 template <bool COUNT>
-__global__ void __launch_bounds__(EXTEND_BLOCK) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
-    __shared__ uint32_t s_stack[TRAVERSAL_STACK * EXTEND_BLOCK];
-    uint32_t* stack = s_stack + threadIdx.x;
+__global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
+    extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
+    __shared__ uint32_t s_cursor;
+    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes) + threadIdx.x;
+    const uint32_t n = W.counters->n_extend[W.parity];
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_cursor = 0;
+    stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
-    const uint32_t n = W.counters->n_extend;
-    // whole warps iterate together so the aggregated append sees a converged warp
-    const uint32_t n_round = (n + 31u) & ~31u;
+    PathIO io{W.ray_q[W.parity], W.hit_q};
+    trace_persistent<COUNT, true>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    if (COUNT) {
+        atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
+        atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
+    }
+}
+
+// ConstantMedium::hit for every medium (volume.rs:37-73) against the surface hit found by k_extend,
+// then the warp-aggregated append to the shade queue of the winner's material class.  Runs fully
+// converged: one thread per extend-queue entry.
+// GENERIC = some boundary is not a single Sphere and needs the BVH traversal (kept out of the common
+// instantiation: it doubles the register footprint of this otherwise small streaming kernel).
+template <bool COUNT, bool GENERIC>
+__global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : 2) k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
+    extern __shared__ float4 s_mem[];  // traversal stacks for boundaries that are not a single sphere
+    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
+    TraceCounters cnt{0, 0};
+    const uint32_t n = W.counters->n_extend[W.parity];
+    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together for the aggregated append
+    const RayRec* __restrict__ rays = W.ray_q[W.parity];
+    const StateRec* __restrict__ states = W.state_q[W.parity];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
         int q = -1;
-        uint32_t slot = 0;
         if (j < n) {
-            slot = W.q_extend[j];
-            PathRec* rec = W.rec + slot;
-            RayD r;
-            load_ray(rec, r);
-            const uint4 ids = reinterpret_cast<const uint4*>(rec)[5];
-            double t = INFINITY;
-            uint32_t prim = 0xFFFFFFFFu;
-            uint32_t kind = HIT_MISS, rank = 0xFFFFFFFFu;
-            if (closest_hit<COUNT, true>(sv, sv.world_root, r, 1e-8, INFINITY, stack, EXTEND_BLOCK, t, prim, &cnt)) {
-                kind = HIT_SURFACE;
-                rank = sv.meta[prim].rank;
-            }
-            // ConstantMedium::hit for every medium, volume.rs:37-73
-            for (uint32_t m = 0; m < sv.n_media; m++) {
-                const Medium& med = sv.media[m];
-                double t1, t2;
-                uint32_t bp;
-                if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, stack, EXTEND_BLOCK, t1, bp, &cnt)) continue;
-                if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, stack, EXTEND_BLOCK, t2, bp, &cnt)) continue;
-                if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
-                if (t1 >= t2) continue;
-                if (t1 < 0.0) t1 = 0.0;
-                D3 dl = med.xform == RT_NONE ? r.d : ray_to_local(sv, med.xform, r).d;
-                double ray_length = length(dl);
-                double distance_inside_boundary = (t2 - t1) * ray_length;
-                double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
-                double hit_distance = med.neg_inv_density * log(xi);
-                if (hit_distance > distance_inside_boundary) continue;
-                double tm = t1 + hit_distance / ray_length;
-                // the medium competes with the other children of its container like any hit
-                if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
-                    t = tm;
-                    prim = m;
-                    kind = HIT_MEDIUM;
-                    rank = med.rank;
+            const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
+            double t = hw.x;
+            uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
+            if (sv.n_media) {
+                RayD r;
+                load_ray(rays + j, r);
+                const uint4 ids = reinterpret_cast<const uint4*>(states + j)[2];
+                uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
+                for (uint32_t m = 0; m < sv.n_media; m++) {
+                    const Medium& med = sv.media[m];
+                    const RayD lr = med.xform == RT_NONE ? r : ray_to_local(sv, med.xform, r);
+                    double t1, t2;
+                    if (med.single_sphere != RT_NONE) {
+                        const uint32_t bx = sv.meta[med.single_sphere].xform;
+                        const RayD br = bx == med.xform ? lr : (bx == RT_NONE ? r : ray_to_local(sv, bx, r));
+                        if (COUNT) cnt.prims += 2;
+                        if (!sphere_entry_exit(sv.geom[med.single_sphere].d, br, t1, t2)) continue;
+                    } else if (GENERIC) {
+                        uint32_t bp;
+                        if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, s_mem, stack, MEDIA_BLOCK, t1, bp, &cnt)) continue;
+                        if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, s_mem, stack, MEDIA_BLOCK, t2, bp, &cnt)) continue;
+                    } else {
+                        continue;  // unreachable: the host launches the GENERIC instantiation for such scenes
+                    }
+                    if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
+                    if (t1 >= t2) continue;
+                    if (t1 < 0.0) t1 = 0.0;
+                    double ray_length = length(lr.d);
+                    double distance_inside_boundary = (t2 - t1) * ray_length;
+                    double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
+                    double hit_distance = med.neg_inv_density * log(xi);
+                    if (hit_distance > distance_inside_boundary) continue;
+                    double tm = t1 + hit_distance / ray_length;
+                    // the medium competes with the other children of its container like any hit
+                    if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
+                        t = tm;
+                        prim = m;
+                        kind = HIT_MEDIUM;
+                        rank = med.rank;
+                    }
                 }
+                if (kind == HIT_MEDIUM) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
             }
-            reinterpret_cast<double2*>(rec)[6] = make_double2(t, __hiloint2double((int)kind, (int)prim));
             if (kind == HIT_MISS)
                 q = SC_MISS;
             else if (kind == HIT_MEDIUM)
@@ -256,7 +323,8 @@ __global__ void __launch_bounds__(EXTEND_BLOCK) k_extend(SceneView sv, RenderPar
                 q = (int)sv.materials[sv.meta[prim].kind_mat & 0x3FFFFFFFu].shade_class;
             if (!P.bin_by_class) q = q == SC_MISS ? SC_MISS : SC_DIFFUSE;
         }
-        queue_append(W.q_shade, W.counters->n_shade, q, slot);
+        const uint32_t pos = queue_reserve(W.counters->n_shade, q);
+        if (q >= 0) W.q_shade[q][pos] = j;
     }
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
@@ -278,38 +346,48 @@ __device__ __forceinline__ void contribute(const RenderParams& P, const Wavefron
     if (c.z != 0.0) atomicAdd(a + 2, c.z);
 }
 
-__global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParams P, WavefrontState W) {
-    // concatenated view over the class queues
-    uint32_t start[SC_COUNT + 1];
-    start[0] = 0;
-#pragma unroll
-    for (int k = 0; k < SC_COUNT; k++) start[k + 1] = start[k] + W.counters->n_shade[k];
-    const uint32_t n = start[SC_COUNT];
-    const uint32_t n_round = (n + 31u) & ~31u;
-    uint32_t* const out_queues[2] = {W.q_extend, W.q_free};
-    uint32_t* out_counts = &W.counters->n_extend;  // n_extend, n_free are adjacent
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+// One instantiation per shade class (scene_types.h ShadeClass): the queue it reads only holds hits
+// of that class, so everything another class would need is compiled out and the kernel keeps few
+// registers.  CLS == SC_OTHER is the fully general version (Mix, Portal, Transparent, lights that
+// wrap a material) and is also what runs when binning is switched off.
+template <uint32_t CLS>
+__global__ void __launch_bounds__(SHADE_BLOCK, 2) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
+    constexpr bool GENERIC = CLS == SC_OTHER;
+    constexpr bool DO_MISS = CLS == SC_MISS;
+    constexpr bool DO_MEDIUM = GENERIC || CLS == SC_ISOTROPIC;
+    constexpr bool DO_EMIT = GENERIC || CLS == SC_EMISSIVE;
+    constexpr bool DO_PDF = GENERIC || CLS == SC_DIFFUSE || CLS == SC_TEXTURED || CLS == SC_ISOTROPIC;
+    constexpr bool DO_METAL = GENERIC || CLS == SC_METAL;
+    constexpr bool DO_DIELECTRIC = GENERIC || CLS == SC_DIELECTRIC;
+    __shared__ uint32_t s_warp_count[SHADE_BLOCK / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t n = W.counters->n_shade[queue];
+    const RayRec* __restrict__ rays = W.ray_q[W.parity];
+    const StateRec* __restrict__ states = W.state_q[W.parity];
+    // the loop bound is uniform over the block: the survivor append is aggregated per block
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
+        const uint32_t j = j0 + threadIdx.x;
         int q = -1;
-        uint32_t slot = 0;
+        RayD nr;
+        D3 nbeta;
+        uint32_t pixel = 0, sidx = 0, segment = 0;
         if (j < n) {
-            int cls = 0;
-#pragma unroll
-            for (int k = 1; k < SC_COUNT; k++) cls += (j >= start[k]);
-            slot = W.q_shade[cls][j - start[cls]];
-            PathRec* rec = W.rec + slot;
+            const uint32_t pos = W.q_shade[queue][j];
             RayD r;
-            load_ray(rec, r);
-            const double2* rp = reinterpret_cast<const double2*>(rec);
-            D3 beta = D3{rp[3].y, rp[4].x, rp[4].y};
-            const uint4 ids = reinterpret_cast<const uint4*>(rec)[5];
-            const uint32_t pixel = ids.x, sidx = ids.y, segment = ids.z;
-            const double t = rp[6].x;
-            const uint32_t kind = (uint32_t)__double2hiint(rp[6].y), prim = (uint32_t)__double2loint(rp[6].y);
+            load_ray(rays + pos, r);
+            const double2* sp2 = reinterpret_cast<const double2*>(states + pos);
+            const double2 b0 = sp2[0], b1 = sp2[1];
+            D3 beta = D3{b0.x, b0.y, b1.x};
+            const uint4 ids = reinterpret_cast<const uint4*>(sp2)[2];
+            pixel = ids.x, sidx = ids.y, segment = ids.z;
+            const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + pos);
+            const double t = hw.x;
+            const uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
             bool alive = false, error = false;
-            RayD nr = r;
-            D3 nbeta = beta;
+            nr = r;
+            nbeta = beta;
 
-            if (kind == HIT_MISS) {
+            if (DO_MISS || (GENERIC && kind == HIT_MISS)) {
                 D3 bg;
                 if (background_value(sv, P.cam.background_tex, r.d, bg))
                     contribute(P, W, pixel, beta * bg);
@@ -318,7 +396,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
             } else {
                 HitInfo h;
                 bool hit_ok = true;
-                if (kind == HIT_MEDIUM) {  // volume.rs:66-72, in the medium's local space
+                if (DO_MEDIUM && kind == HIT_MEDIUM) {  // volume.rs:66-72, in the medium's local space
                     const Medium& med = sv.media[prim];
                     const RayD lr = med.xform == RT_NONE ? r : ray_to_local(sv, med.xform, r);
                     h.p = lr.o + t * lr.d;
@@ -336,13 +414,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
                 // emitted (camera.rs:290) — only light-carrying materials can return non-black
                 uint32_t mat = h.material;
                 uint32_t mk = sv.materials[mat].kind;
-                if (mk == RT_MAT_DIFFUSE_LIGHT || mk == RT_MAT_MIX) {
+                if (DO_EMIT && (mk == RT_MAT_DIFFUSE_LIGHT || mk == RT_MAT_MIX)) {
                     D3 e = material_emitted(sv, mat, h);
                     contribute(P, W, pixel, beta * e);
                 }
                 // resolve DiffuseLight wrappers and Mix picks down to the scattering material
                 uint32_t level = 0;
-                while (mat != RT_NONE) {
+                while (DO_EMIT && mat != RT_NONE) {
                     const Material& M = sv.materials[mat];
                     if (M.kind == RT_MAT_DIFFUSE_LIGHT)
                         mat = M.inner;
@@ -358,7 +436,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
                 if (mat != RT_NONE) {
                     const Material& M = sv.materials[mat];
                     nr.o = h.p;
-                    switch (M.kind) {
+                    // the material kinds this instantiation can meet
+                    const uint32_t mkind = M.kind;
+                    const bool is_metal = DO_METAL && (CLS == SC_METAL || mkind == RT_MAT_METAL);
+                    const bool is_dielectric = DO_DIELECTRIC && (CLS == SC_DIELECTRIC || mkind == RT_MAT_DIELECTRIC);
+                    const bool is_pdf = DO_PDF && (!GENERIC || mkind == RT_MAT_EMPTY || mkind == RT_MAT_LAMBERTIAN || mkind == RT_MAT_ISOTROPIC);
+                    switch (is_metal ? RT_MAT_METAL : is_dielectric ? RT_MAT_DIELECTRIC : is_pdf ? RT_MAT_LAMBERTIAN : (GENERIC ? mkind : 0xFFFFu)) {
                         case RT_MAT_METAL: {  // material.rs:82-95
                             D3 ud, ur;
                             if (unit_vector(r.d, ud) && unit_vector(reflect(ud, h.normal), ur)) {
@@ -397,9 +480,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
                             break;
                         }
                         case RT_MAT_TRANSPARENT:  // material.rs:211-218
-                            alive = true;
+                            alive = GENERIC;
                             break;
                         case RT_MAT_PORTAL: {  // material/portal.rs:21-30
+                            if (!GENERIC) break;
                             nr.o = h.p + ld3(M.v);
                             // quaternion sandwich product, quaternion.rs:72-104
                             double qw = M.v[3], qx = M.v[4], qy = M.v[5], qz = M.v[6];
@@ -415,11 +499,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
                             alive = true;
                             break;
                         }
-                        case RT_MAT_EMPTY:
-                        case RT_MAT_LAMBERTIAN:
-                        case RT_MAT_ISOTROPIC: {
+                        case RT_MAT_LAMBERTIAN: {  // Empty / Lambertian / Isotropic
                             // ScatterRecord::PDF branch, camera.rs:297-312
-                            const bool iso = M.kind == RT_MAT_ISOTROPIC;
+                            const bool iso = CLS == SC_ISOTROPIC || (GENERIC && M.kind == RT_MAT_ISOTROPIC);
                             D3 albedo = M.kind == RT_MAT_EMPTY ? D3{0.75, 0.75, 0.75} : texture_value(sv, M.tex, h.u, h.v, h.p);
                             ONB uvw;
                             if (!iso && !make_onb(h.normal, uvw)) {
@@ -482,18 +564,27 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade(SceneView sv, RenderParam
             }
             // a zero throughput can never contribute again; depth == 0 returns black (camera.rs:282)
             if (alive && (segment + 1 >= P.cam.max_depth || (nbeta.x == 0.0 && nbeta.y == 0.0 && nbeta.z == 0.0))) alive = false;
-            if (alive) {
-                double2* wp = reinterpret_cast<double2*>(rec);
-                wp[0] = make_double2(nr.o.x, nr.o.y);
-                wp[1] = make_double2(nr.o.z, nr.d.x);
-                wp[2] = make_double2(nr.d.y, nr.d.z);
-                wp[3] = make_double2(nr.time, nbeta.x);
-                wp[4] = make_double2(nbeta.y, nbeta.z);
-                reinterpret_cast<uint4*>(wp)[5] = make_uint4(pixel, sidx, segment + 1, 0u);
-            }
-            q = alive ? 0 : 1;
+            q = alive ? 0 : -1;
         }
-        queue_append(out_queues, out_counts, q, slot);
+        // survivors are appended to the other copy of the streams: one atomic per block
+        const unsigned alive_mask = __ballot_sync(0xFFFFFFFFu, q == 0);
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        if (lane == 0) s_warp_count[warp] = __popc(alive_mask);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < SHADE_BLOCK / 32; w++) total += s_warp_count[w];
+            s_base = total ? atomicAdd(&W.counters->n_extend[W.parity ^ 1u], total) : 0u;
+        }
+        __syncthreads();
+        uint32_t npos = s_base + __popc(alive_mask & ((1u << lane) - 1u));
+        for (uint32_t w = 0; w < warp; w++) npos += s_warp_count[w];
+        __syncthreads();  // s_warp_count / s_base are reused by the next iteration
+        if (q == 0) {
+            store_ray(W.ray_q[W.parity ^ 1u] + npos, nr);
+            store_state(W.state_q[W.parity ^ 1u] + npos, nbeta, pixel, sidx, segment + 1);
+        }
     }
 }
 
@@ -550,31 +641,73 @@ void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t too
 // launchers
 // ------------------------------------------------------------------------------------------
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s) {
-    k_init_free<<<grid, 256, 0, s>>>(W.q_free, W.capacity);
     k_pixel_list<<<grid, 256, 0, s>>>(P.cam.image_width, P.cam.image_height, P.part_index, P.part_count, W.pixel_list, &W.counters->n_pixels);
 }
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
     k_generate<<<grid, 256, 0, s>>>(P, W);
     k_step<<<1, 1, 0, s>>>(W, 0);
 }
-void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, cudaStream_t s) {
+void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
     if (count)
-        k_extend<true><<<grid, EXTEND_BLOCK, 0, s>>>(sv, P, W);
+        k_extend<true><<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
     else
-        k_extend<false><<<grid, EXTEND_BLOCK, 0, s>>>(sv, P, W);
-    k_step<<<1, 1, 0, s>>>(W, 1);
+        k_extend<false><<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
 }
-void launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
-    k_shade<<<grid, SHADE_BLOCK, 0, s>>>(sv, P, W);
+void launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
+    // media + binning: global-memory nodes only (its shared memory holds just the stacks)
+    SceneView mv = sv;
+    mv.n_cached_nodes = 0;
+    const size_t media_smem = generic ? (size_t)sv.stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;
+    if (generic) {
+        if (count)
+            k_media_bin<true, true><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+        else
+            k_media_bin<false, true><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+    } else {
+        if (count)
+            k_media_bin<true, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        else
+            k_media_bin<false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+    }
+}
+template <uint32_t CLS>
+static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t queue, int grid, cudaStream_t s) {
+    k_shade<CLS><<<grid, SHADE_BLOCK, 0, s>>>(sv, P, W, queue);
+}
+// class_mask: bit c set when the scene can produce hits of shade class c (the miss queue always runs)
+int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s) {
+    int launches = 2;  // the miss kernel and k_step
+    if (!P.bin_by_class) {  // everything but misses sits in the SC_DIFFUSE queue: general kernel
+        launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, s);
+        launch_shade_cls<SC_OTHER>(sv, P, W, SC_DIFFUSE, grid, s);
+        launches++;
+    } else {
+        launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, s);
+        if (class_mask & (1u << SC_DIFFUSE)) launch_shade_cls<SC_DIFFUSE>(sv, P, W, SC_DIFFUSE, grid, s), launches++;
+        if (class_mask & (1u << SC_TEXTURED)) launch_shade_cls<SC_TEXTURED>(sv, P, W, SC_TEXTURED, grid, s), launches++;
+        if (class_mask & (1u << SC_ISOTROPIC)) launch_shade_cls<SC_ISOTROPIC>(sv, P, W, SC_ISOTROPIC, grid, s), launches++;
+        if (class_mask & (1u << SC_METAL)) launch_shade_cls<SC_METAL>(sv, P, W, SC_METAL, grid, s), launches++;
+        if (class_mask & (1u << SC_DIELECTRIC)) launch_shade_cls<SC_DIELECTRIC>(sv, P, W, SC_DIELECTRIC, grid, s), launches++;
+        if (class_mask & (1u << SC_EMISSIVE)) launch_shade_cls<SC_EMISSIVE>(sv, P, W, SC_EMISSIVE, grid, s), launches++;
+        if (class_mask & (1u << SC_OTHER)) launch_shade_cls<SC_OTHER>(sv, P, W, SC_OTHER, grid, s), launches++;
+    }
     k_step<<<1, 1, 0, s>>>(W, 2);
+    return launches;
 }
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s) {
     k_finalize<<<grid, 256, 0, s>>>(accum, n, scale, out, out_f64 ? 1 : 0);
 }
 
-void kernel_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false>, EXTEND_BLOCK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade, SHADE_BLOCK, 0);
+int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
+    // dynamic shared memory above 48 KB is opt-in
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_closest_hit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(k_closest_hit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false>, EXTEND_BLOCK, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_DIFFUSE>, SHADE_BLOCK, 0);
+    return 0;
 }
 
 }  // namespace rt

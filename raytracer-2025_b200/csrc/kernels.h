@@ -8,35 +8,61 @@
 
 namespace rt {
 
-constexpr int EXTEND_BLOCK = 128;
-constexpr int SHADE_BLOCK = 128;
+// one CTA per SM: its shared memory holds the top of the BVH (all of it for small scenes) + the stacks
+#ifndef RT_EXTEND_BLOCK
+#define RT_EXTEND_BLOCK 512
+#endif
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 1
+#endif
+constexpr int EXTEND_BLOCK = RT_EXTEND_BLOCK;
+constexpr int EXTEND_MIN_BLOCKS = RT_EXTEND_MIN_BLOCKS;
+constexpr size_t EXTEND_SMEM_MAX = 227 * 1024;
+constexpr int SHADE_BLOCK = 256;
+constexpr int MEDIA_BLOCK = 256;
 
 enum HitKind : uint32_t { HIT_MISS = 0, HIT_SURFACE = 1, HIT_MEDIUM = 2 };
 
-// One path, 128 bytes, eight 16-byte words:
-//   0: o.x o.y | 1: o.z d.x | 2: d.y d.z | 3: time beta.x | 4: beta.y beta.z
-//   5: pixel sample segment flags (u32 x4) | 6: hit t, (hit kind, hit prim) | 7: spare
-struct alignas(128) PathRec {
-    double w[16];
+// The wavefront state is a set of dense streams indexed by QUEUE POSITION (no per-path slots):
+//   ray_q[2]   64 B  o(3) d(3) time + 8 spare bytes      read by extend/media/shade, written by shade/generate
+//   state_q[2] 48 B  throughput(3), pixel, sample, segment read by media/shade, written by shade/generate
+//   hit_q      16 B  t, kind, primitive                    written by extend, updated by media, read by shade
+// The two copies of ray_q/state_q alternate every iteration (`parity`): shade reads position p of the
+// current copy and appends survivors to the other one, generate tops that one up with camera rays.
+// Every access by extend and media is coalesced and its address is known from the position alone,
+// so the next item can be prefetched.
+struct alignas(16) RayRec {
+    double w[8];
 };
+struct alignas(16) StateRec {
+    double beta[3];
+    uint32_t pixel, sample, segment, flags;
+    double spare;
+};
+struct alignas(16) HitRec {
+    double t;
+    uint32_t kind, prim;
+};
+static_assert(sizeof(RayRec) == 64 && sizeof(StateRec) == 48 && sizeof(HitRec) == 16, "stream record sizes");
 
 struct Counters {
-    uint32_t n_extend, n_free;  // adjacent: shade appends to queue 0 (extend) or 1 (free)
+    uint32_t n_extend[2];  // entries in ray_q/state_q of each parity
     uint32_t n_shade[SC_COUNT];
     uint32_t n_pixels, pad;
     unsigned long long next_path, segments, iterations, errors, node_visits, prim_tests;
 };
 
 struct WavefrontState {
-    PathRec* rec;
-    uint32_t* q_extend;
-    uint32_t* q_free;
+    RayRec* ray_q[2];
+    StateRec* state_q[2];
+    HitRec* hit_q;
     uint32_t* q_shade[SC_COUNT];
     uint32_t* pixel_list;
     double* accum;  // W*H*3 binary64 sums
     Counters* counters;
     uint32_t capacity, n_pixels;
     uint64_t total_paths;
+    uint32_t parity, pad;
 };
 
 struct RenderParams {
@@ -46,14 +72,15 @@ struct RenderParams {
     uint32_t lights_flat, bin_by_class, pad;
 };
 
-void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint64_t n, double tmin, double tmax, bool count, rt_hit* d_out,
-                        unsigned long long* d_counters, int grid, cudaStream_t stream);
+void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
+                        unsigned long long* d_counters, int grid, size_t smem_bytes, cudaStream_t stream);
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s);
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
-void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, cudaStream_t s);
-void launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
+void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t smem_bytes, cudaStream_t s);
+void launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s);
+int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s);
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s);
 void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb, int* error_flag, cudaStream_t s);
-void kernel_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm);
+int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm);
 
 }  // namespace rt

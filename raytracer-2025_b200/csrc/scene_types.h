@@ -89,6 +89,8 @@ struct Medium {
     double neg_inv_density;
     uint32_t xform;     // Transform chain above the medium (ray_length is local, volume.rs:55) or RT_NONE
     uint32_t medium_index;
+    uint32_t single_sphere;  // primitive index when the boundary is exactly one Sphere, else RT_NONE
+    uint32_t pad;
 };
 
 // One leaf of the lights tree (hits.rs:52-75), geometry in the local space of its Transform chain
@@ -126,6 +128,10 @@ struct SceneView {
     const Light* lights;
     uint32_t world_root;
     uint32_t n_media, n_lights, n_prims;
+    uint32_t n_nodes;
+    uint32_t n_cached_nodes;  // nodes [0, n_cached_nodes) (breadth-first top of the tree) are staged in shared memory
+    uint32_t stack_entries;   // traversal stack entries per thread
+    uint32_t pad;
 };
 
 }  // namespace rt

@@ -194,79 +194,304 @@ struct TraceCounters {
     uint32_t nodes, prims;
 };
 
-// Closest hit below `root` within [tmin, tmax] (both inclusive).  stack[] is this thread's column
-// of the shared-memory traversal stack (entry i at stack[i * stride]).
+// Stage the breadth-first top of the BVH in shared memory (all threads of the CTA, then a barrier).
+__device__ __forceinline__ void stage_nodes(const SceneView& sv, float4* smem_nodes) {
+    const float4* src = reinterpret_cast<const float4*>(sv.nodes);
+    const uint32_t n4 = sv.n_cached_nodes * 4;
+    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) smem_nodes[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// Closest hit below `root` within [tmin, tmax] (both inclusive).  smem_nodes holds nodes
+// [0, n_cached_nodes); stack[] is this thread's column of the shared-memory traversal stack (entry i
+// at stack[i * stride]).
+//
+// Loop structure: "while-while" with postponed leaves.  A lane that reaches a leaf parks it and keeps
+// descending; the warp switches to the (binary64, expensive) primitive tests when every lane still
+// traversing has a parked leaf, or a lane meets a second one.  This keeps the primitive-test code
+// converged: the first version ran it with 3-7 of 32 lanes active (profiles/r01_v1_*).
 template <bool COUNT, bool USE_RANK>
 __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, const RayD& r, double tmin, double tmax,
-                                            uint32_t* __restrict__ stack, int stride, double& best_t, uint32_t& best_prim,
-                                            TraceCounters* cnt) {
+                                            const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
+                                            double& best_t, uint32_t& best_prim, TraceCounters* cnt) {
     if (root == INVALID_REF) return false;
-    RayF f;
-    make_rayf(r, f);
-    const float tmin_f = __double2float_rd(tmin);
-    float tmax_f = __double2float_ru(tmax);
     double tbest = tmax;
     uint32_t prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu;
-    int sp = 0;
-    uint32_t cur = root;
     uint32_t cached_xform = 0xFFFFFFFFu;  // RT_NONE: the world ray itself
     RayD lr = r;                          // the ray in the local space of cached_xform
-    while (true) {
-        if (cur & LEAF_FLAG) {
-            uint32_t first = (cur & ~LEAF_FLAG) >> 3, count = (cur & 7u) + 1;
-            for (uint32_t i = 0; i < count; i++) {
-                uint32_t pi = first + i;
-                const uint4 km = __ldg(reinterpret_cast<const uint4*>(&sv.meta[pi]));  // kind_mat, rank, object, xform
-                const uint32_t kind = km.x >> 30;
-                if (km.w != cached_xform) {
-                    lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
-                    cached_xform = km.w;
-                }
-                const double* g = sv.geom[pi].d;
-                double t;
-                bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, tbest, t);
-                if (COUNT) cnt->prims++;
-                if (hit) {
-                    // t <= tbest here; an exact tie keeps the lower rank
-                    bool better = prim == 0xFFFFFFFFu || t < tbest || (USE_RANK && km.y < prim_rank);
-                    if (better) {
-                        tbest = t;
-                        prim = pi;
-                        prim_rank = km.y;
-                        tmax_f = __double2float_ru(t);
-                    }
+    float tmax_f = __double2float_ru(tmax);
+
+    auto test_leaf = [&](uint32_t leaf) {
+        uint32_t first = (leaf & ~LEAF_FLAG) >> 3, count = (leaf & 7u) + 1;
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t pi = first + i;
+            const uint4 km = __ldg(reinterpret_cast<const uint4*>(&sv.meta[pi]));  // kind_mat, rank, object, xform
+            const uint32_t kind = km.x >> 30;
+            if (km.w != cached_xform) {
+                lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
+                cached_xform = km.w;
+            }
+            const double* g = sv.geom[pi].d;
+            double t;
+            bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, tbest, t);
+            if (COUNT) cnt->prims++;
+            if (hit) {
+                // t <= tbest here; an exact tie keeps the lower rank
+                bool better = prim == 0xFFFFFFFFu || t < tbest || (USE_RANK && km.y < prim_rank);
+                if (better) {
+                    tbest = t;
+                    prim = pi;
+                    prim_rank = km.y;
+                    tmax_f = __double2float_ru(t);
                 }
             }
-            if (sp == 0) break;
-            cur = stack[(--sp) * stride];
-        } else {
-            const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-            if (COUNT) cnt->nodes++;
-            float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
-            float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
-            uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-            float t0, t1;
-            bool h0 = slab(f, lo0, hi0, tmin_f, tmax_f, t0);
-            bool h1 = slab(f, lo1, hi1, tmin_f, tmax_f, t1);
-            if (h0 && h1) {
-                bool swap = t1 < t0;
-                uint32_t nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-                stack[(sp++) * stride] = farc;
-                cur = nearc;
-            } else if (h0) {
-                cur = c0;
-            } else if (h1) {
-                cur = c1;
-            } else {
-                if (sp == 0) break;
-                cur = stack[(--sp) * stride];
+        }
+    };
+
+    if (root & LEAF_FLAG) {  // a group of at most MAX_LEAF_PRIMS primitives (e.g. a medium boundary): no boxes
+        test_leaf(root);
+    } else {
+        RayF f;
+        make_rayf(r, f);
+        const float tmin_f = __double2float_rd(tmin);
+        int sp = 0;
+        uint32_t cur = root;         // node to visit next; INVALID_REF when the stack ran out
+        uint32_t parked = INVALID_REF;  // postponed leaf
+        while (cur != INVALID_REF) {
+            while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
+                float4 n0, n1, n2, n3;
+                if (cur < sv.n_cached_nodes) {  // top of the tree: shared memory
+                    const float4* np = smem_nodes + 4 * cur;
+                    n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                } else {
+                    const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
+                    n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                }
+                if (COUNT) cnt->nodes++;
+                float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
+                float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
+                uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+                float t0, t1;
+                bool h0 = slab(f, lo0, hi0, tmin_f, tmax_f, t0);
+                bool h1 = slab(f, lo1, hi1, tmin_f, tmax_f, t1);
+                if (h0 && h1) {
+                    bool swap = t1 < t0;
+                    stack[(sp++) * stride] = swap ? c0 : c1;
+                    cur = swap ? c1 : c0;
+                } else if (h0 || h1) {
+                    cur = h0 ? c0 : c1;
+                } else {
+                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                }
+                if ((cur & LEAF_FLAG) && parked == INVALID_REF) {  // first leaf: park it, keep descending
+                    parked = cur;
+                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                }
+                if (!__any_sync(__activemask(), parked == INVALID_REF)) break;  // every lane has one
+            }
+            while (parked != INVALID_REF) {
+                test_leaf(parked);
+                parked = INVALID_REF;
+                if (cur & LEAF_FLAG) {  // the node reached after parking is a leaf too
+                    parked = cur;
+                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                }
             }
         }
     }
     if (prim == 0xFFFFFFFFu) return false;
     best_t = tbest;
     best_prim = prim;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent warp-refill traversal.
+//
+// In the per-lane loop above a warp is busy until its LONGEST ray finishes (19 node iterations per
+// warp against 10.4 per ray on the book-2 scene, profiles/r01_v1_*), so almost half of the lanes idle.
+// Here a warp keeps its lanes busy instead: whenever REFILL_MIN lanes have finished, they fetch new
+// work items from the CTA's cursor and join the lanes still traversing.  Items are dealt to CTAs in
+// interleaved groups of 32 so that every CTA sees the same mix of rays.
+//
+// IO::load(item, ray, tmin, tmax) -> bool and IO::store(item, hit, t, prim) bind the routine to the
+// path records (k_extend) or to a plain ray array (k_closest_hit).
+// ------------------------------------------------------------------------------------------------
+constexpr int REFILL_MIN = 12;
+
+template <bool COUNT, bool USE_RANK, class IO>
+__device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
+                                                 const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
+                                                 TraceCounters* cnt) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t G = gridDim.x, b = blockIdx.x;
+    const uint32_t n_groups = (n + 31u) >> 5;
+    const uint32_t local_n = ((n_groups + G - 1u - b) / G) << 5;  // items dealt to this CTA (the tail may exceed n)
+
+    bool have = false, exhausted = false;
+    bool have_next = false;  // an item is already assigned to this lane and its record is being prefetched
+    uint32_t item = 0, next_item = 0;
+    RayD r, lr;
+    RayF f;
+    double tmin = 0.0, tbest = 0.0;
+    float tmin_f = 0.f, tmax_f = 0.f;
+    uint32_t prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu, cached_xform = 0xFFFFFFFFu;
+    uint32_t cur = INVALID_REF, parked = INVALID_REF;
+    int sp = 0;
+
+    // lanes without a pending assignment take one from the CTA cursor and start its prefetch
+    auto grab = [&]() {
+        const unsigned need = __ballot_sync(FULL, !have_next);
+        if (exhausted || !need) return;
+        const uint32_t c = __popc(need);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(s_cursor, c);
+        base = __shfl_sync(FULL, base, 0);
+        if (base + c >= local_n) exhausted = true;
+        if (!have_next) {
+            const uint32_t m = base + __popc(need & ((1u << lane) - 1u));
+            const uint32_t it = ((m >> 5) * G + b) * 32u + (m & 31u);
+            if (m < local_n && it < n) {
+                next_item = it;
+                have_next = true;
+                io.prefetch(it);
+            }
+        }
+    };
+
+    while (true) {
+        const unsigned idle = __ballot_sync(FULL, !have);
+        if (idle && (__popc(idle) >= REFILL_MIN || idle == FULL) && (!exhausted || __ballot_sync(FULL, have_next))) {
+            if (__ballot_sync(FULL, !have && !have_next)) grab();  // first round, or nothing to promote
+            if (!have && have_next) {  // promote the prefetched assignment
+                have_next = false;
+                double tmax;
+                if (io.load(next_item, r, tmin, tmax)) {
+                    item = next_item;
+                    have = true;
+                    tbest = tmax;
+                    tmin_f = __double2float_rd(tmin);
+                    tmax_f = __double2float_ru(tmax);
+                    prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu;
+                    cached_xform = 0xFFFFFFFFu;
+                    lr = r;
+                    sp = 0;
+                    const uint32_t root = sv.world_root;
+                    if (root & LEAF_FLAG) {
+                        parked = root, cur = INVALID_REF;
+                    } else {
+                        parked = INVALID_REF, cur = root;  // INVALID_REF root (empty world) finishes at once
+                        make_rayf(r, f);
+                    }
+                }
+            }
+            grab();  // look one item ahead
+        }
+        if (__ballot_sync(FULL, have) == 0) break;
+        if (have) {
+            // node phase: descend until this lane has parked a leaf and met another, or ran out
+            while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
+                float4 n0, n1, n2, n3;
+                if (cur < sv.n_cached_nodes) {
+                    const float4* np = smem_nodes + 4 * cur;
+                    n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                } else {
+                    const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
+                    n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                }
+                if (COUNT) cnt->nodes++;
+                float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
+                float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
+                uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+                float t0, t1;
+                bool h0 = slab(f, lo0, hi0, tmin_f, tmax_f, t0);
+                bool h1 = slab(f, lo1, hi1, tmin_f, tmax_f, t1);
+                if (h0 && h1) {
+                    bool swap = t1 < t0;
+                    stack[(sp++) * stride] = swap ? c0 : c1;
+                    cur = swap ? c1 : c0;
+                } else if (h0 || h1) {
+                    cur = h0 ? c0 : c1;
+                } else {
+                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                }
+                if ((cur & LEAF_FLAG) && parked == INVALID_REF) {
+                    parked = cur;
+                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                }
+                if (!__any_sync(__activemask(), parked == INVALID_REF)) break;
+            }
+            // leaf phase
+            while (parked != INVALID_REF) {
+                const uint32_t first = (parked & ~LEAF_FLAG) >> 3, count = (parked & 7u) + 1;
+                for (uint32_t i = 0; i < count; i++) {
+                    const uint32_t pi = first + i;
+                    const uint4 km = __ldg(reinterpret_cast<const uint4*>(&sv.meta[pi]));
+                    const uint32_t kind = km.x >> 30;
+                    if (km.w != cached_xform) {
+                        lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
+                        cached_xform = km.w;
+                    }
+                    const double* g = sv.geom[pi].d;
+                    double t;
+                    bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, tbest, t);
+                    if (COUNT) cnt->prims++;
+                    if (hit && (prim == 0xFFFFFFFFu || t < tbest || (USE_RANK && km.y < prim_rank))) {
+                        tbest = t;
+                        prim = pi;
+                        prim_rank = km.y;
+                        tmax_f = __double2float_ru(t);
+                    }
+                }
+                parked = INVALID_REF;
+                if (cur & LEAF_FLAG) {
+                    parked = cur;
+                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                }
+            }
+            if (cur == INVALID_REF) {  // traversal finished
+                io.store(item, prim != 0xFFFFFFFFu, tbest, prim);
+                have = false;
+            }
+        }
+    }
+}
+
+// ConstantMedium boundary that is one untransformed-or-transformed Sphere: both boundary hits of
+// volume.rs:42-45 share a, h, c and the square root.  Same operations, same order, same results as
+// two Sphere::hit calls on (-inf, inf) and [t1 + 1e-4, inf).
+__device__ __forceinline__ bool sphere_entry_exit(const double* __restrict__ g, const RayD& r, double& t1, double& t2) {
+    const double2 a0 = __ldg(reinterpret_cast<const double2*>(g));
+    const double2 a1 = __ldg(reinterpret_cast<const double2*>(g) + 1);
+    const double2 a2 = __ldg(reinterpret_cast<const double2*>(g) + 2);
+    const double2 a3 = __ldg(reinterpret_cast<const double2*>(g) + 3);
+    D3 center = D3{a0.x, a0.y, a1.x}, cvec = D3{a1.y, a2.x, a2.y};
+    double radius = a3.x;
+    D3 current_center = center + r.time * cvec;
+    D3 oc = current_center - r.o;
+    double a = length_squared(r.d);
+    double h = dot(r.d, oc);
+    double c = length_squared(oc) - radius * radius;
+    double discriminant = h * h - a * c;
+    if (discriminant < 0.0) return false;
+    double sqrtd = sqrt(discriminant);
+    const double near_root = (h - sqrtd) / a, far_root = (h + sqrtd) / a;
+    // first hit on Interval::UNIVERSE: only a NaN root is rejected
+    double first = near_root;
+    if (!contains(-INFINITY, INFINITY, first)) {
+        first = far_root;
+        if (!contains(-INFINITY, INFINITY, first)) return false;
+    }
+    // second hit on [first + 1e-4, inf)
+    const double lo = first + 0.0001;
+    double second = near_root;
+    if (!contains(lo, INFINITY, second)) {
+        second = far_root;
+        if (!contains(lo, INFINITY, second)) return false;
+    }
+    t1 = first;
+    t2 = second;
     return true;
 }
 

@@ -178,7 +178,8 @@ def product_lib(required=True):
     """librt2025.so: the CUDA core.  Fails loudly when it is missing — there is no fallback."""
     global _product
     if _product is None:
-        path = os.path.join(PKG_DIR, "librt2025.so")
+        # RT2025_LIB selects another build of the same library (kernel-variant experiments)
+        path = os.environ.get("RT2025_LIB") or os.path.join(PKG_DIR, "librt2025.so")
         if not os.path.exists(path):
             if required:
                 raise RtError(f"{path} is missing: run `make product` (or __graft_entry__.build()); "
@@ -384,12 +385,13 @@ class Scene:
         return st
 
     def render_opts(self, seed=1, accum_type=RT_ACCUM_F64, part_index=0, part_count=1, sample_begin=0, sample_end=0,
-                    flags=0, max_paths_in_flight=0):
+                    flags=0, max_paths_in_flight=0, no_binning=False):
         o = rt_render_opts()
         o.struct_size = C.sizeof(rt_render_opts)
         o.flags, o.seed, o.accum_type = flags, seed, accum_type
         o.part_index, o.part_count = part_index, part_count
         o.sample_begin, o.sample_end, o.max_paths_in_flight = sample_begin, sample_end, max_paths_in_flight
+        o.reserved[0] = 1 if no_binning else 0  # A/B switch: one general shade kernel instead of one per class
         return o
 
     def render(self, camera=None, **kw):
