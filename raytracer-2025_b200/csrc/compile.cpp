@@ -393,16 +393,18 @@ struct Compiler {
         return true;
     }
 
-    // order in which BVH::from_vec + BVH::hit would prefer the children on a tie: right before left
-    void bvh_visit_order(std::vector<uint32_t> objs, std::vector<uint32_t>& order) {
+    // order in which BVH::from_vec + BVH::hit would prefer the children on a tie: right before left.
+    // `out` receives exactly objs.size() ids; the two halves fill disjoint ranges, so big subtrees are
+    // sorted in parallel (the split itself is serial: a stable sort by box-min like bvh.rs:41).
+    void bvh_visit_order(std::vector<uint32_t> objs, uint32_t* out) {
         size_t len = objs.size();
         if (len == 1) {
-            order.push_back(objs[0]);
+            out[0] = objs[0];
             return;
         }
         if (len == 2) {
-            order.push_back(objs[1]);
-            order.push_back(objs[0]);
+            out[0] = objs[1];
+            out[1] = objs[0];
             return;
         }
         double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -420,8 +422,16 @@ struct Compiler {
         std::vector<uint32_t> left(objs.begin(), objs.begin() + mid), right(objs.begin() + mid, objs.end());
         objs.clear();
         objs.shrink_to_fit();
-        bvh_visit_order(std::move(right), order);
-        bvh_visit_order(std::move(left), order);
+        const size_t n_right = right.size();
+        if (len >= 65536) {
+#pragma omp task default(shared) firstprivate(out)
+            bvh_visit_order(std::move(right), out);
+            bvh_visit_order(std::move(left), out + n_right);
+#pragma omp taskwait
+        } else {
+            bvh_visit_order(std::move(right), out);
+            bvh_visit_order(std::move(left), out + n_right);
+        }
     }
 
     // depth-first walk in tie order; group = which primitive set receives the leaves
@@ -450,10 +460,15 @@ struct Compiler {
             case RT_OBJ_BVH: {
                 std::vector<uint32_t> kids(d.children + o.first_child, d.children + o.first_child + o.child_count);
                 std::vector<uint32_t> order;
-                if ((flags & RT_BUILD_NO_REF_RANKS) || in_medium)
+                if ((flags & RT_BUILD_NO_REF_RANKS) || in_medium) {
                     order = kids;
-                else
-                    bvh_visit_order(std::move(kids), order);
+                } else {
+                    order.resize(kids.size());
+                    uint32_t* dst = order.data();
+#pragma omp parallel
+#pragma omp single
+                    bvh_visit_order(std::move(kids), dst);
+                }
                 for (uint32_t c : order) walk(c, chain, group, in_medium);
                 break;
             }

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
 // GENERIC = some boundary is not a single Sphere and needs the BVH traversal (kept out of the common
 // instantiation: it doubles the register footprint of this otherwise small streaming kernel).
 template <bool COUNT, bool GENERIC>
-__global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : 2) k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
+__global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : RT_MEDIA_MIN_BLOCKS) k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // traversal stacks for boundaries that are not a single sphere
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
     TraceCounters cnt{0, 0};
@@ -351,7 +351,7 @@ __device__ __forceinline__ void contribute(const RenderParams& P, const Wavefron
 // registers.  CLS == SC_OTHER is the fully general version (Mix, Portal, Transparent, lights that
 // wrap a material) and is also what runs when binning is switched off.
 template <uint32_t CLS>
-__global__ void __launch_bounds__(SHADE_BLOCK, 2) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
+__global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
     constexpr bool GENERIC = CLS == SC_OTHER;
     constexpr bool DO_MISS = CLS == SC_MISS;
     constexpr bool DO_MEDIUM = GENERIC || CLS == SC_ISOTROPIC;

@@ -20,6 +20,12 @@ constexpr int EXTEND_MIN_BLOCKS = RT_EXTEND_MIN_BLOCKS;
 constexpr size_t EXTEND_SMEM_MAX = 227 * 1024;
 constexpr int SHADE_BLOCK = 256;
 constexpr int MEDIA_BLOCK = 256;
+#ifndef RT_MEDIA_MIN_BLOCKS
+#define RT_MEDIA_MIN_BLOCKS 2
+#endif
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 2
+#endif
 
 enum HitKind : uint32_t { HIT_MISS = 0, HIT_SURFACE = 1, HIT_MEDIUM = 2 };
 

@@ -302,3 +302,45 @@ def test_full_size_properties_book2(gpu, rt):
     assert 0.2 < mean < 1.0
     assert img.max() * full_scale > 5.0  # the 7,7,7 light quad is visible
     assert 3.0 < st.segments / st.paths < 6.0
+
+
+@pytest.mark.parametrize("shape", ["tri_soup", "sphere_soup"])
+def test_soup_closest_hit_matches_oracle(gpu, rt, orc, shape):
+    """Config 5 at a size the oracle finishes in seconds: 200k primitives, primary + incoherent rays."""
+    hs = rt.named_scene(shape, seed=5, params=[200_000])
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    assert np.array_equal(sc.ranks(), osc.ranks())
+    rng = np.random.default_rng(3)
+    n = 60_000
+    o = np.concatenate([np.tile([0.5, 0.5, -2.0], (n // 2, 1)), rng.uniform(0, 1, (n // 2, 3))])
+    tgt = rng.uniform(-0.2, 1.2, (n // 2, 3))
+    tgt[:, 2] = 0.0
+    d = np.concatenate([tgt - o[: n // 2], rng.normal(size=(n // 2, 3))])
+    rays = rt.make_rays(o, d, rng.uniform(0, 1, n))
+    got, st = sc.closest_hit(rays, flags=rt.RT_OPT_COUNT)
+    want = osc.closest_hit(rays, mode=0)
+    compare_hits(rt, got, want)
+    assert (want["prim_id"] != rt.RT_NONE).mean() > 0.3
+    assert st.node_visits / n < 200 and st.prim_tests / n < 40
+
+
+def test_soup_at_full_batch_size_properties(gpu, rt):
+    """1M triangles, 2^22 rays: properties that need no oracle — every reported hit re-verifies against
+    its own primitive record through a second, single-ray query window [t, t]."""
+    hs = rt.named_scene("tri_soup", seed=5, params=[1_000_000])
+    sc = rt.Scene(hs)
+    rng = np.random.default_rng(8)
+    n = 1 << 22
+    rays = rt.make_rays(rng.uniform(0, 1, (n, 3)), rng.normal(size=(n, 3)))
+    got, _ = sc.closest_hit(rays)
+    hit = got["prim_id"] != rt.RT_NONE
+    assert 0.5 < hit.mean() <= 1.0
+    assert np.all(got["t"][hit] >= 1e-8) and np.all(np.isinf(got["t"][~hit]))
+    # idempotence: asking again inside the degenerate interval [t, t] returns the same primitive
+    sub = np.nonzero(hit)[0][:20000]
+    for i in sub[:50]:
+        again, _ = sc.closest_hit(rays[i:i + 1], t_min=got["t"][i], t_max=got["t"][i])
+        assert again["prim_id"][0] == got["prim_id"][i] and again["t"][0] == got["t"][i]
+    # shrinking t_max below the hit must never report that primitive at that distance again
+    far, _ = sc.closest_hit(rays[sub], t_max=1e-3)
+    assert np.all((far["prim_id"] == rt.RT_NONE) | (far["t"] <= 1e-3))
