@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "compile.h"
@@ -40,8 +41,9 @@ struct Box3 {
 };
 
 constexpr int NBINS = 16;
-constexpr float C_TRAV = 1.0f, C_PRIM = 2.0f;
-constexpr uint32_t LEAF_TARGET = 4;  // SAH may stop at <= this many primitives
+// SAH constants; RT2025_SAH_CPRIM / RT2025_SAH_LEAF override them for tuning experiments
+float C_TRAV = 1.0f, C_PRIM = 4.0f;  // a binary64 primitive test costs several binary32 slab tests
+uint32_t LEAF_TARGET = 2;  // SAH may stop at <= this many primitives
 constexpr uint32_t TASK_MIN = 8192;
 
 inline float centroid(const BuildBox& b, int a) { return 0.5f * (b.lo[a] + b.hi[a]); }
@@ -156,6 +158,8 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
 
 uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes,
                    std::vector<uint32_t>& order, uint32_t& depth_out) {
+    if (const char* e = getenv("RT2025_SAH_CPRIM")) C_PRIM = (float)atof(e);
+    if (const char* e = getenv("RT2025_SAH_LEAF")) LEAF_TARGET = (uint32_t)atoi(e);
     const uint32_t n = (uint32_t)boxes.size();
     order.resize(n);
     for (uint32_t i = 0; i < n; i++) order[i] = i;
