@@ -14,7 +14,7 @@ CXXFLAGS  := -O2 -std=c++17 -fPIC -ffp-contract=off -fopenmp -Wall -Wno-unknown-
 PRODUCT_SRC := $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cpp)
 PRODUCT_HDR := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/rt2025.h include/rt2025_rng.h
 
-all: product host oracle
+all: product host oracle examples
 
 product: $(PKG)/$(LIBNAME)
 host: $(PKG)/librt2025_host.so
@@ -29,7 +29,12 @@ $(PKG)/librt2025_host.so: $(PKG)/host/host_capi.cpp $(PKG)/host/rt2025.hpp $(PKG
 oracle/liboracle.so: oracle/oracle.cpp include/rt2025.h include/rt2025_rng.h
 	$(CXX) $(CXXFLAGS) -O3 -shared -o $@ oracle/oracle.cpp
 
+examples: examples/final_scene
+
+examples/final_scene: examples/final_scene.cpp $(PKG)/host/rt2025.hpp $(PKG)/host/scenes.hpp $(PKG)/librt2025.so
+	$(CXX) $(CXXFLAGS) -o $@ examples/final_scene.cpp -L$(PKG) -lrt2025 -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
 clean:
 	rm -f $(PKG)/librt2025.so $(PKG)/librt2025_host.so oracle/liboracle.so
 
-.PHONY: all product host oracle clean
+.PHONY: all product host oracle examples clean

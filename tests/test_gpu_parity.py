@@ -344,3 +344,24 @@ def test_soup_at_full_batch_size_properties(gpu, rt):
     # shrinking t_max below the hit must never report that primitive at that distance again
     far, _ = sc.closest_hit(rays[sub], t_max=1e-3)
     assert np.all((far["prim_id"] == rt.RT_NONE) | (far["t"] <= 1e-3))
+
+
+def test_cpp_dropin_camera_render(gpu, rt, tmp_path):
+    """examples/final_scene.cpp builds the Cornell box with the reference's constructors and calls
+    Camera::render(world, lights) -> RgbImage: the 8-bit result must equal rendering the same flattened
+    scene through the Python binding (same seed) and tone-mapping it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", root, "examples"])
+    out = tmp_path / "c.ppm"
+    msg = subprocess.check_output([os.path.join(root, "examples", "final_scene"), "mini_cornell", "64", "16", "10", str(out)]).decode()
+    assert "0 errors" in msg
+    data = out.read_bytes()
+    header, pixels = data.split(b"\n255\n", 1)
+    assert header == b"P6\n64 64"
+    got = np.frombuffer(pixels, dtype=np.uint8).reshape(64, 64, 3)
+    hs = rt.named_scene("cornell_shipped", seed=7, params=[64, 16, 10])
+    img, st = rt.Scene(hs).render(seed=0x2025)
+    want = rt.tonemap(img, 0)
+    assert np.array_equal(got, want)
+    assert got.mean() > 20
