@@ -115,8 +115,20 @@ typedef enum rt_mat_kind {
     RT_MAT_ISOTROPIC = 5,     /* :188-207 tex                                              */
     RT_MAT_TRANSPARENT = 6,   /* :209-218                                                  */
     RT_MAT_MIX = 7,           /* :220-268 inner, inner2, param = ratio or tex = alpha image */
-    RT_MAT_PORTAL = 8         /* material/portal.rs:9-31 color, v[0..3)=offset v[3..7)=quat */
+    RT_MAT_PORTAL = 8,        /* material/portal.rs:9-31 color, v[0..3)=offset v[3..7)=quat */
+    RT_MAT_DISNEY = 9,        /* material/disney.rs:17-116: color = base_color (or tex = base-colour   */
+                              /* texture, as the OBJ loader builds it, shapes/obj.rs:271-293), v[] =  */
+                              /* the DisneyParameters scalars in RT_DISNEY_* order                     */
+    RT_MAT_REMAPPED = 10      /* shapes/obj.rs:20-81 RemappedMaterial: inner = wrapped material,       */
+                              /* inner2 = index into remaps[]                                          */
 } rt_mat_kind;
+
+/* order of the DisneyParameters scalars in rt_material.v (disney.rs:18-35) */
+enum {
+    RT_DISNEY_ROUGHNESS = 0, RT_DISNEY_ANISOTROPIC, RT_DISNEY_SHEEN, RT_DISNEY_SHEEN_TINT, RT_DISNEY_CLEARCOAT,
+    RT_DISNEY_CLEARCOAT_GLOSS, RT_DISNEY_SPECULAR_TINT, RT_DISNEY_METALLIC, RT_DISNEY_IOR, RT_DISNEY_FLATNESS,
+    RT_DISNEY_SPEC_TRANS, RT_DISNEY_DIFF_TRANS, RT_DISNEY_THIN /* 0.0 or 1.0 */, RT_DISNEY_COUNT
+};
 
 typedef struct rt_material {
     uint32_t kind;
@@ -125,8 +137,17 @@ typedef struct rt_material {
     uint32_t inner2;
     double color[3];
     double param;
-    double v[8];
+    double v[16];
 } rt_material;
+
+/* RemappedMaterial { tex_ori, tex_u, tex_v, u_vec, v_vec, normal[3], normal_tex } — obj.rs:20-29 */
+typedef struct rt_remap {
+    double tex_ori[3], tex_u[3], tex_v[3];
+    double u_vec[3], v_vec[3];   /* valid only when has_uv_vecs (both Options are Some)                */
+    double normal[3][3];         /* the three vertex normals                                          */
+    uint32_t has_uv_vecs;
+    uint32_t normal_tex;         /* texture index of the raw normal map, RT_NONE for None             */
+} rt_remap;
 
 typedef enum rt_tex_kind {
     RT_TEX_SOLID = 0,    /* texture.rs:9-36    color                                       */
@@ -175,6 +196,7 @@ typedef struct rt_scene_desc {
     uint32_t n_transforms, n_media, n_materials, n_textures;
     uint32_t n_images, n_perlins;
     uint64_t n_texels;     /* number of floats in texels[] */
+    uint32_t n_remaps, reserved0;
 
     const rt_object* objects;
     const uint32_t* children;
@@ -187,6 +209,7 @@ typedef struct rt_scene_desc {
     const rt_image* images;
     const float* texels;
     const rt_perlin* perlins;
+    const rt_remap* remaps;
 } rt_scene_desc;
 
 /* ------------------------------------------------------------------------------------ */

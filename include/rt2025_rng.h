@@ -40,6 +40,9 @@
                                /* (quad.rs:122), random_to_sphere (sphere.rs:63), Triangle::random */
 #define RT_SLOT_MIX 6u         /* a = Mix material pick (material.rs:251); nesting level L uses  */
                                /*     slot 6 + 256*L                                            */
+#define RT_SLOT_DISNEY 7u      /* a = lobe pick (disney.rs:674), b = the lobe's own extra decision:     */
+                               /*     diff_trans flip (disney.rs:607) or Fresnel pick (disney.rs:651);   */
+                               /*     the lobe's r0,r1 are RT_SLOT_DIRECTION                             */
 #define RT_SLOT_MEDIUM0 16u    /* a = free-flight draw of medium m (volume.rs:58): slot 16 + m,  */
                                /*     m = index into rt_scene_desc.media                        */
 

@@ -420,13 +420,24 @@ struct HitRecord {
 };
 
 // ---------------------------------------------------------------- material.rs / pdf.rs
-enum ScatterKind { SCATTER_NONE, SCATTER_COSINE, SCATTER_SPHERE, SCATTER_RAY };
+enum ScatterKind { SCATTER_NONE, SCATTER_COSINE, SCATTER_SPHERE, SCATTER_RAY, SCATTER_DISNEY };
+// DisneyParameters, material/disney.rs:18-35
+struct DisneyParameters {
+    Vec3 base_color = Vec3(0.8, 0.8, 0.8);
+    double roughness = 0.5, anisotropic = 0.0, sheen = 0.0, sheen_tint = 0.0, clearcoat = 0.0, clearcoat_gloss = 0.0;
+    double specular_tint = 0.0, metallic = 0.0, ior = 1.45, flatness = 0.0, spec_trans = 0.0, diff_trans = 0.0;
+    bool thin = false;
+};
 struct ScatterRecord {
     ScatterKind kind = SCATTER_NONE;
     Vec3 attenuation;
     ONB uvw;
     Ray ray;
     bool error = false;  // an unwrap()/expect() of the reference would have panicked
+    // DisneyPDF { uvw, v_out, front_face, params }, disney.rs:515-520
+    Vec3 v_out;
+    bool front_face = false;
+    DisneyParameters params;
 };
 struct Material {
     virtual ~Material() {}
@@ -562,8 +573,374 @@ struct Portal : Material {  // material/portal.rs:14-31
     }
 };
 
-// PDF::value for the two material pdfs — pdf.rs:22-29, 51-57
+// PDF::value for the material pdfs — pdf.rs:22-29, 51-57, disney.rs:656-666
+// ---------------------------------------------------------------- utils/fresnel.rs, material/disney.rs
+namespace disney {
+static inline double lerp(double a, double b, double t) { return a * (1.0 - t) + b * t; }  // utils.rs:14-19
+static inline Vec3 lerp(Vec3 a, Vec3 b, double t) { return a * (1.0 - t) + b * t; }
+static inline double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }  // f64::clamp (NaN stays NaN)
+static inline double pow5(double x) { double x2 = x * x; return x * (x2 * x2); }
+// the UnitVec3 helpers of vec3.rs:372-420, quirks included: cos_theta2 is y (not y*y) and
+// cos_phi / sin_phi compare against 1e8, so they are always 1
+static inline double cos_theta(Vec3 w) { return w.y(); }
+static inline double cos_theta2(Vec3 w) { return w.y(); }
+static inline double sin_theta2(Vec3 w) { return clampd(1.0 - cos_theta2(w), 0.0, 1.0); }
+static inline double sin_theta(Vec3 w) { return std::sqrt(sin_theta2(w)); }
+static inline double tan_theta(Vec3 w) { return sin_theta(w) / cos_theta(w); }
+static inline double cos_phi2(Vec3 w) { double st = sin_theta(w); double c = std::fabs(st) < 1e8 ? 1.0 : w.x() / st; return c * c; }
+static inline double sin_phi2(Vec3 w) { double st = sin_theta(w); double c = std::fabs(st) < 1e8 ? 1.0 : w.z() / st; return c * c; }
+static inline Vec3 reflect2(Vec3 v, Vec3 n) { return -v + 2.0 * dot(v, n) * n; }  // vec3.rs:76-78
+static inline bool refract2(Vec3 v, Vec3 n, double eta, Vec3& out) {             // vec3.rs:357-366
+    double ct = rmin(dot(v, n), 1.0);
+    Vec3 out_perp = eta * (-v + ct * n);
+    double len = std::sqrt(1.0 - length_squared(out_perp));
+    if (std::isnan(len)) return false;
+    out = out_perp + (-len * n);
+    return true;
+}
+// fresnel.rs
+static inline Vec3 schlick(Vec3 r0, double radians) { double e = pow5(1.0 - radians); return r0 + (Vec3(1, 1, 1) - r0) * e; }
+static inline double schlick_weight(double u) { return pow5(clampd(1.0 - u, 0.0, 1.0)); }
+static inline double schlick_f64(double r0, double radians) { return lerp(1.0, schlick_weight(radians), r0); }
+static inline double schlick_r0_from_relative_ior(double eta) { return ((eta - 1.0) * (eta - 1.0)) / ((eta + 1.0) * (eta + 1.0)); }
+static inline double dielectric(double cos_theta_in, double n_in, double n_out) {  // fresnel.rs:22-46
+    cos_theta_in = clampd(cos_theta_in, -1.0, 1.0);
+    if (cos_theta_in < 0.0) {
+        std::swap(n_in, n_out);
+        cos_theta_in = -cos_theta_in;
+    }
+    double sin_in = std::sqrt(rmax(1.0 - cos_theta_in * cos_theta_in, 0.0));
+    double sin_out = n_in / n_out * sin_in;
+    if (sin_out >= 1.0) return 1.0;
+    double cos_out = std::sqrt(rmax(1.0 - sin_out * sin_out, 0.0));
+    double r_par = (n_out * cos_theta_in - n_in * cos_out) / (n_out * cos_theta_in + n_in * cos_out);
+    double r_perp = (n_in * cos_theta_in - n_out * cos_out) / (n_in * cos_theta_in + n_out * cos_out);
+    return (r_par * r_par + r_perp * r_perp) / 2.0;
+}
+static inline Vec3 calculate_tint(Vec3 base) {  // disney.rs:425-433
+    double lum = dot(Vec3(0.3, 0.6, 1.0), base);
+    return lum > 0.0 ? base * (1.0 / lum) : Vec3(1, 1, 1);
+}
+static inline double gtr1(double dot_hl, double a) {  // :435-443
+    if (a >= 1.0) return 1.0 / PI;
+    double a2 = a * a;
+    return (a2 - 1.0) / (PI * std::log(a2) * (1.0 + (a2 - 1.0) * dot_hl * dot_hl));
+}
+static inline double separable_smith_ggxg1(Vec3 w, double a) {  // :445-450
+    double a2 = a * a, nv = w.y();
+    return 2.0 / (1.0 + std::sqrt(a2 + (1.0 - a2) * nv * nv));
+}
+static inline double ggx_anisotropic_d(Vec3 h, double ax, double ay) {  // :452-460
+    double hx2 = h.x() * h.x(), hy2 = h.z() * h.z(), ct2 = h.y() * h.y();
+    double ax2 = ax * ax, ay2 = ay * ay;
+    double q = hx2 / ax2 + hy2 / ay2 + ct2;
+    return 1.0 / (PI * ax * ay * (q * q));
+}
+static inline double aniso_smith_g1(Vec3 w, Vec3 h, double ax, double ay, bool& error) {  // :462-480
+    if (dot(w, h) <= 0.0) return 0.0;
+    double att = std::fabs(tan_theta(w));
+    if (std::isnan(att)) error = true;  // assert!
+    if (std::isinf(att)) return 0.0;
+    double a = std::sqrt(cos_phi2(w) * ax * ax + sin_phi2(w) * ay * ay);
+    double at = a * att;
+    double lambda = 0.5 * (-1.0 + std::sqrt(1.0 + at * at));
+    return 1.0 / (1.0 + lambda);
+}
+static inline void aniso_params(double roughness, double anisotropic, double& ax, double& ay) {  // :482-488
+    double aspect = std::sqrt(1.0 - 0.9 * anisotropic);
+    double r2 = roughness * roughness;
+    ax = rmax(0.001, r2 / aspect);
+    ay = rmax(0.001, r2 * aspect);
+}
+static inline void vndf_pdf(Vec3 v_in, Vec3 h, Vec3 v_out, double ax, double ay, double& fwd, double& rev, bool& error) {  // :490-510
+    double d = ggx_anisotropic_d(h, ax, ay);
+    double g1v = aniso_smith_g1(v_out, h, ax, ay, error);
+    fwd = g1v * std::fabs(dot(h, v_out)) * d / std::fabs(cos_theta(v_out));
+    double g1l = aniso_smith_g1(v_in, h, ax, ay, error);
+    rev = g1l * std::fabs(dot(h, v_in)) * d / std::fabs(cos_theta(v_in));
+}
+static inline double thin_transmission_roughness(double ior, double roughness) { return clampd((0.65 * ior - 0.35) * roughness, 0.0, 1.0); }
+
+static Vec3 disney_fresnel(const DisneyParameters& P, Vec3 v_out, Vec3 h, Vec3 v_in, double relative_ior) {  // :177-200
+    double dot_hv = dot(h, v_out);
+    Vec3 tint = calculate_tint(P.base_color);
+    Vec3 r0 = schlick_r0_from_relative_ior(relative_ior) * lerp(Vec3(1, 1, 1), tint, P.specular_tint);
+    r0 = lerp(r0, P.base_color, P.metallic);
+    double df = dielectric(dot_hv, 1.0, P.ior);
+    Vec3 mf = schlick(r0, dot(v_in, h));
+    return lerp(Vec3(df, df, df), mf, P.metallic);
+}
+static void evaluate_brdf(const DisneyParameters& P, Vec3 v_out, Vec3 h, Vec3 v_in, double relative_ior, Vec3& value, double& fwd, double& rev, bool& error) {  // :100-130
+    double nl = cos_theta(v_in), nv = cos_theta(v_out);
+    value = Vec3(0, 0, 0), fwd = 0.0, rev = 0.0;
+    if (nl <= 0.0 || nv <= 0.0) return;
+    double ax, ay;
+    aniso_params(P.roughness, P.anisotropic, ax, ay);
+    double d = ggx_anisotropic_d(h, ax, ay);
+    double gl = aniso_smith_g1(v_in, h, ax, ay, error), gv = aniso_smith_g1(v_out, h, ax, ay, error);
+    Vec3 f = disney_fresnel(P, v_out, h, v_in, relative_ior);
+    vndf_pdf(v_in, h, v_out, ax, ay, fwd, rev, error);
+    fwd = fwd / (4.0 * std::fabs(dot(v_in, h)));
+    rev = rev / (4.0 * std::fabs(dot(v_out, h)));
+    value = (d * gl * gv * f) / (4.0 * nl * nv);
+}
+static Vec3 evaluate_sheen(const DisneyParameters& P, Vec3 h, Vec3 v_in) {  // :132-146
+    if (P.sheen <= 0.0) return Vec3(0, 0, 0);
+    double dot_hl = dot(h, v_in);
+    Vec3 tint = calculate_tint(P.base_color);
+    return (P.sheen * lerp(Vec3(1, 1, 1), tint, P.sheen_tint)) * schlick_weight(dot_hl);
+}
+static void evaluate_clearcoat(const DisneyParameters& P, Vec3 v_out, Vec3 h, Vec3 v_in, double& value, double& fwd, double& rev) {  // :148-175
+    value = fwd = rev = 0.0;
+    if (P.clearcoat <= 0.0) return;
+    double dot_nh = h.y(), dot_hl = dot(h, v_in);
+    double d = gtr1(dot_nh, lerp(0.1, 0.001, P.clearcoat_gloss));
+    double f = schlick_f64(0.04, dot_hl);
+    double gl = separable_smith_ggxg1(v_in, 0.25), gv = separable_smith_ggxg1(v_out, 0.25);
+    value = 0.25 * P.clearcoat * d * f * gl * gv;
+    fwd = d / (4.0 * std::fabs(dot(v_in, h)));
+    rev = d / (4.0 * std::fabs(dot(v_out, h)));
+}
+static Vec3 evaluate_spec_transmission(const DisneyParameters& P, Vec3 v_out, Vec3 h, Vec3 v_in, double ax, double ay, double relative_ior, bool& error) {  // :202-236
+    double n2 = relative_ior * relative_ior;
+    double anl = std::fabs(cos_theta(v_in)), anv = std::fabs(cos_theta(v_out));
+    double dot_hl = dot(h, v_in), dot_hv = dot(h, v_out);
+    double d = ggx_anisotropic_d(h, ax, ay);
+    double gl = aniso_smith_g1(v_in, h, ax, ay, error), gv = aniso_smith_g1(v_out, h, ax, ay, error);
+    double f = dielectric(dot_hv, 1.0, 1.0 / relative_ior);
+    Vec3 color = P.base_color;
+    if (P.thin) {
+        color = Vec3(std::sqrt(color[0]), std::sqrt(color[1]), std::sqrt(color[2]));
+        if (std::isnan(color[0]) || std::isnan(color[1]) || std::isnan(color[2])) error = true;  // Vec3::sqrt panics
+    }
+    double c = (std::fabs(dot_hl) * std::fabs(dot_hv)) / (anl * anv);
+    double q = dot_hl + relative_ior * dot_hv;
+    double t = n2 / (q * q);
+    return (c * t * (1.0 - f) * gl * gv * d) * color;
+}
+static double evaluate_retro_diffuse(const DisneyParameters& P, Vec3 v_out, Vec3 v_in) {  // :272-290
+    double anl = std::fabs(cos_theta(v_in)), anv = std::fabs(cos_theta(v_out));
+    double roughness = P.roughness * P.roughness;
+    double rr = 0.5 + 2.0 * anl * anl * roughness;
+    double fl = schlick_weight(anl), fv = schlick_weight(anv);
+    return rr * (fl + fv + fl * fv * (rr - 1.0));
+}
+static double evaluate_diffuse(const DisneyParameters& P, Vec3 v_out, Vec3 h, Vec3 v_in, bool thin) {  // :238-270
+    double anl = std::fabs(cos_theta(v_in)), anv = std::fabs(cos_theta(v_out));
+    double fl = schlick_weight(anl), fv = schlick_weight(anv);
+    double hk = 0.0;
+    if (thin && P.flatness > 0.0) {
+        double roughness = P.roughness * P.roughness;
+        double dot_hl = dot(h, v_in);
+        double fss90 = dot_hl * dot_hl * roughness;
+        double fss = lerp(1.0, fss90, fl) * lerp(1.0, fss90, fv);
+        hk = 1.25 * (fss * (1.0 / (anl + anv) - 0.5) + 0.5);
+    }
+    double retro = evaluate_retro_diffuse(P, v_out, v_in);
+    double subsurface = lerp(1.0, hk, thin ? P.flatness : 0.0);
+    return 1.0 / PI * (retro + subsurface * (1.0 - 0.5 * fl) * (1.0 - 0.5 * fv));
+}
+static void lobe_pdfs(const DisneyParameters& P, double& p_spec, double& p_diff, double& p_clear, double& p_trans) {  // :403-422
+    double metallic_brdf = P.metallic;
+    double specular_bsdf = (1.0 - P.metallic) * P.spec_trans;
+    double dielectric_brdf = (1.0 - P.spec_trans) * (1.0 - P.metallic);
+    double sw = metallic_brdf + dielectric_brdf, tw = specular_bsdf, dw = dielectric_brdf, cw = 1.0 * clampd(P.clearcoat, 0.0, 1.0);
+    double norm = 1.0 / (sw + tw + dw + cw);
+    p_spec = sw * norm, p_trans = tw * norm, p_diff = dw * norm, p_clear = cw * norm;
+}
+// Disney::evaluate_disney, disney.rs:292-401
+static void evaluate_disney(const DisneyParameters& P, Vec3 v_out, Vec3 v_in, bool front_face, Vec3& reflectance, double& forward_pdf, bool& error) {
+    double relative_ior = front_face ? P.ior : 1.0 / P.ior;
+    double nv = cos_theta(v_out), nl = cos_theta(v_in);
+    bool is_transmission = nv * nl < 0.0;
+    Vec3 h;
+    if (!unit_vector(is_transmission ? v_in - v_out : v_in + v_out, h)) error = true;  // .expect
+    reflectance = Vec3(0, 0, 0);
+    forward_pdf = 0.0;
+    double p_brdf, p_diffuse, p_clearcoat, p_spec_trans;
+    lobe_pdfs(P, p_brdf, p_diffuse, p_clearcoat, p_spec_trans);
+    double diffuse_weight = (1.0 - P.metallic) * (1.0 - P.spec_trans);
+    double trans_weight = (1.0 - P.metallic) * P.spec_trans;
+    bool upper = nl > 0.0 && nv > 0.0;
+    if (upper && P.clearcoat > 0.0) {
+        double cc, f, r;
+        evaluate_clearcoat(P, v_out, h, v_in, cc, f, r);
+        reflectance = reflectance + Vec3(cc, cc, cc);
+        forward_pdf += p_clearcoat * f;
+    }
+    if (diffuse_weight > 0.0) {
+        double fwd = std::fabs(cos_theta(v_in));
+        double diffuse = evaluate_diffuse(P, v_out, h, v_in, P.thin);
+        Vec3 sheen = evaluate_sheen(P, h, v_in);
+        reflectance = reflectance + diffuse_weight * (diffuse * P.base_color + sheen);
+        forward_pdf += p_diffuse * fwd;
+    }
+    if (trans_weight > 0.0) {
+        double rscaled = P.thin ? thin_transmission_roughness(P.ior, P.roughness) : P.roughness;
+        double tax, tay;
+        aniso_params(rscaled, P.anisotropic, tax, tay);
+        Vec3 t_v_out = is_transmission ? -v_out : v_out;
+        Vec3 transmission = evaluate_spec_transmission(P, t_v_out, h, v_in, tax, tay, relative_ior, error);
+        reflectance = reflectance + trans_weight * transmission;
+        double fwd, rev;
+        vndf_pdf(v_in, h, t_v_out, tax, tay, fwd, rev, error);
+        double dot_lh = dot(h, v_in), dot_vh = dot(h, t_v_out);
+        double q = dot_lh + relative_ior * dot_vh;
+        double jacobian = (relative_ior * relative_ior * dot_lh) / (q * q);
+        forward_pdf += p_spec_trans * fwd * std::fabs(jacobian);
+    }
+    if (upper) {
+        Vec3 spec;
+        double f, r;
+        evaluate_brdf(P, v_out, h, v_in, relative_ior, spec, f, r, error);
+        reflectance = reflectance + spec;
+        forward_pdf += p_brdf * f;
+    }
+    reflectance = reflectance * std::fabs(nl);
+    if (forward_pdf == 0.0) forward_pdf = INF;
+}
+// sample_ggx_vndf_anisotropic, disney.rs:690-716
+static bool sample_vndf(Vec3 v_out, double ax, double ay, double u1, double u2, Vec3& out) {
+    Vec3 v;
+    if (!unit_vector(Vec3(v_out.x() * ax, v_out.y(), v_out.z() * ay), v)) return false;
+    Vec3 t1 = v.y() < 0.9999999 ? cross(v, Vec3(0, 1, 0)) : Vec3(1, 0, 0);
+    Vec3 t2 = cross(t1, v);
+    double a = 1.0 / (1.0 + v.y());
+    double r = std::sqrt(u1);
+    double phi = u2 < a ? (u2 / a) * PI : PI + (u2 - a) / (1.0 - a) * PI;
+    double p1 = r * std::cos(phi);
+    double p2 = r * std::sin(phi) * (u2 < a ? 1.0 : v.y());
+    Vec3 n = p1 * t1 + p2 * t2 + std::sqrt(rmax(1.0 - p1 * p1 - p2 * p2, 0.0)) * v;
+    return unit_vector(Vec3(ax * n.x(), n.y(), ay * n.z()), out);
+}
+// DisneyPDF::generate, disney.rs:668-688; returns false for None
+static bool generate(const ScatterRecord& s, const PathCtx& ctx, Vec3& out, bool& error) {
+    const DisneyParameters& P = s.params;
+    double p_spec, p_diff, p_clear, p_trans;
+    lobe_pdfs(P, p_spec, p_diff, p_clear, p_trans);
+    Rand2 pick = ctx.draw(RT_SLOT_DISNEY);
+    Rand2 u = ctx.draw(RT_SLOT_DIRECTION);
+    const Vec3 v_out = s.v_out;
+    double p = pick.a;
+    Vec3 v_in;
+    if (p <= p_spec) {  // sample_disney_brdf :540-556
+        double ax, ay;
+        aniso_params(P.roughness, P.anisotropic, ax, ay);
+        Vec3 h;
+        if (!sample_vndf(v_out, ax, ay, u.a, u.b, h)) { error = true; return false; }
+        if (!unit_vector(reflect2(v_out, h), v_in)) { error = true; return false; }
+        if (cos_theta(v_in) <= 0.0) return false;
+    } else if (p <= p_spec + p_clear) {  // sample_disney_clearcoat :558-587
+        double a = 0.25, a2 = a * a;
+        double ct = std::sqrt(rmax((1.0 - std::pow(a2, 1.0 - u.a)) / (1.0 - a2), 0.0));
+        double st = std::sqrt(rmax(1.0 - ct * ct, 0.0));
+        double phi = 2.0 * PI * u.b;
+        Vec3 h(st * std::cos(phi), ct, st * std::sin(phi));
+        if (dot(h, v_out) < 0.0) h = -h;
+        v_in = reflect2(v_out, h);
+        if (dot(v_in, v_out) < 0.0) return false;
+    } else if (p <= p_spec + p_diff + p_clear) {  // sample_disney_diffuse :589-605
+        double y = cos_theta(v_out);
+        double sign = std::isnan(y) ? y : (std::signbit(y) ? -1.0 : 1.0);  // f64::signum
+        v_in = sign * random_cosine_direction(u.a, u.b);
+        if (pick.b <= P.diff_trans) v_in = -v_in;
+        if (cos_theta(v_in) == 0.0) return false;
+    } else if (p_trans >= 0.0) {  // disney_spec_transmission :607-664
+        double ior = s.front_face ? P.ior : 1.0 / P.ior;
+        if (cos_theta(v_out) == 0.0) return false;
+        double rscaled = P.thin ? thin_transmission_roughness(ior, P.roughness) : P.roughness;
+        double tax, tay;
+        aniso_params(rscaled, P.anisotropic, tax, tay);
+        Vec3 h;
+        if (!sample_vndf(v_out, tax, tay, u.a, u.b, h)) { error = true; return false; }
+        double dot_vh = dot(v_out, h);
+        if (h.y() < 0.0) dot_vh = -dot_vh;
+        double ni = v_out.y() > 0.0 ? 1.0 : ior, nt = v_out.y() > 0.0 ? ior : 1.0;
+        double relative_ior = ni / nt;
+        double f = dielectric(dot_vh, 1.0, P.ior);
+        if (pick.b <= f) {
+            if (!unit_vector(reflect2(v_out, h), v_in)) { error = true; return false; }
+        } else if (P.thin) {
+            Vec3 wi = reflect2(v_out, h);
+            if (!unit_vector(Vec3(wi.x(), -wi.y(), wi.z()), v_in)) { error = true; return false; }
+        } else if (!refract2(v_out, h, relative_ior, v_in)) {
+            if (!unit_vector(reflect2(v_out, h), v_in)) { error = true; return false; }
+        }
+        if (cos_theta(v_in) == 0.0) return false;
+    } else {
+        error = true;  // panic!("The conditions should be exhausted!")
+        return false;
+    }
+    if (!unit_vector(s.uvw.onb_to_world(v_in), out)) { error = true; return false; }
+    return true;
+}
+}  // namespace disney
+
+struct Disney : Material {  // material/disney.rs:57-91
+    DisneyParameters params;
+    const Texture* base_color_tex = nullptr;  // the OBJ loader's param_fn reads base_color from a texture (obj.rs:273-285)
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx&, uint32_t) const override {
+        ScatterRecord s;
+        Vec3 v_out;
+        if (!unit_vector(-r_in.dir, v_out)) {
+            s.error = true;
+            return s;
+        }
+        s.kind = SCATTER_DISNEY;
+        s.uvw = ONB(rec.normal);
+        if (!s.uvw.ok) s.error = true;
+        s.v_out = Vec3(dot(v_out, s.uvw.axis[0]), dot(v_out, s.uvw.axis[1]), dot(v_out, s.uvw.axis[2]));  // world_to_onb, onb.rs:40-45
+        s.front_face = rec.front_face;
+        s.params = params;
+        if (base_color_tex) s.params.base_color = base_color_tex->value(rec.u, rec.v, rec.p);
+        return s;
+    }
+};
+
+struct RemappedMaterial : Material {  // shapes/obj.rs:20-81
+    const Material* material;
+    Vec3 tex_ori, tex_u, tex_v, u_vec, v_vec, normal[3];
+    bool has_uv_vecs = false;
+    const Texture* normal_tex = nullptr;
+    HitRecord remap_record(const HitRecord& rec, bool& error) const {  // :32-62
+        Vec3 tex_coord = tex_ori + rec.u * tex_u + rec.v * tex_v;
+        Vec3 n;
+        if (!unit_vector((1.0 - rec.u - rec.v) * normal[0] + rec.u * normal[1] + rec.v * normal[2], n)) error = true;
+        if (normal_tex) {
+            Vec3 c = normal_tex->value(tex_coord.x(), tex_coord.y(), rec.p);
+            c = c * 2.0 - Vec3(1.0, 1.0, 1.0);
+            if (!has_uv_vecs) error = true;  // .unwrap() on None
+            Vec3 raw = u_vec * c[0] + v_vec * c[1] + n * c[2];
+            if (!unit_vector(raw, n)) error = true;
+        }
+        HitRecord out = rec;
+        out.normal = n;
+        out.u = tex_coord.x();
+        out.v = tex_coord.y();
+        return out;
+    }
+    ScatterRecord scatter(const Ray& r_in, const HitRecord& rec, const PathCtx& ctx, uint32_t lvl) const override {
+        bool error = false;
+        HitRecord r2 = remap_record(rec, error);
+        ScatterRecord s = material->scatter(r_in, r2, ctx, lvl);
+        if (error) s.error = true;
+        return s;
+    }
+    Vec3 emitted(const Ray& r_in, const HitRecord& rec) const override {
+        bool error = false;
+        return material->emitted(r_in, remap_record(rec, error));
+    }
+};
+
 static bool pdf_value(const ScatterRecord& s, Vec3 direction, Vec3& brdf, double& pdf) {
+    if (s.kind == SCATTER_DISNEY) {
+        Vec3 ud;
+        if (!unit_vector(direction, ud)) return false;  // .unwrap()
+        Vec3 v_in(dot(ud, s.uvw.axis[0]), dot(ud, s.uvw.axis[1]), dot(ud, s.uvw.axis[2]));
+        bool error = false;
+        disney::evaluate_disney(s.params, s.v_out, v_in, s.front_face, brdf, pdf, error);
+        return !error;
+    }
     if (s.kind == SCATTER_SPHERE) {
         pdf = 1.0 / (4.0 * PI);
         brdf = s.attenuation / (4.0 * PI);
@@ -576,9 +953,12 @@ static bool pdf_value(const ScatterRecord& s, Vec3 direction, Vec3& brdf, double
     brdf = s.attenuation * rmax(cosine_theta, 0.0) / PI;
     return true;
 }
-static Vec3 pdf_generate(const ScatterRecord& s, double r1, double r2) {  // pdf.rs:31-33, 59-63
-    if (s.kind == SCATTER_SPHERE) return random_unit_vector(r1, r2);
-    return s.uvw.onb_to_world(random_cosine_direction(r1, r2));
+// PDF::generate; false = None (only the Disney lobes can decline, disney.rs:551,583,600,660)
+static bool pdf_generate(const ScatterRecord& s, const PathCtx& ctx, Vec3& out, bool& error) {  // pdf.rs:31-33, 59-63
+    if (s.kind == SCATTER_DISNEY) return disney::generate(s, ctx, out, error);
+    Rand2 u = ctx.draw(RT_SLOT_DIRECTION);
+    out = s.kind == SCATTER_SPHERE ? random_unit_vector(u.a, u.b) : s.uvw.onb_to_world(random_cosine_direction(u.a, u.b));
+    return true;
 }
 
 // ---------------------------------------------------------------- Hittable and its implementors
@@ -1105,6 +1485,32 @@ static Scene* scene_from_desc(const rt_scene_desc* d, std::string& err) {
                 out = x;
                 break;
             }
+            case RT_MAT_DISNEY: {
+                auto* x = new Disney();
+                DisneyParameters& P = x->params;
+                P.base_color = Vec3(m.color);
+                P.roughness = m.v[RT_DISNEY_ROUGHNESS], P.anisotropic = m.v[RT_DISNEY_ANISOTROPIC], P.sheen = m.v[RT_DISNEY_SHEEN];
+                P.sheen_tint = m.v[RT_DISNEY_SHEEN_TINT], P.clearcoat = m.v[RT_DISNEY_CLEARCOAT], P.clearcoat_gloss = m.v[RT_DISNEY_CLEARCOAT_GLOSS];
+                P.specular_tint = m.v[RT_DISNEY_SPECULAR_TINT], P.metallic = m.v[RT_DISNEY_METALLIC], P.ior = m.v[RT_DISNEY_IOR];
+                P.flatness = m.v[RT_DISNEY_FLATNESS], P.spec_trans = m.v[RT_DISNEY_SPEC_TRANS], P.diff_trans = m.v[RT_DISNEY_DIFF_TRANS];
+                P.thin = m.v[RT_DISNEY_THIN] != 0.0;
+                x->base_color_tex = tex(m.tex);
+                out = x;
+                break;
+            }
+            case RT_MAT_REMAPPED: {
+                auto* x = new RemappedMaterial();
+                x->material = inner(m.inner);
+                if (!x->material || m.inner2 >= d->n_remaps) { err = "bad RemappedMaterial"; delete x; return nullptr; }
+                const rt_remap& r = d->remaps[m.inner2];
+                x->tex_ori = Vec3(r.tex_ori), x->tex_u = Vec3(r.tex_u), x->tex_v = Vec3(r.tex_v);
+                x->u_vec = Vec3(r.u_vec), x->v_vec = Vec3(r.v_vec);
+                for (int k = 0; k < 3; k++) x->normal[k] = Vec3(r.normal[k]);
+                x->has_uv_vecs = r.has_uv_vecs != 0;
+                x->normal_tex = tex(r.normal_tex);
+                out = x;
+                break;
+            }
             default: err = "unknown material kind"; return nullptr;
         }
         sc->materials.emplace_back(out);
@@ -1183,29 +1589,25 @@ static Vec3 ray_color(const Scene& sc, const rt_camera& cam, const Ray& r, uint3
     } else {
         // MixturePDF over (material pdf, HittablePDF(lights)) — camera.rs:297-304, pdf.rs:66-120
         Rand2 pick = ctx.draw(RT_SLOT_MIXTURE);
-        Rand2 dirxi = ctx.draw(RT_SLOT_DIRECTION);
         Vec3 generate_vec;
-        if (sc.lights) {
-            if (pick.a < 0.5) {
-                generate_vec = pdf_generate(srec, dirxi.a, dirxi.b);
-            } else {
-                LightSample ls;
-                ls.leaf = (uint32_t)sc.light_leaves.size() - 1;
-                for (uint32_t i = 0; i < sc.light_leaves.size(); i++)
-                    if (pick.b < sc.light_leaves[i].cdf) {
-                        ls.leaf = i;
-                        break;
-                    }
-                ls.r1 = dirxi.a, ls.r2 = dirxi.b;
-                generate_vec = sc.lights->random(rec.p, ls);
-                if (ls.error) {
-                    error = true;
-                    return Vec3(0, 0, 0);
+        bool generated = true;
+        if (sc.lights && !(pick.a < 0.5)) {
+            Rand2 dirxi = ctx.draw(RT_SLOT_DIRECTION);
+            LightSample ls;
+            ls.leaf = (uint32_t)sc.light_leaves.size() - 1;
+            for (uint32_t i = 0; i < sc.light_leaves.size(); i++)
+                if (pick.b < sc.light_leaves[i].cdf) {
+                    ls.leaf = i;
+                    break;
                 }
-            }
+            ls.r1 = dirxi.a, ls.r2 = dirxi.b;
+            generate_vec = sc.lights->random(rec.p, ls);
+            if (ls.error) error = true;
         } else {
-            generate_vec = pdf_generate(srec, dirxi.a, dirxi.b);
+            generated = pdf_generate(srec, ctx, generate_vec, error);
         }
+        if (error) return Vec3(0, 0, 0);
+        if (!generated) return color_from_emission + Vec3(0, 0, 0);  // `generate()` returned None: Color::BLACK (camera.rs:313-315)
         Ray scattered(rec.p, generate_vec, r.time);
         Vec3 albedo_x_pscatter;
         double value0;

@@ -174,6 +174,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.perlins = track(s, upload(cs.perlins));
         v.media = track(s, upload(cs.media));
         v.lights = track(s, upload(cs.lights));
+        v.remaps = track(s, upload(cs.remaps));
         v.world_root = cs.world_root;
         v.n_media = (uint32_t)cs.media.size();
         v.n_lights = (uint32_t)cs.lights.size();

@@ -171,8 +171,11 @@ struct Compiler {
             !need(d.transforms, d.n_transforms, "transforms") || !need(d.media, d.n_media, "media") ||
             !need(d.materials, d.n_materials, "materials") || !need(d.textures, d.n_textures, "textures") ||
             !need(d.images, d.n_images, "images") || !need(d.texels, d.n_texels, "texels") ||
-            !need(d.perlins, d.n_perlins, "perlins"))
+            !need(d.perlins, d.n_perlins, "perlins") || !need(d.remaps, d.n_remaps, "remaps"))
             return false;
+        for (uint32_t i = 0; i < d.n_remaps; i++)
+            if (d.remaps[i].normal_tex != RT_NONE && (d.remaps[i].normal_tex >= d.n_textures || d.textures[d.remaps[i].normal_tex].kind != RT_TEX_IMAGE))
+                return fail(RT_ERR_INVALID, "remap normal texture must be an image texture");
         for (uint32_t i = 0; i < d.n_textures; i++) {
             const rt_texture& t = d.textures[i];
             switch (t.kind) {
@@ -217,6 +220,13 @@ struct Compiler {
                     if (!tex_ok(false)) return fail(RT_ERR_INVALID, "material texture out of range");
                     if (m.tex != RT_NONE && d.textures[m.tex].kind != RT_TEX_IMAGE)
                         return fail(RT_ERR_INVALID, "Mix ratio texture must be an image");
+                    break;
+                case RT_MAT_DISNEY:
+                    if (!tex_ok(false)) return fail(RT_ERR_INVALID, "material texture out of range");
+                    break;
+                case RT_MAT_REMAPPED:
+                    if (m.inner >= i) return fail(RT_ERR_INVALID, "inner material must precede its wrapper");
+                    if (m.inner2 >= d.n_remaps) return fail(RT_ERR_INVALID, "remap index out of range");
                     break;
                 default: return fail(RT_ERR_INVALID, "unknown material kind");
             }
@@ -272,7 +282,7 @@ struct Compiler {
             m.kind = s.kind, m.tex = s.tex, m.inner = s.inner, m.inner2 = s.inner2;
             for (int k = 0; k < 3; k++) m.color[k] = s.color[k];
             m.param = s.param;
-            for (int k = 0; k < 8; k++) m.v[k] = s.v[k];
+            for (int k = 0; k < 16; k++) m.v[k] = s.v[k];
             m.shade_class = shade_class_of(d, s);
             // does shading this material read the surface coordinates (image / checker lookups)?
             auto tex_uv = [&](uint32_t t) { return t != RT_NONE && (d.textures[t].kind == RT_TEX_IMAGE || d.textures[t].kind == RT_TEX_CHECKER); };
@@ -299,6 +309,9 @@ struct Compiler {
                 out.texels[im.texel_offset + k] = t;
             }
         }
+        out.remaps.resize(d.n_remaps);
+        static_assert(sizeof(Remap) == sizeof(rt_remap), "remap layout");
+        for (uint32_t i = 0; i < d.n_remaps; i++) std::memcpy(&out.remaps[i], &d.remaps[i], sizeof(Remap));
         out.perlins.resize(d.n_perlins);
         for (uint32_t i = 0; i < d.n_perlins; i++) std::memcpy(&out.perlins[i], &d.perlins[i], sizeof(Perlin));
         static_assert(sizeof(Perlin) == sizeof(rt_perlin), "perlin layout");

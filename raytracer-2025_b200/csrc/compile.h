@@ -23,6 +23,7 @@ struct CompiledScene {
     std::vector<Perlin> perlins;
     std::vector<Medium> media;
     std::vector<Light> lights;
+    std::vector<Remap> remaps;
     std::vector<uint32_t> ranks;  // per desc object, RT_NONE for containers
     uint32_t world_root = INVALID_REF;
     uint32_t bvh_depth = 0;

@@ -411,8 +411,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                     hit_ok = surface_hit_info(sv, prim, t, r, sv.materials[mat].needs_uv != 0, h);
                 }
                 if (!hit_ok) error = true;
-                // emitted (camera.rs:290) — only light-carrying materials can return non-black
                 uint32_t mat = h.material;
+                // RemappedMaterial is the per-face wrapper the OBJ loader puts outermost (obj.rs:165-176)
+                while (GENERIC && sv.materials[mat].kind == RT_MAT_REMAPPED) {
+                    if (!remap_record(sv, sv.remaps[sv.materials[mat].inner2], h)) error = true;
+                    mat = sv.materials[mat].inner;
+                }
+                // emitted (camera.rs:290) — only light-carrying materials can return non-black
                 uint32_t mk = sv.materials[mat].kind;
                 if (DO_EMIT && (mk == RT_MAT_DIFFUSE_LIGHT || mk == RT_MAT_MIX)) {
                     D3 e = material_emitted(sv, mat, h);
@@ -440,7 +445,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                     const uint32_t mkind = M.kind;
                     const bool is_metal = DO_METAL && (CLS == SC_METAL || mkind == RT_MAT_METAL);
                     const bool is_dielectric = DO_DIELECTRIC && (CLS == SC_DIELECTRIC || mkind == RT_MAT_DIELECTRIC);
-                    const bool is_pdf = DO_PDF && (!GENERIC || mkind == RT_MAT_EMPTY || mkind == RT_MAT_LAMBERTIAN || mkind == RT_MAT_ISOTROPIC);
+                    const bool is_pdf = DO_PDF && (!GENERIC || mkind == RT_MAT_EMPTY || mkind == RT_MAT_LAMBERTIAN || mkind == RT_MAT_ISOTROPIC ||
+                                                   mkind == RT_MAT_DISNEY);
                     switch (is_metal ? RT_MAT_METAL : is_dielectric ? RT_MAT_DIELECTRIC : is_pdf ? RT_MAT_LAMBERTIAN : (GENERIC ? mkind : 0xFFFFu)) {
                         case RT_MAT_METAL: {  // material.rs:82-95
                             D3 ud, ur;
@@ -499,14 +505,31 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                             alive = true;
                             break;
                         }
-                        case RT_MAT_LAMBERTIAN: {  // Empty / Lambertian / Isotropic
+                        case RT_MAT_LAMBERTIAN: {  // Empty / Lambertian / Isotropic / Disney
                             // ScatterRecord::PDF branch, camera.rs:297-312
                             const bool iso = CLS == SC_ISOTROPIC || (GENERIC && M.kind == RT_MAT_ISOTROPIC);
-                            D3 albedo = M.kind == RT_MAT_EMPTY ? D3{0.75, 0.75, 0.75} : texture_value(sv, M.tex, h.u, h.v, h.p);
+                            const bool dis = GENERIC && M.kind == RT_MAT_DISNEY;
+                            D3 albedo = (M.kind == RT_MAT_EMPTY || dis) ? D3{0.75, 0.75, 0.75} : texture_value(sv, M.tex, h.u, h.v, h.p);
                             ONB uvw;
                             if (!iso && !make_onb(h.normal, uvw)) {
                                 error = true;
                                 break;
+                            }
+                            disney::Params DP;
+                            D3 v_out_l = D3{0.0, 1.0, 0.0};
+                            if (dis) {  // Disney::scatter + DisneyPDF::new, disney.rs:71-91, 522-538
+                                DP.base_color = M.tex == RT_NONE ? ld3(M.color) : texture_value(sv, M.tex, h.u, h.v, h.p);
+                                DP.roughness = M.v[RT_DISNEY_ROUGHNESS], DP.anisotropic = M.v[RT_DISNEY_ANISOTROPIC], DP.sheen = M.v[RT_DISNEY_SHEEN];
+                                DP.sheen_tint = M.v[RT_DISNEY_SHEEN_TINT], DP.clearcoat = M.v[RT_DISNEY_CLEARCOAT];
+                                DP.clearcoat_gloss = M.v[RT_DISNEY_CLEARCOAT_GLOSS], DP.specular_tint = M.v[RT_DISNEY_SPECULAR_TINT];
+                                DP.metallic = M.v[RT_DISNEY_METALLIC], DP.ior = M.v[RT_DISNEY_IOR], DP.flatness = M.v[RT_DISNEY_FLATNESS];
+                                DP.spec_trans = M.v[RT_DISNEY_SPEC_TRANS], DP.diff_trans = M.v[RT_DISNEY_DIFF_TRANS], DP.thin = M.v[RT_DISNEY_THIN] != 0.0;
+                                D3 vo;
+                                if (!unit_vector(-r.d, vo)) {
+                                    error = true;
+                                    break;
+                                }
+                                v_out_l = D3{dot(vo, uvw.u), dot(vo, uvw.v), dot(vo, uvw.w)};  // world_to_onb, onb.rs:40-45
                             }
                             Rand2 pick = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_MIXTURE);
                             Rand2 dx = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_DIRECTION);
@@ -517,10 +540,18 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                                     error = true;
                                     break;
                                 }
+                            } else if (dis) {
+                                Rand2 dpick = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_DISNEY);
+                                D3 v_in_l;
+                                if (!disney::generate_local(DP, v_out_l, h.front_face, dpick, dx, v_in_l, error)) break;  // None: black (camera.rs:313-315)
+                                if (!unit_vector(onb_to_world(uvw, v_in_l), gen)) {
+                                    error = true;
+                                    break;
+                                }
                             } else {
                                 gen = iso ? random_unit_vector(dx.a, dx.b) : onb_to_world(uvw, random_cosine_direction(dx.a, dx.b));
                             }
-                            // PDF::value, pdf.rs:22-29, 51-57
+                            // PDF::value, pdf.rs:22-29, 51-57, disney.rs:656-666
                             D3 axp;
                             double value0;
                             if (iso) {
@@ -532,9 +563,15 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                                     error = true;
                                     break;
                                 }
-                                double cosine_theta = dot(ud, uvw.v);
-                                value0 = rmax(0.0, cosine_theta / RT_PI);
-                                axp = albedo * rmax(cosine_theta, 0.0) / RT_PI;
+                                if (dis) {
+                                    D3 v_in_l = D3{dot(ud, uvw.u), dot(ud, uvw.v), dot(ud, uvw.w)};
+                                    disney::evaluate_disney(DP, v_out_l, v_in_l, h.front_face, axp, value0, error);
+                                    if (error) break;
+                                } else {
+                                    double cosine_theta = dot(ud, uvw.v);
+                                    value0 = rmax(0.0, cosine_theta / RT_PI);
+                                    axp = albedo * rmax(cosine_theta, 0.0) / RT_PI;
+                                }
                             }
                             double pdf_val = value0;
                             if (have_lights) {

@@ -60,8 +60,16 @@ struct Material {
     uint32_t kind, tex, inner, inner2;
     double color[3];
     double param;
-    double v[8];
+    double v[16];
     uint32_t shade_class, needs_uv;
+};
+
+// RemappedMaterial payload (shapes/obj.rs:20-29)
+struct Remap {
+    double tex_ori[3], tex_u[3], tex_v[3];
+    double u_vec[3], v_vec[3];
+    double normal[3][3];
+    uint32_t has_uv_vecs, normal_tex;
 };
 
 struct Texture {
@@ -126,6 +134,7 @@ struct SceneView {
     const Perlin* perlins;
     const Medium* media;
     const Light* lights;
+    const Remap* remaps;
     uint32_t world_root;
     uint32_t n_media, n_lights, n_prims;
     uint32_t n_nodes;

@@ -1,6 +1,7 @@
 // shade.cuh — textures, materials, pdfs and light sampling on the device, in the reference's
 // operation order (texture.rs, material.rs, pdf.rs, utils/perlin.rs, shapes/*.rs pdf_value/random).
 #pragma once
+#include "disney.cuh"
 #include "traverse.cuh"
 
 namespace rt {
@@ -171,6 +172,26 @@ __device__ inline bool surface_hit_info(const SceneView& sv, uint32_t prim, doub
     h.normal = h.front_face ? outward : -outward;
     if (m.xform != RT_NONE) return hit_to_world(sv, m.xform, h);
     return true;
+}
+
+// RemappedMaterial::remap_record, shapes/obj.rs:32-62: texture coordinates from the face's uv frame,
+// the interpolated (and optionally normal-mapped) shading normal; front_face is kept as it is
+__device__ inline bool remap_record(const SceneView& sv, const Remap& rm, HitInfo& h) {
+    bool ok = true;
+    D3 tex_coord = ld3(rm.tex_ori) + h.u * ld3(rm.tex_u) + h.v * ld3(rm.tex_v);
+    D3 n;
+    ok = unit_vector((1.0 - h.u - h.v) * ld3(rm.normal[0]) + h.u * ld3(rm.normal[1]) + h.v * ld3(rm.normal[2]), n);
+    if (rm.normal_tex != RT_NONE) {
+        D3 c = texture_value(sv, rm.normal_tex, tex_coord.x, tex_coord.y, h.p);
+        c = c * 2.0 - D3{1.0, 1.0, 1.0};
+        if (!rm.has_uv_vecs) ok = false;  // .unwrap() on None
+        D3 raw = ld3(rm.u_vec) * c.x + ld3(rm.v_vec) * c.y + n * c.z;
+        ok = unit_vector(raw, n) && ok;
+    }
+    h.normal = n;
+    h.u = tex_coord.x;
+    h.v = tex_coord.y;
+    return ok;
 }
 
 // ---- lights: Hittables::pdf_value / random over the flattened leaves (hits.rs:52-75) -----------

@@ -120,9 +120,38 @@ uint32_t rth_mat_transparent(rth_builder* b) { return push(b->mat, std::make_sha
 uint32_t rth_mat_mix(rth_builder* b, uint32_t m1, uint32_t m2, double ratio) {
     return push(b->mat, std::make_shared<Mix>(b->mat.at(m1), b->mat.at(m2), ratio));
 }
+// Mix::from_image(mat1, mat2, tex): the ratio is the image's alpha (material.rs:236-247)
+uint32_t rth_mat_mix_image(rth_builder* b, uint32_t m1, uint32_t m2, uint32_t tex) {
+    auto it = std::dynamic_pointer_cast<const ImageTexture>(b->tex.at(tex));
+    if (!it) {
+        g_err = "Mix::from_image needs an ImageTexture";
+        return RT_NONE;
+    }
+    return push(b->mat, Mix::from_image(b->mat.at(m1), b->mat.at(m2), it));
+}
 uint32_t rth_mat_portal(rth_builder* b, const double* att, const double* offset, const double* quat_wxyz) {
     Quaternion q{quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3]};
     return push(b->mat, std::make_shared<Portal>(V(att), V(offset), q));
+}
+
+// params: the 13 DisneyParameters scalars in RT_DISNEY_* order; tex = base-colour texture or RT_NONE
+uint32_t rth_mat_disney(rth_builder* b, const double* base_color, uint32_t tex, const double* params) {
+    DisneyParameters p;
+    p.base_color = V(base_color);
+    p.roughness = params[RT_DISNEY_ROUGHNESS], p.anisotropic = params[RT_DISNEY_ANISOTROPIC], p.sheen = params[RT_DISNEY_SHEEN];
+    p.sheen_tint = params[RT_DISNEY_SHEEN_TINT], p.clearcoat = params[RT_DISNEY_CLEARCOAT], p.clearcoat_gloss = params[RT_DISNEY_CLEARCOAT_GLOSS];
+    p.specular_tint = params[RT_DISNEY_SPECULAR_TINT], p.metallic = params[RT_DISNEY_METALLIC], p.ior = params[RT_DISNEY_IOR];
+    p.flatness = params[RT_DISNEY_FLATNESS], p.spec_trans = params[RT_DISNEY_SPEC_TRANS], p.diff_trans = params[RT_DISNEY_DIFF_TRANS];
+    p.thin = params[RT_DISNEY_THIN] != 0.0;
+    return push(b->mat, std::make_shared<Disney>(p, tex == RT_NONE ? nullptr : b->tex.at(tex)));
+}
+// one face of an OBJ model as load_object builds it (obj.rs:143-183): pos/uv/nrm are 3x3 doubles
+// (uv rows are (u, v, 0)); returns the RemappedMaterial handle
+uint32_t rth_mat_remapped(rth_builder* b, uint32_t inner, const double* pos, const double* uv, const double* nrm, uint32_t normal_tex) {
+    std::shared_ptr<const ImageTexture> nt;
+    if (normal_tex != RT_NONE) nt = std::dynamic_pointer_cast<const ImageTexture>(b->tex.at(normal_tex));
+    return push(b->mat, std::make_shared<RemappedMaterial>(b->mat.at(inner), V(pos), V(pos + 3), V(pos + 6), V(uv), V(uv + 3), V(uv + 6),
+                                                           V(nrm), V(nrm + 3), V(nrm + 6), nt));
 }
 
 uint32_t rth_sphere(rth_builder* b, const double* c, double r, uint32_t mat) {

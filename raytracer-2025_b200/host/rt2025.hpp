@@ -218,6 +218,7 @@ class Flattener {
     std::vector<rt_image> images;
     std::vector<float> texels;
     std::vector<rt_perlin> perlins;
+    std::vector<rt_remap> remaps;
     uint32_t world_root = RT_NONE, lights_root = RT_NONE;
 
     uint32_t texture(const std::shared_ptr<const Texture>& t);
@@ -257,6 +258,8 @@ class Flattener {
         d.n_images = (uint32_t)images.size();
         d.n_perlins = (uint32_t)perlins.size();
         d.n_texels = texels.size();
+        d.n_remaps = (uint32_t)remaps.size();
+        d.remaps = remaps.data();
         d.objects = objects.data();
         d.children = children.data();
         d.spheres = spheres.data();
@@ -551,6 +554,102 @@ class Portal : public Material {  // material/portal.rs:9-31 — the closure is 
     Color att_;
     Vec3 off_;
     Quaternion q_;
+};
+
+// material/disney.rs:18-116,718-805.  `param_fn` closures become data: the parameters are either
+// constants (DisneyBuilder) or constants + a base-colour texture (the OBJ loader, obj.rs:271-293).
+struct DisneyParameters {
+    Color base_color{0.8, 0.8, 0.8};
+    double roughness = 0.5, anisotropic = 0.0, sheen = 0.0, sheen_tint = 0.0, clearcoat = 0.0, clearcoat_gloss = 0.0;
+    double specular_tint = 0.0, metallic = 0.0, ior = 1.45, flatness = 0.0, spec_trans = 0.0, diff_trans = 0.0;
+    bool thin = false;
+};
+class Disney : public Material {
+  public:
+    Disney() = default;
+    explicit Disney(const DisneyParameters& p, TexturePtr base_color_tex = nullptr) : p_(p), tex_(std::move(base_color_tex)) {}
+    rt_material flatten(Flattener& f) const override {
+        auto m = blank(RT_MAT_DISNEY);
+        for (int i = 0; i < 3; i++) m.color[i] = p_.base_color[i];
+        if (tex_) m.tex = f.texture(tex_);
+        m.v[RT_DISNEY_ROUGHNESS] = p_.roughness, m.v[RT_DISNEY_ANISOTROPIC] = p_.anisotropic, m.v[RT_DISNEY_SHEEN] = p_.sheen;
+        m.v[RT_DISNEY_SHEEN_TINT] = p_.sheen_tint, m.v[RT_DISNEY_CLEARCOAT] = p_.clearcoat, m.v[RT_DISNEY_CLEARCOAT_GLOSS] = p_.clearcoat_gloss;
+        m.v[RT_DISNEY_SPECULAR_TINT] = p_.specular_tint, m.v[RT_DISNEY_METALLIC] = p_.metallic, m.v[RT_DISNEY_IOR] = p_.ior;
+        m.v[RT_DISNEY_FLATNESS] = p_.flatness, m.v[RT_DISNEY_SPEC_TRANS] = p_.spec_trans, m.v[RT_DISNEY_DIFF_TRANS] = p_.diff_trans;
+        m.v[RT_DISNEY_THIN] = p_.thin ? 1.0 : 0.0;
+        return m;
+    }
+
+  private:
+    DisneyParameters p_;
+    TexturePtr tex_;
+};
+// the fluent DisneyBuilder of disney.rs:718-805
+class DisneyBuilder {
+  public:
+    DisneyBuilder& base_color(const Color& c) { p_.base_color = c; return *this; }
+    DisneyBuilder& roughness(double v) { p_.roughness = v; return *this; }
+    DisneyBuilder& anisotropic(double v) { p_.anisotropic = v; return *this; }
+    DisneyBuilder& sheen(double v) { p_.sheen = v; return *this; }
+    DisneyBuilder& sheen_tint(double v) { p_.sheen_tint = v; return *this; }
+    DisneyBuilder& clearcoat(double v) { p_.clearcoat = v; return *this; }
+    DisneyBuilder& clearcoat_gloss(double v) { p_.clearcoat_gloss = v; return *this; }
+    DisneyBuilder& specular_tint(double v) { p_.specular_tint = v; return *this; }
+    DisneyBuilder& metallic(double v) { p_.metallic = v; return *this; }
+    DisneyBuilder& ior(double v) { p_.ior = v; return *this; }
+    DisneyBuilder& flatness(double v) { p_.flatness = v; return *this; }
+    DisneyBuilder& spec_trans(double v) { p_.spec_trans = v; return *this; }
+    DisneyBuilder& diff_trans(double v) { p_.diff_trans = v; return *this; }
+    DisneyBuilder& thin(bool v) { p_.thin = v; return *this; }
+    std::shared_ptr<Disney> build() const { return std::make_shared<Disney>(p_); }
+
+  private:
+    DisneyParameters p_;
+};
+
+// shapes/obj.rs:20-81,150-176,196-211: the per-face material the OBJ loader wraps around a mesh material
+class RemappedMaterial : public Material {
+  public:
+    // what load_object computes for one face: positions p1..p3, texture coordinates t1..t3 (z = 0),
+    // vertex normals n1..n3, the model's raw normal map (or none)
+    RemappedMaterial(MaterialPtr material, const Point3& p1, const Point3& p2, const Point3& p3, const Vec3& t1, const Vec3& t2,
+                     const Vec3& t3, const Vec3& n1, const Vec3& n2, const Vec3& n3, std::shared_ptr<const ImageTexture> normal_tex)
+        : material_(std::move(material)), normal_tex_(std::move(normal_tex)) {
+        tex_ori_ = t1;
+        tex_u_ = t2 - t1;
+        tex_v_ = t3 - t1;
+        Vec3 world_u = p2 - p1, world_v = p3 - p1;
+        // uv_local_to_world, obj.rs:196-211
+        double ua = tex_v_.y() / (-tex_u_.y() * tex_v_.x() + tex_u_.x() * tex_v_.y());
+        double ub = tex_u_.y() / (tex_u_.y() * tex_v_.x() - tex_u_.x() * tex_v_.y());
+        double va = tex_v_.x() / (tex_u_.y() * tex_v_.x() - tex_u_.x() * tex_v_.y());
+        double vb = tex_u_.x() / (-tex_u_.y() * tex_v_.x() + tex_u_.x() * tex_v_.y());
+        auto uv = unit_vector(world_u * ua + world_v * ub), vv = unit_vector(world_u * va + world_v * vb);
+        has_uv_ = uv.has_value() && vv.has_value();
+        if (has_uv_) u_vec_ = *uv, v_vec_ = *vv;
+        normal_[0] = n1, normal_[1] = n2, normal_[2] = n3;
+    }
+    rt_material flatten(Flattener& f) const override {
+        auto m = blank(RT_MAT_REMAPPED);
+        m.inner = f.material(material_);
+        rt_remap r{};
+        for (int i = 0; i < 3; i++) {
+            r.tex_ori[i] = tex_ori_[i], r.tex_u[i] = tex_u_[i], r.tex_v[i] = tex_v_[i];
+            r.u_vec[i] = u_vec_[i], r.v_vec[i] = v_vec_[i];
+            for (int k = 0; k < 3; k++) r.normal[k][i] = normal_[k][i];
+        }
+        r.has_uv_vecs = has_uv_ ? 1u : 0u;
+        r.normal_tex = normal_tex_ ? f.texture(normal_tex_) : RT_NONE;
+        f.remaps.push_back(r);
+        m.inner2 = (uint32_t)f.remaps.size() - 1;
+        return m;
+    }
+
+  private:
+    MaterialPtr material_;
+    Vec3 tex_ori_, tex_u_, tex_v_, u_vec_, v_vec_, normal_[3];
+    bool has_uv_ = false;
+    std::shared_ptr<const ImageTexture> normal_tex_;
 };
 
 // ---- hit.rs: Hittable ------------------------------------------------------------------

@@ -95,9 +95,10 @@ class rt_scene_desc(C.Structure):
         ("n_objects", C.c_uint32), ("n_children", C.c_uint32), ("n_spheres", C.c_uint32), ("n_planars", C.c_uint32),
         ("n_transforms", C.c_uint32), ("n_media", C.c_uint32), ("n_materials", C.c_uint32), ("n_textures", C.c_uint32),
         ("n_images", C.c_uint32), ("n_perlins", C.c_uint32), ("n_texels", C.c_uint64),
+        ("n_remaps", C.c_uint32), ("reserved0", C.c_uint32),
         ("objects", C.c_void_p), ("children", C.c_void_p), ("spheres", C.c_void_p), ("planars", C.c_void_p),
         ("transforms", C.c_void_p), ("media", C.c_void_p), ("materials", C.c_void_p), ("textures", C.c_void_p),
-        ("images", C.c_void_p), ("texels", C.c_void_p), ("perlins", C.c_void_p),
+        ("images", C.c_void_p), ("texels", C.c_void_p), ("perlins", C.c_void_p), ("remaps", C.c_void_p),
     ]
 
 
@@ -154,7 +155,10 @@ def host_lib():
             "rth_mat_isotropic": [C.c_void_p, C.c_uint32],
             "rth_mat_transparent": [C.c_void_p],
             "rth_mat_mix": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_double],
+            "rth_mat_mix_image": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32],
             "rth_mat_portal": [C.c_void_p, D3, D3, D3],
+            "rth_mat_disney": [C.c_void_p, D3, C.c_uint32, D3],
+            "rth_mat_remapped": [C.c_void_p, C.c_uint32, D3, D3, D3, C.c_uint32],
             "rth_sphere": [C.c_void_p, D3, C.c_double, C.c_uint32],
             "rth_sphere_moving": [C.c_void_p, D3, D3, C.c_double, C.c_uint32],
             "rth_quad": [C.c_void_p, D3, D3, D3, C.c_uint32],
@@ -280,7 +284,34 @@ class Builder:
     def isotropic(self, tex): return self.L.rth_mat_isotropic(self.b, tex)
     def transparent(self): return self.L.rth_mat_transparent(self.b)
     def mix(self, m1, m2, ratio): return self.L.rth_mat_mix(self.b, m1, m2, ratio)
+    def mix_image(self, m1, m2, tex): return self.L.rth_mat_mix_image(self.b, m1, m2, tex)
     def portal(self, att, offset, quat): return self.L.rth_mat_portal(self.b, _d3(att), _d3(offset), _d3(quat))
+
+    DISNEY_ORDER = ["roughness", "anisotropic", "sheen", "sheen_tint", "clearcoat", "clearcoat_gloss", "specular_tint", "metallic",
+                    "ior", "flatness", "spec_trans", "diff_trans", "thin"]
+    DISNEY_DEFAULTS = dict(roughness=0.5, anisotropic=0.0, sheen=0.0, sheen_tint=0.0, clearcoat=0.0, clearcoat_gloss=0.0,
+                           specular_tint=0.0, metallic=0.0, ior=1.45, flatness=0.0, spec_trans=0.0, diff_trans=0.0, thin=0.0)
+
+    def disney(self, base_color=(0.8, 0.8, 0.8), tex=RT_NONE, **params):
+        """Disney::builder()...build() (material/disney.rs:718-805); tex = base-colour texture as the OBJ loader uses."""
+        p = dict(self.DISNEY_DEFAULTS)
+        for k, v in params.items():
+            assert k in p, k
+            p[k] = float(v)
+        return self.L.rth_mat_disney(self.b, _d3(base_color), tex, _d3([p[k] for k in self.DISNEY_ORDER]))
+
+    def remapped(self, inner, pos, uv, nrm, normal_tex=RT_NONE):
+        """RemappedMaterial for one OBJ face (shapes/obj.rs:143-183): pos, nrm 3x3; uv 3x2."""
+        uv3 = [[float(a), float(b), 0.0] for a, b in uv]
+        flat = lambda m: _d3([x for row in m for x in row])
+        return self.L.rth_mat_remapped(self.b, inner, flat(pos), flat(uv3), flat(nrm), normal_tex)
+
+    def obj_face(self, inner, pos, uv, nrm, normal_tex=RT_NONE):
+        """One face as load_object emits it: Triangle::new(p1, p2-p1, p3-p1, RemappedMaterial{..}); RT_NONE if degenerate."""
+        m = self.remapped(inner, pos, uv, nrm, normal_tex)
+        p1, p2, p3 = [np.asarray(p, dtype=np.float64) for p in pos]
+        return self.triangle(p1, p2 - p1, p3 - p1, m)
+
     # shapes and containers
     def sphere(self, c, r, mat): return self.L.rth_sphere(self.b, _d3(c), r, mat)
     def sphere_moving(self, c1, c2, r, mat): return self.L.rth_sphere_moving(self.b, _d3(c1), _d3(c2), r, mat)

@@ -23,6 +23,8 @@ pub const RT_MAT_ISOTROPIC: u32 = 5;
 pub const RT_MAT_TRANSPARENT: u32 = 6;
 pub const RT_MAT_MIX: u32 = 7;
 pub const RT_MAT_PORTAL: u32 = 8;
+pub const RT_MAT_DISNEY: u32 = 9;
+pub const RT_MAT_REMAPPED: u32 = 10;
 
 pub const RT_TEX_SOLID: u32 = 0;
 pub const RT_TEX_CHECKER: u32 = 1;
@@ -46,7 +48,9 @@ pub struct rt_transform { pub offset: [f64; 3], pub quat: [f64; 4], pub scale: [
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rt_medium { pub neg_inv_density: f64, pub reserved: f64 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
-pub struct rt_material { pub kind: u32, pub tex: u32, pub inner: u32, pub inner2: u32, pub color: [f64; 3], pub param: f64, pub v: [f64; 8] }
+pub struct rt_material { pub kind: u32, pub tex: u32, pub inner: u32, pub inner2: u32, pub color: [f64; 3], pub param: f64, pub v: [f64; 16] }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct rt_remap { pub tex_ori: [f64; 3], pub tex_u: [f64; 3], pub tex_v: [f64; 3], pub u_vec: [f64; 3], pub v_vec: [f64; 3], pub normal: [[f64; 3]; 3], pub has_uv_vecs: u32, pub normal_tex: u32 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rt_texture { pub kind: u32, pub a: u32, pub b: u32, pub reserved: u32, pub color: [f64; 3], pub color2: [f64; 3], pub scale: f64, pub reserved2: f64 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
@@ -59,10 +63,10 @@ pub struct rt_scene_desc {
     pub version: u32, pub struct_size: u32, pub world_root: u32, pub lights_root: u32,
     pub n_objects: u32, pub n_children: u32, pub n_spheres: u32, pub n_planars: u32,
     pub n_transforms: u32, pub n_media: u32, pub n_materials: u32, pub n_textures: u32,
-    pub n_images: u32, pub n_perlins: u32, pub n_texels: u64,
+    pub n_images: u32, pub n_perlins: u32, pub n_texels: u64, pub n_remaps: u32, pub reserved0: u32,
     pub objects: *const rt_object, pub children: *const u32, pub spheres: *const rt_sphere, pub planars: *const rt_planar,
     pub transforms: *const rt_transform, pub media: *const rt_medium, pub materials: *const rt_material,
-    pub textures: *const rt_texture, pub images: *const rt_image, pub texels: *const f32, pub perlins: *const rt_perlin,
+    pub textures: *const rt_texture, pub images: *const rt_image, pub texels: *const f32, pub perlins: *const rt_perlin, pub remaps: *const rt_remap,
 }
 
 #[repr(C)] #[derive(Clone, Copy, Default)]

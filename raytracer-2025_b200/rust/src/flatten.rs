@@ -11,7 +11,7 @@ pub struct Unsupported(pub &'static str);
 pub struct Flattener {
     pub objects: Vec<rt_object>, pub children: Vec<u32>, pub spheres: Vec<rt_sphere>, pub planars: Vec<rt_planar>,
     pub transforms: Vec<rt_transform>, pub media: Vec<rt_medium>, pub materials: Vec<rt_material>,
-    pub textures: Vec<rt_texture>, pub images: Vec<rt_image>, pub texels: Vec<f32>, pub perlins: Vec<rt_perlin>,
+    pub textures: Vec<rt_texture>, pub images: Vec<rt_image>, pub texels: Vec<f32>, pub perlins: Vec<rt_perlin>, pub remaps: Vec<rt_remap>,
     tex_ids: HashMap<usize, u32>, mat_ids: HashMap<usize, u32>,
 }
 
@@ -51,10 +51,10 @@ impl Flattener {
             n_objects: self.objects.len() as u32, n_children: self.children.len() as u32, n_spheres: self.spheres.len() as u32,
             n_planars: self.planars.len() as u32, n_transforms: self.transforms.len() as u32, n_media: self.media.len() as u32,
             n_materials: self.materials.len() as u32, n_textures: self.textures.len() as u32, n_images: self.images.len() as u32,
-            n_perlins: self.perlins.len() as u32, n_texels: self.texels.len() as u64,
+            n_perlins: self.perlins.len() as u32, n_texels: self.texels.len() as u64, n_remaps: self.remaps.len() as u32, reserved0: 0,
             objects: self.objects.as_ptr(), children: self.children.as_ptr(), spheres: self.spheres.as_ptr(), planars: self.planars.as_ptr(),
             transforms: self.transforms.as_ptr(), media: self.media.as_ptr(), materials: self.materials.as_ptr(),
-            textures: self.textures.as_ptr(), images: self.images.as_ptr(), texels: self.texels.as_ptr(), perlins: self.perlins.as_ptr(),
+            textures: self.textures.as_ptr(), images: self.images.as_ptr(), texels: self.texels.as_ptr(), perlins: self.perlins.as_ptr(), remaps: self.remaps.as_ptr(),
         }
     }
 }
@@ -85,6 +85,9 @@ impl Flattener {
 //         Ok(f.push_object(RT_OBJ_MEDIUM, mat, f.media.len() as u32 - 1, self.boundary.bounding_box(), &[kid]))
 // impl Material for Lambertian / Metal / Dielectric / DiffuseLight / Isotropic / Transparent / Mix / Portal:
 //         one rt_material each (kind, tex, inner, inner2, color, param, v) exactly as host/rt2025.hpp does.
+// impl Material for Disney: the `param_fn` closure is only ever built from constants (DisneyBuilder::build) or constants +
+//         a base-colour texture (obj.rs:271-293), so Disney stores those next to the closure and emits RT_MAT_DISNEY.
+// impl Material for RemappedMaterial (obj.rs): one rt_remap (tex_ori, tex_u, tex_v, u_vec, v_vec, normal[3], normal_tex) + RT_MAT_REMAPPED.
 // impl Texture for SolidColor / CheckerTexture / ImageTexture / NoiseTexture: one rt_texture each; ImageTexture copies
 //         its Rgba32F pixels into f.texels and sets RT_IMG_LINEAR for raw / Hdr / OpenExr / Avif, RT_IMG_INTERP for
 //         ImageInterpMethod::Linear; NoiseTexture copies its Perlin tables into f.perlins.

@@ -91,3 +91,83 @@ def compare_hits(rt, got, want, rel=0.0):
         assert np.abs(got["u"][hit] - want["u"][hit]).max() < 1e-6
         assert np.abs(got["v"][hit] - want["v"][hit]).max() < 1e-6
     assert np.all(np.isinf(got["t"][~hit]))
+
+
+def disney_scene(rt, with_lights=True, width=64, spp=16, depth=8, seed=2):
+    """Five Disney spheres covering every lobe + one with a base-colour image texture (obj.rs:271-293)."""
+    rng = np.random.default_rng(seed)
+    b = rt.Builder(seed)
+    white = b.lambertian(b.solid(0.7, 0.7, 0.7))
+    light = b.diffuse_light(b.solid(8, 8, 8))
+    tex = b.image(rng.uniform(0.1, 1, (8, 16, 4)).astype(np.float32))
+    mats = [b.disney((0.8, 0.3, 0.2), roughness=0.4),
+            b.disney((0.9, 0.8, 0.3), metallic=1.0, roughness=0.3, anisotropic=0.5),
+            b.disney((0.9, 0.9, 0.9), spec_trans=1.0, roughness=0.1, ior=1.5),
+            b.disney((0.2, 0.4, 0.8), clearcoat=1.0, clearcoat_gloss=0.9, sheen=0.5, sheen_tint=0.5, roughness=0.6, specular_tint=0.3),
+            b.disney((0.6, 0.8, 0.6), thin=1.0, flatness=0.5, diff_trans=0.5, spec_trans=0.3, roughness=0.5),
+            b.disney((1, 1, 1), tex=tex, roughness=0.7, metallic=0.2, spec_trans=0.2, clearcoat=0.3)]
+    objs = [b.quad([-9, -1, -8], [18, 0, 0], [0, 0, 16], white), b.quad([-2, 5, -2], [4, 0, 0], [0, 0, 4], light)]
+    for k, m in enumerate(mats):
+        objs.append(b.sphere([k * 2.2 - 5.5, 0, 0], 1.0, m))
+    lights = b.list([b.quad([-2, 5, -2], [4, 0, 0], [0, 0, 4], b.empty())]) if with_lights else rt.RT_NONE
+    hs = b.finish(b.list([b.bvh(objs)]), lights, width=width, aspect=2.0, spp=spp, max_depth=depth, vfov=38, look_from=(0, 3, 13),
+                  look_at=(0, 0, 0), background=b.solid(0.1, 0.1, 0.15))
+    hs._builder = b
+    return hs
+
+
+def obj_mesh_scene(rt, width=56, spp=16, depth=8, seed=3):
+    """A small mesh built face by face the way shapes/obj.rs load_object does: every triangle carries its
+    own RemappedMaterial (uv frame, smooth vertex normals, raw normal map), models in their own BVH."""
+    rng = np.random.default_rng(seed)
+    b = rt.Builder(seed)
+    albedo = b.image(rng.uniform(0.2, 1, (16, 16, 4)).astype(np.float32))
+    nm = rng.uniform(0.35, 0.65, (8, 8, 4)).astype(np.float32)
+    nm[..., 2] = rng.uniform(0.8, 1.0, (8, 8))
+    normal_map = b.image(nm, raw=True)
+    alpha = rng.uniform(0, 1, (8, 8, 4)).astype(np.float32)
+    alpha[..., 3] = (rng.uniform(0, 1, (8, 8)) > 0.3)
+    alpha_tex = b.image(alpha)
+    inner = [b.lambertian(albedo), b.disney((1, 1, 1), tex=albedo, roughness=0.4, metallic=0.3),
+             b.diffuse_light(b.solid(0.4, 0.3, 0.2), inner=b.disney((0.7, 0.7, 0.9), roughness=0.5))]
+    # Mix::from_image(Transparent, mat, alpha texture) as for `dissolve_texture` (obj.rs:318-325) and the
+    # constant-ratio Mix of `dissolve < 1` (obj.rs:326-330)
+    inner.append(b.mix_image(b.transparent(), inner[0], alpha_tex))
+    inner.append(b.mix(b.transparent(), inner[1], 0.6))
+    n = 6
+    xs = np.linspace(-3, 3, n + 1)
+
+    def height(x, z):
+        return 0.4 * np.sin(1.3 * x) * np.cos(1.1 * z)
+
+    def vertex(i, j):
+        x, z = xs[i], xs[j]
+        p = np.array([x, height(x, z), z])
+        dx, dz = 0.4 * 1.3 * np.cos(1.3 * x) * np.cos(1.1 * z), -0.4 * 1.1 * np.sin(1.3 * x) * np.sin(1.1 * z)
+        nrm = np.array([-dx, 1.0, -dz])
+        return p, np.array([i / n, j / n]), nrm / np.linalg.norm(nrm)
+
+    models = []
+    for k, mat in enumerate(inner):
+        faces = []
+        for i in range(n):
+            for j in range(n):
+                if (i + j) % len(inner) != k:
+                    continue
+                quad = [vertex(i, j), vertex(i + 1, j), vertex(i + 1, j + 1), vertex(i, j + 1)]
+                for tri in ((0, 1, 2), (0, 2, 3)):
+                    pos = [quad[t][0] for t in tri]
+                    uv = [quad[t][1] for t in tri]
+                    nr = [quad[t][2] for t in tri]
+                    f = b.obj_face(mat, pos, uv, nr, normal_map if k % 2 == 0 else rt.RT_NONE)
+                    if f != rt.RT_NONE:
+                        faces.append(f)
+        models.append(b.bvh(faces))
+    wavefont = b.list(models)
+    light = b.quad([-2, 5, -2], [4, 0, 0], [0, 0, 4], b.diffuse_light(b.solid(9, 9, 9)))
+    floor = b.quad([-8, -2, -8], [16, 0, 0], [0, 0, 16], b.lambertian(b.solid(0.6, 0.6, 0.6)))
+    lights = b.list([b.quad([-2, 5, -2], [4, 0, 0], [0, 0, 4], b.empty())])
+    hs = b.finish(b.list([wavefont, light, floor]), lights, width=width, spp=spp, max_depth=depth, vfov=40, look_from=(0, 5, 9), look_at=(0, 0, 0),
+                  background=b.solid(0.15, 0.15, 0.2))
+    hs._builder = b
+    return hs

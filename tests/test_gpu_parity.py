@@ -365,3 +365,29 @@ def test_cpp_dropin_camera_render(gpu, rt, tmp_path):
     want = rt.tonemap(img, 0)
     assert np.array_equal(got, want)
     assert got.mean() > 20
+
+
+def test_disney_vs_oracle(gpu, rt, orc):
+    from scenes_util import disney_scene
+    for lights in (True, False):
+        hs = disney_scene(rt, lights, width=64, spp=16)
+        sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+        img, st = sc.render(seed=9)
+        ref, ost = osc.render(seed=9)
+        assert st.paths == ost.paths and int(st.errors) <= int(ost.errors)
+        image_close(img, ref, frac_bad=5e-3)
+
+
+def test_obj_faces_with_remapped_materials_vs_oracle(gpu, rt, orc):
+    from scenes_util import obj_mesh_scene
+    hs = obj_mesh_scene(rt)
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    rng = np.random.default_rng(1)
+    o, d, t = random_rays(rng, 20000, extent=4.0)
+    rays = rt.make_rays(o, d, t)
+    got, _ = sc.closest_hit(rays)
+    compare_hits(rt, got, osc.closest_hit(rays, mode=0))
+    img, st = sc.render(seed=4)
+    ref, ost = osc.render(seed=4)
+    assert st.paths == ost.paths and int(st.errors) <= int(ost.errors)
+    image_close(img, ref, frac_bad=5e-3)

@@ -164,3 +164,31 @@ def test_tonemap_curve(orc):
     m = np.clip(x * (2.51 * x + 0.03) / (x * (2.43 * x + 0.59) + 0.14), 0, 1)
     enc = np.where(m <= 0.0031308, 12.92 * m, 1.055 * m ** (1 / 2.4) - 0.055)
     assert aces[0, 0].tolist() == np.round(enc * 255).astype(int).tolist()
+
+
+def test_disney_oracle_is_sane(rt, orc):
+    """material/disney.rs has no vectors in the reference (parity unpinned).  Sanity only: no panics,
+    light sampling does not change the expectation much, and a white environment is not amplified."""
+    from scenes_util import disney_scene
+    a, sa = orc.OracleScene(disney_scene(rt, True, width=48, spp=144)).render(seed=4)
+    c, sc = orc.OracleScene(disney_scene(rt, False, width=48, spp=144)).render(seed=4)
+    assert sa.errors == 0 and sc.errors == 0
+    assert abs(a.mean() - c.mean()) < 0.08 * c.mean()
+    # furnace: one Disney sphere under a uniform white sky never looks brighter than the sky by more than noise
+    for params in (dict(roughness=0.5), dict(metallic=1.0, roughness=0.2), dict(clearcoat=1.0, roughness=0.7),
+                   dict(spec_trans=1.0, roughness=0.3)):
+        b = rt.Builder(1)
+        s = b.sphere([0, 0, 0], 1.0, b.disney((1, 1, 1), **params))
+        hs = b.finish(b.list([s]), width=24, spp=64, max_depth=12, vfov=25, look_from=(0, 0, 6), background=b.solid(1, 1, 1))
+        img, st = orc.OracleScene(hs).render(seed=2)
+        assert st.errors == 0
+        assert img.mean() < 1.15, params
+
+
+def test_remapped_material_oracle(rt, orc):
+    from scenes_util import obj_mesh_scene
+    hs = obj_mesh_scene(rt, width=32, spp=9)
+    d = hs.desc.contents
+    assert d.n_remaps == 72 and d.n_images == 3 and d.n_materials > 72
+    img, st = orc.OracleScene(hs).render(seed=1)
+    assert st.errors == 0 and np.isfinite(img).all() and img.mean() > 0.01
