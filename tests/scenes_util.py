@@ -171,3 +171,104 @@ def obj_mesh_scene(rt, width=56, spp=16, depth=8, seed=3):
                   background=b.solid(0.15, 0.15, 0.2))
     hs._builder = b
     return hs
+
+
+def write_synthetic_assets(root, n=24, seed=5):
+    """A config-4-like asset directory: OBJ/MTL text + PNG textures, generated (no reference files)."""
+    import os
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    d = os.path.join(root, "Synth")
+    os.makedirs(d, exist_ok=True)
+    Image.fromarray((rng.uniform(0.2, 1, (32, 32, 3)) * 255).astype(np.uint8)).save(os.path.join(d, "albedo.png"))
+    em = np.zeros((16, 16, 3), dtype=np.uint8)
+    em[4:8, 4:12] = (255, 180, 60)
+    Image.fromarray(em).save(os.path.join(d, "emit.png"))
+    nm = (rng.uniform(0.4, 0.6, (16, 16, 3)) * 255).astype(np.uint8)
+    nm[..., 2] = 255
+    Image.fromarray(nm).save(os.path.join(d, "normal.png"))
+    al = np.zeros((16, 16, 4), dtype=np.uint8)
+    al[..., :3] = 255
+    al[..., 3] = (rng.uniform(0, 1, (16, 16)) > 0.4) * 255
+    Image.fromarray(al, "RGBA").save(os.path.join(d, "alpha.png"))
+    with open(os.path.join(d, "terrain.mtl"), "w") as f:
+        f.write("newmtl ground\nKd 0.8 0.8 0.8\nNi 1.45\nPr 0.7\nPm 0.0\nPc 0.2\nPcr 0.03\nmap_Kd albedo.png\nmap_Bump -bm 1.000000 normal.png\n\n"
+                "newmtl glow\nKd 0.5 0.5 0.6\nNi 1.5\nPr 0.4\nPm 0.3\nmap_Ke emit.png\n\n"
+                "newmtl leaves\nKd 0.2 0.7 0.3\nPr 0.6\nmap_d alpha.png\nd 0.8\nKe 0.0 0.1 0.0\n")
+    xs = np.linspace(-4, 4, n + 1)
+    with open(os.path.join(d, "terrain.obj"), "w") as f:
+        f.write("mtllib terrain.mtl\no terrain\n")
+        for j in range(n + 1):
+            for i in range(n + 1):
+                x, z = xs[i], xs[j]
+                f.write(f"v {x:.6f} {0.5 * np.sin(x) * np.cos(0.8 * z):.6f} {z:.6f}\n")
+        for j in range(n + 1):
+            for i in range(n + 1):
+                f.write(f"vt {i / n:.6f} {j / n:.6f}\n")
+        for j in range(n + 1):
+            for i in range(n + 1):
+                x, z = xs[i], xs[j]
+                nv = np.array([-0.5 * np.cos(x) * np.cos(0.8 * z), 1.0, 0.4 * np.sin(x) * np.sin(0.8 * z)])
+                nv /= np.linalg.norm(nv)
+                f.write(f"vn {nv[0]:.4f} {nv[1]:.4f} {nv[2]:.4f}\n")
+        vid = lambda i, j: j * (n + 1) + i + 1
+        for k, name in enumerate(["ground", "glow", "leaves"]):
+            f.write(f"usemtl {name}\n")
+            for j in range(n):
+                for i in range(n):
+                    if (i // 4 + j // 4) % 3 != k:
+                        continue
+                    a, b_, c, e = vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)
+                    f.write(f"f {a}/{a}/{a} {c}/{c}/{c} {b_}/{b_}/{b_}\nf {a}/{a}/{a} {e}/{e}/{e} {c}/{c}/{c}\n")
+    # a glass ball (vanilla dielectric: Tf 1 1 1) and a closed fog shell, both UV spheres
+    def uv_sphere(path, mtl, mat, centre, radius, seg):
+        with open(path, "w") as f:
+            f.write(f"mtllib {mtl}\no ball\n")
+            for a in range(seg + 1):
+                for b2 in range(2 * seg):
+                    th, ph = np.pi * a / seg, np.pi * b2 / seg
+                    nv = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+                    p = centre + radius * nv
+                    f.write(f"v {p[0]:.6f} {p[1]:.6f} {p[2]:.6f}\nvt {b2 / (2 * seg):.6f} {1 - a / seg:.6f}\nvn {nv[0]:.4f} {nv[1]:.4f} {nv[2]:.4f}\n")
+            f.write(f"usemtl {mat}\n")
+            vid2 = lambda a, b2: a * 2 * seg + (b2 % (2 * seg)) + 1
+            for a in range(seg):
+                for b2 in range(2 * seg):
+                    q = [vid2(a, b2), vid2(a + 1, b2), vid2(a + 1, b2 + 1), vid2(a, b2 + 1)]
+                    f.write("f " + " ".join(f"{v}/{v}/{v}" for v in q) + "\n")  # quads: exercises the fan triangulation
+    with open(os.path.join(d, "ball.mtl"), "w") as f:
+        f.write("newmtl glass\nKd 1.0 1.0 1.0\nNi 1.5\nTf 1.0 1.0 1.0\n")
+    with open(os.path.join(d, "fog.mtl"), "w") as f:
+        f.write("newmtl fog\nKd 1.0 1.0 1.0\n")
+    uv_sphere(os.path.join(d, "ball.obj"), "ball.mtl", "glass", np.array([0.0, 1.6, 0.5]), 0.9, 8)
+    uv_sphere(os.path.join(d, "fog.obj"), "fog.mtl", "fog", np.array([-1.5, 1.2, -1.0]), 1.4, 5)
+    return root
+
+
+def synthetic_obj_scene(rt, assets_root, width=64, spp=16, depth=10, seed=6):
+    """The shape of obj_scene() (main.rs:207-382): Wavefont meshes, a fog mesh medium, a portal, transformed boards as
+    lights, a thin translucent Disney board — built from generated assets through the Python OBJ loader."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("objload", os.path.join(os.path.dirname(rt.__file__), "objload.py"))
+    objload = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(objload)
+    b = rt.Builder(seed)
+    wf = objload.Wavefont(b, assets_root)
+    terrain = wf.new("terrain.obj", "Synth", False)
+    ball = wf.new("ball.obj", "Synth", True)
+    fog = b.medium(wf.new("fog.obj", "Synth", False), 0.6, b.solid(1.0, 0.936, 0.381))
+    portal = b.quad([-3.5, 0.2, -3.0], [1.5, 0, -0.5], [0, 2.5, 0], b.portal([1, 1, 1], [5.0, 0.0, 2.0], [1, 0, 0, 0]))
+    trans = b.transform(b.quad([-1, 0, -1], [0, 0, 2], [2, 0, 0], b.disney((0.8, 0.8, 0.8), diff_trans=1.0, roughness=1.0, thin=1.0)),
+                        offset=[2.5, 1.5, -2.0], quat=b.quat_axis_angle([0.993, -0.082, 0.082], 90.4), scale=[1.6, 1.0, 1.0])
+    def board(mat, off, axis, deg, s):
+        return b.transform(b.quad([-1, 0, -1], [0, 0, 2], [2, 0, 0], mat), offset=off, quat=b.quat_axis_angle(axis, deg), scale=[s, s, s])
+    l1 = ([-0.4, 5.3, 0.9], [0.921, 0.021, 0.389], 34.7, 2.0)
+    l2 = ([-3.0, 2.5, 2.5], [0.766, 0.483, -0.423], 85.7, 0.8)
+    world = b.list([terrain, board(b.diffuse_light(b.solid(6, 6, 6)), *l1), ball, trans, portal,
+                    board(b.diffuse_light(b.solid(5.0, 3.4, 0.0)), *l2), fog])
+    lights = b.list([board(b.empty(), *l1), board(b.empty(), *l2)])
+    hs = b.finish(world, lights, width=width, aspect=16 / 9, spp=spp, max_depth=depth, vfov=35, look_from=(0.5, 4.0, 9.5), look_at=(0, 0.8, 0),
+                  background=b.gradient([0.6, 0.6, 0.7], [0.2, 0.3, 0.6]))
+    hs._builder = b
+    return hs
