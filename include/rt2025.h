@@ -315,6 +315,19 @@ int rt_render(const rt_scene* scene, const rt_camera* camera, const rt_render_op
 int rt_render_device(const rt_scene* scene, const rt_camera* camera, const rt_render_opts* opts,
                      void* d_accum, void* stream, rt_stats* stats);
 
+/* Camera::render end to end (camera.rs:161-202): render, then Color::to_rgb on the device; only the
+ * 3-byte pixels cross PCIe.  `rgb` is a host pointer to image_width*image_height*3 bytes (RgbImage order).
+ * Fails with RT_ERR_INVALID if a pixel is NaN (utils/color.rs:28 asserts). */
+int rt_render_rgb8(const rt_scene* scene, const rt_camera* camera, const rt_render_opts* opts, uint8_t* rgb,
+                   rt_stats* stats);
+
+/* One process, several GPUs: scenes[i] must be the same description created on distinct devices.
+ * GPU i renders partition i of n (interleaved 8x8 tiles) from its own host thread; the partial
+ * framebuffers are disjoint and are summed on the host.  `accum` as in rt_render.  opts->part_index /
+ * part_count must be 0: the partitioning is done here.  stats are totals (ms_total = slowest GPU). */
+int rt_render_multi(rt_scene* const* scenes, uint32_t n_scenes, const rt_camera* camera, const rt_render_opts* opts,
+                    void* accum, rt_stats* stats);
+
 /* Color::to_rgb — utils/color.rs:27-36: optional ACES, then linear -> sRGB 8 bit.
  * `accum` holds mean linear radiance (host pointer), `rgb` receives n_pixels*3 bytes. */
 int rt_tonemap(const void* accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map,

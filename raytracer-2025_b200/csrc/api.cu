@@ -8,6 +8,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "compile.h"
@@ -493,6 +494,104 @@ int rt_render(const rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
     }
     cudaFree(d);
     return rc;
+}
+
+int rt_render_rgb8(const rt_scene* s, const rt_camera* cam, const rt_render_opts* opts, uint8_t* rgb, rt_stats* stats) {
+    if (!s || !cam || !rgb) return set_err(RT_ERR_INVALID, "null argument");
+    rt_render_opts o{};
+    if (opts) o = *opts;
+    o.struct_size = sizeof(o);
+    o.accum_type = RT_ACCUM_F64;
+    const uint64_t n_px = (uint64_t)cam->image_width * cam->image_height;
+    double* d_accum = nullptr;
+    uint8_t* d_rgb = nullptr;
+    int* d_flag = nullptr;
+    int rc = RT_OK;
+    try {
+        CU(cudaSetDevice(s->device));
+        CU(cudaMalloc(&d_accum, n_px * 3 * sizeof(double)));
+        CU(cudaMalloc(&d_rgb, n_px * 3));
+        CU(cudaMalloc(&d_flag, sizeof(int)));
+        CU(cudaMemset(d_flag, 0, sizeof(int)));
+        rc = rt_render_device(s, cam, &o, d_accum, nullptr, stats);
+        if (rc == RT_OK) {
+            launch_tonemap(d_accum, true, n_px, cam->toon_map, d_rgb, d_flag, nullptr);
+            CU(cudaGetLastError());
+            CU(cudaMemcpy(rgb, d_rgb, n_px * 3, cudaMemcpyDeviceToHost));
+            int flag = 0;
+            CU(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+            if (flag) rc = set_err(RT_ERR_INVALID, "NaN radiance in the image (utils/color.rs:28 asserts)");
+            if (stats) stats->kernel_launches += 1;
+        }
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    cudaFree(d_accum);
+    cudaFree(d_rgb);
+    cudaFree(d_flag);
+    return rc;
+}
+
+int rt_render_multi(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, const rt_render_opts* opts, void* accum, rt_stats* stats) {
+    if (!scenes || !n || !cam || !accum) return set_err(RT_ERR_INVALID, "null argument");
+    rt_render_opts base{};
+    if (opts) {
+        if (opts->struct_size != sizeof(rt_render_opts)) return set_err(RT_ERR_VERSION, "rt_render_opts.struct_size mismatch");
+        base = *opts;
+    }
+    base.struct_size = sizeof(base);
+    if (base.part_count > 1 || base.part_index != 0) return set_err(RT_ERR_INVALID, "rt_render_multi partitions the image itself");
+    for (uint32_t i = 0; i < n; i++) {
+        if (!scenes[i]) return set_err(RT_ERR_INVALID, "null scene");
+        for (uint32_t j = 0; j < i; j++)
+            if (scenes[j]->device == scenes[i]->device) return set_err(RT_ERR_INVALID, "two scenes on the same device");
+    }
+    const size_t n_val = (size_t)cam->image_width * cam->image_height * 3;
+    const bool f64 = base.accum_type == RT_ACCUM_F64;
+    std::vector<std::vector<char>> part(n);
+    std::vector<rt_stats> st(n);
+    std::vector<int> rcs(n, RT_OK);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> threads;
+    for (uint32_t i = 0; i < n; i++) {
+        threads.emplace_back([&, i]() {
+            rt_render_opts o = base;
+            o.part_index = i;
+            o.part_count = n;
+            part[i].resize(n_val * (f64 ? 8 : 4));
+            rcs[i] = rt_render(scenes[i], cam, &o, part[i].data(), &st[i]);
+            if (rcs[i] != RT_OK) errs[i] = rt_last_error();  // thread-local: carry it to the caller's thread
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (uint32_t i = 0; i < n; i++)
+        if (rcs[i] != RT_OK) return set_err(rcs[i], errs[i]);
+    // partitions are disjoint pixel sets: the sum is also the gather
+    if (f64) {
+        double* out = (double*)accum;
+        std::fill(out, out + n_val, 0.0);
+        for (uint32_t i = 0; i < n; i++) {
+            const double* p = (const double*)part[i].data();
+            for (size_t k = 0; k < n_val; k++) out[k] += p[k];
+        }
+    } else {
+        float* out = (float*)accum;
+        std::fill(out, out + n_val, 0.0f);
+        for (uint32_t i = 0; i < n; i++) {
+            const float* p = (const float*)part[i].data();
+            for (size_t k = 0; k < n_val; k++) out[k] += p[k];
+        }
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        for (uint32_t i = 0; i < n; i++) {
+            stats->paths += st[i].paths, stats->segments += st[i].segments, stats->errors += st[i].errors;
+            stats->node_visits += st[i].node_visits, stats->prim_tests += st[i].prim_tests;
+            stats->kernel_launches += st[i].kernel_launches, stats->iterations += st[i].iterations;
+            stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
+        }
+    }
+    return RT_OK;
 }
 
 int rt_tonemap(const void* accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb) {

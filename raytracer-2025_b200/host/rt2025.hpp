@@ -999,19 +999,15 @@ class Camera {  // camera.rs:46-75
         rt_render_opts o{};
         o.struct_size = sizeof(o);
         o.seed = seed;
-        o.accum_type = RT_ACCUM_F64;
-        std::vector<double> accum((size_t)cam.image_width * cam.image_height * 3);
-        int rc = rt_render(scene, &cam, &o, accum.data(), &last_stats);
-        std::string err = rc == RT_OK ? "" : rt_last_error();
-        rt_scene_destroy(scene);
-        if (rc != RT_OK) throw std::runtime_error(err);
         RgbImage img;
         img.width = cam.image_width;
         img.height = cam.image_height;
-        img.data.resize(accum.size());
-        if (rt_tonemap(accum.data(), RT_ACCUM_F64, (uint64_t)cam.image_width * cam.image_height, cam.toon_map,
-                       img.data.data()) != RT_OK)
-            throw std::runtime_error(rt_last_error());
+        img.data.resize((size_t)cam.image_width * cam.image_height * 3);
+        // render + Color::to_rgb on the device: only the 8-bit pixels come back
+        int rc = rt_render_rgb8(scene, &cam, &o, img.data.data(), &last_stats);
+        std::string err = rc == RT_OK ? "" : rt_last_error();
+        rt_scene_destroy(scene);
+        if (rc != RT_OK) throw std::runtime_error(err);
         return img;
     }
 };

@@ -23,7 +23,7 @@ RT_BUILD_NO_REF_RANKS = 1
 # every symbol include/rt2025.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [
     "rt_scene_create", "rt_scene_destroy", "rt_closest_hit", "rt_closest_hit_device", "rt_render",
-    "rt_render_device", "rt_tonemap", "rt_scene_get_info", "rt_scene_get_ranks", "rt_last_error",
+    "rt_render_device", "rt_render_rgb8", "rt_render_multi", "rt_tonemap", "rt_scene_get_info", "rt_scene_get_ranks", "rt_last_error",
     "rt_abi_version", "rt_device_count",
 ]
 
@@ -202,6 +202,9 @@ def product_lib(required=True):
                                 C.POINTER(rt_stats)]
         L.rt_render_device.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p,
                                        C.c_void_p, C.POINTER(rt_stats)]
+        L.rt_render_rgb8.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p, C.POINTER(rt_stats)]
+        L.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p,
+                                      C.POINTER(rt_stats)]
         L.rt_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
         L.rt_scene_get_info.argtypes = [C.c_void_p, C.POINTER(rt_scene_info)]
         L.rt_scene_get_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
@@ -435,12 +438,34 @@ class Scene:
         _check(self.L.rt_render(self.h, C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st)), self.L)
         return img, st
 
+    def render_rgb8(self, camera=None, **kw):
+        """Camera::render: the RgbImage bytes (H, W, 3) straight from the device."""
+        cam = camera if camera is not None else self.host.camera
+        o = self.render_opts(**kw)
+        img = np.zeros((cam.image_height, cam.image_width, 3), dtype=np.uint8)
+        st = rt_stats()
+        _check(self.L.rt_render_rgb8(self.h, C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st)), self.L)
+        return img, st
+
     def render_device(self, d_accum_ptr, camera=None, stream=None, **kw):
         cam = camera if camera is not None else self.host.camera
         o = self.render_opts(**kw)
         st = rt_stats()
         _check(self.L.rt_render_device(self.h, C.byref(cam), C.byref(o), d_accum_ptr, stream, C.byref(st)), self.L)
         return st
+
+
+def render_multi(scenes, camera=None, **kw):
+    """rt_render_multi: one process, scenes[i] on distinct GPUs, interleaved-tile partitions summed on the host."""
+    L = product_lib()
+    cam = camera if camera is not None else scenes[0].host.camera
+    o = scenes[0].render_opts(**kw)
+    dt = np.float64 if o.accum_type == RT_ACCUM_F64 else np.float32
+    img = np.zeros((cam.image_height, cam.image_width, 3), dtype=dt)
+    handles = (C.c_void_p * len(scenes))(*[s.h for s in scenes])
+    st = rt_stats()
+    _check(L.rt_render_multi(handles, len(scenes), C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st)), L)
+    return img, st
 
 
 def tonemap(accum, toon_map=0):

@@ -391,3 +391,24 @@ def test_obj_faces_with_remapped_materials_vs_oracle(gpu, rt, orc):
     ref, ost = osc.render(seed=4)
     assert st.paths == ost.paths and int(st.errors) <= int(ost.errors)
     image_close(img, ref, frac_bad=5e-3)
+
+
+def test_render_rgb8_equals_render_then_tonemap(gpu, rt):
+    hs = rt.named_scene("cornell_glass", seed=3, params=[48, 9, 12])
+    sc = rt.Scene(hs)
+    rgb, st = sc.render_rgb8(seed=6)
+    img, _ = sc.render(seed=6)
+    assert np.array_equal(rgb, rt.tonemap(img, 0)) and rgb.dtype == np.uint8 and st.paths == 48 * 48 * 9
+
+
+def test_render_multi_in_one_process(gpu, rt):
+    """rt_render_multi with as many GPUs as the box has (1 on the default test box): equals rt_render."""
+    n = gpu.rt_device_count()
+    hs = rt.named_scene("book2_final", seed=5, params=[64, 9, 20])
+    scenes = [rt.Scene(hs, device=k) for k in range(min(n, 4))]
+    img, st = rt.render_multi(scenes, seed=3)
+    ref, rst = scenes[0].render(seed=3)
+    assert st.paths == rst.paths and st.segments == rst.segments
+    assert np.allclose(img, ref, rtol=1e-12, atol=1e-14)
+    with pytest.raises(rt.RtError):
+        rt.render_multi([scenes[0], scenes[0]], seed=3)  # two handles on one device
