@@ -194,12 +194,43 @@ struct TraceCounters {
     uint32_t nodes, prims;
 };
 
-// Stage the breadth-first top of the BVH in shared memory (all threads of the CTA, then a barrier).
+// Stage the breadth-first top of the BVH in shared memory with the TMA bulk-copy engine: one elected
+// thread arms an mbarrier with the byte count and issues cp.async.bulk (global -> shared, UBLKCP in
+// SASS) in 32 KB pieces; every thread then waits on the barrier's phase.  No register or LSU traffic
+// is spent on the copy, and it overlaps with the rest of the CTA's prologue.
 __device__ __forceinline__ void stage_nodes(const SceneView& sv, float4* smem_nodes) {
-    const float4* src = reinterpret_cast<const float4*>(sv.nodes);
-    const uint32_t n4 = sv.n_cached_nodes * 4;
-    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) smem_nodes[i] = __ldg(src + i);
+    __shared__ alignas(8) unsigned long long s_bar;
+    const uint32_t bytes = sv.n_cached_nodes * (uint32_t)sizeof(Node);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (bytes == 0) return;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        const char* src = reinterpret_cast<const char*>(sv.nodes);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_nodes);
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t n = min(32768u, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                         "l"(src + off), "r"(n), "r"(bar)
+                         : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
 }
 
 // Closest hit below `root` within [tmin, tmax] (both inclusive).  smem_nodes holds nodes
