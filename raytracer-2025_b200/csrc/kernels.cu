@@ -271,6 +271,14 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : RT_MEDIA_MIN_BLOCKS
     const StateRec* __restrict__ states = W.state_q[W.parity];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
         int q = -1;
+        {  // pull the next iteration's records towards L2/L1 while this one computes
+            const uint32_t jn = j + gridDim.x * blockDim.x;
+            if (jn < n) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + jn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(states + jn) + 32));
+            }
+        }
         if (j < n) {
             const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
             double t = hw.x;
@@ -302,6 +310,13 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : RT_MEDIA_MIN_BLOCKS
                     double ray_length = length(lr.d);
                     double distance_inside_boundary = (t2 - t1) * ray_length;
                     double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
+                    // binary32 screen: when even a pessimistic binary32 estimate of the free-flight distance clears the
+                    // segment by a wide margin the path does not scatter here and the binary64 ln is not needed
+                    // (the outcome of the exact comparison below is unchanged; only clear misses skip it)
+                    {
+                        const float hf = (float)med.neg_inv_density * logf((float)xi);
+                        if (hf > (float)distance_inside_boundary * 1.001f + 4e-7f * fabsf((float)med.neg_inv_density)) continue;  // > relative + absolute error of hf
+                    }
                     double hit_distance = med.neg_inv_density * log(xi);
                     if (hit_distance > distance_inside_boundary) continue;
                     double tm = t1 + hit_distance / ray_length;

@@ -337,18 +337,23 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent warp-refill traversal.
+// Persistent traversal with one-ahead prefetch.
 //
-// In the per-lane loop above a warp is busy until its LONGEST ray finishes (19 node iterations per
-// warp against 10.4 per ray on the book-2 scene, profiles/r01_v1_*), so almost half of the lanes idle.
-// Here a warp keeps its lanes busy instead: whenever REFILL_MIN lanes have finished, they fetch new
-// work items from the CTA's cursor and join the lanes still traversing.  Items are dealt to CTAs in
-// interleaved groups of 32 so that every CTA sees the same mix of rays.
+// Work items are dealt to CTAs in interleaved groups of 32, every lane always knows the NEXT item it
+// will trace and prefetches its ray record while the current one is traversed.  REFILL_MIN is the
+// number of idle lanes that triggers a refill.  Measured (profiles/README.md): refilling a warp while
+// some of its lanes are still traversing (REFILL_MIN 1..20) is SLOWER than letting the warp drain
+// (REFILL_MIN 32: 48.7 ms vs 51.5 ms at 12 and 54.5 ms at 1 on the 800x800x144 frame) — the refill code
+// runs with few lanes active and its three divisions per new ray cost more than the idle lanes save.
+// The default therefore drains the warp; the knob stays for other scenes.
 //
 // IO::load(item, ray, tmin, tmax) -> bool and IO::store(item, hit, t, prim) bind the routine to the
-// path records (k_extend) or to a plain ray array (k_closest_hit).
+// path streams (k_extend) or to a plain ray array (k_closest_hit).
 // ------------------------------------------------------------------------------------------------
-constexpr int REFILL_MIN = 12;
+#ifndef RT_REFILL_MIN
+#define RT_REFILL_MIN 32
+#endif
+constexpr int REFILL_MIN = RT_REFILL_MIN;
 
 template <bool COUNT, bool USE_RANK, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
