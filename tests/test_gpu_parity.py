@@ -412,3 +412,35 @@ def test_render_multi_in_one_process(gpu, rt):
     assert np.allclose(img, ref, rtol=1e-12, atol=1e-14)
     with pytest.raises(rt.RtError):
         rt.render_multi([scenes[0], scenes[0]], seed=3)  # two handles on one device
+
+
+def _psnr8(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 10 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+
+
+def test_independent_seeds_are_statistically_consistent(gpu, rt, orc):
+    """North-star checks (2) and (3): an oracle render with ANOTHER seed differs from the GPU render only
+    by Monte Carlo noise, and both converge to the same image (PSNR >= 40 dB at high spp).  Config 3
+    (Cornell + glass sphere, mixture-pdf light sampling) at reduced resolution, full 961 spp."""
+    hs = rt.named_scene("cornell_glass", seed=7, params=[64, 1000, 50])
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    assert hs.camera.sqrt_spp == 31
+    ref_other_seed, ost = osc.render(seed=1001)         # the "reference" at the config's spp, its own seed
+    gpu = [sc.render(seed=s)[0] for s in range(1, 41)]   # 40 independent GPU renders of 961 spp each
+    assert ost.errors == 0
+    # (3) same-spp check: E|a-b|^2 = var_a + var_b for independent estimates, whoever produced them
+    clip = lambda x: np.minimum(x, 4.0)  # the light itself is 15: keep fireflies from dominating the statistic
+    mse_gpu_pairs = np.mean([np.mean((clip(gpu[2 * k]) - clip(gpu[2 * k + 1])) ** 2) for k in range(8)])
+    mse_vs_oracle = np.mean([np.mean((clip(ref_other_seed) - clip(g)) ** 2) for g in gpu[:8]])
+    assert 0.8 < mse_vs_oracle / mse_gpu_pairs < 1.25
+    # per-pixel: the oracle image lies within 6 sigma of the GPU sample mean (sigma from the 40 renders)
+    stack = np.stack([clip(g) for g in gpu])
+    mean, sd = stack.mean(axis=0), stack.std(axis=0, ddof=1)
+    z = np.abs(clip(ref_other_seed) - mean) / (sd * np.sqrt(1 + 1 / 40) + 1e-3)
+    assert (z > 6).mean() < 2e-3
+    # (2) convergence: 8 x 961 spp against the disjoint 32 x 961 spp average, and the oracle's single render
+    converged = rt.tonemap(np.mean(gpu[8:], axis=0))
+    high = rt.tonemap(np.mean(gpu[:8], axis=0))
+    assert _psnr8(high, converged) >= 40.0
+    assert _psnr8(rt.tonemap(ref_other_seed), converged) >= 30.0
