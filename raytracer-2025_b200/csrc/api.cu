@@ -66,6 +66,7 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
         events.clear();
         for (int k = 0; k < 2; k++) cudaFree(W.ray_q[k]), cudaFree(W.state_q[k]);
         cudaFree(W.hit_q);
+        cudaFree(W.cls_q);
         for (auto& q : W.q_shade) cudaFree(q);
         cudaFree(W.pixel_list);
         cudaFree(W.accum);
@@ -383,6 +384,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                 CU(cudaMalloc(&W.state_q[k], (size_t)capacity_alloc * sizeof(StateRec)));
             }
             CU(cudaMalloc(&W.hit_q, (size_t)capacity_alloc * sizeof(HitRec)));
+            CU(cudaMalloc(&W.cls_q, (size_t)capacity_alloc));
             for (auto& q : W.q_shade) CU(cudaMalloc(&q, (size_t)capacity_alloc * 4));
             CU(cudaMalloc(&W.pixel_list, n_px_alloc * 4));
             CU(cudaMalloc(&W.accum, n_px_alloc * 3 * sizeof(double)));
@@ -429,9 +431,9 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 1), st));
                     launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 2), st));
-                    launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st);
+                    launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st);
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 3), st));
-                    launches += 4 + launch_shade(s->view, P, W, s->class_mask, grid_s, st);  // generate, k_step, extend, media_bin + shade
+                    launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st);  // generate, k_step, extend + shade
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 4), st));
                 }
                 CU(cudaMemcpyAsync(ws.h_counters, W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -125,8 +125,10 @@ uint64_t total_order_key(double x) {  // f64::total_cmp (bvh.rs:52)
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-uint32_t shade_class_of(const rt_scene_desc& d, const rt_material& m) {
+uint32_t shade_class_of(const rt_scene_desc& d, const rt_material& m, const std::vector<Material>& done) {
     switch (m.kind) {
+        case RT_MAT_DISNEY: return SC_DISNEY;
+        case RT_MAT_REMAPPED: return done[m.inner].shade_class == SC_DISNEY && d.materials[m.inner].kind == RT_MAT_DISNEY ? SC_DISNEY : SC_OTHER;
         case RT_MAT_EMPTY: return SC_DIFFUSE;
         case RT_MAT_LAMBERTIAN: return d.textures[m.tex].kind == RT_TEX_SOLID ? SC_DIFFUSE : SC_TEXTURED;
         case RT_MAT_METAL: return SC_METAL;
@@ -283,7 +285,7 @@ struct Compiler {
             for (int k = 0; k < 3; k++) m.color[k] = s.color[k];
             m.param = s.param;
             for (int k = 0; k < 16; k++) m.v[k] = s.v[k];
-            m.shade_class = shade_class_of(d, s);
+            m.shade_class = shade_class_of(d, s, out.materials);
             // does shading this material read the surface coordinates (image / checker lookups)?
             auto tex_uv = [&](uint32_t t) { return t != RT_NONE && (d.textures[t].kind == RT_TEX_IMAGE || d.textures[t].kind == RT_TEX_CHECKER); };
             m.needs_uv = tex_uv(s.tex) ? 1u : 0u;

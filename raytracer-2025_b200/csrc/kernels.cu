@@ -260,13 +260,28 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
 // converged: one thread per extend-queue entry.
 // GENERIC = some boundary is not a single Sphere and needs the BVH traversal (kept out of the common
 // instantiation: it doubles the register footprint of this otherwise small streaming kernel).
-template <bool COUNT, bool GENERIC>
-__global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : RT_MEDIA_MIN_BLOCKS) k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
+// MODE 0: the scene has no media, this pass only bins the hits (a lean, memory-bound instantiation);
+// MODE 1: every boundary is a single Sphere; MODE 2: general boundaries (BVH traversal per lane);
+// MODE 3: second phase of 1 and 2 - bins the class bytes they left in cls_q.
+template <bool COUNT, int MODE>
+__global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_BLOCKS : (MODE == 0 ? 4 : RT_MEDIA_MIN_BLOCKS)) k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
+    constexpr bool GENERIC = MODE == 2;
     extern __shared__ float4 s_mem[];  // traversal stacks for boundaries that are not a single sphere
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
     TraceCounters cnt{0, 0};
     const uint32_t n = W.counters->n_extend[W.parity];
-    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together for the aggregated append
+    // the append to the class queues is aggregated per CTA where the per-thread work is uniform (one global
+    // atomic per class per 256 hits: same-address atomics were what bounded the lean instantiation) and per
+    // warp where lanes run a traversal of their own and a CTA-wide barrier would idle the fast warps
+    constexpr bool BLOCK_AGG = MODE == 0 || MODE == 3 || (MODE == 1 && RT_MEDIA_BLOCK_AGG);
+    constexpr bool DEFER = (MODE == 1 || MODE == 2) && RT_MEDIA_TWO_PHASE;  // leave the append to a MODE 3 pass
+    __shared__ uint32_t s_cnt[2][SC_COUNT], s_base[SC_COUNT];
+    if (BLOCK_AGG) {
+        if (threadIdx.x < 2 * SC_COUNT) (&s_cnt[0][0])[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    uint32_t it = 0;
+    const uint32_t n_round = BLOCK_AGG ? (n + MEDIA_BLOCK - 1u) / MEDIA_BLOCK * MEDIA_BLOCK : (n + 31u) & ~31u;  // whole warps / CTAs iterate together
     const RayRec* __restrict__ rays = W.ray_q[W.parity];
     const StateRec* __restrict__ states = W.state_q[W.parity];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
@@ -274,16 +289,18 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : RT_MEDIA_MIN_BLOCKS
         {  // pull the next iteration's records towards L2/L1 while this one computes
             const uint32_t jn = j + gridDim.x * blockDim.x;
             if (jn < n) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + jn));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(states + jn) + 32));
+                if (MODE == 1 || MODE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + jn));
+                if (MODE != 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
+                if (MODE == 1 || MODE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(states + jn) + 32));
             }
         }
-        if (j < n) {
+        if (MODE == 3) {
+            if (j < n) q = W.cls_q[j];
+        } else if (j < n) {
             const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
             double t = hw.x;
             uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
-            if (sv.n_media) {
+            if ((MODE == 1 || MODE == 2) && sv.n_media) {
                 RayD r;
                 load_ray(rays + j, r);
                 const uint4 ids = reinterpret_cast<const uint4*>(states + j)[2];
@@ -337,9 +354,25 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, GENERIC ? 1 : RT_MEDIA_MIN_BLOCKS
             else
                 q = (int)sv.materials[sv.meta[prim].kind_mat & 0x3FFFFFFFu].shade_class;
             if (!P.bin_by_class) q = q == SC_MISS ? SC_MISS : SC_DIFFUSE;
+            if (DEFER) W.cls_q[j] = (uint8_t)q;
         }
-        const uint32_t pos = queue_reserve(W.counters->n_shade, q);
-        if (q >= 0) W.q_shade[q][pos] = j;
+        if (DEFER) continue;
+        if (BLOCK_AGG) {
+            uint32_t* cntb = s_cnt[it & 1];
+            const uint32_t local = queue_reserve(cntb, q);
+            __syncthreads();
+            if (threadIdx.x < SC_COUNT) {
+                const uint32_t c = cntb[threadIdx.x];
+                if (c) s_base[threadIdx.x] = atomicAdd(&W.counters->n_shade[threadIdx.x], c);
+                s_cnt[(it & 1) ^ 1][threadIdx.x] = 0;
+            }
+            __syncthreads();
+            if (q >= 0) W.q_shade[q][s_base[q] + local] = j;
+            it++;
+        } else {
+            const uint32_t pos = queue_reserve(W.counters->n_shade, q);
+            if (q >= 0) W.q_shade[q][pos] = j;
+        }
     }
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
@@ -371,7 +404,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
     constexpr bool DO_MISS = CLS == SC_MISS;
     constexpr bool DO_MEDIUM = GENERIC || CLS == SC_ISOTROPIC;
     constexpr bool DO_EMIT = GENERIC || CLS == SC_EMISSIVE;
-    constexpr bool DO_PDF = GENERIC || CLS == SC_DIFFUSE || CLS == SC_TEXTURED || CLS == SC_ISOTROPIC;
+    constexpr bool DO_PDF = GENERIC || CLS == SC_DIFFUSE || CLS == SC_TEXTURED || CLS == SC_ISOTROPIC || CLS == SC_DISNEY;
+    constexpr bool DO_REMAP = GENERIC || CLS == SC_DISNEY;
     constexpr bool DO_METAL = GENERIC || CLS == SC_METAL;
     constexpr bool DO_DIELECTRIC = GENERIC || CLS == SC_DIELECTRIC;
     __shared__ uint32_t s_warp_count[SHADE_BLOCK / 32];
@@ -428,7 +462,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                 if (!hit_ok) error = true;
                 uint32_t mat = h.material;
                 // RemappedMaterial is the per-face wrapper the OBJ loader puts outermost (obj.rs:165-176)
-                while (GENERIC && sv.materials[mat].kind == RT_MAT_REMAPPED) {
+                while (DO_REMAP && sv.materials[mat].kind == RT_MAT_REMAPPED) {
                     if (!remap_record(sv, sv.remaps[sv.materials[mat].inner2], h)) error = true;
                     mat = sv.materials[mat].inner;
                 }
@@ -523,7 +557,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                         case RT_MAT_LAMBERTIAN: {  // Empty / Lambertian / Isotropic / Disney
                             // ScatterRecord::PDF branch, camera.rs:297-312
                             const bool iso = CLS == SC_ISOTROPIC || (GENERIC && M.kind == RT_MAT_ISOTROPIC);
-                            const bool dis = GENERIC && M.kind == RT_MAT_DISNEY;
+                            const bool dis = CLS == SC_DISNEY || (GENERIC && M.kind == RT_MAT_DISNEY);
                             D3 albedo = (M.kind == RT_MAT_EMPTY || dis) ? D3{0.75, 0.75, 0.75} : texture_value(sv, M.tex, h.u, h.v, h.p);
                             ONB uvw;
                             if (!iso && !make_onb(h.normal, uvw)) {
@@ -705,22 +739,30 @@ void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontSt
     else
         k_extend<false><<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
 }
-void launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
+int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
     // media + binning: global-memory nodes only (its shared memory holds just the stacks)
     SceneView mv = sv;
     mv.n_cached_nodes = 0;
     const size_t media_smem = generic ? (size_t)sv.stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;
-    if (generic) {
+    const int mode = sv.n_media == 0 ? 0 : (generic ? 2 : 1);
+    if (mode == 2) {
         if (count)
-            k_media_bin<true, true><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+            k_media_bin<true, 2><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
         else
-            k_media_bin<false, true><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+            k_media_bin<false, 2><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+    } else if (mode == 1) {
+        if (count)
+            k_media_bin<true, 1><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        else
+            k_media_bin<false, 1><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
     } else {
-        if (count)
-            k_media_bin<true, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
-        else
-            k_media_bin<false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        k_media_bin<false, 0><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
     }
+    if (mode != 0 && RT_MEDIA_TWO_PHASE) {
+        k_media_bin<false, 3><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        return 2;
+    }
+    return 1;
 }
 template <uint32_t CLS>
 static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t queue, int grid, cudaStream_t s) {
@@ -741,6 +783,7 @@ int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontStat
         if (class_mask & (1u << SC_METAL)) launch_shade_cls<SC_METAL>(sv, P, W, SC_METAL, grid, s), launches++;
         if (class_mask & (1u << SC_DIELECTRIC)) launch_shade_cls<SC_DIELECTRIC>(sv, P, W, SC_DIELECTRIC, grid, s), launches++;
         if (class_mask & (1u << SC_EMISSIVE)) launch_shade_cls<SC_EMISSIVE>(sv, P, W, SC_EMISSIVE, grid, s), launches++;
+        if (class_mask & (1u << SC_DISNEY)) launch_shade_cls<SC_DISNEY>(sv, P, W, SC_DISNEY, grid, s), launches++;
         if (class_mask & (1u << SC_OTHER)) launch_shade_cls<SC_OTHER>(sv, P, W, SC_OTHER, grid, s), launches++;
     }
     k_step<<<1, 1, 0, s>>>(W, 2);

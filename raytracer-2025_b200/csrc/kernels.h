@@ -23,6 +23,15 @@ constexpr int MEDIA_BLOCK = 256;
 #ifndef RT_MEDIA_MIN_BLOCKS
 #define RT_MEDIA_MIN_BLOCKS 2
 #endif
+#ifndef RT_MEDIA_GENERIC_MIN_BLOCKS
+#define RT_MEDIA_GENERIC_MIN_BLOCKS 2
+#endif
+#ifndef RT_MEDIA_BLOCK_AGG
+#define RT_MEDIA_BLOCK_AGG 0
+#endif
+#ifndef RT_MEDIA_TWO_PHASE
+#define RT_MEDIA_TWO_PHASE 1
+#endif
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 2
 #endif
@@ -62,6 +71,7 @@ struct WavefrontState {
     RayRec* ray_q[2];
     StateRec* state_q[2];
     HitRec* hit_q;
+    uint8_t* cls_q;  // shade class of every hit (written by the media pass when it leaves the append to a second pass)
     uint32_t* q_shade[SC_COUNT];
     uint32_t* pixel_list;
     double* accum;  // W*H*3 binary64 sums
@@ -83,7 +93,7 @@ void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, d
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s);
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t smem_bytes, cudaStream_t s);
-void launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s);
+int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s);
 int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s);
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s);
 void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb, int* error_flag, cudaStream_t s);
