@@ -199,6 +199,12 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.n_nodes = (uint32_t)cs.nodes.size();
         v.stack_entries = std::min<uint32_t>(cs.bvh_depth + 2, TRAVERSAL_STACK);
         const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t);
+        // persistent traversal: a warp whose BVH lives in L1/shared memory is issue-bound and runs best when it
+        // drains completely before taking 32 new rays; once node fetches go to L2/HBM the idle lanes are worth
+        // more as loads in flight and every finished lane is refilled at once (profiles/README.md: 1M-triangle
+        // soup, incoherent rays, 392 vs 274 Mrays/s; book2_final 49.4 vs 48.7 ms the other way round)
+        v.refill_min = cs.nodes.size() > 100000 ? 1 : REFILL_MIN;
+        if (const char* e = getenv("RT2025_REFILL_MIN")) v.refill_min = (uint32_t)std::min(32l, std::max(1l, atol(e)));  // tuning knob
         // when several CTAs share an SM each gets its share of the 227 KB
         const size_t room = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024 - stack_bytes;
         size_t cache_bytes = room;

@@ -308,6 +308,14 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
                 for (uint32_t m = 0; m < sv.n_media; m++) {
                     const Medium& med = sv.media[m];
                     const RayD lr = med.xform == RT_NONE ? r : ray_to_local(sv, med.xform, r);
+                    const double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
+                    // binary32 screens: hf is the free-flight distance in binary32, pessimistic by the margins below.
+                    // (1) the scatter point lies at t1 + dist/len with t1 >= 0, so a free flight that clearly
+                    // overshoots the surface hit cannot win whatever the boundary does: skip the boundary test.
+                    const float hf = (float)med.neg_inv_density * logf((float)xi);
+                    const float hf_err = 4e-7f * fabsf((float)med.neg_inv_density);  // absolute error of hf ((float)xi near 1)
+                    const float len_f = sqrtf((float)lr.d.x * (float)lr.d.x + (float)lr.d.y * (float)lr.d.y + (float)lr.d.z * (float)lr.d.z);
+                    if (RT_MEDIA_EARLY_SCREEN && kind != HIT_MISS && hf > (float)t * len_f * 1.001f + hf_err) continue;
                     double t1, t2;
                     if (med.single_sphere != RT_NONE) {
                         const uint32_t bx = sv.meta[med.single_sphere].xform;
@@ -326,14 +334,10 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
                     if (t1 < 0.0) t1 = 0.0;
                     double ray_length = length(lr.d);
                     double distance_inside_boundary = (t2 - t1) * ray_length;
-                    double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
-                    // binary32 screen: when even a pessimistic binary32 estimate of the free-flight distance clears the
-                    // segment by a wide margin the path does not scatter here and the binary64 ln is not needed
-                    // (the outcome of the exact comparison below is unchanged; only clear misses skip it)
-                    {
-                        const float hf = (float)med.neg_inv_density * logf((float)xi);
-                        if (hf > (float)distance_inside_boundary * 1.001f + 4e-7f * fabsf((float)med.neg_inv_density)) continue;  // > relative + absolute error of hf
-                    }
+                    // (2) when even the pessimistic estimate clears the segment inside the boundary by a wide margin the
+                    // path does not scatter here and the binary64 ln is not needed (the exact comparison below is
+                    // unchanged; only clear misses skip it)
+                    if (hf > (float)distance_inside_boundary * 1.001f + hf_err) continue;
                     double hit_distance = med.neg_inv_density * log(xi);
                     if (hit_distance > distance_inside_boundary) continue;
                     double tm = t1 + hit_distance / ray_length;

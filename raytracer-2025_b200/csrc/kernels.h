@@ -20,6 +20,10 @@ constexpr int EXTEND_MIN_BLOCKS = RT_EXTEND_MIN_BLOCKS;
 constexpr size_t EXTEND_SMEM_MAX = 227 * 1024;
 constexpr int SHADE_BLOCK = 256;
 constexpr int MEDIA_BLOCK = 256;
+#ifndef RT_REFILL_MIN
+#define RT_REFILL_MIN 32  // SceneView::refill_min default (traverse.cuh, trace_persistent)
+#endif
+constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_MEDIA_MIN_BLOCKS
 #define RT_MEDIA_MIN_BLOCKS 2
 #endif
@@ -31,6 +35,9 @@ constexpr int MEDIA_BLOCK = 256;
 #endif
 #ifndef RT_MEDIA_TWO_PHASE
 #define RT_MEDIA_TWO_PHASE 1
+#endif
+#ifndef RT_MEDIA_EARLY_SCREEN
+#define RT_MEDIA_EARLY_SCREEN 1
 #endif
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 2

@@ -345,15 +345,13 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
 // some of its lanes are still traversing (REFILL_MIN 1..20) is SLOWER than letting the warp drain
 // (REFILL_MIN 32: 48.7 ms vs 51.5 ms at 12 and 54.5 ms at 1 on the 800x800x144 frame) — the refill code
 // runs with few lanes active and its three divisions per new ray cost more than the idle lanes save.
-// The default therefore drains the warp; the knob stays for other scenes.
+// Cache-resident scenes therefore drain the warp (SceneView::refill_min = 32).  Scenes whose nodes come from
+// L2/HBM behave the other way round (config-5 soups: 1M triangles incoherent 392 Mrays/s at refill_min 1 vs
+// 274 at 32; 10M: 242 vs 167) and get refill_min = 1; rt_scene_create picks by node count.
 //
 // IO::load(item, ray, tmin, tmax) -> bool and IO::store(item, hit, t, prim) bind the routine to the
 // path streams (k_extend) or to a plain ray array (k_closest_hit).
 // ------------------------------------------------------------------------------------------------
-#ifndef RT_REFILL_MIN
-#define RT_REFILL_MIN 32
-#endif
-constexpr int REFILL_MIN = RT_REFILL_MIN;
 
 template <bool COUNT, bool USE_RANK, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
@@ -398,7 +396,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
 
     while (true) {
         const unsigned idle = __ballot_sync(FULL, !have);
-        if (idle && (__popc(idle) >= REFILL_MIN || idle == FULL) && (!exhausted || __ballot_sync(FULL, have_next))) {
+        if (idle && (__popc(idle) >= (int)sv.refill_min || idle == FULL) && (!exhausted || __ballot_sync(FULL, have_next))) {
             if (__ballot_sync(FULL, !have && !have_next)) grab();  // first round, or nothing to promote
             if (!have && have_next) {  // promote the prefetched assignment
                 have_next = false;
