@@ -34,7 +34,16 @@ examples: examples/final_scene
 examples/final_scene: examples/final_scene.cpp $(PKG)/host/rt2025.hpp $(PKG)/host/scenes.hpp $(PKG)/librt2025.so
 	$(CXX) $(CXXFLAGS) -o $@ examples/final_scene.cpp -L$(PKG) -lrt2025 -Wl,-rpath,'$$ORIGIN/../$(PKG)'
 
+# host-only checks and tools of the scene compiler (no CUDA runtime needed)
+HOSTTOOL_SRC := $(PKG)/csrc/compile.cpp $(PKG)/csrc/bvh_build.cpp
+build/check_tie_order: scripts/check_tie_order.cpp $(HOSTTOOL_SRC) $(PRODUCT_HDR)
+	mkdir -p build && $(CXX) $(CXXFLAGS) -I$(PKG)/csrc -I/usr/local/cuda/include -o $@ scripts/check_tie_order.cpp $(HOSTTOOL_SRC)
+build/time_compile: scripts/time_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp $(PRODUCT_HDR)
+	mkdir -p build && $(CXX) $(CXXFLAGS) -O3 -I$(PKG)/csrc -I$(PKG)/host -I/usr/local/cuda/include -o $@ scripts/time_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp
+check_tie_order: build/check_tie_order
+	build/check_tie_order
+
 clean:
 	rm -f $(PKG)/librt2025.so $(PKG)/librt2025_host.so oracle/liboracle.so
 
-.PHONY: all product host oracle examples clean
+.PHONY: all product host oracle examples clean check_tie_order

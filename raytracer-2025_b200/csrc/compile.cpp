@@ -14,6 +14,10 @@
 //   6. build one SAH BVH per group and store primitives in leaf order.
 #include "compile.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <vector_functions.h>
 
 #include <algorithm>
@@ -343,7 +347,7 @@ struct Compiler {
 
     // Local geometry of a leaf shape (verbatim from the description) and its WORLD-space bounds
     // under the affine image of the Transform chain.
-    bool leaf(uint32_t obj, const Affine& a, PrimGeom& g, uint32_t& kind, double lo[3], double hi[3], double* area_out) {
+    bool leaf(uint32_t obj, const Affine& a, PrimGeom& g, uint32_t& kind, double lo[3], double hi[3], double* area_out, bool quiet = false) {
         const rt_object& o = d.objects[obj];
         std::memset(&g, 0, sizeof(g));
         V3 pts[8];
@@ -404,49 +408,177 @@ struct Compiler {
             }
         }
         for (int k = 0; k < 3; k++)
-            if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) return fail(RT_ERR_INVALID, "primitive with non-finite bounds");
+            if (!std::isfinite(lo[k]) || !std::isfinite(hi[k])) return quiet ? false : fail(RT_ERR_INVALID, "primitive with non-finite bounds");
         return true;
     }
 
-    // order in which BVH::from_vec + BVH::hit would prefer the children on a tie: right before left.
-    // `out` receives exactly objs.size() ids; the two halves fill disjoint ranges, so big subtrees are
-    // sorted in parallel (the split itself is serial: a stable sort by box-min like bvh.rs:41).
-    void bvh_visit_order(std::vector<uint32_t> objs, uint32_t* out) {
-        size_t len = objs.size();
+    // Order in which BVH::from_vec + BVH::hit would prefer the children on a tie: right before left.
+    // Each node is the reference's split: bounds of the set, longest axis (ties towards z, aabb.rs:80-92),
+    // STABLE sort by box-min (bvh.rs:41, f64::total_cmp), halves at len/2.
+    //
+    // The reference sorts at every node (N log^2 N).  Box-mins never change, so this walk sorts the children
+    // ONCE per axis and carries the three sorted lists down the tree by stable partition, like a kd-tree
+    // build: O(N) per level, no comparator indirection, subtrees as OpenMP tasks.  Invariant at the entry of
+    // a node: each axis list holds the node's children sorted by (box-min on that axis, position in the order P
+    // the parent left them in) - exactly what a stable sort of P would produce, so the list of the chosen
+    // axis IS the sorted node.  Partitioning keeps a list sorted by box-min but leaves equal keys in the
+    // PARENT's P order; runs of equal keys are therefore re-sorted by the position in the new order.
+    struct AxisEnt {
+        double mn, mx;  // bounding-box interval of the child on this axis
+        uint32_t id;    // index into the BVH's child list
+        uint32_t pad;
+    };
+    struct TieOrder {
+        const uint32_t* kids = nullptr;  // child list -> object ids
+        AxisEnt* list[2][3] = {};        // ping-pong copies of the three axis lists
+        uint32_t* pos = nullptr;         // position of a child in the order its parent left
+    };
+    static bool key_less(const AxisEnt& x, const AxisEnt& y) { return total_order_key(x.mn) < total_order_key(y.mn); }
+    static void sort_ents(AxisEnt* a, AxisEnt* tmp, size_t n) {  // stable, task-parallel merge sort
+        if (n < (1u << 15)) {
+            std::stable_sort(a, a + n, key_less);
+            return;
+        }
+        const size_t h = n / 2;
+#pragma omp task default(shared)
+        sort_ents(a, tmp, h);
+        sort_ents(a + h, tmp + h, n - h);
+#pragma omp taskwait
+        std::merge(a, a + h, a + h, a + n, tmp, key_less);  // stable: equal keys keep the left run first
+        std::memcpy(a, tmp, n * sizeof(AxisEnt));
+    }
+    void tie_order_node(const TieOrder& T, size_t off, size_t len, int buf, uint32_t* out) {
+        AxisEnt* const* cur = T.list[buf];
         if (len == 1) {
-            out[0] = objs[0];
+            out[0] = T.kids[cur[0][off].id];
             return;
         }
-        if (len == 2) {
-            out[0] = objs[1];
-            out[1] = objs[0];
+        if (len == 2) {  // no sort: left = P[0], right = P[1] (bvh.rs:24-27), right first
+            const uint32_t a = cur[0][off].id, b = cur[0][off + 1].id;
+            const bool a_first = T.pos[a] < T.pos[b];
+            out[0] = T.kids[a_first ? b : a];
+            out[1] = T.kids[a_first ? a : b];
             return;
-        }
-        double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (uint32_t o : objs) {
-            const double* b = d.objects[o].bbox;
-            for (int k = 0; k < 3; k++) mn[k] = std::fmin(mn[k], b[2 * k]), mx[k] = std::fmax(mx[k], b[2 * k + 1]);
         }
         double s[3];
-        for (int k = 0; k < 3; k++) s[k] = std::fmax(mx[k] - mn[k], 0.0);
-        int axis = s[0] > s[1] ? (s[0] > s[2] ? 0 : 2) : (s[1] > s[2] ? 1 : 2);  // aabb.rs:80-92
-        std::stable_sort(objs.begin(), objs.end(), [&](uint32_t x, uint32_t y) {
-            return total_order_key(d.objects[x].bbox[2 * axis]) < total_order_key(d.objects[y].bbox[2 * axis]);
-        });
-        size_t mid = len / 2;
-        std::vector<uint32_t> left(objs.begin(), objs.begin() + mid), right(objs.begin() + mid, objs.end());
-        objs.clear();
-        objs.shrink_to_fit();
-        const size_t n_right = right.size();
-        if (len >= 65536) {
-#pragma omp task default(shared) firstprivate(out)
-            bvh_visit_order(std::move(right), out);
-            bvh_visit_order(std::move(left), out + n_right);
+        for (int k = 0; k < 3; k++) {
+            double mn = INFINITY, mx = -INFINITY;
+            const AxisEnt* e = cur[k] + off;
+            for (size_t i = 0; i < len; i++) mn = std::fmin(mn, e[i].mn), mx = std::fmax(mx, e[i].mx);
+            s[k] = std::fmax(mx - mn, 0.0);
+        }
+        const int axis = s[0] > s[1] ? (s[0] > s[2] ? 0 : 2) : (s[1] > s[2] ? 1 : 2);  // aabb.rs:80-92
+        const size_t mid = len / 2, n_right = len - mid;
+        {
+            const AxisEnt* e = cur[axis] + off;  // the node in sorted order
+            for (size_t i = 0; i < len; i++) T.pos[e[i].id] = (uint32_t)i;
+        }
+        AxisEnt* const* nxt = T.list[buf ^ 1];
+        for (int k = 0; k < 3; k++) {
+            const AxisEnt* e = cur[k] + off;
+            AxisEnt* lo = nxt[k] + off;
+            AxisEnt* hi = nxt[k] + off + mid;
+            if (k == axis) {
+                std::memcpy(lo, e, len * sizeof(AxisEnt));
+                continue;
+            }
+            for (size_t i = 0; i < len; i++) {
+                if (T.pos[e[i].id] < mid)
+                    *lo++ = e[i];
+                else
+                    *hi++ = e[i];
+            }
+            // equal keys: from the parent's order to this node's sorted order
+            for (AxisEnt* half : {nxt[k] + off, nxt[k] + off + mid}) {
+                const size_t n = half == nxt[k] + off ? mid : n_right;
+                for (size_t i = 0; i + 1 < n;) {
+                    size_t j = i + 1;
+                    const uint64_t key = total_order_key(half[i].mn);
+                    while (j < n && total_order_key(half[j].mn) == key) j++;
+                    if (j - i > 1) std::sort(half + i, half + j, [&](const AxisEnt& x, const AxisEnt& y) { return T.pos[x.id] < T.pos[y.id]; });
+                    i = j;
+                }
+            }
+        }
+        if (len >= 16384) {
+#pragma omp task default(shared)
+            tie_order_node(T, off + mid, n_right, buf ^ 1, out);
+            tie_order_node(T, off, mid, buf ^ 1, out + n_right);
 #pragma omp taskwait
         } else {
-            bvh_visit_order(std::move(right), out);
-            bvh_visit_order(std::move(left), out + n_right);
+            tie_order_node(T, off + mid, n_right, buf ^ 1, out);
+            tie_order_node(T, off, mid, buf ^ 1, out + n_right);
         }
+    }
+    // kids[0..n) -> the same ids in tie order
+    void bvh_visit_order(std::vector<uint32_t>& kids) {
+        const size_t n = kids.size();
+        if (n < 2) return;
+        std::vector<AxisEnt> store[2][3];
+        std::vector<uint32_t> pos(n), out(n);
+        TieOrder T;
+        T.kids = kids.data();
+        T.pos = pos.data();
+        for (int b = 0; b < 2; b++)
+            for (int k = 0; k < 3; k++) store[b][k].resize(n), T.list[b][k] = store[b][k].data();
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n; i++) {
+            const double* bb = d.objects[kids[i]].bbox;
+            for (int k = 0; k < 3; k++) T.list[0][k][i] = AxisEnt{bb[2 * k], bb[2 * k + 1], (uint32_t)i, 0};
+            pos[i] = (uint32_t)i;
+        }
+#pragma omp parallel
+#pragma omp single
+        {
+            for (int k = 0; k < 3; k++) {
+#pragma omp task default(shared) firstprivate(k)
+                sort_ents(T.list[0][k], T.list[1][k], n);
+            }
+#pragma omp taskwait
+            tie_order_node(T, 0, n, 0, out.data());
+        }
+        kids.swap(out);
+    }
+
+    // A BVH whose children are all shapes (a mesh, a soup): the leaves of walk() computed by all cores.
+    // Returns false - with nothing changed - when a child is a container or fails, so that the serial
+    // walk handles it and reports the error.
+    bool leaves_in_parallel(const std::vector<uint32_t>& order, const Affine& chain, uint32_t group, bool in_medium) {
+        const size_t n = order.size();
+        for (uint32_t c : order) {
+            const uint32_t k = d.objects[c].kind;
+            if (k != RT_OBJ_SPHERE && k != RT_OBJ_QUAD && k != RT_OBJ_TRIANGLE) return false;
+        }
+        std::vector<FlatPrim>& G = groups[group];
+        const size_t base = G.size();
+        G.resize(base + n);
+        const uint32_t rank0 = next_rank;
+        bool ok = true;
+        uint64_t n_sph = 0;
+#pragma omp parallel for schedule(static) reduction(&& : ok) reduction(+ : n_sph)
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t obj = order[i];
+            FlatPrim& fp = G[base + i];
+            uint32_t kind = 0;
+            if (!leaf(obj, chain, fp.g, kind, fp.lo, fp.hi, nullptr, true)) {
+                ok = false;
+                continue;
+            }
+            fp.m.kind_mat = (kind << 30) | d.objects[obj].material;
+            fp.m.object = obj;
+            fp.m.rank = in_medium ? 0 : rank0 + (uint32_t)i;
+            fp.m.xform = chain.xform;
+            if (!in_medium) out.ranks[obj] = fp.m.rank;
+            n_sph += kind == PRIM_SPHERE;
+        }
+        if (!ok) {
+            G.resize(base);
+            return false;
+        }
+        if (!in_medium) next_rank += (uint32_t)n;
+        out.n_spheres += (uint32_t)n_sph;
+        out.n_planars += (uint32_t)(n - n_sph);
+        return true;
     }
 
     // depth-first walk in tie order; group = which primitive set receives the leaves
@@ -473,17 +605,10 @@ struct Compiler {
                 for (uint32_t k = 0; k < o.child_count; k++) walk(d.children[o.first_child + k], chain, group, in_medium);
                 break;
             case RT_OBJ_BVH: {
-                std::vector<uint32_t> kids(d.children + o.first_child, d.children + o.first_child + o.child_count);
-                std::vector<uint32_t> order;
-                if ((flags & RT_BUILD_NO_REF_RANKS) || in_medium) {
-                    order = kids;
-                } else {
-                    order.resize(kids.size());
-                    uint32_t* dst = order.data();
-#pragma omp parallel
-#pragma omp single
-                    bvh_visit_order(std::move(kids), dst);
-                }
+                std::vector<uint32_t> order(d.children + o.first_child, d.children + o.first_child + o.child_count);
+                if (!((flags & RT_BUILD_NO_REF_RANKS) || in_medium)) bvh_visit_order(order);
+                if (order.size() > 100000) timer.lap("  BVH::from_vec tie order");
+                if (order.size() >= 4096 && leaves_in_parallel(order, chain, group, in_medium)) break;
                 for (uint32_t c : order) walk(c, chain, group, in_medium);
                 break;
             }
@@ -550,13 +675,29 @@ struct Compiler {
         }
     }
 
+    // RT2025_TIMING=1 prints the wall time of every phase to stderr
+    struct PhaseTimer {
+        bool on = getenv("RT2025_TIMING") != nullptr;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        void lap(const char* what) {
+            if (!on) return;
+            auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[rt2025 compile] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+            t0 = t1;
+        }
+    };
+
+    PhaseTimer timer;
     int run() {
         if (!validate()) return status;
+        timer.lap("validate");
         copy_tables();
+        timer.lap("copy tables");
         out.ranks.assign(d.n_objects, RT_NONE);
         groups.emplace_back();
         walk(d.world_root, Affine(), 0, false);
         if (status != RT_OK) return status;
+        timer.lap("walk (ranks + leaves)");
         if (d.lights_root != RT_NONE) {
             walk_lights(d.lights_root, Affine(), 1.0);
             if (status != RT_OK) return status;
@@ -578,10 +719,14 @@ struct Compiler {
         std::vector<uint32_t> roots;
         for (auto& g : groups) {
             std::vector<BuildBox> boxes(g.size());
+#pragma omp parallel for schedule(static) if (g.size() > 65536)
             for (size_t i = 0; i < g.size(); i++)
                 for (int k = 0; k < 3; k++) boxes[i].lo[k] = round_down(g[i].lo[k]), boxes[i].hi[k] = round_up(g[i].hi[k]);
             std::vector<uint32_t> order;
+            timer.lap("build boxes");
             uint32_t root = build_bvh(boxes, base, out.nodes, order, out.bvh_depth);
+            timer.lap("SAH build");
+#pragma omp parallel for schedule(static) if (g.size() > 65536)
             for (size_t i = 0; i < g.size(); i++) {
                 out.geom[base + i] = g[order[i]].g;
                 out.meta[base + i] = g[order[i]].m;
@@ -589,6 +734,7 @@ struct Compiler {
             roots.push_back(root);
             base += (uint32_t)g.size();
             std::vector<FlatPrim>().swap(g);
+            timer.lap("reorder primitives");
         }
         // Renumber the nodes breadth first from the world root (then the media groups): any prefix of
         // the array is then the top of the tree, which the kernels stage in shared memory.
@@ -622,6 +768,7 @@ struct Compiler {
             for (uint32_t& root : roots)
                 if (root != INVALID_REF && !(root & LEAF_FLAG)) root = new_index[root];
         }
+        timer.lap("breadth-first renumbering");
         out.world_root = roots[0];
         for (size_t m = 0; m < out.media.size(); m++) {
             Medium& med = out.media[m];
