@@ -7,7 +7,8 @@ directions uniform on the sphere).  One JSON line per (shape, N, ray set).
     python bench_closest_hit.py [--sizes 1000000 10000000] [--rays 16777216] [--oracle-rays 200000]
 
 Rays live in HBM (torch tensors); timing is CUDA events around rt_closest_hit_device, best of 5 after 2
-warm-ups.  Algorithmic bytes per ray (roofline): 56 (ray in) + 24 (hit out) + node_visits*64 +
+warm-ups.  Under torchrun (N ranks) every rank holds a replica of the scene and traces its 1/N slice of the same batch - no
+collective on the data path (replicas only) - and the time is the max over ranks.  Algorithmic bytes per ray (roofline): 56 (ray in) + 24 (hit out) + node_visits*64 +
 prim_tests*P with P = 128 (triangle record) or 64 (sphere), counts measured by the RT_OPT_COUNT
 instantiation of the same kernel.  The CPU figure is the oracle's reference-semantics traversal
 (median-split BVH, virtual dispatch) on `--oracle-rays` rays of the same batch, with an id/t parity
@@ -56,9 +57,18 @@ def main():
     ap.add_argument("--oracle-rays", type=int, default=200_000)
     ap.add_argument("--no-oracle", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # the scene compile step is OpenMP: share the host cores between the ranks (torchrun presets 1 thread)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -71,39 +81,53 @@ def main():
             hs = rt.named_scene(shape, seed=5, params=[n])
             t_host = time.perf_counter() - t0
             t0 = time.perf_counter()
-            sc = rt.Scene(hs)
+            sc = rt.Scene(hs, device=local_rank)
             t_build = time.perf_counter() - t0
             info = sc.info()
             osc = None
-            if not args.no_oracle:
+            if not args.no_oracle and rank == 0:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import orc
                 t0 = time.perf_counter()
                 osc = orc.OracleScene(hs)
                 t_orc_build = time.perf_counter() - t0
             for kind in ("primary", "incoherent"):
-                rays = make_rays(torch, args.rays, kind, 11)
-                out = torch.empty((args.rays, 3), dtype=torch.float64, device="cuda")  # 24-byte rt_hit records
+                rays_all = make_rays(torch, args.rays, kind, 11)  # same batch on every rank (seeded)
+                per = args.rays // world
+                rays = rays_all[rank * per:(rank + 1) * per].contiguous() if world > 1 else rays_all
+                n_mine = rays.shape[0]
+                out = torch.empty((n_mine, 3), dtype=torch.float64, device="cuda")  # 24-byte rt_hit records
                 stream = torch.cuda.current_stream().cuda_stream
                 best = None
                 for k in range(7):
-                    st = sc.closest_hit_device(rays.data_ptr(), args.rays, out.data_ptr(), stream=stream)
-                    if k >= 2 and (best is None or st.ms_total < best):
-                        best = st.ms_total
-                cst = sc.closest_hit_device(rays.data_ptr(), args.rays, out.data_ptr(), flags=rt.RT_OPT_COUNT, stream=stream)
-                nodes, prims = cst.node_visits / args.rays, cst.prim_tests / args.rays
+                    if world > 1:
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    st = sc.closest_hit_device(rays.data_ptr(), n_mine, out.data_ptr(), stream=stream)
+                    ms = st.ms_total
+                    if world > 1:  # device time, max over ranks
+                        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+                        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                        ms = float(tmax.item())
+                    if k >= 2 and (best is None or ms < best):
+                        best = ms
+                cst = sc.closest_hit_device(rays.data_ptr(), n_mine, out.data_ptr(), flags=rt.RT_OPT_COUNT, stream=stream)
+                nodes, prims = cst.node_visits / n_mine, cst.prim_tests / n_mine
+                if rank != 0:
+                    del rays, out, rays_all
+                    continue
                 P = 128 if shape == "tri_soup" else 64
                 bytes_per_ray = 56 + 24 + nodes * 64 + prims * P
-                mrays = args.rays / best / 1e3
-                line = {"metric": "closest_hit_mrays_per_sec", "value": mrays, "unit": "Mrays/s", "n_gpus": 1, "dtype": "f64",
+                mrays = per * world / best / 1e3
+                line = {"metric": "closest_hit_mrays_per_sec", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "dtype": "f64", "scaling": "strong",
                         "config": {"workload": f"{shape} N={n} rays={args.rays} {kind}", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth,
                                    "device_bytes": info.device_bytes, "host_scene_s": t_host, "scene_create_s": t_build},
                         "ms": best, "nodes_per_ray": nodes, "prims_per_ray": prims,
                         "roofline": {"bound": "hbm", "achieved": mrays * 1e6 * bytes_per_ray / 1e9, "peak": peak, "unit": "GB/s",
-                                     "frac": mrays * 1e6 * bytes_per_ray / 1e9 / peak, "bytes_per_ray": bytes_per_ray}}
+                                     "frac": mrays * 1e6 * bytes_per_ray / 1e9 / peak / world, "bytes_per_ray": bytes_per_ray}}
                 if osc is not None:
-                    m = min(args.oracle_rays, args.rays)
-                    pick = torch.arange(m, device="cuda") * (args.rays // m)  # a strided sample of the batch
+                    m = min(args.oracle_rays, n_mine)
+                    pick = torch.arange(m, device="cuda") * (n_mine // m)  # a strided sample of this rank's slice
                     sub = rays[pick].cpu().numpy().view(rt.rt_ray_dtype).reshape(-1)
                     t0 = time.perf_counter()
                     want = osc.closest_hit(sub, mode=0)
@@ -116,9 +140,14 @@ def main():
                                             "sample": f"{m} rays strided through the batch, reference-semantics traversal (median-split BVH built in {t_orc_build:.1f} s)"}
                     line["parity"] = {"rays": int(m), "hits": int(hit.sum()), "ids_bit_exact": ids_ok, "t_bit_exact": t_ok}
                 print(json.dumps(line), flush=True)
-                del rays, out
+                del rays, out, rays_all
             sc.close()
             del sc, hs, osc
+
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
