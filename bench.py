@@ -22,6 +22,11 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# torchrun presets OMP_NUM_THREADS=1 for its workers.  The host side here is OpenMP (scene compile, and the CPU
+# reference arm, which has to use every host thread and runs on rank 0 alone): size it before libgomp loads.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    _cores = os.cpu_count() or 8
+    os.environ["OMP_NUM_THREADS"] = str(_cores if "reference" in sys.argv else max(1, _cores // int(os.environ["WORLD_SIZE"])))
 _spec = importlib.util.spec_from_file_location("rt2025", os.path.join(ROOT, "raytracer-2025_b200", "rt2025.py"))
 rt = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(rt)
