@@ -332,6 +332,11 @@ int rt_render_multi(rt_scene* const* scenes, uint32_t n_scenes, const rt_camera*
  * `accum` holds mean linear radiance (host pointer), `rgb` receives n_pixels*3 bytes. */
 int rt_tonemap(const void* accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map,
                uint8_t* rgb);
+/* The same on buffers that already live on the current device (e.g. the framebuffer a multi-GPU client
+ * has just reduced with NCCL): `d_accum` and `d_rgb` are device pointers, the work is ordered on
+ * `stream` (a cudaStream_t, NULL = default stream) and the call returns once the image is complete. */
+int rt_tonemap_device(const void* d_accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map,
+                      uint8_t* d_rgb, void* stream);
 
 /* Introspection used by tests and the roofline arithmetic (not needed by a renderer client). */
 typedef struct rt_scene_info {

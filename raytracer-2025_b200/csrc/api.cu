@@ -38,13 +38,53 @@ struct CudaFail {
     std::string what;
 };
 
+// All tables of a scene live in ONE stream-ordered allocation (cudaMallocAsync: freed blocks stay in the
+// device's pool, so a client that builds a scene per frame - Camera::render does - pays no driver call
+// after the first frame; a dozen cudaMalloc/cudaFree pairs per scene cost 10-50 ms with visible jitter).
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    template <class T>
+    size_t reserve(const std::vector<T>& v) {
+        size = (size + 255) & ~size_t(255);
+        const size_t at = size;
+        size += v.size() * sizeof(T);
+        return at;
+    }
+    void allocate(cudaStream_t st) {
+        size = (size + 255) & ~size_t(255);
+        if (size) CU(cudaMallocAsync((void**)&base, size, st));
+    }
+    template <class T>
+    T* put(const std::vector<T>& v, cudaStream_t st) {
+        used = (used + 255) & ~size_t(255);
+        if (v.empty()) return nullptr;
+        T* d = reinterpret_cast<T*>(base + used);
+        CU(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        used += v.size() * sizeof(T);
+        return d;
+    }
+};
+
+void keep_pool_memory(int device) {  // once per device: the default pool keeps up to 1 GiB of freed blocks
+    static std::mutex mu;
+    static std::vector<int> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (std::find(done.begin(), done.end(), device) != done.end()) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done.push_back(device);
+}
+
+// short-lived device buffers of the host-pointer entry points: stream-ordered (default stream), pooled
 template <class T>
-T* upload(const std::vector<T>& v) {
-    if (v.empty()) return nullptr;
-    T* d = nullptr;
-    CU(cudaMalloc(&d, v.size() * sizeof(T)));
-    CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return d;
+void scratch_alloc(T** p, size_t bytes) { CU(cudaMallocAsync((void**)p, bytes, nullptr)); }
+inline void scratch_free(void* p) {
+    if (p) cudaFreeAsync(p, nullptr);
 }
 
 struct Workspace {  // wavefront buffers, cached on the scene between renders
@@ -95,7 +135,7 @@ struct rt_scene {
     int device = 0;
     int sm_count = 148;
     SceneView view{};
-    std::vector<void*> allocs;
+    void* arena = nullptr;  // one stream-ordered allocation holding every table of the view
     std::vector<uint32_t> ranks;
     rt_scene_info info{};
     uint32_t lights_flat = 1;
@@ -119,18 +159,28 @@ int check_device(int requested, int& device, int& sm_count) {
         if (cudaSetDevice(requested) != cudaSuccess) return set_err(RT_ERR_CUDA, "cudaSetDevice failed");
     }
     cudaGetDevice(&device);
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return set_err(RT_ERR_CUDA, "cudaGetDeviceProperties failed");
-    if (p.major != 10)
-        return set_err(RT_ERR_NO_DEVICE, std::string("built for sm_100a only; device is sm_") + std::to_string(p.major) + std::to_string(p.minor));
-    sm_count = p.multiProcessorCount;
+    // cudaGetDeviceProperties costs 5-45 ms per call on this platform (it was most of rt_tonemap and a third of
+    // rt_scene_create): three attributes, asked once per device
+    struct Cached {
+        int major = -1, minor = 0, sms = 0;
+    };
+    static std::mutex mu;
+    static std::vector<Cached> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    if ((int)cache.size() <= device) cache.resize(device + 1);
+    Cached& c = cache[device];
+    if (c.major < 0) {
+        int major = 0, minor = 0, sms = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+            cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+            return set_err(RT_ERR_CUDA, "cudaDeviceGetAttribute failed");
+        c.major = major, c.minor = minor, c.sms = sms;
+    }
+    if (c.major != 10)
+        return set_err(RT_ERR_NO_DEVICE, std::string("built for sm_100a only; device is sm_") + std::to_string(c.major) + std::to_string(c.minor));
+    sm_count = c.sms;
     return RT_OK;
-}
-
-template <class T>
-T* track(rt_scene* s, T* p) {
-    if (p) s->allocs.push_back((void*)p);
-    return p;
 }
 
 }  // namespace
@@ -165,18 +215,20 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         s->device = device;
         s->sm_count = sms;
         SceneView& v = s->view;
-        v.nodes = track(s, upload(cs.nodes));
-        v.geom = track(s, upload(cs.geom));
-        v.meta = track(s, upload(cs.meta));
-        v.xforms = track(s, upload(cs.xforms));
-        v.materials = track(s, upload(cs.materials));
-        v.textures = track(s, upload(cs.textures));
-        v.images = track(s, upload(cs.images));
-        v.texels = track(s, upload(cs.texels));
-        v.perlins = track(s, upload(cs.perlins));
-        v.media = track(s, upload(cs.media));
-        v.lights = track(s, upload(cs.lights));
-        v.remaps = track(s, upload(cs.remaps));
+        keep_pool_memory(device);
+        {
+            cudaStream_t st = cudaStreamPerThread;
+            Arena a;
+            a.reserve(cs.nodes), a.reserve(cs.geom), a.reserve(cs.meta), a.reserve(cs.xforms), a.reserve(cs.materials), a.reserve(cs.textures);
+            a.reserve(cs.images), a.reserve(cs.texels), a.reserve(cs.perlins), a.reserve(cs.media), a.reserve(cs.lights), a.reserve(cs.remaps);
+            a.allocate(st);
+            s->arena = a.base;
+            v.nodes = a.put(cs.nodes, st), v.geom = a.put(cs.geom, st), v.meta = a.put(cs.meta, st), v.xforms = a.put(cs.xforms, st);
+            v.materials = a.put(cs.materials, st), v.textures = a.put(cs.textures, st), v.images = a.put(cs.images, st);
+            v.texels = a.put(cs.texels, st), v.perlins = a.put(cs.perlins, st), v.media = a.put(cs.media, st);
+            v.lights = a.put(cs.lights, st), v.remaps = a.put(cs.remaps, st);
+            CU(cudaStreamSynchronize(st));  // the host vectors die with this call
+        }
         v.world_root = cs.world_root;
         v.n_media = (uint32_t)cs.media.size();
         v.n_lights = (uint32_t)cs.lights.size();
@@ -233,7 +285,10 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
 int rt_scene_destroy(rt_scene* s) {
     if (!s) return RT_OK;
     cudaSetDevice(s->device);
-    for (void* p : s->allocs) cudaFree(p);
+    if (s->arena) {
+        cudaDeviceSynchronize();  // renders of this scene may still be in flight on caller streams
+        cudaFreeAsync(s->arena, cudaStreamPerThread);
+    }
     delete s;
     return RT_OK;
 }
@@ -265,7 +320,7 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
         CU(cudaSetDevice(s->device));
         const bool count = (flags & RT_OPT_COUNT) != 0;
         if (count) {
-            CU(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+            scratch_alloc(&d_cnt, 2 * sizeof(unsigned long long));
             CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
         }
         int grid = s->sm_count * s->extend_blocks_per_sm;
@@ -298,7 +353,7 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    if (d_cnt) cudaFree(d_cnt);
+    scratch_free(d_cnt);
     return rc;
 }
 
@@ -314,8 +369,8 @@ int rt_closest_hit(const rt_scene* s, const rt_ray* rays, uint64_t n, double t_m
     int rc = RT_OK;
     try {
         CU(cudaSetDevice(s->device));
-        CU(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
-        CU(cudaMalloc(&d_out, n * sizeof(rt_hit)));
+        scratch_alloc(&d_rays, n * sizeof(rt_ray));
+        scratch_alloc(&d_out, n * sizeof(rt_hit));
         CU(cudaMemcpy(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice));
         rc = rt_closest_hit_device(s, d_rays, n, t_min, t_max, flags, d_out, nullptr, stats);
         if (rc == RT_OK) {
@@ -325,8 +380,8 @@ int rt_closest_hit(const rt_scene* s, const rt_ray* rays, uint64_t n, double t_m
     } catch (const CudaFail& f) {
         rc = set_err(RT_ERR_CUDA, f.what);
     }
-    cudaFree(d_rays);
-    cudaFree(d_out);
+    scratch_free(d_rays);
+    scratch_free(d_out);
     return rc;
 }
 
@@ -494,13 +549,13 @@ int rt_render(const rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
     int rc = RT_OK;
     try {
         CU(cudaSetDevice(s->device));
-        CU(cudaMalloc(&d, bytes));
+        scratch_alloc(&d, bytes);
         rc = rt_render_device(s, cam, opts, d, nullptr, stats);
         if (rc == RT_OK) CU(cudaMemcpy(accum, d, bytes, cudaMemcpyDeviceToHost));
     } catch (const CudaFail& f) {
         rc = set_err(RT_ERR_CUDA, f.what);
     }
-    cudaFree(d);
+    scratch_free(d);
     return rc;
 }
 
@@ -517,9 +572,9 @@ int rt_render_rgb8(const rt_scene* s, const rt_camera* cam, const rt_render_opts
     int rc = RT_OK;
     try {
         CU(cudaSetDevice(s->device));
-        CU(cudaMalloc(&d_accum, n_px * 3 * sizeof(double)));
-        CU(cudaMalloc(&d_rgb, n_px * 3));
-        CU(cudaMalloc(&d_flag, sizeof(int)));
+        scratch_alloc(&d_accum, n_px * 3 * sizeof(double));
+        scratch_alloc(&d_rgb, n_px * 3);
+        scratch_alloc(&d_flag, sizeof(int));
         CU(cudaMemset(d_flag, 0, sizeof(int)));
         rc = rt_render_device(s, cam, &o, d_accum, nullptr, stats);
         if (rc == RT_OK) {
@@ -534,9 +589,9 @@ int rt_render_rgb8(const rt_scene* s, const rt_camera* cam, const rt_render_opts
     } catch (const CudaFail& f) {
         rc = set_err(RT_ERR_CUDA, f.what);
     }
-    cudaFree(d_accum);
-    cudaFree(d_rgb);
-    cudaFree(d_flag);
+    scratch_free(d_accum);
+    scratch_free(d_rgb);
+    scratch_free(d_flag);
     return rc;
 }
 
@@ -607,28 +662,51 @@ int rt_tonemap(const void* accum, uint32_t accum_type, uint64_t n_pixels, uint32
     int device, sms;
     int rc = check_device(-1, device, sms);
     if (rc != RT_OK) return rc;
-    const size_t elem = accum_type == RT_ACCUM_F64 ? 8 : 4;
-    void* d_in = nullptr;
-    uint8_t* d_out = nullptr;
-    int* d_flag = nullptr;
+    keep_pool_memory(device);
+    const size_t in_bytes = ((size_t)n_pixels * 3 * (accum_type == RT_ACCUM_F64 ? 8 : 4) + 255) & ~size_t(255);
+    const size_t out_bytes = ((size_t)n_pixels * 3 + 255) & ~size_t(255);
+    char* d = nullptr;
+    cudaStream_t st = cudaStreamPerThread;
     try {
-        CU(cudaMalloc(&d_in, n_pixels * 3 * elem));
-        CU(cudaMalloc(&d_out, n_pixels * 3));
-        CU(cudaMalloc(&d_flag, sizeof(int)));
-        CU(cudaMemset(d_flag, 0, sizeof(int)));
-        CU(cudaMemcpy(d_in, accum, n_pixels * 3 * elem, cudaMemcpyHostToDevice));
-        launch_tonemap(d_in, accum_type == RT_ACCUM_F64, n_pixels, toon_map, d_out, d_flag, nullptr);
+        CU(cudaMallocAsync((void**)&d, in_bytes + out_bytes + 256, st));
+        int* d_flag = reinterpret_cast<int*>(d + in_bytes + out_bytes);
+        CU(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        CU(cudaMemcpyAsync(d, accum, (size_t)n_pixels * 3 * (accum_type == RT_ACCUM_F64 ? 8 : 4), cudaMemcpyHostToDevice, st));
+        launch_tonemap(d, accum_type == RT_ACCUM_F64, n_pixels, toon_map, reinterpret_cast<uint8_t*>(d + in_bytes), d_flag, st);
         CU(cudaGetLastError());
-        CU(cudaMemcpy(rgb, d_out, n_pixels * 3, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(rgb, d + in_bytes, (size_t)n_pixels * 3, cudaMemcpyDeviceToHost, st));
         int flag = 0;
-        CU(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         if (flag) rc = set_err(RT_ERR_INVALID, "NaN radiance in the image (utils/color.rs:28 asserts)");
     } catch (const CudaFail& f) {
         rc = set_err(RT_ERR_CUDA, f.what);
     }
-    cudaFree(d_in);
-    cudaFree(d_out);
-    cudaFree(d_flag);
+    if (d) cudaFreeAsync(d, st);
+    return rc;
+}
+
+int rt_tonemap_device(const void* d_accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map, uint8_t* d_rgb, void* stream) {
+    if (!d_accum || !d_rgb) return set_err(RT_ERR_INVALID, "null argument");
+    int device, sms;
+    int rc = check_device(-1, device, sms);
+    if (rc != RT_OK) return rc;
+    keep_pool_memory(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_flag = nullptr;
+    try {
+        CU(cudaMallocAsync((void**)&d_flag, 256, st));
+        CU(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        launch_tonemap(d_accum, accum_type == RT_ACCUM_F64, n_pixels, toon_map, d_rgb, d_flag, st);
+        CU(cudaGetLastError());
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (flag) rc = set_err(RT_ERR_INVALID, "NaN radiance in the image (utils/color.rs:28 asserts)");
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    if (d_flag) cudaFreeAsync(d_flag, st);
     return rc;
 }
 

@@ -23,7 +23,7 @@ RT_BUILD_NO_REF_RANKS = 1
 # every symbol include/rt2025.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [
     "rt_scene_create", "rt_scene_destroy", "rt_closest_hit", "rt_closest_hit_device", "rt_render",
-    "rt_render_device", "rt_render_rgb8", "rt_render_multi", "rt_tonemap", "rt_scene_get_info", "rt_scene_get_ranks", "rt_last_error",
+    "rt_render_device", "rt_render_rgb8", "rt_render_multi", "rt_tonemap", "rt_tonemap_device", "rt_scene_get_info", "rt_scene_get_ranks", "rt_last_error",
     "rt_abi_version", "rt_device_count",
 ]
 
@@ -206,6 +206,7 @@ def product_lib(required=True):
         L.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p,
                                       C.POINTER(rt_stats)]
         L.rt_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.rt_tonemap_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         L.rt_scene_get_info.argtypes = [C.c_void_p, C.POINTER(rt_scene_info)]
         L.rt_scene_get_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         _product = L
@@ -466,6 +467,12 @@ def render_multi(scenes, camera=None, **kw):
     st = rt_stats()
     _check(L.rt_render_multi(handles, len(scenes), C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st)), L)
     return img, st
+
+
+def tonemap_device(d_accum_ptr, n_pixels, d_rgb_ptr, toon_map=0, accum_type=RT_ACCUM_F32, stream=None):
+    """rt_tonemap_device: Color::to_rgb on a framebuffer that already lives on the current device."""
+    L = product_lib()
+    _check(L.rt_tonemap_device(d_accum_ptr, accum_type, n_pixels, toon_map, d_rgb_ptr, stream), L)
 
 
 def tonemap(accum, toon_map=0):

@@ -100,6 +100,7 @@ extern "C" {
     pub fn rt_closest_hit(scene: *const rt_scene, rays: *const rt_ray, n: u64, t_min: f64, t_max: f64, flags: u32, out: *mut rt_hit, stats: *mut rt_stats) -> i32;
     pub fn rt_render(scene: *const rt_scene, cam: *const rt_camera, opts: *const rt_render_opts, accum: *mut c_void, stats: *mut rt_stats) -> i32;
     pub fn rt_tonemap(accum: *const c_void, accum_type: u32, n_pixels: u64, toon_map: u32, rgb: *mut u8) -> i32;
+    pub fn rt_tonemap_device(d_accum: *const c_void, accum_type: u32, n_pixels: u64, toon_map: u32, d_rgb: *mut u8, stream: *mut c_void) -> i32;
     pub fn rt_last_error() -> *const c_char;
     pub fn rt_abi_version() -> u32;
     pub fn rt_device_count() -> i32;

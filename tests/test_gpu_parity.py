@@ -393,6 +393,22 @@ def test_obj_faces_with_remapped_materials_vs_oracle(gpu, rt, orc):
     image_close(img, ref, frac_bad=5e-3)
 
 
+def test_tonemap_device_equals_host_entry(gpu, rt):
+    import torch
+    rng = np.random.default_rng(3)
+    img = (rng.random((37, 53, 3)) * 1.6).astype(np.float32)
+    for toon in (0, 1):
+        want = rt.tonemap(img, toon)
+        d_in = torch.from_numpy(img).cuda()
+        d_out = torch.empty((37, 53, 3), dtype=torch.uint8, device="cuda")
+        rt.tonemap_device(d_in.data_ptr(), 37 * 53, d_out.data_ptr(), toon, rt.RT_ACCUM_F32, torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    bad = torch.full((4, 4, 3), float("nan"), dtype=torch.float32, device="cuda")
+    out = torch.empty((4, 4, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError):
+        rt.tonemap_device(bad.data_ptr(), 16, out.data_ptr())
+
+
 def test_render_rgb8_equals_render_then_tonemap(gpu, rt):
     hs = rt.named_scene("cornell_glass", seed=3, params=[48, 9, 12])
     sc = rt.Scene(hs)
