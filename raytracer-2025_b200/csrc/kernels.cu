@@ -586,62 +586,63 @@ __global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(Scen
                             }
                             Rand2 pick = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_MIXTURE);
                             Rand2 dx = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_DIRECTION);
-                            D3 gen;
+                            D3 gen = D3{0.0, 0.0, 0.0};
                             const bool have_lights = sv.n_lights > 0;
+                            // No `break` inside the divergent sampling branch below: with an early-exit edge the warp would
+                            // only reconverge at the end of the switch and run the whole pdf evaluation once per side
+                            // (measured: 16 of 32 lanes active from here on).  stop: 1 = the reference panics, 2 = None (black).
+                            int stop = 0;
                             if (have_lights && !(pick.a < 0.5)) {
-                                if (!lights_random(sv, h.p, pick.b, dx.a, dx.b, gen)) {
-                                    error = true;
-                                    break;
-                                }
+                                if (!lights_random(sv, h.p, pick.b, dx.a, dx.b, gen)) stop = 1;
                             } else if (dis) {
                                 Rand2 dpick = philox_pair(P.seed, pixel, sidx, segment, RT_SLOT_DISNEY);
                                 D3 v_in_l;
-                                if (!disney::generate_local(DP, v_out_l, h.front_face, dpick, dx, v_in_l, error)) break;  // None: black (camera.rs:313-315)
-                                if (!unit_vector(onb_to_world(uvw, v_in_l), gen)) {
-                                    error = true;
-                                    break;
-                                }
+                                bool derr = false;
+                                if (!disney::generate_local(DP, v_out_l, h.front_face, dpick, dx, v_in_l, derr))
+                                    stop = derr ? 1 : 2;  // None: black (camera.rs:313-315)
+                                else if (!unit_vector(onb_to_world(uvw, v_in_l), gen))
+                                    stop = 1;
                             } else {
                                 gen = iso ? random_unit_vector(dx.a, dx.b) : onb_to_world(uvw, random_cosine_direction(dx.a, dx.b));
                             }
                             // PDF::value, pdf.rs:22-29, 51-57, disney.rs:656-666
-                            D3 axp;
-                            double value0;
-                            if (iso) {
-                                value0 = 1.0 / (4.0 * RT_PI);
-                                axp = albedo / (4.0 * RT_PI);
-                            } else {
-                                D3 ud;
-                                if (!unit_vector(gen, ud)) {
-                                    error = true;
-                                    break;
-                                }
-                                if (dis) {
-                                    D3 v_in_l = D3{dot(ud, uvw.u), dot(ud, uvw.v), dot(ud, uvw.w)};
-                                    disney::evaluate_disney(DP, v_out_l, v_in_l, h.front_face, axp, value0, error);
-                                    if (error) break;
+                            D3 axp = D3{0.0, 0.0, 0.0};
+                            double value0 = 0.0;
+                            if (!stop) {
+                                if (iso) {
+                                    value0 = 1.0 / (4.0 * RT_PI);
+                                    axp = albedo / (4.0 * RT_PI);
                                 } else {
-                                    double cosine_theta = dot(ud, uvw.v);
-                                    value0 = rmax(0.0, cosine_theta / RT_PI);
-                                    axp = albedo * rmax(cosine_theta, 0.0) / RT_PI;
+                                    D3 ud;
+                                    if (!unit_vector(gen, ud)) {
+                                        stop = 1;
+                                    } else if (dis) {
+                                        D3 v_in_l = D3{dot(ud, uvw.u), dot(ud, uvw.v), dot(ud, uvw.w)};
+                                        bool derr = false;
+                                        disney::evaluate_disney(DP, v_out_l, v_in_l, h.front_face, axp, value0, derr);
+                                        if (derr) stop = 1;
+                                    } else {
+                                        double cosine_theta = dot(ud, uvw.v);
+                                        value0 = rmax(0.0, cosine_theta / RT_PI);
+                                        axp = albedo * rmax(cosine_theta, 0.0) / RT_PI;
+                                    }
                                 }
                             }
                             double pdf_val = value0;
-                            if (have_lights) {
+                            if (!stop && have_lights) {
                                 double value1 = lights_pdf_value(sv, P.lights_flat, h.p, gen);
-                                if (isnan(value1) || (value0 == 0.0 && value1 == 0.0)) {  // hits.rs:64, pdf.rs:105-109
-                                    error = true;
-                                    break;
-                                }
-                                pdf_val = value0 * 0.5 + value1 * 0.5;
+                                if (isnan(value1) || (value0 == 0.0 && value1 == 0.0))  // hits.rs:64, pdf.rs:105-109
+                                    stop = 1;
+                                else
+                                    pdf_val = value0 * 0.5 + value1 * 0.5;
                             }
-                            if (pdf_val == 0.0) {  // camera.rs:309
-                                error = true;
-                                break;
+                            if (!stop && pdf_val == 0.0) stop = 1;  // camera.rs:309
+                            if (!stop) {
+                                nr.d = gen;
+                                nbeta = beta * (axp / pdf_val);
+                                alive = true;
                             }
-                            nr.d = gen;
-                            nbeta = beta * (axp / pdf_val);
-                            alive = true;
+                            if (stop == 1) error = true;
                             break;
                         }
                         default: break;

@@ -27,5 +27,7 @@ for l in lines:
     byfile[l[0]][0] += l[3]; byfile[l[0]][1] += l[4]; byfile[l[0]][2] += l[5]
 for k, v in byfile.items(): print(f"  {k:20s} samples {v[0]/ts*100:5.1f}%  warp-instr {v[1]/ti*100:5.1f}%  lanes {v[2]/max(v[1],1):.1f}")
 print("top lines by samples:")
-for l in sorted(lines, key=lambda l: -l[3])[:45]:
+import os
+by = 4 if os.environ.get("BY") == "ins" else 3  # BY=ins sorts by executed warp instructions instead of stall samples
+for l in sorted(lines, key=lambda l: -l[by])[:int(os.environ.get("TOP", "45"))]:
     print(f"{l[0]:18s}:{l[1]:4d} smp {l[3]/ts*100:5.1f}% ins {l[4]/ti*100:5.1f}% lanes {l[5]/max(l[4],1):5.1f} | {l[2]}")
