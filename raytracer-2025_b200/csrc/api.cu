@@ -256,6 +256,10 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // more as loads in flight and every finished lane is refilled at once (profiles/README.md: 1M-triangle
         // soup, incoherent rays, 392 vs 274 Mrays/s; book2_final 49.4 vs 48.7 ms the other way round)
         v.refill_min = cs.nodes.size() > 100000 ? 1 : REFILL_MIN;
+        // postponed leaves pay off when traversals are long (traverse.cuh); measured crossover between the 3.2 k-node
+        // book-2 scene (off: extend 281 vs 299 ms) and the 11.5 k-face mesh scene (on: 487 vs 502 ms)
+        v.park_leaves = cs.nodes.size() > 4096 ? 1 : 0;
+        if (const char* e = getenv("RT2025_PARK_LEAVES")) v.park_leaves = atoi(e) != 0;  // tuning knob
         if (const char* e = getenv("RT2025_REFILL_MIN")) v.refill_min = (uint32_t)std::min(32l, std::max(1l, atol(e)));  // tuning knob
         // when several CTAs share an SM each gets its share of the 227 KB
         const size_t room = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024 - stack_bytes;

@@ -59,7 +59,7 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
     }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool PARK>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint32_t n, double tmin,
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     RayArrayIO io{sv, rays, out, tmin, tmax};
-    trace_persistent<COUNT, true>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    trace_persistent<COUNT, true, PARK>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
         atomicAdd(&counters[1], (unsigned long long)cnt.prims);
@@ -78,10 +78,9 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
-    if (count)
-        k_closest_hit<true><<<grid, EXTEND_BLOCK, stack_bytes, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
-    else
-        k_closest_hit<false><<<grid, EXTEND_BLOCK, stack_bytes, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
+    auto k = count ? (sv.park_leaves ? k_closest_hit<true, true> : k_closest_hit<true, false>)
+                   : (sv.park_leaves ? k_closest_hit<false, true> : k_closest_hit<false, false>);
+    k<<<grid, EXTEND_BLOCK, stack_bytes, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -237,7 +236,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
 };
 
 // closest surface hit of every path in the extend queue (world.hit without the media, camera.rs:286)
-template <bool COUNT>
+template <bool COUNT, bool PARK>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
     __shared__ uint32_t s_cursor;
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     PathIO io{W.ray_q[W.parity], W.hit_q};
-    trace_persistent<COUNT, true>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    trace_persistent<COUNT, true, PARK>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
         atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
@@ -739,10 +738,8 @@ void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, c
     k_step<<<1, 1, 0, s>>>(W, 0);
 }
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
-    if (count)
-        k_extend<true><<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
-    else
-        k_extend<false><<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
+    auto k = count ? (sv.park_leaves ? k_extend<true, true> : k_extend<true, false>) : (sv.park_leaves ? k_extend<false, true> : k_extend<false, false>);
+    k<<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
 }
 int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
     // media + binning: global-memory nodes only (its shared memory holds just the stacks)
@@ -801,11 +798,12 @@ void launch_finalize(const double* accum, uint64_t n, double scale, void* out, b
 int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
     // dynamic shared memory above 48 KB is opt-in
     cudaError_t e = cudaSuccess;
-    if ((e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(k_closest_hit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
-    if ((e = cudaFuncSetAttribute(k_closest_hit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false>, EXTEND_BLOCK, smem_bytes);
+    const void* big_smem[] = {(const void*)k_extend<false, false>,      (const void*)k_extend<false, true>,      (const void*)k_extend<true, false>,
+                              (const void*)k_extend<true, true>,        (const void*)k_closest_hit<false, false>, (const void*)k_closest_hit<false, true>,
+                              (const void*)k_closest_hit<true, false>,  (const void*)k_closest_hit<true, true>};
+    for (const void* f : big_smem)
+        if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_DIFFUSE>, SHADE_BLOCK, 0);
     return 0;
 }

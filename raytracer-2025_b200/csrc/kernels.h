@@ -24,6 +24,9 @@ constexpr int MEDIA_BLOCK = 256;
 #define RT_REFILL_MIN 32  // SceneView::refill_min default (traverse.cuh, trace_persistent)
 #endif
 constexpr int REFILL_MIN = RT_REFILL_MIN;
+#ifndef RT_SLAB_SIGNSEL
+#define RT_SLAB_SIGNSEL 1  // slab test: near/far planes picked by the sign of 1/d, error bound folded into the addend
+#endif
 #ifndef RT_MEDIA_MIN_BLOCKS
 #define RT_MEDIA_MIN_BLOCKS 2
 #endif

@@ -68,11 +68,23 @@ __device__ __forceinline__ D3 point_to_local(const SceneView& sv, uint32_t xform
 }
 
 // binary32 image of the ray for the slab test: t = fma(plane, idf, noidf)
+#if RT_SLAB_SIGNSEL
+// The absolute error bound of a slab distance is folded into the addend (one copy rounded towards the near side,
+// one towards the far side) and the near/far plane of every axis is picked by the sign of 1/d, so a box costs
+// 6 selects + 6 FMA + 4 min/max instead of 6 FMA + 6 min/max pairs + 6 adds + 4 min/max.
+struct RayF {
+    float idx, idy, idz;          // 1/d, clamped to +-1e30
+    float nxl, nyl, nzl;          // -o * idf - error bound   (-inf on an axis that takes no part in culling)
+    float nxh, nyh, nzh;          // -o * idf + error bound   (+inf ...)
+    bool sx, sy, sz;              // 1/d < 0: the far plane is `lo`
+};
+#else
 struct RayF {
     float idx, idy, idz;     // 1/d, clamped to +-1e30
     float nox, noy, noz;     // -o * idf (rounded once from binary64)
     float ex, ey, ez;        // per-axis absolute error bound of the slab distances
 };
+#endif
 
 __device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
     // An axis whose 1/d overflows binary32 range (d == 0, denormal, NaN) takes no part in culling:
@@ -86,23 +98,40 @@ __device__ __forceinline__ void make_rayf(const RayD& r, RayF& f) {
     };
     bool cx, cy, cz;
     f.idx = inv(r.d.x, cx), f.idy = inv(r.d.y, cy), f.idz = inv(r.d.z, cz);
-    f.nox = (float)(-r.o.x * (double)f.idx);
-    f.noy = (float)(-r.o.y * (double)f.idy);
-    f.noz = (float)(-r.o.z * (double)f.idz);
+    const float nox = (float)(-r.o.x * (double)f.idx);
+    const float noy = (float)(-r.o.y * (double)f.idy);
+    const float noz = (float)(-r.o.z * (double)f.idz);
     // |t_computed - t_exact| <= (|t| + |o*idf|) * 2^-24 ; the |t| part is applied as a relative slack
     const float k = 1.0f / 4194304.0f;  // 2^-22
+#if RT_SLAB_SIGNSEL
+    const float ex = fabsf(nox) * k, ey = fabsf(noy) * k, ez = fabsf(noz) * k;
+    f.nxl = cx ? -INFINITY : nox - ex, f.nxh = cx ? INFINITY : nox + ex;
+    f.nyl = cy ? -INFINITY : noy - ey, f.nyh = cy ? INFINITY : noy + ey;
+    f.nzl = cz ? -INFINITY : noz - ez, f.nzh = cz ? INFINITY : noz + ez;
+    f.sx = f.idx < 0.f, f.sy = f.idy < 0.f, f.sz = f.idz < 0.f;
+#else
+    f.nox = nox, f.noy = noy, f.noz = noz;
     f.ex = cx ? INFINITY : fabsf(f.nox) * k;
     f.ey = cy ? INFINITY : fabsf(f.noy) * k;
     f.ez = cz ? INFINITY : fabsf(f.noz) * k;
+#endif
 }
 
 // returns true when the box may intersect the ray within [tmin_f, tmax_f]; tnear for ordering
 __device__ __forceinline__ bool slab(const RayF& f, const float* lo, const float* hi, float tmin_f, float tmax_f, float& tnear) {
+#if RT_SLAB_SIGNSEL
+    // a NaN candidate (inf - inf on a degenerate axis) is ignored by fmaxf/fminf, i.e. that axis does not cull
+    float tn = fmaxf(fmaxf(__fmaf_rn(f.sx ? hi[0] : lo[0], f.idx, f.nxl), __fmaf_rn(f.sy ? hi[1] : lo[1], f.idy, f.nyl)),
+                     __fmaf_rn(f.sz ? hi[2] : lo[2], f.idz, f.nzl));
+    float tf = fminf(fminf(__fmaf_rn(f.sx ? lo[0] : hi[0], f.idx, f.nxh), __fmaf_rn(f.sy ? lo[1] : hi[1], f.idy, f.nyh)),
+                     __fmaf_rn(f.sz ? lo[2] : hi[2], f.idz, f.nzh));
+#else
     float x0 = __fmaf_rn(lo[0], f.idx, f.nox), x1 = __fmaf_rn(hi[0], f.idx, f.nox);
     float y0 = __fmaf_rn(lo[1], f.idy, f.noy), y1 = __fmaf_rn(hi[1], f.idy, f.noy);
     float z0 = __fmaf_rn(lo[2], f.idz, f.noz), z1 = __fmaf_rn(hi[2], f.idz, f.noz);
     float tn = fmaxf(fmaxf(fminf(x0, x1) - f.ex, fminf(y0, y1) - f.ey), fminf(z0, z1) - f.ez);
     float tf = fminf(fminf(fmaxf(x0, x1) + f.ex, fmaxf(y0, y1) + f.ey), fmaxf(z0, z1) + f.ez);
+#endif
     const float rel = 1.0f / 2097152.0f;  // 2^-21
     tn = __fmaf_rn(-fabsf(tn), rel, tn);
     tf = __fmaf_rn(fabsf(tf), rel, tf);
@@ -349,11 +378,17 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
 // L2/HBM behave the other way round (config-5 soups: 1M triangles incoherent 392 Mrays/s at refill_min 1 vs
 // 274 at 32; 10M: 242 vs 167) and get refill_min = 1; rt_scene_create picks by node count.
 //
+// PARK = postponed leaves: a lane that reaches a leaf parks it and keeps descending until every lane of the
+// warp holds one, so the binary64 primitive tests run converged.  Worth it when traversals are long (1M-triangle
+// soup, 106 nodes per ray: 1099 / 392 Mrays/s primary / incoherent with, 907 / 338 without); on the book scenes
+// (11 nodes + 3.7 primitive tests per ray) the extra votes cost more than they save (extend 299 vs 282 ms), so
+// rt_scene_create picks per scene (SceneView::park_leaves).
+//
 // IO::load(item, ray, tmin, tmax) -> bool and IO::store(item, hit, t, prim) bind the routine to the
 // path streams (k_extend) or to a plain ray array (k_closest_hit).
 // ------------------------------------------------------------------------------------------------
 
-template <bool COUNT, bool USE_RANK, class IO>
+template <bool COUNT, bool USE_RANK, bool PARK, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
                                                  TraceCounters* cnt) {
@@ -450,11 +485,17 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                 } else {
                     cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
                 }
-                if ((cur & LEAF_FLAG) && parked == INVALID_REF) {
+                if (PARK) {  // keep descending with one postponed leaf until every lane of the warp has one
+                    if ((cur & LEAF_FLAG) && parked == INVALID_REF) {
+                        parked = cur;
+                        cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                    }
+                    if (!__any_sync(__activemask(), parked == INVALID_REF)) break;
+                } else if (cur & LEAF_FLAG) {  // plain while-while: leave the node loop with the leaf
                     parked = cur;
                     cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                    break;
                 }
-                if (!__any_sync(__activemask(), parked == INVALID_REF)) break;
             }
             // leaf phase
             while (parked != INVALID_REF) {

@@ -21,6 +21,8 @@ for name, make, strata in cfgs:
         _, st = sc.render(seed=1, accum_type=rt.RT_ACCUM_F32, flags=rt.RT_OPT_STAGE_TIMES)
         if best is None or st.ms_total < best.ms_total:
             best = st
+    _, cst = sc.render(seed=1, accum_type=rt.RT_ACCUM_F32, flags=rt.RT_OPT_COUNT)
+    ctxt = f", {cst.node_visits/cst.segments:.1f} nodes + {cst.prim_tests/cst.segments:.1f} prims per segment"
     otxt = ""
     if not os.environ.get("NO_ORACLE"):
         osc = orc.OracleScene(hs)
@@ -29,5 +31,5 @@ for name, make, strata in cfgs:
         dt = time.perf_counter() - t0
         otxt = f"; oracle {ost.paths/dt/1e6:.2f} Mpaths/s on {orc.lib().orc_num_threads()} threads ({strata} strata)"
     print(f"{name}: {best.paths/1e6:.1f} M paths in {best.ms_total:.1f} ms = {best.paths/best.ms_total/1e3:.1f} Mpaths/s, {best.segments/best.paths:.2f} seg/path, "
-          f"errors {best.errors}, stages gen/ext/media/shade {best.ms_raygen:.0f}/{best.ms_extend:.0f}/{best.ms_other:.0f}/{best.ms_shade:.0f} ms" + otxt, flush=True)
+          f"errors {best.errors}, stages gen/ext/media/shade {best.ms_raygen:.0f}/{best.ms_extend:.0f}/{best.ms_other:.0f}/{best.ms_shade:.0f} ms" + ctxt + otxt, flush=True)
     sc.close()
