@@ -27,6 +27,9 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_SLAB_SIGNSEL
 #define RT_SLAB_SIGNSEL 1  // slab test: near/far planes picked by the sign of 1/d, error bound folded into the addend
 #endif
+#ifndef RT_LDG256
+#define RT_LDG256 1  // 256-bit global loads for nodes and primitive records
+#endif
 #ifndef RT_MEDIA_MIN_BLOCKS
 #define RT_MEDIA_MIN_BLOCKS 2
 #endif

@@ -21,7 +21,7 @@ constexpr int MAX_LEAF_PRIMS = 8;
 constexpr int TRAVERSAL_STACK = 64;
 
 // child reference: interior -> node index; leaf -> LEAF_FLAG | first_prim << 3 | (count - 1)
-struct alignas(16) Node {
+struct alignas(32) Node {
     float lo0[3], hi0[3];
     float lo1[3], hi1[3];
     uint32_t child0, child1;
@@ -31,7 +31,7 @@ static_assert(sizeof(Node) == 64, "node must be 64 bytes");
 
 enum PrimKind : uint32_t { PRIM_SPHERE = 0, PRIM_QUAD = 1, PRIM_TRIANGLE = 2 };
 
-struct alignas(16) PrimGeom {
+struct alignas(32) PrimGeom {
     double d[16];
 };
 static_assert(sizeof(PrimGeom) == 128, "primitive record must be 128 bytes");

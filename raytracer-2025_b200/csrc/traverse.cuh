@@ -142,12 +142,31 @@ __device__ __forceinline__ bool slab(const RayF& f, const float* lo, const float
 
 __device__ __forceinline__ bool contains(double mn, double mx, double x) { return x >= mn && x <= mx; }  // interval.rs:65-67
 
+// 256-bit read-only global loads (LDG.E.256 on sm_100): a diverged warp pays one L1 tag lookup per lane and
+// request, so fetching a 64-byte node or a 128-byte primitive in 32-byte pieces halves the L1 work of the
+// 16-byte version.  The address must be 32-byte aligned (nodes and primitive records are).
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+#if RT_LDG256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+#else
+    a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+}
+__device__ __forceinline__ void ldg256(const void* p, double2& a, double2& b) {
+#if RT_LDG256
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#else
+    a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+#endif
+}
+
 // Sphere::hit, sphere.rs:77-108 (geometry only)
 __device__ __forceinline__ bool sphere_hit(const double* __restrict__ g, const RayD& r, double tmin, double tmax, double& t_out) {
-    const double2 a0 = __ldg(reinterpret_cast<const double2*>(g));
-    const double2 a1 = __ldg(reinterpret_cast<const double2*>(g) + 1);
-    const double2 a2 = __ldg(reinterpret_cast<const double2*>(g) + 2);
-    const double2 a3 = __ldg(reinterpret_cast<const double2*>(g) + 3);
+    double2 a0, a1, a2, a3;
+    ldg256(g, a0, a1);
+    ldg256(g + 4, a2, a3);
     D3 center = D3{a0.x, a0.y, a1.x}, cvec = D3{a1.y, a2.x, a2.y};
     double radius = a3.x;
     D3 current_center = center + r.time * cvec;
@@ -200,14 +219,17 @@ __device__ __forceinline__ bool planar_hit_loaded(const Planar& p, bool triangle
 }
 __device__ __forceinline__ bool planar_hit(const double* __restrict__ g, bool triangle, const RayD& r, double tmin, double tmax, double& t_out) {
     // plane first: most candidates are rejected before the rest of the record is needed
-    const double2* s = reinterpret_cast<const double2*>(g);
-    double2 a4 = __ldg(s + 4), a5 = __ldg(s + 5), a6 = __ldg(s + 6);
+    double2 a4, a5, a6, a7;
+    ldg256(g + 8, a4, a5);
+    ldg256(g + 12, a6, a7);
     D3 n = D3{a4.y, a5.x, a5.y};
     double denom = dot(n, r.d);
     if (fabs(denom) < 1e-8) return false;
     double t = (a6.x - dot(n, r.o)) / denom;
     if (!contains(tmin, tmax, t)) return false;
-    double2 a0 = __ldg(s), a1 = __ldg(s + 1), a2 = __ldg(s + 2), a3 = __ldg(s + 3), a7 = __ldg(s + 7);
+    double2 a0, a1, a2, a3;
+    ldg256(g, a0, a1);
+    ldg256(g + 4, a2, a3);
     D3 q = D3{a0.x, a0.y, a1.x}, u = D3{a1.y, a2.x, a2.y}, v = D3{a3.x, a3.y, a4.x}, w = D3{a6.y, a7.x, a7.y};
     D3 intersection = r.o + t * r.d;
     D3 hp = intersection - q;
@@ -325,7 +347,8 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
                     n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
                 } else {
                     const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
-                    n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                    ldg256(np, n0, n1);
+                    ldg256(np + 2, n2, n3);
                 }
                 if (COUNT) cnt->nodes++;
                 float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
@@ -467,7 +490,8 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                     n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
                 } else {
                     const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
-                    n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                    ldg256(np, n0, n1);
+                    ldg256(np + 2, n2, n3);
                 }
                 if (COUNT) cnt->nodes++;
                 float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
