@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -256,6 +257,28 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // more as loads in flight and every finished lane is refilled at once (profiles/README.md: 1M-triangle
         // soup, incoherent rays, 392 vs 274 Mrays/s; book2_final 49.4 vs 48.7 ms the other way round)
         v.refill_min = cs.nodes.size() > 100000 ? 1 : REFILL_MIN;
+        // scenes that do not fit the L2: pin the top of the tree (kernels.cu, launch_with_l2_window)
+        v.l2_window_bytes = 0;
+        {
+            const size_t scene_bytes = cs.nodes.size() * sizeof(Node) + cs.geom.size() * (sizeof(PrimGeom) + sizeof(PrimMeta));
+            int l2 = 0, max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+            size_t want = 0;
+            if (const char* e = getenv("RT2025_L2_WINDOW_MB")) want = (size_t)atol(e) << 20;  // tuning knob (0 disables)
+            // measured (profiles/README.md): a window that holds the WHOLE node array helps incoherent rays (1M-triangle
+            // soup 392 -> 416 Mrays/s, primary unchanged); a partial window over a bigger tree gains 2-5 % on incoherent
+            // rays and costs coherent ones up to 15 % (10M soup, 79 MB window), so it is only set when everything fits
+            else if (scene_bytes > (size_t)l2 && cs.nodes.size() * sizeof(Node) <= (size_t)max_persist) want = cs.nodes.size() * sizeof(Node);
+            want = std::min({want, (size_t)max_persist, (size_t)max_window, cs.nodes.size() * sizeof(Node)});
+            if (want >= (1u << 20)) {
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) v.l2_window_bytes = (uint32_t)want;
+                cudaGetLastError();
+            }
+            if (getenv("RT2025_TIMING")) fprintf(stderr, "[rt2025] L2 %d MB, max persisting %d MB, max window %d MB, scene %zu MB -> window %u MB\n",
+                                                 l2 >> 20, max_persist >> 20, max_window >> 20, scene_bytes >> 20, v.l2_window_bytes >> 20);
+        }
         // postponed leaves pay off when traversals are long (traverse.cuh); measured crossover between the 3.2 k-node
         // book-2 scene (off: extend 281 vs 299 ms) and the 11.5 k-face mesh scene (on: 487 vs 502 ms)
         v.park_leaves = cs.nodes.size() > 4096 ? 1 : 0;

@@ -76,11 +76,34 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
     }
 }
 
+// Launch with the top of the BVH pinned in L2.  A scene whose nodes + primitives exceed the L2 makes almost every
+// warp-wide node visit wait for at least one lane's DRAM miss; nodes are stored breadth first, so a persisting
+// access-policy window over a prefix of the array is "the top of the tree" and keeps it resident while the
+// primitive records stream through the rest of the cache.  sv.l2_window_bytes == 0 (cache-resident scenes) is
+// a plain launch.  The window is a per-launch attribute: the caller's stream is left untouched.
+template <class K, class... Args>
+static void launch_with_l2_window(K kernel, const SceneView& sv, int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (sv.l2_window_bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<Node*>(sv.nodes);
+        attr[0].val.accessPolicyWindow.num_bytes = sv.l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
     auto k = count ? (sv.park_leaves ? k_closest_hit<true, true> : k_closest_hit<true, false>)
                    : (sv.park_leaves ? k_closest_hit<false, true> : k_closest_hit<false, false>);
-    k<<<grid, EXTEND_BLOCK, stack_bytes, stream>>>(sv, d_rays, n, tmin, tmax, d_out, d_counters);
+    launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, stream, sv, d_rays, n, tmin, tmax, d_out, d_counters);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -739,7 +762,7 @@ void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, c
 }
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
     auto k = count ? (sv.park_leaves ? k_extend<true, true> : k_extend<true, false>) : (sv.park_leaves ? k_extend<false, true> : k_extend<false, false>);
-    k<<<grid, EXTEND_BLOCK, stack_bytes, s>>>(sv, P, W);
+    launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, s, sv, P, W);
 }
 int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
     // media + binning: global-memory nodes only (its shared memory holds just the stacks)

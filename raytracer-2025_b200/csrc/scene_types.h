@@ -141,6 +141,7 @@ struct SceneView {
     uint32_t n_nodes;
     uint32_t n_cached_nodes;  // nodes [0, n_cached_nodes) (breadth-first top of the tree) are staged in shared memory
     uint32_t stack_entries;   // traversal stack entries per thread
+    uint32_t l2_window_bytes; // prefix of nodes[] (breadth first = top of the tree) pinned in L2 by the traversal launches; 0 = none
     uint32_t park_leaves;     // persistent traversal postpones leaves (long traversals) or not (book-sized scenes)
     uint32_t refill_min;      // idle lanes a warp of the persistent traversal waits for before it takes new rays (1..32)
     uint32_t pad;
