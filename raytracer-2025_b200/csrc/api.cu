@@ -94,6 +94,22 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
     uint64_t n_pixels_alloc = 0;
     Counters* h_counters = nullptr;  // pinned
     std::vector<cudaEvent_t> events;  // stage-timing pool: 4 per iteration, read back after the render
+    ShadeFan fan;                     // side streams of the shade stage
+    bool fan_ready = false;
+    const ShadeFan* shade_fan() {
+        if (!fan_ready) {
+            fan_ready = true;
+            int n = RT_SHADE_SIDE_STREAMS;
+            if (const char* e = getenv("RT2025_SHADE_STREAMS")) n = std::max(0, std::min(3, atoi(e)));  // tuning knob
+            bool ok = cudaEventCreateWithFlags(&fan.fork, cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; i < n && ok; i++)
+                ok = cudaStreamCreateWithFlags(&fan.side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&fan.join[i], cudaEventDisableTiming) == cudaSuccess;
+            fan.n_side = ok ? n : 0;
+            cudaGetLastError();
+        }
+        return &fan;
+    }
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) {
             cudaEvent_t e;
@@ -105,6 +121,11 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
     void release() {
         for (auto e : events) cudaEventDestroy(e);
         events.clear();
+        if (fan.fork) cudaEventDestroy(fan.fork);
+        for (int i = 0; i < 3; i++) {
+            if (fan.side[i]) cudaStreamDestroy(fan.side[i]);
+            if (fan.join[i]) cudaEventDestroy(fan.join[i]);
+        }
         for (int k = 0; k < 2; k++) cudaFree(W.ray_q[k]), cudaFree(W.state_q[k]);
         cudaFree(W.hit_q);
         cudaFree(W.cls_q);
@@ -521,7 +542,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 2), st));
                     launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st);
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 3), st));
-                    launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st);  // generate, k_step, extend + shade
+                    launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan());  // generate, k_step, extend + shade
                     if (stage) CU(cudaEventRecord(ws.event(5 * iters + 4), st));
                 }
                 CU(cudaMemcpyAsync(ws.h_counters, W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -793,23 +793,41 @@ template <uint32_t CLS>
 static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t queue, int grid, cudaStream_t s) {
     k_shade<CLS><<<grid, SHADE_BLOCK, 0, s>>>(sv, P, W, queue);
 }
-// class_mask: bit c set when the scene can produce hits of shade class c (the miss queue always runs)
-int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s) {
+// class_mask: bit c set when the scene can produce hits of shade class c (the miss queue always runs).
+// The class kernels are independent (own queue each, atomics on the shared outputs): with `fan` they are dealt
+// over side streams between a fork and a join event so that the tail of one overlaps the start of the next.
+int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
+                 const ShadeFan* fan) {
     int launches = 2;  // the miss kernel and k_step
     if (!P.bin_by_class) {  // everything but misses sits in the SC_DIFFUSE queue: general kernel
         launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, s);
         launch_shade_cls<SC_OTHER>(sv, P, W, SC_DIFFUSE, grid, s);
         launches++;
     } else {
-        launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, s);
-        if (class_mask & (1u << SC_DIFFUSE)) launch_shade_cls<SC_DIFFUSE>(sv, P, W, SC_DIFFUSE, grid, s), launches++;
-        if (class_mask & (1u << SC_TEXTURED)) launch_shade_cls<SC_TEXTURED>(sv, P, W, SC_TEXTURED, grid, s), launches++;
-        if (class_mask & (1u << SC_ISOTROPIC)) launch_shade_cls<SC_ISOTROPIC>(sv, P, W, SC_ISOTROPIC, grid, s), launches++;
-        if (class_mask & (1u << SC_METAL)) launch_shade_cls<SC_METAL>(sv, P, W, SC_METAL, grid, s), launches++;
-        if (class_mask & (1u << SC_DIELECTRIC)) launch_shade_cls<SC_DIELECTRIC>(sv, P, W, SC_DIELECTRIC, grid, s), launches++;
-        if (class_mask & (1u << SC_EMISSIVE)) launch_shade_cls<SC_EMISSIVE>(sv, P, W, SC_EMISSIVE, grid, s), launches++;
-        if (class_mask & (1u << SC_DISNEY)) launch_shade_cls<SC_DISNEY>(sv, P, W, SC_DISNEY, grid, s), launches++;
-        if (class_mask & (1u << SC_OTHER)) launch_shade_cls<SC_OTHER>(sv, P, W, SC_OTHER, grid, s), launches++;
+        const int n_side = fan ? fan->n_side : 0;
+        if (n_side) {
+            cudaEventRecord(fan->fork, s);
+            for (int i = 0; i < n_side; i++) cudaStreamWaitEvent(fan->side[i], fan->fork, 0);
+        }
+        int next = 0;
+        auto lane = [&]() {  // main stream first, then the side streams, round robin
+            const int k = next++ % (n_side + 1);
+            return k == 0 ? s : fan->side[k - 1];
+        };
+        // the classes that usually hold most hits first, so they start on different streams
+        if (class_mask & (1u << SC_DIFFUSE)) launch_shade_cls<SC_DIFFUSE>(sv, P, W, SC_DIFFUSE, grid, lane()), launches++;
+        if (class_mask & (1u << SC_ISOTROPIC)) launch_shade_cls<SC_ISOTROPIC>(sv, P, W, SC_ISOTROPIC, grid, lane()), launches++;
+        if (class_mask & (1u << SC_DISNEY)) launch_shade_cls<SC_DISNEY>(sv, P, W, SC_DISNEY, grid, lane()), launches++;
+        if (class_mask & (1u << SC_TEXTURED)) launch_shade_cls<SC_TEXTURED>(sv, P, W, SC_TEXTURED, grid, lane()), launches++;
+        launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, lane());
+        if (class_mask & (1u << SC_DIELECTRIC)) launch_shade_cls<SC_DIELECTRIC>(sv, P, W, SC_DIELECTRIC, grid, lane()), launches++;
+        if (class_mask & (1u << SC_EMISSIVE)) launch_shade_cls<SC_EMISSIVE>(sv, P, W, SC_EMISSIVE, grid, lane()), launches++;
+        if (class_mask & (1u << SC_METAL)) launch_shade_cls<SC_METAL>(sv, P, W, SC_METAL, grid, lane()), launches++;
+        if (class_mask & (1u << SC_OTHER)) launch_shade_cls<SC_OTHER>(sv, P, W, SC_OTHER, grid, lane()), launches++;
+        for (int i = 0; i < n_side; i++) {
+            cudaEventRecord(fan->join[i], fan->side[i]);
+            cudaStreamWaitEvent(s, fan->join[i], 0);
+        }
     }
     k_step<<<1, 1, 0, s>>>(W, 2);
     return launches;

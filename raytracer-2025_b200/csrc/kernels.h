@@ -30,6 +30,9 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_LDG256
 #define RT_LDG256 1  // 256-bit global loads for nodes and primitive records
 #endif
+#ifndef RT_SHADE_SIDE_STREAMS
+#define RT_SHADE_SIDE_STREAMS 2  // side streams the per-class shade kernels are dealt over (0: all on the render stream)
+#endif
 #ifndef RT_MEDIA_MIN_BLOCKS
 #define RT_MEDIA_MIN_BLOCKS 2
 #endif
@@ -107,7 +110,13 @@ void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaS
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t smem_bytes, cudaStream_t s);
 int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s);
-int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s);
+struct ShadeFan {  // side streams for the per-class shade kernels (owned by the workspace)
+    int n_side = 0;
+    cudaStream_t side[3] = {};
+    cudaEvent_t fork = nullptr, join[3] = {};
+};
+int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
+                 const ShadeFan* fan);
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s);
 void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb, int* error_flag, cudaStream_t s);
 int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm);
