@@ -138,7 +138,7 @@ def closest_hit_metric(torch, n_prims=1_000_000, n_rays=1 << 24):
             best = st.ms_total
     cst = sc.closest_hit_device(rays.data_ptr(), n_rays, out.data_ptr(), flags=rt.RT_OPT_COUNT, stream=stream)
     nodes, prims = cst.node_visits / n_rays, cst.prim_tests / n_rays
-    bytes_per_ray = 56 + 24 + nodes * 64 + prims * 128
+    bytes_per_ray = 56 + 24 + nodes * sc.info().node_bytes + prims * 128
     mrays = n_rays / best / 1e3
     sc.close()
     return {"value": mrays, "unit": "Mrays/s", "workload": f"tri_soup N={n_prims}, {n_rays} incoherent rays, binary64 primitive tests",

@@ -7,9 +7,10 @@ directions uniform on the sphere).  One JSON line per (shape, N, ray set).
     python bench_closest_hit.py [--sizes 1000000 10000000] [--rays 16777216] [--oracle-rays 200000]
 
 Rays live in HBM (torch tensors); timing is CUDA events around rt_closest_hit_device, best of 5 after 2
-warm-ups.  Under torchrun (N ranks) every rank holds a replica of the scene and traces its 1/N slice of the same batch - no
+warm-ups.  Scenes beyond the caches are traversed through a four-wide collapse of the SAH tree (128-byte nodes; rt_scene_info.node_bytes
+says which).  Under torchrun (N ranks) every rank holds a replica of the scene and traces its 1/N slice of the same batch - no
 collective on the data path (replicas only) - and the time is the max over ranks.  Algorithmic bytes per ray (roofline): 56 (ray in) + 24 (hit out) + node_visits*64 +
-prim_tests*P with P = 128 (triangle record) or 64 (sphere), counts measured by the RT_OPT_COUNT
+prim_tests*P with P = 128 (triangle record) or 64 (sphere) and node_visits*node_bytes for the nodes, counts measured by the RT_OPT_COUNT
 instantiation of the same kernel.  The CPU figure is the oracle's reference-semantics traversal
 (median-split BVH, virtual dispatch) on `--oracle-rays` rays of the same batch, with an id/t parity
 check on exactly those rays.
@@ -117,10 +118,10 @@ def main():
                     del rays, out, rays_all
                     continue
                 P = 128 if shape == "tri_soup" else 64
-                bytes_per_ray = 56 + 24 + nodes * 64 + prims * P
+                bytes_per_ray = 56 + 24 + nodes * info.node_bytes + prims * P
                 mrays = per * world / best / 1e3
                 line = {"metric": "closest_hit_mrays_per_sec", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "dtype": "f64", "scaling": "strong",
-                        "config": {"workload": f"{shape} N={n} rays={args.rays} {kind}", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth,
+                        "config": {"workload": f"{shape} N={n} rays={args.rays} {kind}", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth, "node_bytes": info.node_bytes,
                                    "device_bytes": info.device_bytes, "host_scene_s": t_host, "scene_create_s": t_build},
                         "ms": best, "nodes_per_ray": nodes, "prims_per_ray": prims,
                         "roofline": {"bound": "hbm", "achieved": mrays * 1e6 * bytes_per_ray / 1e9, "peak": peak, "unit": "GB/s",

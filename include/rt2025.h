@@ -342,7 +342,9 @@ int rt_tonemap_device(const void* d_accum, uint32_t accum_type, uint64_t n_pixel
 typedef struct rt_scene_info {
     uint32_t n_prims, n_spheres, n_planars, n_nodes;
     uint32_t n_media, n_lights, n_materials, n_textures;
-    uint32_t bvh_depth, reserved;
+    uint32_t bvh_depth;
+    uint32_t node_bytes; /* bytes read per node visit of a world traversal: 64 (binary tree) or 128 (four-wide collapse
+                            used for scenes beyond the caches; node_visits then counts wide nodes) */
     uint64_t device_bytes;
 } rt_scene_info;
 int rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);

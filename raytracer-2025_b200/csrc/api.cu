@@ -241,10 +241,11 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         {
             cudaStream_t st = cudaStreamPerThread;
             Arena a;
-            a.reserve(cs.nodes), a.reserve(cs.geom), a.reserve(cs.meta), a.reserve(cs.xforms), a.reserve(cs.materials), a.reserve(cs.textures);
+            a.reserve(cs.nodes4), a.reserve(cs.nodes), a.reserve(cs.geom), a.reserve(cs.meta), a.reserve(cs.xforms), a.reserve(cs.materials), a.reserve(cs.textures);
             a.reserve(cs.images), a.reserve(cs.texels), a.reserve(cs.perlins), a.reserve(cs.media), a.reserve(cs.lights), a.reserve(cs.remaps);
             a.allocate(st);
             s->arena = a.base;
+            v.nodes4 = a.put(cs.nodes4, st), v.world_root4 = cs.world_root4;
             v.nodes = a.put(cs.nodes, st), v.geom = a.put(cs.geom, st), v.meta = a.put(cs.meta, st), v.xforms = a.put(cs.xforms, st);
             v.materials = a.put(cs.materials, st), v.textures = a.put(cs.textures, st), v.images = a.put(cs.images, st);
             v.texels = a.put(cs.texels, st), v.perlins = a.put(cs.perlins, st), v.media = a.put(cs.media, st);
@@ -266,12 +267,14 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         i.n_prims = v.n_prims, i.n_spheres = cs.n_spheres, i.n_planars = cs.n_planars, i.n_nodes = (uint32_t)cs.nodes.size();
         i.n_media = v.n_media, i.n_lights = v.n_lights, i.n_materials = (uint32_t)cs.materials.size(), i.n_textures = (uint32_t)cs.textures.size();
         i.bvh_depth = cs.bvh_depth;
-        i.device_bytes = cs.nodes.size() * sizeof(Node) + cs.geom.size() * sizeof(PrimGeom) + cs.meta.size() * sizeof(PrimMeta) +
-                         cs.texels.size() * sizeof(float4) + cs.perlins.size() * sizeof(Perlin);
+        i.node_bytes = cs.nodes4.empty() ? (uint32_t)sizeof(Node) : (uint32_t)sizeof(Node4);
+        i.device_bytes = cs.nodes.size() * sizeof(Node) + cs.nodes4.size() * sizeof(Node4) + cs.geom.size() * sizeof(PrimGeom) +
+                         cs.meta.size() * sizeof(PrimMeta) + cs.texels.size() * sizeof(float4) + cs.perlins.size() * sizeof(Perlin);
         // shared memory of the traversal kernels: per-thread stacks sized by this scene's tree depth,
         // the rest (up to 227 KB) holds the breadth-first top of the BVH
         v.n_nodes = (uint32_t)cs.nodes.size();
-        v.stack_entries = std::min<uint32_t>(cs.bvh_depth + 2, TRAVERSAL_STACK);
+        // the binary tree pushes one reference per level, the four-wide one up to three (compile.cpp keeps it within the limit)
+        v.stack_entries = std::min<uint32_t>(std::max(cs.bvh_depth + 2, cs.nodes4.empty() ? 0u : 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK);
         const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t);
         // persistent traversal: a warp whose BVH lives in L1/shared memory is issue-bound and runs best when it
         // drains completely before taking 32 new rays; once node fetches go to L2/HBM the idle lanes are worth
@@ -281,7 +284,9 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // scenes that do not fit the L2: pin the top of the tree (kernels.cu, launch_with_l2_window)
         v.l2_window_bytes = 0;
         {
-            const size_t scene_bytes = cs.nodes.size() * sizeof(Node) + cs.geom.size() * (sizeof(PrimGeom) + sizeof(PrimMeta));
+            // bytes of the tree the traversal kernels actually read (the four-wide collapse when there is one)
+            const size_t tree_bytes = cs.nodes4.empty() ? cs.nodes.size() * sizeof(Node) : cs.nodes4.size() * sizeof(Node4);
+            const size_t scene_bytes = tree_bytes + cs.geom.size() * (sizeof(PrimGeom) + sizeof(PrimMeta));
             int l2 = 0, max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device);
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
@@ -291,8 +296,8 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
             // measured (profiles/README.md): a window that holds the WHOLE node array helps incoherent rays (1M-triangle
             // soup 392 -> 416 Mrays/s, primary unchanged); a partial window over a bigger tree gains 2-5 % on incoherent
             // rays and costs coherent ones up to 15 % (10M soup, 79 MB window), so it is only set when everything fits
-            else if (scene_bytes > (size_t)l2 && cs.nodes.size() * sizeof(Node) <= (size_t)max_persist) want = cs.nodes.size() * sizeof(Node);
-            want = std::min({want, (size_t)max_persist, (size_t)max_window, cs.nodes.size() * sizeof(Node)});
+            else if (scene_bytes > (size_t)l2 && tree_bytes <= (size_t)max_persist) want = tree_bytes;
+            want = std::min({want, (size_t)max_persist, (size_t)max_window, tree_bytes});
             if (want >= (1u << 20)) {
                 if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) v.l2_window_bytes = (uint32_t)want;
                 cudaGetLastError();

@@ -178,4 +178,85 @@ uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base,
     return root;
 }
 
+// ---- four-wide collapse -------------------------------------------------------------------------
+// Each wide node starts from the two children of a binary node and repeatedly opens the interior child with
+// the largest surface area until it has four entries (or only leaves are left): the standard SAH-guided
+// collapse.  Boxes are copied, never recomputed, so they stay the conservative bounds of the binary tree.
+uint32_t collapse_bvh4(const std::vector<Node>& nodes, uint32_t root, std::vector<Node4>& out, uint32_t& depth_out) {
+    depth_out = 0;
+    if (root == INVALID_REF || (root & LEAF_FLAG)) return root;
+    struct Entry {
+        uint32_t ref;
+        float b[6];
+    };
+    auto area = [](const Entry& e) {
+        const float dx = e.b[3] - e.b[0], dy = e.b[4] - e.b[1], dz = e.b[5] - e.b[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    auto children_of = [&](uint32_t n2, Entry* two) {
+        const Node& nd = nodes[n2];
+        two[0].ref = nd.child0, two[1].ref = nd.child1;
+        for (int k = 0; k < 3; k++) {
+            two[0].b[k] = nd.lo0[k], two[0].b[3 + k] = nd.hi0[k];
+            two[1].b[k] = nd.lo1[k], two[1].b[3 + k] = nd.hi1[k];
+        }
+    };
+    struct Pending {
+        uint32_t n2, n4, depth;
+    };
+    std::vector<Pending> queue;
+    out.emplace_back();
+    queue.push_back({root, (uint32_t)out.size() - 1, 1});
+    for (size_t head = 0; head < queue.size(); head++) {
+        const Pending p = queue[head];
+        depth_out = std::max(depth_out, p.depth);
+        Entry e[4];
+        int n = 0;
+        {
+            Entry two[2];
+            children_of(p.n2, two);
+            for (int k = 0; k < 2; k++)
+                if (two[k].ref != INVALID_REF) e[n++] = two[k];
+        }
+        while (n < 4) {
+            int best = -1;
+            float best_area = -1.f;
+            for (int k = 0; k < n; k++)
+                if (!(e[k].ref & LEAF_FLAG) && area(e[k]) > best_area) best = k, best_area = area(e[k]);
+            if (best < 0) break;
+            Entry two[2];
+            children_of(e[best].ref, two);
+            int m = 0;
+            for (int k = 0; k < 2; k++)
+                if (two[k].ref != INVALID_REF) {
+                    if (m == 0) e[best] = two[k]; else e[n++] = two[k];
+                    m++;
+                }
+            if (m == 0) {  // a binary node without children: drop the entry
+                e[best] = e[n - 1];
+                n--;
+            }
+        }
+        Node4 w;
+        for (int k = 0; k < 4; k++) {
+            if (k < n) {
+                for (int q = 0; q < 6; q++) w.box[k][q] = e[k].b[q];
+                if (e[k].ref & LEAF_FLAG) {
+                    w.child[k] = e[k].ref;
+                } else {
+                    out.emplace_back();
+                    w.child[k] = (uint32_t)out.size() - 1;
+                    queue.push_back({e[k].ref, w.child[k], p.depth + 1});
+                }
+            } else {
+                for (int q = 0; q < 3; q++) w.box[k][q] = INFINITY, w.box[k][3 + q] = -INFINITY;
+                w.child[k] = INVALID_REF;
+            }
+            w.pad[k] = 0;
+        }
+        out[p.n4] = w;
+    }
+    return queue[0].n4;
+}
+
 }  // namespace rt

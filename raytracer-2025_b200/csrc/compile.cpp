@@ -770,6 +770,20 @@ struct Compiler {
         }
         timer.lap("breadth-first renumbering");
         out.world_root = roots[0];
+        // Scenes that cannot stay in the caches are traversed through a four-wide collapse of the world tree (half
+        // the dependent node fetches); RT2025_WIDE_BVH=0/1 overrides the size rule (tests force it on small scenes).
+        {
+            bool wide = out.nodes.size() > 100000;
+            if (const char* e = getenv("RT2025_WIDE_BVH")) wide = atoi(e) != 0;
+            if (wide) {
+                out.world_root4 = collapse_bvh4(out.nodes, out.world_root, out.nodes4, out.bvh4_depth);
+                if (3 * out.bvh4_depth + 2 > (uint32_t)TRAVERSAL_STACK) {  // would not fit the traversal stack: keep the binary tree
+                    out.nodes4.clear();
+                    out.world_root4 = INVALID_REF;
+                }
+                timer.lap("four-wide collapse");
+            }
+        }
         for (size_t m = 0; m < out.media.size(); m++) {
             Medium& med = out.media[m];
             med.root = roots[group_of_medium[m]];

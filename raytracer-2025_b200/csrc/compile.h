@@ -13,6 +13,9 @@ namespace rt {
 
 struct CompiledScene {
     std::vector<Node> nodes;
+    std::vector<Node4> nodes4;  // four-wide collapse of the world tree (empty: not built)
+    uint32_t world_root4 = INVALID_REF;
+    uint32_t bvh4_depth = 0;
     std::vector<PrimGeom> geom;
     std::vector<PrimMeta> meta;
     std::vector<Xform> xforms;
@@ -32,6 +35,10 @@ struct CompiledScene {
 
 // returns RT_OK or a negative rt_status and fills err
 int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err);
+
+// Collapse the binary tree below `root` (a reference into `nodes`) into four-wide nodes, breadth first.
+// Returns the root reference into `out` (a leaf / INVALID root is returned unchanged) and the depth of the result.
+uint32_t collapse_bvh4(const std::vector<Node>& nodes, uint32_t root, std::vector<Node4>& out, uint32_t& depth_out);
 
 // Binned-SAH BVH2 over conservative binary32 boxes.  `order` receives the leaf order (a
 // permutation of 0..n-1); nodes are appended to `nodes`; leaf references point at

@@ -59,7 +59,7 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
     }
 };
 
-template <bool COUNT, bool PARK>
+template <bool COUNT, bool PARK, bool WIDE>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint32_t n, double tmin,
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     RayArrayIO io{sv, rays, out, tmin, tmax};
-    trace_persistent<COUNT, true, PARK>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
         atomicAdd(&counters[1], (unsigned long long)cnt.prims);
@@ -89,7 +89,7 @@ static void launch_with_l2_window(K kernel, const SceneView& sv, int grid, int b
     cudaLaunchAttribute attr[1];
     if (sv.l2_window_bytes) {
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<Node*>(sv.nodes);
+        attr[0].val.accessPolicyWindow.base_ptr = sv.nodes4 ? (void*)const_cast<Node4*>(sv.nodes4) : (void*)const_cast<Node*>(sv.nodes);
         attr[0].val.accessPolicyWindow.num_bytes = sv.l2_window_bytes;
         attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -101,8 +101,9 @@ static void launch_with_l2_window(K kernel, const SceneView& sv, int grid, int b
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
-    auto k = count ? (sv.park_leaves ? k_closest_hit<true, true> : k_closest_hit<true, false>)
-                   : (sv.park_leaves ? k_closest_hit<false, true> : k_closest_hit<false, false>);
+    auto k = sv.nodes4 ? (count ? k_closest_hit<true, true, true> : k_closest_hit<false, true, true>)
+             : count   ? (sv.park_leaves ? k_closest_hit<true, true, false> : k_closest_hit<true, false, false>)
+                       : (sv.park_leaves ? k_closest_hit<false, true, false> : k_closest_hit<false, false, false>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, stream, sv, d_rays, n, tmin, tmax, d_out, d_counters);
 }
 
@@ -259,7 +260,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
 };
 
 // closest surface hit of every path in the extend queue (world.hit without the media, camera.rs:286)
-template <bool COUNT, bool PARK>
+template <bool COUNT, bool PARK, bool WIDE>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
     __shared__ uint32_t s_cursor;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     PathIO io{W.ray_q[W.parity], W.hit_q};
-    trace_persistent<COUNT, true, PARK>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
         atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
@@ -761,7 +762,9 @@ void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, c
     k_step<<<1, 1, 0, s>>>(W, 0);
 }
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
-    auto k = count ? (sv.park_leaves ? k_extend<true, true> : k_extend<true, false>) : (sv.park_leaves ? k_extend<false, true> : k_extend<false, false>);
+    auto k = sv.nodes4 ? (count ? k_extend<true, true, true> : k_extend<false, true, true>)
+             : count   ? (sv.park_leaves ? k_extend<true, true, false> : k_extend<true, false, false>)
+                       : (sv.park_leaves ? k_extend<false, true, false> : k_extend<false, false, false>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, s, sv, P, W);
 }
 int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
@@ -839,12 +842,13 @@ void launch_finalize(const double* accum, uint64_t n, double scale, void* out, b
 int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
     // dynamic shared memory above 48 KB is opt-in
     cudaError_t e = cudaSuccess;
-    const void* big_smem[] = {(const void*)k_extend<false, false>,      (const void*)k_extend<false, true>,      (const void*)k_extend<true, false>,
-                              (const void*)k_extend<true, true>,        (const void*)k_closest_hit<false, false>, (const void*)k_closest_hit<false, true>,
-                              (const void*)k_closest_hit<true, false>,  (const void*)k_closest_hit<true, true>};
+    const void* big_smem[] = {(const void*)k_extend<false, false, false>,      (const void*)k_extend<false, true, false>,      (const void*)k_extend<false, true, true>,
+                              (const void*)k_extend<true, false, false>,       (const void*)k_extend<true, true, false>,       (const void*)k_extend<true, true, true>,
+                              (const void*)k_closest_hit<false, false, false>, (const void*)k_closest_hit<false, true, false>, (const void*)k_closest_hit<false, true, true>,
+                              (const void*)k_closest_hit<true, false, false>,  (const void*)k_closest_hit<true, true, false>,  (const void*)k_closest_hit<true, true, true>};
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false>, EXTEND_BLOCK, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_DIFFUSE>, SHADE_BLOCK, 0);
     return 0;
 }

@@ -29,6 +29,16 @@ struct alignas(32) Node {
 };
 static_assert(sizeof(Node) == 64, "node must be 64 bytes");
 
+// Four-wide node of the collapsed BVH used for scenes that do not fit the caches (world group only): the boxes of
+// up to four children as conservative binary32 bounds, child references as in Node.  An unused slot has an
+// inverted box and INVALID_REF.  128 bytes = four 256-bit loads; half the dependent fetches of the binary tree.
+struct alignas(32) Node4 {
+    float box[4][6];  // lo.xyz, hi.xyz per child
+    uint32_t child[4];
+    uint32_t pad[4];
+};
+static_assert(sizeof(Node4) == 128, "wide node must be 128 bytes");
+
 enum PrimKind : uint32_t { PRIM_SPHERE = 0, PRIM_QUAD = 1, PRIM_TRIANGLE = 2 };
 
 struct alignas(32) PrimGeom {
@@ -136,6 +146,9 @@ struct SceneView {
     const Medium* media;
     const Light* lights;
     const Remap* remaps;
+    const Node4* nodes4;  // collapsed four-wide tree of the world group, or nullptr
+    uint32_t world_root4; // root reference into nodes4 (only when nodes4 != nullptr)
+    uint32_t wide_pad;
     uint32_t world_root;
     uint32_t n_media, n_lights, n_prims;
     uint32_t n_nodes;

@@ -411,7 +411,10 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
 // path streams (k_extend) or to a plain ray array (k_closest_hit).
 // ------------------------------------------------------------------------------------------------
 
-template <bool COUNT, bool USE_RANK, bool PARK, class IO>
+// WIDE = traverse the four-wide collapse (sv.nodes4, out-of-cache scenes): four slab tests per fetch, the hit
+// children are ordered by entry distance with a five-exchange network, the nearest is followed and the others
+// are pushed farthest first.
+template <bool COUNT, bool USE_RANK, bool PARK, bool WIDE, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
                                                  TraceCounters* cnt) {
@@ -469,7 +472,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                     cached_xform = 0xFFFFFFFFu;
                     lr = r;
                     sp = 0;
-                    const uint32_t root = sv.world_root;
+                    const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
                     if (root & LEAF_FLAG) {
                         parked = root, cur = INVALID_REF;
                     } else {
@@ -484,30 +487,73 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
         if (have) {
             // node phase: descend until this lane has parked a leaf and met another, or ran out
             while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
-                float4 n0, n1, n2, n3;
-                if (cur < sv.n_cached_nodes) {
-                    const float4* np = smem_nodes + 4 * cur;
-                    n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                if (WIDE) {
+                    const float4* np = reinterpret_cast<const float4*>(sv.nodes4 + cur);
+                    float4 a0, a1, a2, a3, a4, a5;
+                    ldg256(np, a0, a1);
+                    ldg256(np + 2, a2, a3);
+                    ldg256(np + 4, a4, a5);
+                    const uint4 cr = __ldg(reinterpret_cast<const uint4*>(np + 6));
+                    if (COUNT) cnt->nodes++;
+                    const float l0[3] = {a0.x, a0.y, a0.z}, u0[3] = {a0.w, a1.x, a1.y};
+                    const float l1[3] = {a1.z, a1.w, a2.x}, u1[3] = {a2.y, a2.z, a2.w};
+                    const float l2[3] = {a3.x, a3.y, a3.z}, u2[3] = {a3.w, a4.x, a4.y};
+                    const float l3[3] = {a4.z, a4.w, a5.x}, u3[3] = {a5.y, a5.z, a5.w};
+                    float k0, k1, k2, k3;
+                    uint32_t r0 = cr.x, r1 = cr.y, r2 = cr.z, r3 = cr.w;
+                    // a child that is missed (or an unused slot: inverted box, and the explicit test covers the degenerate ray
+                    // whose three axes take no part in culling) becomes INVALID_REF with an infinite key and sorts last
+                    if (!slab(f, l0, u0, tmin_f, tmax_f, k0) || r0 == INVALID_REF) r0 = INVALID_REF, k0 = INFINITY;
+                    if (!slab(f, l1, u1, tmin_f, tmax_f, k1) || r1 == INVALID_REF) r1 = INVALID_REF, k1 = INFINITY;
+                    if (!slab(f, l2, u2, tmin_f, tmax_f, k2) || r2 == INVALID_REF) r2 = INVALID_REF, k2 = INFINITY;
+                    if (!slab(f, l3, u3, tmin_f, tmax_f, k3) || r3 == INVALID_REF) r3 = INVALID_REF, k3 = INFINITY;
+                    auto cswap = [](float& ka, uint32_t& ra, float& kb, uint32_t& rb) {
+                        const bool s = kb < ka;
+                        const float kt = s ? kb : ka;
+                        const uint32_t rt_ = s ? rb : ra;
+                        kb = s ? ka : kb, rb = s ? ra : rb;
+                        ka = kt, ra = rt_;
+                    };
+                    cswap(k0, r0, k1, r1);
+                    cswap(k2, r2, k3, r3);
+                    cswap(k0, r0, k2, r2);
+                    cswap(k1, r1, k3, r3);
+                    cswap(k1, r1, k2, r2);
+                    // hits sort before misses, except that a NaN key (a box kept because nothing could be decided) may sit
+                    // anywhere: validity is the reference, not the key
+                    if (r3 != INVALID_REF) stack[(sp++) * stride] = r3;
+                    if (r2 != INVALID_REF) stack[(sp++) * stride] = r2;
+                    if (r1 != INVALID_REF) stack[(sp++) * stride] = r1;
+                    if (r0 != INVALID_REF)
+                        cur = r0;
+                    else
+                        cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
                 } else {
-                    const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
-                    ldg256(np, n0, n1);
-                    ldg256(np + 2, n2, n3);
-                }
-                if (COUNT) cnt->nodes++;
-                float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
-                float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
-                uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
-                float t0, t1;
-                bool h0 = slab(f, lo0, hi0, tmin_f, tmax_f, t0);
-                bool h1 = slab(f, lo1, hi1, tmin_f, tmax_f, t1);
-                if (h0 && h1) {
-                    bool swap = t1 < t0;
-                    stack[(sp++) * stride] = swap ? c0 : c1;
-                    cur = swap ? c1 : c0;
-                } else if (h0 || h1) {
-                    cur = h0 ? c0 : c1;
-                } else {
-                    cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                    float4 n0, n1, n2, n3;
+                    if (cur < sv.n_cached_nodes) {
+                        const float4* np = smem_nodes + 4 * cur;
+                        n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                    } else {
+                        const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
+                        ldg256(np, n0, n1);
+                        ldg256(np + 2, n2, n3);
+                    }
+                    if (COUNT) cnt->nodes++;
+                    float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
+                    float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
+                    uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+                    float t0, t1;
+                    bool h0 = slab(f, lo0, hi0, tmin_f, tmax_f, t0);
+                    bool h1 = slab(f, lo1, hi1, tmin_f, tmax_f, t1);
+                    if (h0 && h1) {
+                        bool swap = t1 < t0;
+                        stack[(sp++) * stride] = swap ? c0 : c1;
+                        cur = swap ? c1 : c0;
+                    } else if (h0 || h1) {
+                        cur = h0 ? c0 : c1;
+                    } else {
+                        cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
+                    }
                 }
                 if (PARK) {  // keep descending with one postponed leaf until every lane of the warp has one
                     if ((cur & LEAF_FLAG) && parked == INVALID_REF) {

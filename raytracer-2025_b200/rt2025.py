@@ -74,7 +74,7 @@ class rt_scene_info(C.Structure):
     _fields_ = [
         ("n_prims", C.c_uint32), ("n_spheres", C.c_uint32), ("n_planars", C.c_uint32), ("n_nodes", C.c_uint32),
         ("n_media", C.c_uint32), ("n_lights", C.c_uint32), ("n_materials", C.c_uint32), ("n_textures", C.c_uint32),
-        ("bvh_depth", C.c_uint32), ("reserved", C.c_uint32), ("device_bytes", C.c_uint64),
+        ("bvh_depth", C.c_uint32), ("node_bytes", C.c_uint32), ("device_bytes", C.c_uint64),
     ]
 
 

@@ -89,7 +89,42 @@ static int run_case(uint32_t n, int lattice, uint64_t seed) {
     for (uint32_t r = 0; r < n; r++)
         if (cs.ranks[expect[r]] != r) bad++;
     printf("n=%u lattice=%d seed=%llu: %zu rank mismatches\n", n, lattice, (unsigned long long)seed, bad);
-    return bad != 0;
+    // four-wide collapse (bvh_build.cpp): same leaves as the binary tree, each exactly once, every child box copied
+    // from the binary tree, depth within the traversal stack
+    std::vector<rt::Node4> wide;
+    uint32_t depth4 = 0;
+    const uint32_t root4 = rt::collapse_bvh4(cs.nodes, cs.world_root, wide, depth4);
+    std::vector<uint32_t> leaves2, leaves4, todo;
+    if (cs.world_root != rt::INVALID_REF) todo.push_back(cs.world_root);
+    while (!todo.empty()) {
+        const uint32_t ref = todo.back();
+        todo.pop_back();
+        if (ref & rt::LEAF_FLAG) { leaves2.push_back(ref); continue; }
+        for (uint32_t c : {cs.nodes[ref].child0, cs.nodes[ref].child1})
+            if (c != rt::INVALID_REF) todo.push_back(c);
+    }
+    size_t bad4 = 0, inner4 = 0;
+    if (root4 != rt::INVALID_REF) todo.push_back(root4);
+    while (!todo.empty()) {
+        const uint32_t ref = todo.back();
+        todo.pop_back();
+        if (ref & rt::LEAF_FLAG) { leaves4.push_back(ref); continue; }
+        inner4++;
+        const rt::Node4& w = wide[ref];
+        for (int k = 0; k < 4; k++) {
+            if (w.child[k] == rt::INVALID_REF) { bad4 += !(w.box[k][0] > w.box[k][3]); continue; }
+            bad4 += !(w.box[k][0] <= w.box[k][3] && w.box[k][1] <= w.box[k][4] && w.box[k][2] <= w.box[k][5]);
+            todo.push_back(w.child[k]);
+        }
+    }
+    std::sort(leaves2.begin(), leaves2.end());
+    std::sort(leaves4.begin(), leaves4.end());
+    bad4 += leaves2 != leaves4;
+    bad4 += inner4 != wide.size() && !(cs.world_root & rt::LEAF_FLAG);
+    bad4 += 3 * depth4 + 2 > (uint32_t)rt::TRAVERSAL_STACK;
+    printf("  four-wide collapse: %zu binary nodes -> %zu wide nodes, depth %u, %zu leaves, %zu problems\n", cs.nodes.size(), wide.size(), depth4,
+           leaves4.size(), bad4);
+    return bad != 0 || bad4 != 0;
 }
 
 int main() {

@@ -324,6 +324,33 @@ def test_soup_closest_hit_matches_oracle(gpu, rt, orc, shape):
     assert st.node_visits / n < 200 and st.prim_tests / n < 40
 
 
+def test_four_wide_tree_gives_the_same_hits_and_images(gpu, rt, orc, monkeypatch):
+    """Scenes beyond the caches are traversed through a four-wide collapse of the SAH tree (the 200k soups above take
+    that path by size).  Forced here on small scenes with Transforms, media and every tie rule: ids, t and same-seed
+    images must not depend on which tree was walked."""
+    monkeypatch.setenv("RT2025_WIDE_BVH", "1")
+    for seed in (2, 5):
+        hs = random_graph_scene(rt, seed, n_prims=120, with_media=True, width=24, spp=4, depth=6)
+        sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+        assert sc.info().node_bytes == 128
+        rng = np.random.default_rng(seed)
+        o, d, t = random_rays(rng, 20000)
+        rays = rt.make_rays(o, d, t)
+        compare_hits(rt, sc.closest_hit(rays)[0], osc.closest_hit(rays, mode=0))
+        img, st = sc.render(seed=3)
+        ref, _ = osc.render(seed=3)
+        image_close(img, ref)
+    hs = rt.named_scene("book2_final", seed=7, params=[32, 4, 12])
+    wide = rt.Scene(hs)
+    monkeypatch.setenv("RT2025_WIDE_BVH", "0")
+    binary = rt.Scene(hs)
+    assert wide.info().node_bytes == 128 and binary.info().node_bytes == 64
+    fx = np.load(os.path.join(GOLDEN, "book2_final.npz"))
+    a, b = wide.closest_hit(fx["rays"])[0], binary.closest_hit(fx["rays"])[0]
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["t"], b["t"])
+    image_close(wide.render(seed=2025)[0], binary.render(seed=2025)[0])
+
+
 def test_soup_at_full_batch_size_properties(gpu, rt):
     """1M triangles, 2^22 rays: properties that need no oracle — every reported hit re-verifies against
     its own primitive record through a second, single-ray query window [t, t]."""
