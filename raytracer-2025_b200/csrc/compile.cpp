@@ -773,7 +773,7 @@ struct Compiler {
         // Scenes that cannot stay in the caches are traversed through a four-wide collapse of the world tree (half
         // the dependent node fetches); RT2025_WIDE_BVH=0/1 overrides the size rule (tests force it on small scenes).
         {
-            bool wide = out.nodes.size() > 100000;
+            bool wide = out.nodes.size() > 8192;  // book-sized trees stay binary: their top lives in shared memory (book2 extend 276 vs 299 ms; an 11.5 k-face mesh scene 477 vs 459 ms the other way)
             if (const char* e = getenv("RT2025_WIDE_BVH")) wide = atoi(e) != 0;
             if (wide) {
                 out.world_root4 = collapse_bvh4(out.nodes, out.world_root, out.nodes4, out.bvh4_depth);
