@@ -10,6 +10,16 @@ import pytest
 from scenes_util import compare_hits, random_graph_scene, random_rays
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["by_size", "four_wide"])
+def tree_variant(request, monkeypatch):
+    """Every test of this module runs twice: with the tree rt_scene_create picks by scene size (binary for these
+    small scenes, four-wide for the soups) and with the four-wide collapse forced, so that empty worlds, single
+    primitives, ties, Transforms, media and degenerate rays are all checked on both traversal kernels."""
+    if request.param == "four_wide":
+        monkeypatch.setenv("RT2025_WIDE_BVH", "1")
+    return request.param
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 NAMED = {
