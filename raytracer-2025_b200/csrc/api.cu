@@ -461,6 +461,8 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     }
     if (cam->image_width == 0 || cam->image_height == 0 || cam->sqrt_spp == 0)
         return set_err(RT_ERR_INVALID, "camera has an empty image or zero samples");
+    if ((uint64_t)cam->image_width * cam->image_height >= (1ull << 31))
+        return set_err(RT_ERR_UNSUPPORTED, "more than 2^31 pixels (pixel indices are 32-bit)");
     if (cam->background_tex >= s->info.n_textures) return set_err(RT_ERR_INVALID, "camera.background_tex out of range");
     const uint32_t part_count = o.part_count ? o.part_count : 1;
     if (o.part_index >= part_count) return set_err(RT_ERR_INVALID, "part_index >= part_count");

@@ -258,6 +258,8 @@ struct Compiler {
                     break;
                 case RT_OBJ_MEDIUM:
                     if (o.data >= d.n_media || o.child_count != 1 || o.material >= d.n_materials) return fail(RT_ERR_INVALID, "bad ConstantMedium");
+                    // volume.rs:23-35: the phase function is always an Isotropic; the shade kernels rely on it
+                    if (d.materials[o.material].kind != RT_MAT_ISOTROPIC) return fail(RT_ERR_INVALID, "the phase function of a ConstantMedium must be an Isotropic material");
                     break;
                 default: return fail(RT_ERR_INVALID, "unknown object kind");
             }
@@ -291,7 +293,8 @@ struct Compiler {
             for (int k = 0; k < 16; k++) m.v[k] = s.v[k];
             m.shade_class = shade_class_of(d, s, out.materials);
             // does shading this material read the surface coordinates (image / checker lookups)?
-            auto tex_uv = [&](uint32_t t) { return t != RT_NONE && (d.textures[t].kind == RT_TEX_IMAGE || d.textures[t].kind == RT_TEX_CHECKER); };
+            // (kinds that ignore `tex` may carry anything there: bounds first)
+            auto tex_uv = [&](uint32_t t) { return t < d.n_textures && (d.textures[t].kind == RT_TEX_IMAGE || d.textures[t].kind == RT_TEX_CHECKER); };
             m.needs_uv = tex_uv(s.tex) ? 1u : 0u;
             if (s.inner != RT_NONE && s.inner < i) m.needs_uv |= out.materials[s.inner].needs_uv;
             if (s.inner2 != RT_NONE && s.inner2 < i) m.needs_uv |= out.materials[s.inner2].needs_uv;

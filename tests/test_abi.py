@@ -81,6 +81,43 @@ def test_description_is_validated_before_any_device_work(rt):
     del objs
 
 
+def test_corrupted_descriptions_never_crash(rt):
+    """Single-word corruptions of every index-bearing table: rt_scene_create must answer with a status (invalid,
+    unsupported, or - when the damage is only numeric - the no-device / success path), never fault."""
+    from scenes_util import disney_scene, obj_mesh_scene, random_graph_scene
+    rng = np.random.default_rng(7)
+    scenes = [random_graph_scene(rt, 3, n_prims=40, with_media=True, width=8, spp=1, depth=2), disney_scene(rt, True, width=8, spp=1),
+              obj_mesh_scene(rt, width=8, spp=1)]
+    sizes = {"objects": 72, "children": 4, "materials": 176, "textures": 80, "media": 16, "transforms": 80, "images": 24, "remaps": 200}
+    seen = set()
+    for it in range(3000):
+        good = scenes[it % len(scenes)].desc.contents
+        name = list(sizes)[rng.integers(len(sizes))]
+        n = getattr(good, "n_" + name)
+        if n == 0:
+            continue
+        raw = np.ctypeslib.as_array((C.c_uint32 * (n * sizes[name] // 4)).from_address(getattr(good, name))).copy()
+        raw[rng.integers(raw.size)] = rng.choice([0, 1, 2, 3, 7, 0xFFFFFFFF, 0xFFFFFFFE, 1000, 1 << 20, int(rng.integers(1 << 32))])
+        bad = rt.rt_scene_desc.from_buffer_copy(good)
+        setattr(bad, name, raw.ctypes.data)
+        rc, h, msg = _create(rt, bad)
+        seen.add(rc)
+        if rc == 0:
+            rt.product_lib().rt_scene_destroy(h)
+    assert seen <= {0, -1, -2, -3} and -1 in seen
+    # a ConstantMedium whose phase function is not an Isotropic (volume.rs:23-35 cannot build one)
+    b = rt.Builder(1)
+    med = b.medium(b.sphere([0, 0, 0], 1.0, b.empty()), 0.5, b.solid(1, 1, 1))
+    hs = b.finish(b.list([med]))
+    mats = np.ctypeslib.as_array((C.c_uint32 * (hs.desc.contents.n_materials * 44)).from_address(hs.desc.contents.materials)).copy()
+    objs = hs.objects()
+    mats[int(objs["material"][objs["kind"] == 7][0]) * 44] = 1  # RT_OBJ_MEDIUM -> its material becomes RT_MAT_LAMBERTIAN
+    bad = rt.rt_scene_desc.from_buffer_copy(hs.desc.contents)
+    bad.materials = mats.ctypes.data
+    rc, h, msg = _create(rt, bad)
+    assert rc == -1 and "Isotropic" in msg
+
+
 def test_unsupported_constructs_are_reported(rt):
     # more than 4 nested Transforms exceed the device's chain table -> RT_ERR_UNSUPPORTED
     b = rt.Builder(1)
