@@ -179,6 +179,10 @@ struct Compiler {
             !need(d.images, d.n_images, "images") || !need(d.texels, d.n_texels, "texels") ||
             !need(d.perlins, d.n_perlins, "perlins") || !need(d.remaps, d.n_remaps, "remaps"))
             return false;
+        for (uint32_t i = 0; i < d.n_perlins; i++)  // utils/perlin.rs:25-38: permutations of 0..255; they index randvec on the device
+            for (int k = 0; k < 256; k++)
+                if (d.perlins[i].perm_x[k] > 255u || d.perlins[i].perm_y[k] > 255u || d.perlins[i].perm_z[k] > 255u)
+                    return fail(RT_ERR_INVALID, "perlin permutation entry out of range");
         for (uint32_t i = 0; i < d.n_remaps; i++)
             if (d.remaps[i].normal_tex != RT_NONE && (d.remaps[i].normal_tex >= d.n_textures || d.textures[d.remaps[i].normal_tex].kind != RT_TEX_IMAGE))
                 return fail(RT_ERR_INVALID, "remap normal texture must be an image texture");
