@@ -383,6 +383,17 @@ def test_soup_at_full_batch_size_properties(gpu, rt):
     assert np.all((far["prim_id"] == rt.RT_NONE) | (far["t"] <= 1e-3))
 
 
+def test_corrupted_descriptions_do_not_fault_the_device(gpu, rt):
+    """scripts/fuzz_gpu.py: single-word corruptions (indices and numbers) of every table, then create + closest hit +
+    render.  In a process of its own: a CUDA fault would poison the context of the remaining tests."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_gpu.py"), "11", "800"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "create=0 hit=0 render=0" in r.stdout and "create=-1" in r.stdout
+
+
 def test_cpp_dropin_camera_render(gpu, rt, tmp_path):
     """examples/final_scene.cpp builds the Cornell box with the reference's constructors and calls
     Camera::render(world, lights) -> RgbImage: the 8-bit result must equal rendering the same flattened
