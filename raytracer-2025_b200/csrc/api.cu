@@ -258,6 +258,9 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.n_prims = (uint32_t)cs.geom.size();
         s->ranks = cs.ranks;
         for (auto& m : cs.media) s->generic_media |= m.single_sphere == RT_NONE;
+        v.media_xform = 0;
+        for (auto& m : cs.media)
+            if (m.xform != RT_NONE || (m.single_sphere != RT_NONE && cs.meta[m.single_sphere].xform != RT_NONE)) v.media_xform = 1;
         for (auto& m : cs.materials) s->class_mask |= 1u << m.shade_class;
         // lights is "flat" when every leaf has the same weight 1/n (a single-level list)
         s->lights_flat = 1;

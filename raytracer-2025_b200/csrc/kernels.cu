@@ -286,8 +286,11 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
 // MODE 0: the scene has no media, this pass only bins the hits (a lean, memory-bound instantiation);
 // MODE 1: every boundary is a single Sphere; MODE 2: general boundaries (BVH traversal per lane);
 // MODE 3: second phase of 1 and 2 - bins the class bytes they left in cls_q.
-template <bool COUNT, int MODE>
-__global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_BLOCKS : (MODE == 0 ? 4 : RT_MEDIA_MIN_BLOCKS)) k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
+// XF = some medium (or its sphere boundary) sits under a Transform.  Without the detransform code the single-sphere
+// pass needs 81 registers instead of 126 and runs three CTAs per SM (book2: 111 -> 85 ms per step).
+template <bool COUNT, int MODE, bool XF>
+__global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_BLOCKS : (MODE == 0 || MODE == 3 ? 4 : (XF ? RT_MEDIA_MIN_BLOCKS : RT_MEDIA_MIN_BLOCKS_NOXF)))
+    k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
     constexpr bool GENERIC = MODE == 2;
     extern __shared__ float4 s_mem[];  // traversal stacks for boundaries that are not a single sphere
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
@@ -330,7 +333,8 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
                 uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
                 for (uint32_t m = 0; m < sv.n_media; m++) {
                     const Medium& med = sv.media[m];
-                    const RayD lr = med.xform == RT_NONE ? r : ray_to_local(sv, med.xform, r);
+                    RayD lr = r;
+                    if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
                     const double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
                     // binary32 screens: hf is the free-flight distance in binary32, pessimistic by the margins below.
                     // (1) the scatter point lies at t1 + dist/len with t1 >= 0, so a free flight that clearly
@@ -341,8 +345,11 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
                     if (RT_MEDIA_EARLY_SCREEN && kind != HIT_MISS && hf > (float)t * len_f * 1.001f + hf_err) continue;
                     double t1, t2;
                     if (med.single_sphere != RT_NONE) {
-                        const uint32_t bx = sv.meta[med.single_sphere].xform;
-                        const RayD br = bx == med.xform ? lr : (bx == RT_NONE ? r : ray_to_local(sv, bx, r));
+                        RayD br = lr;
+                        if (XF) {
+                            const uint32_t bx = sv.meta[med.single_sphere].xform;
+                            if (bx != med.xform) br = bx == RT_NONE ? r : ray_to_local(sv, bx, r);
+                        }
                         if (COUNT) cnt.prims += 2;
                         if (!sphere_entry_exit(sv.geom[med.single_sphere].d, br, t1, t2)) continue;
                     } else if (GENERIC) {
@@ -773,21 +780,18 @@ int launch_media_bin(const SceneView& sv, const RenderParams& P, const Wavefront
     mv.n_cached_nodes = 0;
     const size_t media_smem = generic ? (size_t)sv.stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;
     const int mode = sv.n_media == 0 ? 0 : (generic ? 2 : 1);
+    const bool xf = sv.media_xform != 0;
     if (mode == 2) {
-        if (count)
-            k_media_bin<true, 2><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
-        else
-            k_media_bin<false, 2><<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+        auto k = count ? (xf ? k_media_bin<true, 2, true> : k_media_bin<true, 2, false>) : (xf ? k_media_bin<false, 2, true> : k_media_bin<false, 2, false>);
+        k<<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
     } else if (mode == 1) {
-        if (count)
-            k_media_bin<true, 1><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
-        else
-            k_media_bin<false, 1><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        auto k = count ? (xf ? k_media_bin<true, 1, true> : k_media_bin<true, 1, false>) : (xf ? k_media_bin<false, 1, true> : k_media_bin<false, 1, false>);
+        k<<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
     } else {
-        k_media_bin<false, 0><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        k_media_bin<false, 0, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
     }
     if (mode != 0 && RT_MEDIA_TWO_PHASE) {
-        k_media_bin<false, 3><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        k_media_bin<false, 3, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
         return 2;
     }
     return 1;

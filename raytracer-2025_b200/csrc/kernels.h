@@ -36,6 +36,9 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_MEDIA_MIN_BLOCKS
 #define RT_MEDIA_MIN_BLOCKS 2
 #endif
+#ifndef RT_MEDIA_MIN_BLOCKS_NOXF
+#define RT_MEDIA_MIN_BLOCKS_NOXF 3
+#endif
 #ifndef RT_MEDIA_GENERIC_MIN_BLOCKS
 #define RT_MEDIA_GENERIC_MIN_BLOCKS 2
 #endif

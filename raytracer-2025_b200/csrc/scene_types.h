@@ -148,7 +148,7 @@ struct SceneView {
     const Remap* remaps;
     const Node4* nodes4;  // collapsed four-wide tree of the world group, or nullptr
     uint32_t world_root4; // root reference into nodes4 (only when nodes4 != nullptr)
-    uint32_t wide_pad;
+    uint32_t media_xform;  // some ConstantMedium (or its single-sphere boundary) sits under a Transform
     uint32_t world_root;
     uint32_t n_media, n_lights, n_prims;
     uint32_t n_nodes;
