@@ -433,7 +433,7 @@ __device__ __forceinline__ void contribute(const RenderParams& P, const Wavefron
 // registers.  CLS == SC_OTHER is the fully general version (Mix, Portal, Transparent, lights that
 // wrap a material) and is also what runs when binning is switched off.
 template <uint32_t CLS>
-__global__ void __launch_bounds__(SHADE_BLOCK, RT_SHADE_MIN_BLOCKS) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
+__global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 1u) ? 3 : RT_SHADE_MIN_BLOCKS) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
     constexpr bool GENERIC = CLS == SC_OTHER;
     constexpr bool DO_MISS = CLS == SC_MISS;
     constexpr bool DO_MEDIUM = GENERIC || CLS == SC_ISOTROPIC;
@@ -798,6 +798,8 @@ int launch_media_bin(const SceneView& sv, const RenderParams& P, const Wavefront
 }
 template <uint32_t CLS>
 static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t queue, int grid, cudaStream_t s) {
+    // `grid` is sized for RT_SHADE_MIN_BLOCKS resident CTAs per SM; classes compiled for three get the matching grid
+    if ((RT_SHADE_3BLOCK_MASK >> CLS) & 1u) grid = grid / RT_SHADE_MIN_BLOCKS * 3;
     k_shade<CLS><<<grid, SHADE_BLOCK, 0, s>>>(sv, P, W, queue);
 }
 // class_mask: bit c set when the scene can produce hits of shade class c (the miss queue always runs).
@@ -853,7 +855,7 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false>, EXTEND_BLOCK, smem_bytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_DIFFUSE>, SHADE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_OTHER>, SHADE_BLOCK, 0);  // a class never compiled for three
     return 0;
 }
 

@@ -51,6 +51,9 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_MEDIA_EARLY_SCREEN
 #define RT_MEDIA_EARLY_SCREEN 1
 #endif
+#ifndef RT_SHADE_3BLOCK_MASK
+#define RT_SHADE_3BLOCK_MASK 0x73u  // shade classes compiled for three CTAs per SM (85 registers) instead of RT_SHADE_MIN_BLOCKS
+#endif
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 2
 #endif
