@@ -302,9 +302,13 @@ def main():
         ext_bytes_per_launch = seg_rank0 * EXTEND_BYTES_PER_SEGMENT / n_ext_launches
         ext_ms_per_launch = ms_extend / n_ext_launches
         achieved = ext_bytes_per_launch / (ext_ms_per_launch * 1e-3) / 1e9 if ext_ms_per_launch > 0 else 0.0
-        traffic = None
+        traffic, ncu_issue = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json"))).get("dram_bytes_per_launch")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "extend_traffic.json")))
+            traffic = prof.get("dram_bytes_per_launch")
+            # the figures that describe an issue-bound kernel, from the same ncu capture (not measured live)
+            ncu_issue = {"issue_active_pct": prof.get("issue_active_pct"), "active_lanes_per_instruction": prof.get("active_lanes_per_instruction"),
+                         "warps_active_pct": prof.get("warps_active_pct"), "source": "profiles/r01_v7_ncu_full_summary.csv"}
         except Exception:
             pass
         line = {
@@ -323,7 +327,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_segment": EXTEND_BYTES_PER_SEGMENT, "segments_per_launch": seg_rank0 / n_ext_launches,
-                         "ms_per_launch": ext_ms_per_launch,
+                         "ms_per_launch": ext_ms_per_launch, "ncu": ncu_issue,
                          "stage_ms_per_step": {"generate": ms_gen / args.steps, "extend": ms_extend / args.steps,
                                                "media_bin": ms_media / args.steps, "shade": ms_shade / args.steps},
                          "note": "configs 1-3 keep the scene in L1/L2: the binding limit is SM issue rate under divergence, "
