@@ -170,7 +170,7 @@ uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base,
     Ctx c{boxes.data(), order.data(), nodes.data(), &count, &depth, first_prim_base};
     Box3 b;
     uint32_t root = 0;
-#pragma omp parallel
+#pragma omp parallel if (n > 32768)  // no team for book-sized scenes (the build itself is ~1 us per primitive)
 #pragma omp single
     root = build_range(c, 0, n, 1, b);
     nodes.resize(count.load());

@@ -528,13 +528,13 @@ struct Compiler {
         T.pos = pos.data();
         for (int b = 0; b < 2; b++)
             for (int k = 0; k < 3; k++) store[b][k].resize(n), T.list[b][k] = store[b][k].data();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (n > 32768)
         for (size_t i = 0; i < n; i++) {
             const double* bb = d.objects[kids[i]].bbox;
             for (int k = 0; k < 3; k++) T.list[0][k][i] = AxisEnt{bb[2 * k], bb[2 * k + 1], (uint32_t)i, 0};
             pos[i] = (uint32_t)i;
         }
-#pragma omp parallel
+#pragma omp parallel if (n > 32768)  // waking the team costs more than a book-sized tree (a few thousand children) takes
 #pragma omp single
         {
             for (int k = 0; k < 3; k++) {
