@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--rays", type=int, default=1 << 24)
     ap.add_argument("--oracle-rays", type=int, default=200_000)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--device-lbvh", action="store_true", help="build the tree with the device LBVH builder (RT_BUILD_DEVICE_LBVH)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -82,7 +83,7 @@ def main():
             hs = rt.named_scene(shape, seed=5, params=[n])
             t_host = time.perf_counter() - t0
             t0 = time.perf_counter()
-            sc = rt.Scene(hs, device=local_rank)
+            sc = rt.Scene(hs, device=local_rank, flags=rt.RT_BUILD_DEVICE_LBVH if args.device_lbvh else 0)
             t_build = time.perf_counter() - t0
             info = sc.info()
             osc = None
@@ -121,7 +122,7 @@ def main():
                 bytes_per_ray = 56 + 24 + nodes * info.node_bytes + prims * P
                 mrays = per * world / best / 1e3
                 line = {"metric": "closest_hit_mrays_per_sec", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "dtype": "f64", "scaling": "strong",
-                        "config": {"workload": f"{shape} N={n} rays={args.rays} {kind}", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth, "node_bytes": info.node_bytes,
+                        "config": {"workload": f"{shape} N={n} rays={args.rays} {kind}", "builder": "device LBVH" if args.device_lbvh else "host binned SAH", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth, "node_bytes": info.node_bytes,
                                    "device_bytes": info.device_bytes, "host_scene_s": t_host, "scene_create_s": t_build},
                         "ms": best, "nodes_per_ray": nodes, "prims_per_ray": prims,
                         "roofline": {"bound": "hbm", "achieved": mrays * 1e6 * bytes_per_ray / 1e9, "peak": peak, "unit": "GB/s",

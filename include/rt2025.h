@@ -241,6 +241,9 @@ typedef struct rt_scene rt_scene;
 
 #define RT_BUILD_NO_REF_RANKS 1u /* skip the median-split walk that reproduces the reference's
                                     tie order (bvh.rs:78-84, hits.rs:42); ranks = object id  */
+#define RT_BUILD_DEVICE_LBVH 2u  /* build the world BVH on the GPU (Morton-code LBVH, one primitive per leaf) instead
+                                    of the host binned-SAH builder: a much faster rt_scene_create for very large
+                                    scenes, a tree that traverses slower; ids and t do not depend on the tree */
 
 typedef struct rt_build_opts {
     uint32_t struct_size;

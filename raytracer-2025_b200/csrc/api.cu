@@ -228,11 +228,19 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         CompiledScene cs;
         std::string err;
         uint32_t flags = opts ? opts->flags : 0;
-        int rc = compile_scene(*desc, flags, cs, err);
-        if (rc != RT_OK) return set_err(rc, err);
         int device = 0, sms = 0;
-        rc = check_device(opts ? opts->device : -1, device, sms);
-        if (rc != RT_OK) return rc;
+        int rc = RT_OK;
+        const bool device_build = (flags & RT_BUILD_DEVICE_LBVH) != 0;
+        if (device_build) {  // the builder runs on the scene's device: select it before compiling
+            rc = check_device(opts ? opts->device : -1, device, sms);
+            if (rc != RT_OK) return rc;
+        }
+        rc = compile_scene(*desc, flags, cs, err, device_build ? build_bvh_device : nullptr);
+        if (rc != RT_OK) return set_err(rc, err);
+        if (!device_build) {
+            rc = check_device(opts ? opts->device : -1, device, sms);
+            if (rc != RT_OK) return rc;
+        }
         s = new rt_scene();
         s->device = device;
         s->sm_count = sms;

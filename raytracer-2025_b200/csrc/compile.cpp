@@ -153,6 +153,7 @@ struct Compiler {
     uint32_t flags;
     CompiledScene& out;
     std::string& err;
+    WorldBuilder world_builder = nullptr;
     std::vector<std::vector<FlatPrim>> groups;  // 0 = world surfaces, 1+m = boundary of media[m]
     std::vector<uint32_t> group_of_medium;
     uint32_t next_rank = 0;
@@ -731,8 +732,14 @@ struct Compiler {
                 for (int k = 0; k < 3; k++) boxes[i].lo[k] = round_down(g[i].lo[k]), boxes[i].hi[k] = round_up(g[i].hi[k]);
             std::vector<uint32_t> order;
             timer.lap("build boxes");
-            uint32_t root = build_bvh(boxes, base, out.nodes, order, out.bvh_depth);
-            timer.lap("SAH build");
+            uint32_t root = INVALID_REF;
+            const bool is_world = &g == &groups[0];
+            if (is_world && world_builder && g.size() >= 4096 && world_builder(boxes, base, out.nodes, order, out.bvh_depth, root)) {
+                timer.lap("device LBVH build");
+            } else {
+                root = build_bvh(boxes, base, out.nodes, order, out.bvh_depth);
+                timer.lap("SAH build");
+            }
 #pragma omp parallel for schedule(static) if (g.size() > 65536)
             for (size_t i = 0; i < g.size(); i++) {
                 out.geom[base + i] = g[order[i]].g;
@@ -806,8 +813,9 @@ struct Compiler {
 
 }  // namespace
 
-int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err) {
+int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err, WorldBuilder world_builder) {
     Compiler c{d, flags, out, err};
+    c.world_builder = world_builder;
     return c.run();
 }
 

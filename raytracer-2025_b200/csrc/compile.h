@@ -33,8 +33,14 @@ struct CompiledScene {
     uint32_t n_spheres = 0, n_planars = 0;
 };
 
+struct BuildBox;
+// Optional replacement for the host SAH builder on the world group (lbvh.cu); same contract as build_bvh below,
+// returns false to decline (the host builder then runs).
+using WorldBuilder = bool (*)(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes,
+                              std::vector<uint32_t>& order, uint32_t& depth_out, uint32_t& root_out);
+
 // returns RT_OK or a negative rt_status and fills err
-int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err);
+int compile_scene(const rt_scene_desc& d, uint32_t flags, CompiledScene& out, std::string& err, WorldBuilder world_builder = nullptr);
 
 // Collapse the binary tree below `root` (a reference into `nodes`) into four-wide nodes, breadth first.
 // Returns the root reference into `out` (a leaf / INVALID root is returned unchanged) and the depth of the result.
@@ -48,5 +54,8 @@ struct BuildBox {
 };
 uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes,
                    std::vector<uint32_t>& order, uint32_t& depth_out);
+// lbvh.cu: Morton-code LBVH built on the current CUDA device (RT_BUILD_DEVICE_LBVH)
+bool build_bvh_device(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes, std::vector<uint32_t>& order,
+                      uint32_t& depth_out, uint32_t& root_out);
 
 }  // namespace rt

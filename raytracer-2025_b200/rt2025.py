@@ -19,6 +19,7 @@ RT_OPT_STAGE_TIMES = 2
 RT_ACCUM_F32 = 0
 RT_ACCUM_F64 = 1
 RT_BUILD_NO_REF_RANKS = 1
+RT_BUILD_DEVICE_LBVH = 2
 
 # every symbol include/rt2025.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [

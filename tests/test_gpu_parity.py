@@ -361,6 +361,29 @@ def test_four_wide_tree_gives_the_same_hits_and_images(gpu, rt, orc, monkeypatch
     image_close(wide.render(seed=2025)[0], binary.render(seed=2025)[0])
 
 
+def test_device_lbvh_build_gives_the_same_hits(gpu, rt, orc):
+    """RT_BUILD_DEVICE_LBVH: the world tree comes from the Morton-code builder on the GPU (csrc/lbvh.cu).  Ids, t and
+    tie ranks must not depend on the builder."""
+    for shape in ("tri_soup", "sphere_soup"):
+        hs = rt.named_scene(shape, seed=9, params=[60_000])
+        sc, osc = rt.Scene(hs, flags=rt.RT_BUILD_DEVICE_LBVH), orc.OracleScene(hs)
+        info = sc.info()
+        assert info.n_nodes == 60_000 - 1  # one primitive per leaf: the radix tree, not the SAH tree
+        assert np.array_equal(sc.ranks(), osc.ranks())
+        rng = np.random.default_rng(4)
+        n = 40_000
+        o = np.concatenate([np.tile([0.5, 0.5, -2.0], (n // 2, 1)), rng.uniform(0, 1, (n // 2, 3))])
+        tgt = rng.uniform(-0.2, 1.2, (n // 2, 3))
+        tgt[:, 2] = 0.0
+        d = np.concatenate([tgt - o[: n // 2], rng.normal(size=(n // 2, 3))])
+        rays = rt.make_rays(o, d, rng.uniform(0, 1, n))
+        compare_hits(rt, sc.closest_hit(rays)[0], osc.closest_hit(rays, mode=0))
+    # a small world (below the builder's minimum) silently takes the host builder
+    hs = rt.named_scene("cornell_glass", seed=7, params=[32, 4, 12])
+    a, b = rt.Scene(hs, flags=rt.RT_BUILD_DEVICE_LBVH), rt.Scene(hs)
+    assert a.info().n_nodes == b.info().n_nodes
+
+
 def test_soup_at_full_batch_size_properties(gpu, rt):
     """1M triangles, 2^22 rays: properties that need no oracle — every reported hit re-verifies against
     its own primitive record through a second, single-ray query window [t, t]."""
