@@ -6,7 +6,7 @@ fn main() {
     let root = std::env::var("RT2025_ROOT").unwrap_or_else(|_| "../..".into()); // repo that holds include/ and csrc/
     let csrc = format!("{root}/raytracer-2025_b200/csrc");
     let mut objs = Vec::new();
-    for s in ["api.cu", "kernels.cu", "compile.cpp", "bvh_build.cpp"] {
+    for s in ["api.cu", "kernels.cu", "lbvh.cu", "compile.cpp", "bvh_build.cpp"] {
         let o = format!("{out}/{s}.o");
         let ok = Command::new("nvcc")
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false"])
