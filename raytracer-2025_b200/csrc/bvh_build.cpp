@@ -201,30 +201,23 @@ uint32_t collapse_bvh4(const std::vector<Node>& nodes, uint32_t root, std::vecto
             two[1].b[k] = nd.lo1[k], two[1].b[3 + k] = nd.hi1[k];
         }
     };
+    // level by level: every node of a level is expanded independently (all host cores), the interior children of
+    // the level get consecutive indices from a prefix sum, so the array comes out breadth first
     struct Pending {
-        uint32_t n2, n4, depth;
+        uint32_t n2, n4;
     };
-    std::vector<Pending> queue;
-    out.emplace_back();
-    queue.push_back({root, (uint32_t)out.size() - 1, 1});
-    for (size_t head = 0; head < queue.size(); head++) {
-        const Pending p = queue[head];
-        depth_out = std::max(depth_out, p.depth);
-        Entry e[4];
+    auto expand = [&](uint32_t n2, Entry* e) {  // -> number of entries
         int n = 0;
-        {
-            Entry two[2];
-            children_of(p.n2, two);
-            for (int k = 0; k < 2; k++)
-                if (two[k].ref != INVALID_REF) e[n++] = two[k];
-        }
+        Entry two[2];
+        children_of(n2, two);
+        for (int k = 0; k < 2; k++)
+            if (two[k].ref != INVALID_REF) e[n++] = two[k];
         while (n < 4) {
             int best = -1;
             float best_area = -1.f;
             for (int k = 0; k < n; k++)
                 if (!(e[k].ref & LEAF_FLAG) && area(e[k]) > best_area) best = k, best_area = area(e[k]);
             if (best < 0) break;
-            Entry two[2];
             children_of(e[best].ref, two);
             int m = 0;
             for (int k = 0; k < 2; k++)
@@ -237,26 +230,55 @@ uint32_t collapse_bvh4(const std::vector<Node>& nodes, uint32_t root, std::vecto
                 n--;
             }
         }
-        Node4 w;
-        for (int k = 0; k < 4; k++) {
-            if (k < n) {
-                for (int q = 0; q < 6; q++) w.box[k][q] = e[k].b[q];
-                if (e[k].ref & LEAF_FLAG) {
-                    w.child[k] = e[k].ref;
-                } else {
-                    out.emplace_back();
-                    w.child[k] = (uint32_t)out.size() - 1;
-                    queue.push_back({e[k].ref, w.child[k], p.depth + 1});
-                }
-            } else {
-                for (int q = 0; q < 3; q++) w.box[k][q] = INFINITY, w.box[k][3 + q] = -INFINITY;
-                w.child[k] = INVALID_REF;
-            }
-            w.pad[k] = 0;
+        return n;
+    };
+    std::vector<Pending> level{{root, 0u}}, next;
+    out.emplace_back();
+    std::vector<uint32_t> first_child;  // per node of the level: index of its first interior child (after the scan)
+    while (!level.empty()) {
+        depth_out++;
+        const size_t m = level.size();
+        first_child.assign(m + 1, 0);
+#pragma omp parallel for schedule(static) if (m > 4096)
+        for (size_t i = 0; i < m; i++) {
+            Entry e[4];
+            const int n = expand(level[i].n2, e);
+            uint32_t inner = 0;
+            for (int k = 0; k < n; k++) inner += !(e[k].ref & LEAF_FLAG);
+            first_child[i + 1] = inner;
         }
-        out[p.n4] = w;
+        for (size_t i = 0; i < m; i++) first_child[i + 1] += first_child[i];
+        const uint32_t base = (uint32_t)out.size();
+        out.resize((size_t)base + first_child[m]);
+        next.resize(first_child[m]);
+#pragma omp parallel for schedule(static) if (m > 4096)
+        for (size_t i = 0; i < m; i++) {
+            Entry e[4];
+            const int n = expand(level[i].n2, e);
+            uint32_t slot = first_child[i];
+            Node4 w;
+            for (int k = 0; k < 4; k++) {
+                if (k < n) {
+                    for (int q = 0; q < 6; q++) w.box[k][q] = e[k].b[q];
+                    if (e[k].ref & LEAF_FLAG) {
+                        w.child[k] = e[k].ref;
+                    } else {
+                        w.child[k] = base + slot;
+                        next[slot] = Pending{e[k].ref, base + slot};
+                        slot++;
+                    }
+                } else {
+                    for (int q = 0; q < 3; q++) w.box[k][q] = INFINITY, w.box[k][3 + q] = -INFINITY;
+                    w.child[k] = INVALID_REF;
+                }
+                w.pad[k] = 0;
+            }
+            out[level[i].n4] = w;
+        }
+        level.swap(next);
+        next.clear();
     }
-    return queue[0].n4;
+    return 0;  // the root is the first wide node
 }
 
 }  // namespace rt

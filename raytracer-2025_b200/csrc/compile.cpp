@@ -750,9 +750,15 @@ struct Compiler {
             std::vector<FlatPrim>().swap(g);
             timer.lap("reorder primitives");
         }
+        // Scenes that cannot stay in the caches are traversed through a four-wide collapse of the world tree (half
+        // the dependent node fetches); RT2025_WIDE_BVH=0/1 overrides the size rule (tests force it on small scenes).
+        bool wide = out.nodes.size() > 8192;  // book-sized trees stay binary: their top lives in shared memory (book2 extend 276 vs 299 ms; an 11.5 k-face mesh scene 477 vs 459 ms the other way)
+        if (const char* e = getenv("RT2025_WIDE_BVH")) wide = atoi(e) != 0;
         // Renumber the nodes breadth first from the world root (then the media groups): any prefix of
-        // the array is then the top of the tree, which the kernels stage in shared memory.
-        {
+        // the array is then the top of the tree, which the kernels stage in shared memory.  Skipped when the
+        // world is traversed through the collapse (which is emitted breadth first itself): only the small media
+        // trees still walk these nodes, and a 100 M-node renumbering is 6 s of serial host time.
+        if (!wide) {
             const size_t n = out.nodes.size();
             std::vector<uint32_t> order;
             order.reserve(n);
@@ -784,11 +790,7 @@ struct Compiler {
         }
         timer.lap("breadth-first renumbering");
         out.world_root = roots[0];
-        // Scenes that cannot stay in the caches are traversed through a four-wide collapse of the world tree (half
-        // the dependent node fetches); RT2025_WIDE_BVH=0/1 overrides the size rule (tests force it on small scenes).
         {
-            bool wide = out.nodes.size() > 8192;  // book-sized trees stay binary: their top lives in shared memory (book2 extend 276 vs 299 ms; an 11.5 k-face mesh scene 477 vs 459 ms the other way)
-            if (const char* e = getenv("RT2025_WIDE_BVH")) wide = atoi(e) != 0;
             if (wide) {
                 out.world_root4 = collapse_bvh4(out.nodes, out.world_root, out.nodes4, out.bvh4_depth);
                 if (3 * out.bvh4_depth + 2 > (uint32_t)TRAVERSAL_STACK) {  // would not fit the traversal stack: keep the binary tree
