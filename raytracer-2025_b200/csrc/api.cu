@@ -351,6 +351,7 @@ int rt_scene_destroy(rt_scene* s) {
     cudaSetDevice(s->device);
     if (s->arena) {
         cudaDeviceSynchronize();  // renders of this scene may still be in flight on caller streams
+        if (s->view.l2_window_bytes) cudaCtxResetPersistingL2Cache();  // hand the pinned lines back to ordinary traffic
         cudaFreeAsync(s->arena, cudaStreamPerThread);
     }
     delete s;
