@@ -378,6 +378,14 @@ def test_device_lbvh_build_gives_the_same_hits(gpu, rt, orc):
         d = np.concatenate([tgt - o[: n // 2], rng.normal(size=(n // 2, 3))])
         rays = rt.make_rays(o, d, rng.uniform(0, 1, n))
         compare_hits(rt, sc.closest_hit(rays)[0], osc.closest_hit(rays, mode=0))
+    # a rendered frame through the device-built tree: 6000 primitives of every kind under lists, BVHs and Transforms
+    hs = random_graph_scene(rt, 21, n_prims=6000, with_media=True, width=24, spp=4, depth=5)
+    sc, osc = rt.Scene(hs, flags=rt.RT_BUILD_DEVICE_LBVH), orc.OracleScene(hs)
+    assert np.array_equal(sc.ranks(), osc.ranks())
+    o, d, t = random_rays(np.random.default_rng(2), 20000)
+    rays = rt.make_rays(o, d, t)
+    compare_hits(rt, sc.closest_hit(rays)[0], osc.closest_hit(rays, mode=0))
+    image_close(sc.render(seed=6)[0], osc.render(seed=6)[0])
     # a small world (below the builder's minimum) silently takes the host builder
     hs = rt.named_scene("cornell_glass", seed=7, params=[32, 4, 12])
     a, b = rt.Scene(hs, flags=rt.RT_BUILD_DEVICE_LBVH), rt.Scene(hs)
