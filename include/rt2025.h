@@ -306,7 +306,10 @@ typedef struct rt_render_opts {
     uint32_t sample_begin;   /* stratum range [sample_begin, sample_end) of sqrt_spp^2;       */
     uint32_t sample_end;     /*   0,0 = all                                                  */
     uint32_t max_paths_in_flight; /* wavefront capacity; 0 = library default                 */
-    uint32_t reserved[4];
+    uint32_t reserved[4];    /* zero.  reserved[0] carries two measurement switches that never change the image:
+                                bit 0 = one general shade kernel instead of one per material class,
+                                bit 1 = sample the media after the surface hit is known (the order of
+                                        Hittables::hit) instead of before it                          */
 } rt_render_opts;
 
 /* Render: the pixel loop of Camera::render (camera.rs:179-197) without the 8-bit encode.

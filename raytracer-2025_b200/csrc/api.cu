@@ -532,6 +532,12 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         P.part_index = o.part_index, P.part_count = part_count;
         P.lights_flat = s->lights_flat;
         P.bin_by_class = (o.reserved[0] & 1u) ? 0u : 1u;  // reserved[0] bit 0: disable material binning (A/B evidence)
+        // media-first order (kernels.cu, k_media_bin<PRE>) when every boundary is a single sphere: book2 extend 273 -> 263 ms.
+        // With general boundaries the sampling pass loses its cheapest screen (free flight vs surface distance) and the
+        // extra boundary traversals cost more than extend saves (mesh-fog scene 1092 -> 1104 ms), so those keep the
+        // classic order.  reserved[0] bit 1 or RT2025_MEDIA_FIRST=0/1 override.
+        P.media_first = (s->view.n_media > 0 && !s->generic_media && !(o.reserved[0] & 2u)) ? 1u : 0u;
+        if (const char* e = getenv("RT2025_MEDIA_FIRST")) P.media_first = (s->view.n_media > 0 && atoi(e) != 0) ? 1u : 0u;
 
         const bool count = (o.flags & RT_OPT_COUNT) != 0, stage = (o.flags & RT_OPT_STAGE_TIMES) != 0;
         const int grid_e = s->sm_count * s->extend_blocks_per_sm, grid_s = s->sm_count * s->shade_blocks_per_sm;
@@ -554,15 +560,23 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     W.parity = (uint32_t)(iters & 1);
                     // stage times: events are only recorded here and read after the render, so the
                     // measurement does not add a host synchronisation to the timed region
-                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 0), st));
+                    if (stage) CU(cudaEventRecord(ws.event(6 * iters + 0), st));
                     launch_generate(P, W, grid_g, st);
-                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 1), st));
-                    launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
-                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 2), st));
-                    launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st);
-                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 3), st));
+                    if (stage) CU(cudaEventRecord(ws.event(6 * iters + 1), st));
+                    if (P.media_first) {  // sample the media, then look for surfaces only up to the scatter point, then bin
+                        launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 1);
+                        if (stage) CU(cudaEventRecord(ws.event(6 * iters + 5), st));
+                        launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
+                        if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
+                        launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 2);
+                    } else {
+                        launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
+                        if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
+                        launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 0);
+                    }
+                    if (stage) CU(cudaEventRecord(ws.event(6 * iters + 3), st));
                     launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan());  // generate, k_step, extend + shade
-                    if (stage) CU(cudaEventRecord(ws.event(5 * iters + 4), st));
+                    if (stage) CU(cudaEventRecord(ws.event(6 * iters + 4), st));
                 }
                 CU(cudaMemcpyAsync(ws.h_counters, W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
                 CU(cudaStreamSynchronize(st));
@@ -572,10 +586,18 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
             if (stage) {
                 for (size_t i = 0; i < iters; i++) {
                     float a, b, c, d;
-                    CU(cudaEventElapsedTime(&a, ws.events[5 * i], ws.events[5 * i + 1]));
-                    CU(cudaEventElapsedTime(&b, ws.events[5 * i + 1], ws.events[5 * i + 2]));
-                    CU(cudaEventElapsedTime(&c, ws.events[5 * i + 2], ws.events[5 * i + 3]));
-                    CU(cudaEventElapsedTime(&d, ws.events[5 * i + 3], ws.events[5 * i + 4]));
+                    CU(cudaEventElapsedTime(&a, ws.events[6 * i], ws.events[6 * i + 1]));
+                    if (P.media_first) {  // generate | media sampling | extend | binning | shade
+                        float m1;
+                        CU(cudaEventElapsedTime(&m1, ws.events[6 * i + 1], ws.events[6 * i + 5]));
+                        CU(cudaEventElapsedTime(&b, ws.events[6 * i + 5], ws.events[6 * i + 2]));
+                        CU(cudaEventElapsedTime(&c, ws.events[6 * i + 2], ws.events[6 * i + 3]));
+                        c += m1;
+                    } else {
+                        CU(cudaEventElapsedTime(&b, ws.events[6 * i + 1], ws.events[6 * i + 2]));
+                        CU(cudaEventElapsedTime(&c, ws.events[6 * i + 2], ws.events[6 * i + 3]));
+                    }
+                    CU(cudaEventElapsedTime(&d, ws.events[6 * i + 3], ws.events[6 * i + 4]));
                     ms_gen += a, ms_ext += b, ms_med += c, ms_shd += d;
                 }
             }

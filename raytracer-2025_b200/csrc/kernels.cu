@@ -28,12 +28,13 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
     const rt_ray* __restrict__ rays;
     rt_hit* __restrict__ out;
     double tmin, tmax;
-    __device__ __forceinline__ bool load(uint32_t i, RayD& r, double& t0, double& t1) const {
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r, double& t0, double& t1, uint32_t& prim0, uint32_t& rank0) const {
         const double* rp = reinterpret_cast<const double*>(rays + i);
         r.o = D3{rp[0], rp[1], rp[2]};
         r.d = D3{rp[3], rp[4], rp[5]};
         r.time = rp[6];
         t0 = tmin, t1 = tmax;
+        prim0 = 0xFFFFFFFFu, rank0 = 0xFFFFFFFFu;
         return true;
     }
     __device__ __forceinline__ void prefetch(uint32_t i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + i)); }
@@ -42,7 +43,8 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
         if (hit) {
             RayD r;
             double a, b;
-            load(i, r, a, b);
+            uint32_t p0, r0;
+            load(i, r, a, b, p0, r0);
             HitInfo hi;
             surface_hit_info(sv, prim, t, r, true, hi);
             const PrimMeta m = sv.meta[prim];
@@ -242,18 +244,32 @@ __global__ void k_step(WavefrontState W, int phase) {
 // ------------------------------------------------------------------------------------------
 // extend
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t MEDIUM_INCUMBENT = 0x80000000u;  // `prim` of a traversal whose incumbent is a medium scatter point: flag | medium index
 struct PathIO {  // k_extend: rays come from the current ray stream, hits go to the hit stream
     const RayRec* __restrict__ rays;
     HitRec* __restrict__ hits;
-    __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t0, double& t1) const {
+    const Medium* __restrict__ media;
+    bool media_first;  // the hit stream already holds the nearest medium scatter point of every ray (k_media_bin<PRE>)
+    __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t0, double& t1, uint32_t& prim0, uint32_t& rank0) const {
         load_ray(rays + j, r);
         t0 = 1e-8, t1 = INFINITY;  // camera.rs:286
+        prim0 = 0xFFFFFFFFu, rank0 = 0xFFFFFFFFu;
+        if (media_first) {
+            const double2 hw = *reinterpret_cast<const double2*>(hits + j);
+            if ((uint32_t)__double2loint(hw.y) == HIT_MEDIUM) {  // a surface must beat this point (or tie it with a lower rank)
+                const uint32_t m = (uint32_t)__double2hiint(hw.y);
+                t1 = hw.x;
+                prim0 = MEDIUM_INCUMBENT | m;
+                rank0 = media[m].rank;
+            }
+        }
         return true;
     }
     __device__ __forceinline__ void prefetch(uint32_t j) const {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + j));
     }
     __device__ __forceinline__ void store(uint32_t j, bool hit, double t, uint32_t prim) const {
+        if (hit && (prim & MEDIUM_INCUMBENT)) return;  // the medium kept its place: the record is already right
         *reinterpret_cast<double2*>(hits + j) =
             make_double2(hit ? t : INFINITY, __hiloint2double((int)prim, (int)(hit ? HIT_SURFACE : HIT_MISS)));
     }
@@ -270,7 +286,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     if (threadIdx.x == 0) s_cursor = 0;
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
-    PathIO io{W.ray_q[W.parity], W.hit_q};
+    PathIO io{W.ray_q[W.parity], W.hit_q, sv.media, P.media_first != 0};
     trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
@@ -288,7 +304,12 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
 // MODE 3: second phase of 1 and 2 - bins the class bytes they left in cls_q.
 // XF = some medium (or its sphere boundary) sits under a Transform.  Without the detransform code the single-sphere
 // pass needs 81 registers instead of 126 and runs three CTAs per SM (book2: 111 -> 85 ms per step).
-template <bool COUNT, int MODE, bool XF>
+// PRE = the media pass runs BEFORE extend: it samples every medium along the ray without knowing the surface hit and
+// leaves the nearest scatter point (or a miss) in the hit stream; extend then looks for a surface hit only up to that
+// distance (with the medium's tie rank as the incumbent), so a path scattering inside a dense medium - book2's trapped
+// paths bounce there up to max_depth times - costs a traversal of a few units instead of the whole scene.  The winner
+// is the same: a surface beyond the scatter point could never have won (hits.rs:39-46 takes the minimum t).
+template <bool COUNT, int MODE, bool XF, bool PRE>
 __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_BLOCKS : (MODE == 0 || MODE == 3 ? 4 : (XF ? RT_MEDIA_MIN_BLOCKS : RT_MEDIA_MIN_BLOCKS_NOXF)))
     k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
     constexpr bool GENERIC = MODE == 2;
@@ -300,7 +321,7 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
     // atomic per class per 256 hits: same-address atomics were what bounded the lean instantiation) and per
     // warp where lanes run a traversal of their own and a CTA-wide barrier would idle the fast warps
     constexpr bool BLOCK_AGG = MODE == 0 || MODE == 3 || (MODE == 1 && RT_MEDIA_BLOCK_AGG);
-    constexpr bool DEFER = (MODE == 1 || MODE == 2) && RT_MEDIA_TWO_PHASE;  // leave the append to a MODE 3 pass
+    constexpr bool DEFER = (MODE == 1 || MODE == 2) && (RT_MEDIA_TWO_PHASE || PRE);  // leave the append to a later pass
     __shared__ uint32_t s_cnt[2][SC_COUNT], s_base[SC_COUNT];
     if (BLOCK_AGG) {
         if (threadIdx.x < 2 * SC_COUNT) (&s_cnt[0][0])[threadIdx.x] = 0;
@@ -316,16 +337,20 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
             const uint32_t jn = j + gridDim.x * blockDim.x;
             if (jn < n) {
                 if (MODE == 1 || MODE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + jn));
-                if (MODE != 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
+                if (MODE != 3 && !PRE) asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
                 if (MODE == 1 || MODE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(states + jn) + 32));
             }
         }
         if (MODE == 3) {
             if (j < n) q = W.cls_q[j];
         } else if (j < n) {
-            const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
-            double t = hw.x;
-            uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
+            double t = INFINITY;
+            uint32_t prim = 0xFFFFFFFFu, kind = HIT_MISS;
+            if (!PRE) {
+                const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
+                t = hw.x;
+                prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
+            }
             if ((MODE == 1 || MODE == 2) && sv.n_media) {
                 RayD r;
                 load_ray(rays + j, r);
@@ -379,8 +404,9 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
                         rank = med.rank;
                     }
                 }
-                if (kind == HIT_MEDIUM) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
+                if (PRE || kind == HIT_MEDIUM) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
             }
+            if (PRE) continue;  // classes are binned after extend
             if (kind == HIT_MISS)
                 q = SC_MISS;
             else if (kind == HIT_MEDIUM)
@@ -774,24 +800,42 @@ void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontSt
                        : (sv.park_leaves ? k_extend<false, true, false> : k_extend<false, false, false>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, s, sv, P, W);
 }
-int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s) {
+int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s, int phase) {
     // media + binning: global-memory nodes only (its shared memory holds just the stacks)
     SceneView mv = sv;
     mv.n_cached_nodes = 0;
     const size_t media_smem = generic ? (size_t)sv.stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;
     const int mode = sv.n_media == 0 ? 0 : (generic ? 2 : 1);
     const bool xf = sv.media_xform != 0;
+    if (phase == 2) {  // media-first order: classes are binned from the final hit stream after extend
+        k_media_bin<false, 0, false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        return 1;
+    }
+    if (phase == 1) {  // media-first order: the sampling pass ahead of extend
+        if (mode == 2) {
+            auto k = count ? (xf ? k_media_bin<true, 2, true, true> : k_media_bin<true, 2, false, true>)
+                           : (xf ? k_media_bin<false, 2, true, true> : k_media_bin<false, 2, false, true>);
+            k<<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
+        } else {
+            auto k = count ? (xf ? k_media_bin<true, 1, true, true> : k_media_bin<true, 1, false, true>)
+                           : (xf ? k_media_bin<false, 1, true, true> : k_media_bin<false, 1, false, true>);
+            k<<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        }
+        return 1;
+    }
     if (mode == 2) {
-        auto k = count ? (xf ? k_media_bin<true, 2, true> : k_media_bin<true, 2, false>) : (xf ? k_media_bin<false, 2, true> : k_media_bin<false, 2, false>);
+        auto k = count ? (xf ? k_media_bin<true, 2, true, false> : k_media_bin<true, 2, false, false>)
+                       : (xf ? k_media_bin<false, 2, true, false> : k_media_bin<false, 2, false, false>);
         k<<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
     } else if (mode == 1) {
-        auto k = count ? (xf ? k_media_bin<true, 1, true> : k_media_bin<true, 1, false>) : (xf ? k_media_bin<false, 1, true> : k_media_bin<false, 1, false>);
+        auto k = count ? (xf ? k_media_bin<true, 1, true, false> : k_media_bin<true, 1, false, false>)
+                       : (xf ? k_media_bin<false, 1, true, false> : k_media_bin<false, 1, false, false>);
         k<<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
     } else {
-        k_media_bin<false, 0, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        k_media_bin<false, 0, false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
     }
     if (mode != 0 && RT_MEDIA_TWO_PHASE) {
-        k_media_bin<false, 3, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+        k_media_bin<false, 3, false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
         return 2;
     }
     return 1;

@@ -107,7 +107,8 @@ struct RenderParams {
     rt_camera cam;
     uint64_t seed;
     uint32_t sample_begin, part_index, part_count;
-    uint32_t lights_flat, bin_by_class, pad;
+    uint32_t lights_flat, bin_by_class;
+    uint32_t media_first;  // the media are sampled before extend, which then only looks for surfaces up to the scatter point
 };
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
@@ -115,7 +116,8 @@ void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, d
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s);
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t smem_bytes, cudaStream_t s);
-int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s);
+// phase 0: media sampling + binning after extend; 1 / 2: the sampling pass ahead of extend / the binning pass after it (RenderParams::media_first)
+int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s, int phase);
 struct ShadeFan {  // side streams for the per-class shade kernels (owned by the workspace)
     int n_side = 0;
     cudaStream_t side[3] = {};

@@ -462,13 +462,13 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
             if (!have && have_next) {  // promote the prefetched assignment
                 have_next = false;
                 double tmax;
-                if (io.load(next_item, r, tmin, tmax)) {
+                // prim / prim_rank may start from an incumbent the caller already knows (a medium scatter point)
+                if (io.load(next_item, r, tmin, tmax, prim, prim_rank)) {
                     item = next_item;
                     have = true;
                     tbest = tmax;
                     tmin_f = __double2float_rd(tmin);
                     tmax_f = __double2float_ru(tmax);
-                    prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu;
                     cached_xform = 0xFFFFFFFFu;
                     lr = r;
                     sp = 0;

@@ -421,13 +421,15 @@ class Scene:
         return st
 
     def render_opts(self, seed=1, accum_type=RT_ACCUM_F64, part_index=0, part_count=1, sample_begin=0, sample_end=0,
-                    flags=0, max_paths_in_flight=0, no_binning=False):
+                    flags=0, max_paths_in_flight=0, no_binning=False, classic_media_order=False):
         o = rt_render_opts()
         o.struct_size = C.sizeof(rt_render_opts)
         o.flags, o.seed, o.accum_type = flags, seed, accum_type
         o.part_index, o.part_count = part_index, part_count
         o.sample_begin, o.sample_end, o.max_paths_in_flight = sample_begin, sample_end, max_paths_in_flight
-        o.reserved[0] = 1 if no_binning else 0  # A/B switch: one general shade kernel instead of one per class
+        # A/B switches: bit 0 = one general shade kernel instead of one per class, bit 1 = sample the media after extend
+        # (the order of the reference's loop) instead of before it
+        o.reserved[0] = (1 if no_binning else 0) | (2 if classic_media_order else 0)
         return o
 
     def render(self, camera=None, **kw):
