@@ -34,8 +34,9 @@ _spec.loader.exec_module(rt)
 SCENE = ("book2_final", 7, [800, 1000, 40])  # name, scene seed, [width, spp, max_depth]
 RENDER_SEED = 2025
 # algorithmic HBM bytes of the dominant kernel (extend) per unit (= one path segment), DESIGN.md §5:
-# ray stream record read (64) + hit stream record written (16)
-EXTEND_BYTES_PER_SEGMENT = 64 + 16
+# ray stream record read (64) + hit stream record read (16: the medium scatter point the sampling pass left as the
+# incumbent; book2_final has media, so that pass runs first) + hit stream record written (16)
+EXTEND_BYTES_PER_SEGMENT = 64 + 16 + 16
 
 
 def partition_for_rank(rank, world):
@@ -308,7 +309,7 @@ def main():
             traffic = prof.get("dram_bytes_per_launch")
             # the figures that describe an issue-bound kernel, from the same ncu capture (not measured live)
             ncu_issue = {"issue_active_pct": prof.get("issue_active_pct"), "active_lanes_per_instruction": prof.get("active_lanes_per_instruction"),
-                         "warps_active_pct": prof.get("warps_active_pct"), "source": "profiles/r01_v7_ncu_full_summary.csv"}
+                         "warps_active_pct": prof.get("warps_active_pct"), "source": "profiles/r01_v8_ncu_full_summary.csv"}
         except Exception:
             pass
         line = {
