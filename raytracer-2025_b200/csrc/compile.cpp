@@ -14,6 +14,9 @@
 //   6. build one SAH BVH per group and store primitives in leaf order.
 #include "compile.h"
 
+#include <memory>
+#include <parallel/algorithm>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -439,33 +442,27 @@ struct Compiler {
     struct TieOrder {
         const uint32_t* kids = nullptr;  // child list -> object ids
         AxisEnt* list[2][3] = {};        // ping-pong copies of the three axis lists
-        uint32_t* pos = nullptr;         // position of a child in the order its parent left
+        uint8_t* side = nullptr;         // scratch, one byte per child: 1 = goes to the right half of its node
+        uint32_t* pos = nullptr;         // scratch, written only by nodes that have equal keys: position in the sorted node
     };
     static bool key_less(const AxisEnt& x, const AxisEnt& y) { return total_order_key(x.mn) < total_order_key(y.mn); }
-    static void sort_ents(AxisEnt* a, AxisEnt* tmp, size_t n) {  // stable, task-parallel merge sort
-        if (n < (1u << 15)) {
-            std::stable_sort(a, a + n, key_less);
-            return;
-        }
-        const size_t h = n / 2;
-#pragma omp task default(shared)
-        sort_ents(a, tmp, h);
-        sort_ents(a + h, tmp + h, n - h);
-#pragma omp taskwait
-        std::merge(a, a + h, a + h, a + n, tmp, key_less);  // stable: equal keys keep the left run first
-        std::memcpy(a, tmp, n * sizeof(AxisEnt));
-    }
-    void tie_order_node(const TieOrder& T, size_t off, size_t len, int buf, uint32_t* out) {
+    // p_axis: the axis whose list holds this node's children in the order P their parent left them (the parent's
+    // sorted order survives the stable partition); -1 at the root, where the ids themselves are P.
+    void tie_order_node(const TieOrder& T, size_t off, size_t len, int buf, int p_axis, uint32_t* out) {
         AxisEnt* const* cur = T.list[buf];
         if (len == 1) {
             out[0] = T.kids[cur[0][off].id];
             return;
         }
         if (len == 2) {  // no sort: left = P[0], right = P[1] (bvh.rs:24-27), right first
-            const uint32_t a = cur[0][off].id, b = cur[0][off + 1].id;
-            const bool a_first = T.pos[a] < T.pos[b];
-            out[0] = T.kids[a_first ? b : a];
-            out[1] = T.kids[a_first ? a : b];
+            uint32_t a, b;
+            if (p_axis >= 0) {
+                a = cur[p_axis][off].id, b = cur[p_axis][off + 1].id;
+            } else {
+                a = std::min(cur[0][off].id, cur[0][off + 1].id), b = std::max(cur[0][off].id, cur[0][off + 1].id);
+            }
+            out[0] = T.kids[b];
+            out[1] = T.kids[a];
             return;
         }
         double s[3];
@@ -478,10 +475,13 @@ struct Compiler {
         const int axis = s[0] > s[1] ? (s[0] > s[2] ? 0 : 2) : (s[1] > s[2] ? 1 : 2);  // aabb.rs:80-92
         const size_t mid = len / 2, n_right = len - mid;
         {
+            // one byte per child instead of its 4-byte position: the partitions below look it up at random, and a
+            // quarter of the footprint is what stays in cache on a 10^8-child tree
             const AxisEnt* e = cur[axis] + off;  // the node in sorted order
-            for (size_t i = 0; i < len; i++) T.pos[e[i].id] = (uint32_t)i;
+            for (size_t i = 0; i < len; i++) T.side[e[i].id] = i >= mid;
         }
         AxisEnt* const* nxt = T.list[buf ^ 1];
+        bool ties = false;
         for (int k = 0; k < 3; k++) {
             const AxisEnt* e = cur[k] + off;
             AxisEnt* lo = nxt[k] + off;
@@ -490,61 +490,78 @@ struct Compiler {
                 std::memcpy(lo, e, len * sizeof(AxisEnt));
                 continue;
             }
+            uint64_t last_lo = 0, last_hi = 0;  // keys are never 0 for a finite value... compare only after the first write
+            bool any_lo = false, any_hi = false;
             for (size_t i = 0; i < len; i++) {
-                if (T.pos[e[i].id] < mid)
+                const uint64_t key = total_order_key(e[i].mn);
+                if (!T.side[e[i].id]) {
+                    ties |= any_lo && key == last_lo;
+                    last_lo = key, any_lo = true;
                     *lo++ = e[i];
-                else
+                } else {
+                    ties |= any_hi && key == last_hi;
+                    last_hi = key, any_hi = true;
                     *hi++ = e[i];
+                }
             }
-            // equal keys: from the parent's order to this node's sorted order
-            for (AxisEnt* half : {nxt[k] + off, nxt[k] + off + mid}) {
-                const size_t n = half == nxt[k] + off ? mid : n_right;
-                for (size_t i = 0; i + 1 < n;) {
-                    size_t j = i + 1;
-                    const uint64_t key = total_order_key(half[i].mn);
-                    while (j < n && total_order_key(half[j].mn) == key) j++;
-                    if (j - i > 1) std::sort(half + i, half + j, [&](const AxisEnt& x, const AxisEnt& y) { return T.pos[x.id] < T.pos[y.id]; });
-                    i = j;
+        }
+        if (ties) {
+            // equal keys: a partitioned list keeps them in the PARENT's order; put them in this node's sorted order
+            const AxisEnt* e = cur[axis] + off;
+            for (size_t i = 0; i < len; i++) T.pos[e[i].id] = (uint32_t)i;
+            for (int k = 0; k < 3; k++) {
+                if (k == axis) continue;
+                for (AxisEnt* half : {nxt[k] + off, nxt[k] + off + mid}) {
+                    const size_t n = half == nxt[k] + off ? mid : n_right;
+                    for (size_t i = 0; i + 1 < n;) {
+                        size_t j = i + 1;
+                        const uint64_t key = total_order_key(half[i].mn);
+                        while (j < n && total_order_key(half[j].mn) == key) j++;
+                        if (j - i > 1) std::sort(half + i, half + j, [&](const AxisEnt& x, const AxisEnt& y) { return T.pos[x.id] < T.pos[y.id]; });
+                        i = j;
+                    }
                 }
             }
         }
         if (len >= 16384) {
 #pragma omp task default(shared)
-            tie_order_node(T, off + mid, n_right, buf ^ 1, out);
-            tie_order_node(T, off, mid, buf ^ 1, out + n_right);
+            tie_order_node(T, off + mid, n_right, buf ^ 1, axis, out);
+            tie_order_node(T, off, mid, buf ^ 1, axis, out + n_right);
 #pragma omp taskwait
         } else {
-            tie_order_node(T, off + mid, n_right, buf ^ 1, out);
-            tie_order_node(T, off, mid, buf ^ 1, out + n_right);
+            tie_order_node(T, off + mid, n_right, buf ^ 1, axis, out);
+            tie_order_node(T, off, mid, buf ^ 1, axis, out + n_right);
         }
     }
     // kids[0..n) -> the same ids in tie order
     void bvh_visit_order(std::vector<uint32_t>& kids) {
         const size_t n = kids.size();
         if (n < 2) return;
-        std::vector<AxisEnt> store[2][3];
+        std::unique_ptr<AxisEnt[]> store[2][3];  // not value-initialised: 144 bytes per child that the loops below fill
         std::vector<uint32_t> pos(n), out(n);
+        std::vector<uint8_t> side(n);
         TieOrder T;
         T.kids = kids.data();
         T.pos = pos.data();
+        T.side = side.data();
         for (int b = 0; b < 2; b++)
-            for (int k = 0; k < 3; k++) store[b][k].resize(n), T.list[b][k] = store[b][k].data();
+            for (int k = 0; k < 3; k++) store[b][k].reset(new AxisEnt[n]), T.list[b][k] = store[b][k].get();
 #pragma omp parallel for schedule(static) if (n > 32768)
         for (size_t i = 0; i < n; i++) {
             const double* bb = d.objects[kids[i]].bbox;
             for (int k = 0; k < 3; k++) T.list[0][k][i] = AxisEnt{bb[2 * k], bb[2 * k + 1], (uint32_t)i, 0};
-            pos[i] = (uint32_t)i;
+        }
+        // the three stable sorts by box-min: libstdc++'s parallel multiway merge sort for big inputs (it brings its own
+        // team, so it runs outside the task region of the walk)
+        for (int k = 0; k < 3; k++) {
+            if (n > 32768)
+                __gnu_parallel::stable_sort(T.list[0][k], T.list[0][k] + n, key_less);
+            else
+                std::stable_sort(T.list[0][k], T.list[0][k] + n, key_less);
         }
 #pragma omp parallel if (n > 32768)  // waking the team costs more than a book-sized tree (a few thousand children) takes
 #pragma omp single
-        {
-            for (int k = 0; k < 3; k++) {
-#pragma omp task default(shared) firstprivate(k)
-                sort_ents(T.list[0][k], T.list[1][k], n);
-            }
-#pragma omp taskwait
-            tie_order_node(T, 0, n, 0, out.data());
-        }
+        tie_order_node(T, 0, n, 0, -1, out.data());
         kids.swap(out);
     }
 
