@@ -45,19 +45,19 @@ struct CudaFail {
 struct Arena {
     char* base = nullptr;
     size_t size = 0, used = 0;
-    template <class T>
-    size_t reserve(const std::vector<T>& v) {
+    template <class V>
+    size_t reserve(const V& v) {
         size = (size + 255) & ~size_t(255);
         const size_t at = size;
-        size += v.size() * sizeof(T);
+        size += v.size() * sizeof(typename V::value_type);
         return at;
     }
     void allocate(cudaStream_t st) {
         size = (size + 255) & ~size_t(255);
         if (size) CU(cudaMallocAsync((void**)&base, size, st));
     }
-    template <class T>
-    T* put(const std::vector<T>& v, cudaStream_t st) {
+    template <class V, class T = typename V::value_type>
+    T* put(const V& v, cudaStream_t st) {
         used = (used + 255) & ~size_t(255);
         if (v.empty()) return nullptr;
         T* d = reinterpret_cast<T*>(base + used);

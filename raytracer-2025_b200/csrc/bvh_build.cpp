@@ -156,8 +156,8 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
 
 }  // namespace
 
-uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes,
-                   std::vector<uint32_t>& order, uint32_t& depth_out) {
+uint32_t build_bvh(const RawVec<BuildBox>& boxes, uint32_t first_prim_base, RawVec<Node>& nodes,
+                   RawVec<uint32_t>& order, uint32_t& depth_out) {
     if (const char* e = getenv("RT2025_SAH_CPRIM")) C_PRIM = (float)atof(e);
     if (const char* e = getenv("RT2025_SAH_LEAF")) LEAF_TARGET = (uint32_t)atoi(e);
     const uint32_t n = (uint32_t)boxes.size();
@@ -182,7 +182,7 @@ uint32_t build_bvh(const std::vector<BuildBox>& boxes, uint32_t first_prim_base,
 // Each wide node starts from the two children of a binary node and repeatedly opens the interior child with
 // the largest surface area until it has four entries (or only leaves are left): the standard SAH-guided
 // collapse.  Boxes are copied, never recomputed, so they stay the conservative bounds of the binary tree.
-uint32_t collapse_bvh4(const std::vector<Node>& nodes, uint32_t root, std::vector<Node4>& out, uint32_t& depth_out) {
+uint32_t collapse_bvh4(const RawVec<Node>& nodes, uint32_t root, RawVec<Node4>& out, uint32_t& depth_out) {
     depth_out = 0;
     if (root == INVALID_REF || (root & LEAF_FLAG)) return root;
     struct Entry {

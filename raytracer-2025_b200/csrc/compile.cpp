@@ -157,7 +157,7 @@ struct Compiler {
     CompiledScene& out;
     std::string& err;
     WorldBuilder world_builder = nullptr;
-    std::vector<std::vector<FlatPrim>> groups;  // 0 = world surfaces, 1+m = boundary of media[m]
+    std::vector<RawVec<FlatPrim>> groups;  // 0 = world surfaces, 1+m = boundary of media[m]
     std::vector<uint32_t> group_of_medium;
     uint32_t next_rank = 0;
     int status = RT_OK;
@@ -574,7 +574,7 @@ struct Compiler {
             const uint32_t k = d.objects[c].kind;
             if (k != RT_OBJ_SPHERE && k != RT_OBJ_QUAD && k != RT_OBJ_TRIANGLE) return false;
         }
-        std::vector<FlatPrim>& G = groups[group];
+        RawVec<FlatPrim>& G = groups[group];
         const size_t base = G.size();
         G.resize(base + n);
         const uint32_t rank0 = next_rank;
@@ -743,11 +743,11 @@ struct Compiler {
         uint32_t base = 0;
         std::vector<uint32_t> roots;
         for (auto& g : groups) {
-            std::vector<BuildBox> boxes(g.size());
+            RawVec<BuildBox> boxes(g.size());
 #pragma omp parallel for schedule(static) if (g.size() > 65536)
             for (size_t i = 0; i < g.size(); i++)
                 for (int k = 0; k < 3; k++) boxes[i].lo[k] = round_down(g[i].lo[k]), boxes[i].hi[k] = round_up(g[i].hi[k]);
-            std::vector<uint32_t> order;
+            RawVec<uint32_t> order;
             timer.lap("build boxes");
             uint32_t root = INVALID_REF;
             const bool is_world = &g == &groups[0];
@@ -764,7 +764,7 @@ struct Compiler {
             }
             roots.push_back(root);
             base += (uint32_t)g.size();
-            std::vector<FlatPrim>().swap(g);
+            RawVec<FlatPrim>().swap(g);
             timer.lap("reorder primitives");
         }
         // Scenes that cannot stay in the caches are traversed through a four-wide collapse of the world tree (half
@@ -794,7 +794,7 @@ struct Compiler {
                         }
                 }
             }
-            std::vector<Node> sorted(order.size());
+            RawVec<Node> sorted(order.size());
             for (size_t i = 0; i < order.size(); i++) {
                 Node nd = out.nodes[order[i]];
                 if (!(nd.child0 & LEAF_FLAG) && nd.child0 != INVALID_REF) nd.child0 = new_index[nd.child0];

@@ -183,7 +183,7 @@ struct DevBuf {
 
 }  // namespace
 
-bool build_bvh_device(const std::vector<BuildBox>& boxes, uint32_t first_prim_base, std::vector<Node>& nodes, std::vector<uint32_t>& order,
+bool build_bvh_device(const RawVec<BuildBox>& boxes, uint32_t first_prim_base, RawVec<Node>& nodes, RawVec<uint32_t>& order,
                       uint32_t& depth_out, uint32_t& root_out) {
     const uint32_t n = (uint32_t)boxes.size();
     if (n < 2 || n >= (1u << 28)) return false;  // trivial inputs go to the host builder

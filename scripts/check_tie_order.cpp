@@ -91,7 +91,7 @@ static int run_case(uint32_t n, int lattice, uint64_t seed) {
     printf("n=%u lattice=%d seed=%llu: %zu rank mismatches\n", n, lattice, (unsigned long long)seed, bad);
     // four-wide collapse (bvh_build.cpp): same leaves as the binary tree, each exactly once, every child box copied
     // from the binary tree, depth within the traversal stack
-    std::vector<rt::Node4> wide;
+    rt::RawVec<rt::Node4> wide;
     uint32_t depth4 = 0;
     const uint32_t root4 = rt::collapse_bvh4(cs.nodes, cs.world_root, wide, depth4);
     std::vector<uint32_t> leaves2, leaves4, todo;
