@@ -42,8 +42,12 @@ build/time_compile: scripts/time_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_ca
 	mkdir -p build && $(CXX) $(CXXFLAGS) -O3 -I$(PKG)/csrc -I$(PKG)/host -I/usr/local/cuda/include -o $@ scripts/time_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp
 check_tie_order: build/check_tie_order
 	build/check_tie_order
+build/fuzz_compile: scripts/fuzz_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp $(PRODUCT_HDR)
+	mkdir -p build && $(CXX) -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fopenmp -std=c++17 -ffp-contract=off -Iinclude -I$(PKG)/csrc -I$(PKG)/host -I/usr/local/cuda/include -o $@ scripts/fuzz_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp
+fuzz_compile: build/fuzz_compile
+	ASAN_OPTIONS=detect_leaks=0 build/fuzz_compile 4000 1
 
 clean:
 	rm -f $(PKG)/librt2025.so $(PKG)/librt2025_host.so oracle/liboracle.so
 
-.PHONY: all product host oracle examples clean check_tie_order
+.PHONY: all product host oracle examples clean check_tie_order fuzz_compile
