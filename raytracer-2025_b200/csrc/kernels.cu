@@ -3,12 +3,14 @@
 // Pipeline per iteration (all queues and counters live in HBM; no host round trip is needed to
 // size a launch — kernels are persistent grid-stride loops that read the counts themselves):
 //
-//   generate : refill free path slots with camera rays      (Camera::get_ray, camera.rs:247-273)
-//   extend   : closest surface hit, persistent warp-refill traversal (world.hit, camera.rs:286)
-//   media_bin: constant-medium sampling (volume.rs:37-73) against that hit, then the append of the
-//              queue position to the shade queue of the winner's material class
-//   shade    : emitted + scatter + mixture-pdf light sampling (camera.rs:290-321)
-//              -> survivors are appended to the other copy of the ray/state streams
+//   generate : tops the current ray stream up to capacity with camera rays (Camera::get_ray, camera.rs:247-273)
+//   media    : constant-medium sampling (volume.rs:37-73).  When every boundary is a sphere it runs BEFORE extend and
+//              leaves the nearest scatter point in the hit stream as the incumbent; otherwise after it, against the
+//              surface hit
+//   extend   : closest surface hit, persistent traversal (world.hit, camera.rs:286)
+//   bin      : the append of every queue position to the shade queue of the winner's material class
+//   shade    : one kernel per class - emitted + scatter + mixture-pdf light sampling (camera.rs:290-321);
+//              survivors are appended to the other copy of the ray/state streams
 //
 // Paths flow through dense, position-indexed streams (kernels.h); terminated paths simply are not
 // re-appended.  Radiance is accumulated with binary64 atomics into a per-pixel framebuffer.
