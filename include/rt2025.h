@@ -252,8 +252,13 @@ typedef struct rt_build_opts {
     uint32_t reserved;
 } rt_build_opts;
 
-/* Flatten the object graph: bake transforms, build the SAH BVH, upload to the device. */
+/* Takes the place of everything Camera::render receives by reference - `world: &dyn Hittable` and
+ * `lights: Option<&dyn Hittable>` (camera.rs:161) - and of the work BVH::from_vec does when client code builds the
+ * scene (bvh.rs:16-46): validates the description, computes the reference's tie order, keeps primitives below a
+ * Transform in their local space (shapes.rs:88-111), builds the traversal tree(s) and uploads everything to the
+ * device.  The description is copied; the caller may free it on return. */
 int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_scene** out);
+/* Drop of the scene (the reference's Box<dyn Hittable> going out of scope). */
 int rt_scene_destroy(rt_scene* scene);
 
 typedef struct rt_ray {
