@@ -119,17 +119,118 @@ def pil_image_loader(path):
     return a, linear
 
 
-class Wavefont:
-    """Wavefont::new(file_name, prefix, vanilla_material) — obj.rs:117-134."""
+class FileAssets:
+    """The asset directory the reference reads (`assets/<prefix>/<file>`): parse on demand."""
 
-    def __init__(self, builder, assets_dir, image_loader=pil_image_loader):
-        self.b, self.dir, self.load_image = builder, assets_dir, image_loader
+    def __init__(self, assets_dir, image_loader=pil_image_loader):
+        self.dir, self.load_image = assets_dir, image_loader
+
+    def obj(self, prefix, file_name):
+        path = os.path.join(self.dir, prefix, file_name)
+        return parse_obj(path) if os.path.isfile(path) else None
+
+    def mtl(self, prefix, lib):
+        path = os.path.join(self.dir, prefix, lib)
+        return parse_mtl(path) if os.path.isfile(path) else None
+
+    def image(self, rel_path):
+        return self.load_image(os.path.join(self.dir, rel_path))
+
+
+class AssetPack:
+    """The same three lookups served from one .npz: the parsed OBJ tables, the parsed MTL records and the decoded
+    8-bit images of an asset directory, written once by `write_pack` (tests/golden/make_final_pack.py does it for
+    the reference's assets/Final, which does not exist on the GPU box).  Nothing is re-derived: `obj()` returns
+    exactly what `parse_obj` returned when the pack was written."""
+
+    def __init__(self, path):
+        import json
+        self.z = np.load(path, allow_pickle=False)
+        self.meta = json.loads(bytes(self.z["meta"]).decode("utf-8"))
+
+    def obj(self, prefix, file_name):
+        rec = self.meta["objs"].get(prefix + "/" + file_name)
+        if rec is None:
+            return None
+        k = rec["key"]
+        corners, face_model = self.z[k + "/corners"], self.z[k + "/face_model"]
+        models = [{"name": m["name"], "material": m["material"], "faces": []} for m in rec["models"]]
+        for f, mi in zip(corners.tolist(), face_model.tolist()):
+            models[mi]["faces"].append([tuple(None if i < 0 else i for i in c) for c in f])
+        return models, rec["mtllibs"], self.z[k + "/pos"], self.z[k + "/tex"], self.z[k + "/nrm"]
+
+    def mtl(self, prefix, lib):
+        return self.meta["mtls"].get(prefix + "/" + lib)
+
+    def image(self, rel_path):
+        rec = self.meta["images"].get(rel_path)
+        if rec is None:
+            return None
+        return self.z[rec["key"]].astype(np.float32) / 255.0, bool(rec["linear"])
+
+
+def write_pack(path, assets_dir, obj_files, max_image_side=None):
+    """Parse `obj_files` [(prefix, file)], their MTL libraries and every image those name, and store the results.
+    Images are kept as decoded RGBA8 (optionally box-reduced so that the longer side is <= max_image_side)."""
+    import json
+    src = FileAssets(assets_dir)
+    arrays, meta = {}, {"objs": {}, "mtls": {}, "images": {}}
+    tex_keys = ("diffuse_texture", "dissolve_texture", "normal_texture", "ambient_texture", "specular_texture", "shininess_texture")
+    for n, (prefix, file_name) in enumerate(obj_files):
+        got = src.obj(prefix, file_name)
+        if got is None:
+            continue
+        models, mtllibs, pos, tex, nrm = got
+        k = f"obj{n}"
+        corners = [[[-1 if i is None else i for i in c] for c in f] for m in models for f in m["faces"]]
+        arrays[k + "/corners"] = np.array(corners, dtype=np.int32).reshape(-1, 3, 3)
+        arrays[k + "/face_model"] = np.array([i for i, m in enumerate(models) for _ in m["faces"]], dtype=np.int32)
+        arrays[k + "/pos"], arrays[k + "/tex"], arrays[k + "/nrm"] = pos, tex, nrm
+        meta["objs"][prefix + "/" + file_name] = {"key": k, "mtllibs": mtllibs,
+                                                  "models": [{"name": m["name"], "material": m["material"]} for m in models]}
+        for lib in mtllibs:
+            mats = src.mtl(prefix, lib)
+            if mats is None:
+                continue
+            meta["mtls"][prefix + "/" + lib] = mats
+            for m in mats:
+                names = [m[t] for t in tex_keys if t in m] + [v for kk, v in m["unknown_param"].items() if kk.startswith("map_")]
+                for name in names:
+                    if name.startswith("-bm"):
+                        name = name[3:].split()[-1]
+                    rel = prefix + "/" + name
+                    if rel in meta["images"]:
+                        continue
+                    img = src.image(rel)
+                    if img is None:
+                        continue
+                    px, linear = img
+                    a = np.clip(np.rint(px * 255.0), 0, 255).astype(np.uint8)
+                    if max_image_side and max(a.shape[:2]) > max_image_side:
+                        from PIL import Image
+                        s = max_image_side / max(a.shape[:2])
+                        a = np.asarray(Image.fromarray(a, "RGBA").resize((max(1, round(a.shape[1] * s)), max(1, round(a.shape[0] * s))), Image.BOX))
+                    ik = f"img{len(meta['images'])}"
+                    arrays[ik] = a
+                    meta["images"][rel] = {"key": ik, "linear": bool(linear)}
+    arrays["meta"] = np.frombuffer(json.dumps(meta, ensure_ascii=False).encode("utf-8"), dtype=np.uint8)
+    np.savez_compressed(path, **arrays)
+    return meta
+
+
+class Wavefont:
+    """Wavefont::new(file_name, prefix, vanilla_material) — obj.rs:117-134.  `assets` is an asset directory
+    (str), a FileAssets or an AssetPack."""
+
+    def __init__(self, builder, assets, image_loader=pil_image_loader):
+        self.b = builder
+        self.src = FileAssets(assets, image_loader) if isinstance(assets, (str, os.PathLike)) else assets
         self._tex_cache = {}
 
     def _image_texture(self, rel_path, raw=False):
         key = (rel_path, raw)
         if key not in self._tex_cache:
-            got = self.load_image(os.path.join(self.dir, rel_path))
+            got = self.src.image(rel_path)
             if got is None:
                 self._tex_cache[key] = self.b.image_missing()  # renders cyan, alpha 1 (texture.rs:102-105,167-169)
             else:
@@ -207,16 +308,16 @@ class Wavefont:
     def new(self, file_name, prefix, vanilla_material):
         """-> hittable id of `Hittables[ BVH per model ]`, or None when the OBJ cannot be read."""
         b = self.b
-        path = os.path.join(self.dir, prefix, file_name)
-        if not os.path.isfile(path):
+        got = self.src.obj(prefix, file_name)
+        if got is None:
             return None
-        models, mtllibs, pos, tex, nrm = parse_obj(path)
+        models, mtllibs, pos, tex, nrm = got
         mtl_mats = []
         ok = True
         for lib in mtllibs:
-            p = os.path.join(self.dir, prefix, lib)
-            if os.path.isfile(p):
-                mtl_mats += parse_mtl(p)
+            lib_mats = self.src.mtl(prefix, lib)
+            if lib_mats is not None:
+                mtl_mats += lib_mats
             else:
                 ok = False
         mats, normals = self._materials(mtl_mats, prefix, vanilla_material) if ok else ([], [])

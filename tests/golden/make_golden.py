@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import orc  # noqa: E402
-from scenes_util import random_graph_scene  # noqa: E402
+from scenes_util import final_reduced_scene, random_graph_scene  # noqa: E402
 
 rt = orc.rt
 RENDER_SEED = 2025
@@ -31,6 +31,7 @@ SCENES = {
     "cornell_glass": lambda: rt.named_scene("cornell_glass", seed=7, params=[32, 4, 12]),
     "book1_final": lambda: rt.named_scene("book1_final", seed=7, params=[48, 4, 12]),
     "random_graph": lambda: random_graph_scene(rt, 11, n_prims=72, with_media=True, width=32, spp=4, depth=8),
+    "final_reduced": lambda: final_reduced_scene(rt, width=96, spp=4, depth=12),
 }
 
 
@@ -52,7 +53,10 @@ def fixture_rays(hs, seed):
 
 
 def main():
+    only = sys.argv[1:]
     for name, make in SCENES.items():
+        if only and name not in only:
+            continue
         hs = make()
         osc = orc.OracleScene(hs)
         rays = fixture_rays(hs, 99)

@@ -2,6 +2,26 @@
 import numpy as np
 
 
+def _pkg_module(rt, name):
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(rt.__file__), name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def final_reduced_scene(rt, width=96, spp=4, depth=12):
+    """BASELINE.json config 4 on the assets the reference ships: obj_scene() (src/main.rs:207-382) built from
+    tests/golden/final_assets_pack.npz (13 of the 15 OBJ files, their MTL records and images; make_final_pack.py),
+    with the generated HDR equirect environment in place of assets/13.hdr."""
+    import os
+    pack = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "final_assets_pack.npz")
+    hs, missing = _pkg_module(rt, "scenes").obj_scene(rt, _pkg_module(rt, "objload").AssetPack(pack), width=width, spp=spp, depth=depth)
+    assert missing == ["初音未来.obj", "卒.obj"], missing  # .MISSING_LARGE_BLOBS
+    return hs
+
+
 def random_graph_scene(rt, seed, n_prims=60, with_transforms=True, with_media=False, with_lights=True, width=24, spp=4, depth=6):
     """A random object graph mixing every container the reference has."""
     rng = np.random.default_rng(seed)

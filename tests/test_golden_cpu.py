@@ -8,7 +8,7 @@ import pytest
 from test_gpu_parity import GOLDEN, golden_scene
 
 
-@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph"])
+@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph", "final_reduced"])
 def test_oracle_reproduces_golden(rt, orc, name):
     fx = np.load(os.path.join(GOLDEN, name + ".npz"))
     osc = orc.OracleScene(golden_scene(rt, name))

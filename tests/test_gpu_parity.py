@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from scenes_util import compare_hits, random_graph_scene, random_rays
+from scenes_util import compare_hits, final_reduced_scene, random_graph_scene, random_rays
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +32,8 @@ NAMED = {
 def golden_scene(rt, name):
     if name == "random_graph":
         return random_graph_scene(rt, 11, n_prims=72, with_media=True, width=32, spp=4, depth=8)
+    if name == "final_reduced":
+        return final_reduced_scene(rt, width=96, spp=4, depth=12)
     n, seed, params = NAMED[name]
     return rt.named_scene(n, seed=seed, params=params)
 
@@ -43,7 +45,7 @@ def image_close(img, ref, frac_bad=2e-3, rel=1e-6):
     assert abs(img.mean() - ref.mean()) <= 1e-3 * ref.mean() + 1e-9
 
 
-@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph"])
+@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph", "final_reduced"])
 def test_closest_hit_matches_golden(gpu, rt, name):
     fx = np.load(os.path.join(GOLDEN, name + ".npz"))
     sc = rt.Scene(golden_scene(rt, name))
@@ -52,7 +54,7 @@ def test_closest_hit_matches_golden(gpu, rt, name):
     assert st.kernel_launches == 1
 
 
-@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph"])
+@pytest.mark.parametrize("name", ["book2_final", "cornell_glass", "book1_final", "random_graph", "final_reduced"])
 def test_render_matches_golden_image(gpu, rt, name):
     fx = np.load(os.path.join(GOLDEN, name + ".npz"))
     sc = rt.Scene(golden_scene(rt, name))
