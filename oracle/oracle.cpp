@@ -231,7 +231,8 @@ struct PathCtx {
     uint64_t seed = 0;
     uint32_t pixel = 0, sample = 0, segment = 0;
     bool media_enabled = true;  // orc_closest_hit leaves media out (they are stochastic)
-    Rand2 draw(uint32_t slot) const { return philox_pair(seed, pixel, sample, segment, slot); }
+    const double* forced = nullptr;  // known-answer hooks only: every draw returns (forced[0], forced[1])
+    Rand2 draw(uint32_t slot) const { return forced ? Rand2{forced[0], forced[1]} : philox_pair(seed, pixel, sample, segment, slot); }
 };
 
 // ---------------------------------------------------------------- sampling helpers, vec3.rs
@@ -1852,6 +1853,66 @@ void orc_kat_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
 void orc_kat_draw(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t segment, uint32_t slot, double* ab) {
     Rand2 r = philox_pair(seed, pixel, sample, segment, slot);
     ab[0] = r.a, ab[1] = r.b;
+}
+// ---- hooks for the hand-derived vectors of tests/test_oracle_kat.py (hit records, scatter, pdfs) ----------
+// world.hit with every random draw forced to (xi[0], xi[1]).  out: t, p(3), normal(3), u, v, front_face, prim_id, inst_id
+int orc_kat_world_hit(const void* s, const rt_ray* ray, double tmin, double tmax, const double* xi, double* out12) {
+    const Scene& sc = *(const Scene*)s;
+    PathCtx ctx;
+    ctx.forced = xi;
+    ctx.media_enabled = xi != nullptr;
+    HitRecord rec;
+    Ray r(Vec3(ray->origin), Vec3(ray->direction), ray->time);
+    if (!sc.world->hit(r, Interval::make(tmin, tmax), ctx, rec)) return 0;
+    out12[0] = rec.t;
+    for (int k = 0; k < 3; k++) out12[1 + k] = rec.p[k], out12[4 + k] = rec.normal[k];
+    out12[7] = rec.u, out12[8] = rec.v, out12[9] = rec.front_face ? 1.0 : 0.0;
+    out12[10] = (double)rec.prim_id, out12[11] = (double)rec.inst_id;
+    return 1;
+}
+// materials[mat].scatter on a hand-made hit record.  hit9: p(3) normal(3) u v front_face.  Returns the ScatterKind;
+// out: attenuation(3), ray direction(3) (SCATTER_RAY only), error flag
+int orc_kat_scatter(const void* s, uint32_t mat, const rt_ray* ray, const double* hit9, const double* xi, double* out7) {
+    const Scene& sc = *(const Scene*)s;
+    PathCtx ctx;
+    ctx.forced = xi;
+    HitRecord rec;
+    rec.p = Vec3(hit9), rec.normal = Vec3(hit9 + 3), rec.u = hit9[6], rec.v = hit9[7], rec.front_face = hit9[8] != 0.0;
+    Ray r(Vec3(ray->origin), Vec3(ray->direction), ray->time);
+    ScatterRecord sr = sc.materials[mat]->scatter(r, rec, ctx, 0);
+    for (int k = 0; k < 3; k++) out7[k] = sr.attenuation[k], out7[3 + k] = sr.ray.dir[k];
+    out7[6] = sr.error ? 1.0 : 0.0;
+    return (int)sr.kind;
+}
+// CosinePDF::new(albedo, normal).value(direction) and .generate() with forced draws (pdf.rs:36-64).  out: brdf(3), pdf, generated(3)
+int orc_kat_cosine_pdf(const double* albedo, const double* normal, const double* direction, const double* xi, double* out7) {
+    ScatterRecord sr = cosine_record(Vec3(albedo), Vec3(normal));
+    if (sr.error) return 0;
+    Vec3 brdf;
+    double pdf;
+    if (!pdf_value(sr, Vec3(direction), brdf, pdf)) return 0;
+    PathCtx ctx;
+    ctx.forced = xi;
+    Vec3 gen;
+    bool err = false;
+    pdf_generate(sr, ctx, gen, err);
+    for (int k = 0; k < 3; k++) out7[k] = brdf[k], out7[4 + k] = gen[k];
+    out7[3] = pdf;
+    return err ? 0 : 1;
+}
+// lights.pdf_value(origin, direction) and lights.random(origin) of the scene's lights tree (hits.rs:52-75 and the shapes below it)
+double orc_kat_lights_pdf_value(const void* s, const double* origin, const double* direction) {
+    const Scene& sc = *(const Scene*)s;
+    return sc.lights ? sc.lights->pdf_value(Vec3(origin), Vec3(direction)) : std::nan("");
+}
+int orc_kat_lights_random(const void* s, const double* origin, uint32_t leaf, double r1, double r2, double* out3) {
+    const Scene& sc = *(const Scene*)s;
+    if (!sc.lights) return 0;
+    LightSample ls;
+    ls.leaf = leaf, ls.r1 = r1, ls.r2 = r2;
+    Vec3 d = sc.lights->random(Vec3(origin), ls);
+    for (int k = 0; k < 3; k++) out3[k] = d[k];
+    return ls.error ? 0 : 1;
 }
 // texture / environment lookups on a built scene (used to cross-check the device textures)
 void orc_texture_value(const void* s, uint32_t tex, double u, double v, const double* p, double* out) {

@@ -88,6 +88,23 @@ inline void scratch_free(void* p) {
     if (p) cudaFreeAsync(p, nullptr);
 }
 
+// Entry points select the scene's device; the caller's current device is put back on return (the library is
+// meant to sit next to torch or another CUDA client in one process).
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// scenes that hold a persisting-L2 window, per device: the carve-out is handed back when the last one dies
+std::mutex g_l2_mu;
+int g_l2_users[64] = {};
+
 struct Workspace {  // wavefront buffers, cached on the scene between renders
     WavefrontState W{};
     uint32_t capacity = 0;
@@ -224,6 +241,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
     if (!desc || !out) return set_err(RT_ERR_INVALID, "null argument");
     *out = nullptr;
     rt_scene* s = nullptr;
+    DeviceGuard guard;
     try {
         CompiledScene cs;
         std::string err;
@@ -286,12 +304,13 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.n_nodes = (uint32_t)cs.nodes.size();
         // the binary tree pushes one reference per level, the four-wide one up to three (compile.cpp keeps it within the limit)
         v.stack_entries = std::min<uint32_t>(std::max(cs.bvh_depth + 2, cs.nodes4.empty() ? 0u : 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK);
+        v.media_stack_entries = std::min<uint32_t>(cs.media_bvh_depth + 2, TRAVERSAL_STACK);  // the media kernel walks boundary groups only
         const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t);
         // persistent traversal: a warp whose BVH lives in L1/shared memory is issue-bound and runs best when it
         // drains completely before taking 32 new rays; once node fetches go to L2/HBM the idle lanes are worth
         // more as loads in flight and every finished lane is refilled at once (profiles/README.md: 1M-triangle
         // soup, incoherent rays, 392 vs 274 Mrays/s; book2_final 49.4 vs 48.7 ms the other way round)
-        v.refill_min = cs.nodes.size() > 100000 ? 1 : REFILL_MIN;
+        v.refill_min = cs.nodes.size() > 100000 ? 1 : 16;  // FIFO mode: idle lanes a warp collects before it pops (sweeps in profiles/README.md)
         // scenes that do not fit the L2: pin the top of the tree (kernels.cu, launch_with_l2_window)
         v.l2_window_bytes = 0;
         {
@@ -310,7 +329,14 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
             else if (scene_bytes > (size_t)l2 && tree_bytes <= (size_t)max_persist) want = tree_bytes;
             want = std::min({want, (size_t)max_persist, (size_t)max_window, tree_bytes});
             if (want >= (1u << 20)) {
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) v.l2_window_bytes = (uint32_t)want;
+                std::lock_guard<std::mutex> lock(g_l2_mu);
+                size_t have = 0;
+                cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+                // never shrink a carve-out another live scene (or the host framework) asked for
+                if (have >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    v.l2_window_bytes = (uint32_t)want;
+                    g_l2_users[device & 63]++;
+                }
                 cudaGetLastError();
             }
             if (getenv("RT2025_TIMING")) fprintf(stderr, "[rt2025] L2 %d MB, max persisting %d MB, max window %d MB, scene %zu MB -> window %u MB\n",
@@ -321,12 +347,26 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.park_leaves = cs.nodes.size() > 4096 ? 1 : 0;
         if (const char* e = getenv("RT2025_PARK_LEAVES")) v.park_leaves = atoi(e) != 0;  // tuning knob
         if (const char* e = getenv("RT2025_REFILL_MIN")) v.refill_min = (uint32_t)std::min(32l, std::max(1l, atol(e)));  // tuning knob
-        // when several CTAs share an SM each gets its share of the 227 KB
-        const size_t room = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024 - stack_bytes;
+        // shared memory of a traversal CTA: [cached nodes | stacks | per-warp FIFOs of prepared rays].  The FIFOs come first
+        // (64 slots per warp when they fit next to the stacks, else 32), the node cache gets what is left.
+        const size_t budget = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024;
+        auto fifo_bytes = [](uint32_t slots) { return (size_t)(EXTEND_BLOCK / 32) * slots * 28 * sizeof(uint32_t); };
+        v.fifo_slots = stack_bytes + fifo_bytes(64) <= budget ? 64u : 32u;
+        // A tree that fits in shared memory only WITHOUT the FIFOs keeps the round-1 scheme (fifo_slots = 0: a warp
+        // takes 32 rays, drains, takes 32 more): measured on book2_final (3201 nodes = 205 KB), extend 39.8 ms with the
+        // whole tree in shared memory vs 43.5 ms with FIFOs and a third of it; smaller trees (cornell) and trees that
+        // never fit (the 76 k-node mesh scene: 61.8 vs 69.6 ms; the soups: +12..24 %) gain from the FIFO.
+        {
+            const size_t tree = cs.nodes.size() * sizeof(Node);
+            if (cs.nodes4.empty() && stack_bytes + tree <= budget && stack_bytes + fifo_bytes(v.fifo_slots) + tree > budget) v.fifo_slots = 0;
+        }
+        if (const char* e = getenv("RT2025_FIFO_SLOTS")) v.fifo_slots = atoi(e) >= 64 ? 64u : (atoi(e) >= 32 ? 32u : 0u);  // tuning knob
+        if (stack_bytes + fifo_bytes(v.fifo_slots) > budget) throw CudaFail{"traversal stacks and ray FIFOs do not fit in shared memory"};
+        const size_t room = budget - stack_bytes - fifo_bytes(v.fifo_slots);
         size_t cache_bytes = room;
         if (const char* e = getenv("RT2025_SMEM_NODES_KB")) cache_bytes = std::min<size_t>(room, (size_t)atol(e) * 1024);  // tuning knob
         v.n_cached_nodes = (uint32_t)std::min<size_t>(cs.nodes.size(), cache_bytes / sizeof(Node));
-        s->stack_bytes = stack_bytes + (size_t)v.n_cached_nodes * sizeof(Node);
+        s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (size_t)v.n_cached_nodes * sizeof(Node);
         if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
         if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;
@@ -348,10 +388,15 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
 
 int rt_scene_destroy(rt_scene* s) {
     if (!s) return RT_OK;
+    DeviceGuard guard;
     cudaSetDevice(s->device);
     if (s->arena) {
         cudaDeviceSynchronize();  // renders of this scene may still be in flight on caller streams
-        if (s->view.l2_window_bytes) cudaCtxResetPersistingL2Cache();  // hand the pinned lines back to ordinary traffic
+        if (s->view.l2_window_bytes) {
+            std::lock_guard<std::mutex> lock(g_l2_mu);
+            // hand the pinned lines back to ordinary traffic once no scene of this process uses a window on the device
+            if (--g_l2_users[s->device & 63] == 0) cudaCtxResetPersistingL2Cache();
+        }
         cudaFreeAsync(s->arena, cudaStreamPerThread);
     }
     delete s;
@@ -381,11 +426,14 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
     unsigned long long* d_cnt = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = RT_OK;
+    DeviceGuard guard;
     try {
         CU(cudaSetDevice(s->device));
-        const bool count = (flags & RT_OPT_COUNT) != 0;
+        // counters are only read back through `stats`: without it the kernel runs the uncounted instantiation.
+        // The buffer is allocated and freed in stream order on the caller's stream, like the kernel that writes it.
+        const bool count = (flags & RT_OPT_COUNT) != 0 && stats != nullptr;
         if (count) {
-            scratch_alloc(&d_cnt, 2 * sizeof(unsigned long long));
+            CU(cudaMallocAsync((void**)&d_cnt, 2 * sizeof(unsigned long long), st));
             CU(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st));
         }
         int grid = s->sm_count * s->extend_blocks_per_sm;
@@ -409,7 +457,8 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
             stats->kernel_launches = 1;
             if (count) {
                 unsigned long long h[2];
-                CU(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+                CU(cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
                 stats->node_visits = h[0], stats->prim_tests = h[1];
             }
         }
@@ -418,7 +467,7 @@ int rt_closest_hit_device(const rt_scene* s, const rt_ray* d_rays, uint64_t n, d
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    scratch_free(d_cnt);
+    if (d_cnt) cudaFreeAsync(d_cnt, st);
     return rc;
 }
 
@@ -432,6 +481,7 @@ int rt_closest_hit(const rt_scene* s, const rt_ray* rays, uint64_t n, double t_m
     rt_ray* d_rays = nullptr;
     rt_hit* d_out = nullptr;
     int rc = RT_OK;
+    DeviceGuard guard;
     try {
         CU(cudaSetDevice(s->device));
         scratch_alloc(&d_rays, n * sizeof(rt_ray));

@@ -190,6 +190,14 @@ struct Compiler {
         for (uint32_t i = 0; i < d.n_remaps; i++)
             if (d.remaps[i].normal_tex != RT_NONE && (d.remaps[i].normal_tex >= d.n_textures || d.textures[d.remaps[i].normal_tex].kind != RT_TEX_IMAGE))
                 return fail(RT_ERR_INVALID, "remap normal texture must be an image texture");
+        // every image is copied (and sRGB-decoded) by copy_tables, referenced or not: bound them all, overflow-safe
+        for (uint32_t i = 0; i < d.n_images; i++) {
+            const rt_image& im = d.images[i];
+            if (im.width == 0 || im.height == 0) return fail(RT_ERR_INVALID, "image with zero width or height (a missing file is texture.a == RT_NONE)");
+            const uint64_t n_texel = (uint64_t)im.width * im.height;  // < 2^64: both factors are 32-bit
+            if (n_texel > (d.n_texels >> 2) || im.texel_offset > d.n_texels - 4 * n_texel || (im.texel_offset & 3u))
+                return fail(RT_ERR_INVALID, "image texels out of range");
+        }
         for (uint32_t i = 0; i < d.n_textures; i++) {
             const rt_texture& t = d.textures[i];
             switch (t.kind) {
@@ -199,12 +207,7 @@ struct Compiler {
                     if (t.a >= i || t.b >= i) return fail(RT_ERR_INVALID, "checker children must precede the checker");
                     break;
                 case RT_TEX_IMAGE:
-                    if (t.a != RT_NONE) {
-                        if (t.a >= d.n_images) return fail(RT_ERR_INVALID, "image index out of range");
-                        const rt_image& im = d.images[t.a];
-                        if (im.texel_offset + (uint64_t)im.width * im.height * 4 > d.n_texels)
-                            return fail(RT_ERR_INVALID, "image texels out of range");
-                    }
+                    if (t.a != RT_NONE && t.a >= d.n_images) return fail(RT_ERR_INVALID, "image index out of range");
                     break;
                 case RT_TEX_NOISE:
                     if (t.a >= d.n_perlins) return fail(RT_ERR_INVALID, "perlin index out of range");
@@ -245,7 +248,11 @@ struct Compiler {
                 default: return fail(RT_ERR_INVALID, "unknown material kind");
             }
         }
+        // The graph is a tree (Box<dyn Hittable> owns its children): one parent per object, nesting bounded so that the
+        // recursive walks below cannot overflow the stack
         std::vector<uint8_t> seen(d.n_objects, 0);
+        std::vector<uint16_t> height(d.n_objects, 0);
+        constexpr uint32_t MAX_NESTING = 256;
         for (uint32_t i = 0; i < d.n_objects; i++) {
             const rt_object& o = d.objects[i];
             if ((uint64_t)o.first_child + o.child_count > d.n_children) return fail(RT_ERR_INVALID, "children range out of bounds");
@@ -275,9 +282,14 @@ struct Compiler {
                 uint32_t c = d.children[o.first_child + k];
                 if (c >= d.n_objects) return fail(RT_ERR_INVALID, "child index out of range");
                 if (c >= i) return fail(RT_ERR_INVALID, "children must precede their parent (the graph is a tree emitted bottom-up)");
+                if (seen[c]) return fail(RT_ERR_INVALID, "an object has two parents (the graph must be a tree)");
+                seen[c] = 1;
+                height[i] = std::max<uint16_t>(height[i], (uint16_t)(height[c] + 1));
             }
+            if (height[i] > MAX_NESTING) return fail(RT_ERR_UNSUPPORTED, "containers nested more than 256 deep");
         }
-        (void)seen;
+        if (seen[d.world_root] || (d.lights_root != RT_NONE && (seen[d.lights_root] || d.lights_root == d.world_root)))
+            return fail(RT_ERR_INVALID, "world / lights root is the child of another object");
         return true;
     }
 
@@ -754,7 +766,8 @@ struct Compiler {
             if (is_world && world_builder && g.size() >= 4096 && world_builder(boxes, base, out.nodes, order, out.bvh_depth, root)) {
                 timer.lap("device LBVH build");
             } else {
-                root = build_bvh(boxes, base, out.nodes, order, out.bvh_depth);
+                // the boundary groups of the media are walked by the media kernel with a stack of their own depth
+                root = build_bvh(boxes, base, out.nodes, order, is_world ? out.bvh_depth : out.media_bvh_depth);
                 timer.lap("SAH build");
             }
 #pragma omp parallel for schedule(static) if (g.size() > 65536)

@@ -54,7 +54,8 @@ struct CompiledScene {
     std::vector<Remap> remaps;
     std::vector<uint32_t> ranks;  // per desc object, RT_NONE for containers
     uint32_t world_root = INVALID_REF;
-    uint32_t bvh_depth = 0;
+    uint32_t bvh_depth = 0;        // world group (binary tree)
+    uint32_t media_bvh_depth = 0;  // deepest ConstantMedium boundary group
     uint32_t n_spheres = 0, n_planars = 0;
 };
 

@@ -30,12 +30,13 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
     const rt_ray* __restrict__ rays;
     rt_hit* __restrict__ out;
     double tmin, tmax;
-    __device__ __forceinline__ bool load(uint32_t i, RayD& r, double& t0, double& t1, uint32_t& prim0, uint32_t& rank0) const {
+    __device__ __forceinline__ double t_min() const { return tmin; }
+    __device__ __forceinline__ bool load(uint32_t i, RayD& r, double& t1, uint32_t& prim0, uint32_t& rank0) const {
         const double* rp = reinterpret_cast<const double*>(rays + i);
         r.o = D3{rp[0], rp[1], rp[2]};
         r.d = D3{rp[3], rp[4], rp[5]};
         r.time = rp[6];
-        t0 = tmin, t1 = tmax;
+        t1 = tmax;
         prim0 = 0xFFFFFFFFu, rank0 = 0xFFFFFFFFu;
         return true;
     }
@@ -44,9 +45,9 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
         rt_hit h;
         if (hit) {
             RayD r;
-            double a, b;
+            double b;
             uint32_t p0, r0;
-            load(i, r, a, b, p0, r0);
+            load(i, r, b, p0, r0);
             HitInfo hi;
             surface_hit_info(sv, prim, t, r, true, hi);
             const PrimMeta m = sv.meta[prim];
@@ -66,14 +67,16 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
 template <bool COUNT, bool PARK, bool WIDE>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint32_t n, double tmin,
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
-    extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
+    extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
-    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes) + threadIdx.x;
+    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes);
+    uint32_t* stack = stack_base + threadIdx.x;
+    uint32_t* fifo = stack_base + sv.stack_entries * EXTEND_BLOCK + (threadIdx.x >> 5) * sv.fifo_slots * FIFO_SLOT_WORDS;
     if (threadIdx.x == 0) s_cursor = 0;
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     RayArrayIO io{sv, rays, out, tmin, tmax};
-    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
         atomicAdd(&counters[1], (unsigned long long)cnt.prims);
@@ -252,9 +255,10 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
     HitRec* __restrict__ hits;
     const Medium* __restrict__ media;
     bool media_first;  // the hit stream already holds the nearest medium scatter point of every ray (k_media_bin<PRE>)
-    __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t0, double& t1, uint32_t& prim0, uint32_t& rank0) const {
+    __device__ __forceinline__ double t_min() const { return 1e-8; }  // camera.rs:286
+    __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t1, uint32_t& prim0, uint32_t& rank0) const {
         load_ray(rays + j, r);
-        t0 = 1e-8, t1 = INFINITY;  // camera.rs:286
+        t1 = INFINITY;
         prim0 = 0xFFFFFFFFu, rank0 = 0xFFFFFFFFu;
         if (media_first) {
             const double2 hw = *reinterpret_cast<const double2*>(hits + j);
@@ -269,6 +273,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
     }
     __device__ __forceinline__ void prefetch(uint32_t j) const {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + j));
+        if (media_first) asm volatile("prefetch.global.L2 [%0];" ::"l"(hits + j));
     }
     __device__ __forceinline__ void store(uint32_t j, bool hit, double t, uint32_t prim) const {
         if (hit && (prim & MEDIUM_INCUMBENT)) return;  // the medium kept its place: the record is already right
@@ -280,16 +285,18 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
 // closest surface hit of every path in the extend queue (world.hit without the media, camera.rs:286)
 template <bool COUNT, bool PARK, bool WIDE>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
-    extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks]
+    extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
-    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes) + threadIdx.x;
+    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes);
+    uint32_t* stack = stack_base + threadIdx.x;
+    uint32_t* fifo = stack_base + sv.stack_entries * EXTEND_BLOCK + (threadIdx.x >> 5) * sv.fifo_slots * FIFO_SLOT_WORDS;
     const uint32_t n = W.counters->n_extend[W.parity];
     if (n == 0) return;
     if (threadIdx.x == 0) s_cursor = 0;
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     PathIO io{W.ray_q[W.parity], W.hit_q, sv.media, P.media_first != 0};
-    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, &cnt);
+    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
         atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
@@ -806,7 +813,7 @@ int launch_media_bin(const SceneView& sv, const RenderParams& P, const Wavefront
     // media + binning: global-memory nodes only (its shared memory holds just the stacks)
     SceneView mv = sv;
     mv.n_cached_nodes = 0;
-    const size_t media_smem = generic ? (size_t)sv.stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;
+    const size_t media_smem = generic ? (size_t)sv.media_stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;  // <= 64 KB, opted in by kernel_setup
     const int mode = sv.n_media == 0 ? 0 : (generic ? 2 : 1);
     const bool xf = sv.media_xform != 0;
     if (phase == 2) {  // media-first order: classes are binned from the final hit stream after extend
@@ -900,6 +907,13 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
                               (const void*)k_closest_hit<true, false, false>,  (const void*)k_closest_hit<true, true, false>,  (const void*)k_closest_hit<true, true, true>};
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
+    // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB
+    const void* media_smem[] = {(const void*)k_media_bin<false, 2, false, false>, (const void*)k_media_bin<false, 2, true, false>,
+                                (const void*)k_media_bin<true, 2, false, false>,  (const void*)k_media_bin<true, 2, true, false>,
+                                (const void*)k_media_bin<false, 2, false, true>,  (const void*)k_media_bin<false, 2, true, true>,
+                                (const void*)k_media_bin<true, 2, false, true>,   (const void*)k_media_bin<true, 2, true, true>};
+    for (const void* f : media_smem)
+        if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * MEDIA_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_OTHER>, SHADE_BLOCK, 0);  // a class never compiled for three
     return 0;

@@ -157,6 +157,8 @@ struct SceneView {
     uint32_t l2_window_bytes; // prefix of nodes[] (breadth first = top of the tree) pinned in L2 by the traversal launches; 0 = none
     uint32_t park_leaves;     // persistent traversal postpones leaves (long traversals) or not (book-sized scenes)
     uint32_t refill_min;      // idle lanes a warp of the persistent traversal waits for before it takes new rays (1..32)
+    uint32_t media_stack_entries;  // traversal stack entries per thread of the media kernel (depth of the deepest boundary group)
+    uint32_t fifo_slots;      // prepared-ray FIFO slots per warp of the persistent traversal: 32 or 64; 0 = no FIFO (traverse.cuh)
     uint32_t pad;
 };
 

@@ -389,27 +389,35 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Persistent traversal with one-ahead prefetch.
+// Persistent "while-while" traversal fed from a per-warp FIFO of PREPARED rays.
 //
-// Work items are dealt to CTAs in interleaved groups of 32, every lane always knows the NEXT item it
-// will trace and prefetches its ray record while the current one is traversed.  REFILL_MIN is the
-// number of idle lanes that triggers a refill.  Measured (profiles/README.md): refilling a warp while
-// some of its lanes are still traversing (REFILL_MIN 1..20) is SLOWER than letting the warp drain
-// (REFILL_MIN 32: 48.7 ms vs 51.5 ms at 12 and 54.5 ms at 1 on the 800x800x144 frame) — the refill code
-// runs with few lanes active and its three divisions per new ray cost more than the idle lanes save.
-// Cache-resident scenes therefore drain the warp (SceneView::refill_min = 32).  Scenes whose nodes come from
-// L2/HBM behave the other way round (config-5 soups: 1M triangles incoherent 392 Mrays/s at refill_min 1 vs
-// 274 at 32; 10M: 242 vs 167) and get refill_min = 1; rt_scene_create picks by node count.
+// Work items are dealt to CTAs in interleaved groups of 32.  A warp refills its FIFO with all 32 lanes at
+// once: lane i loads item i of the warp's next group (one coalesced 2 KB read, prefetched into L2 when the
+// group was claimed, one refill earlier), derives the binary32 slab image of the ray (three binary64
+// divisions) and stores the prepared ray in shared memory.  A lane whose traversal has finished POPS a
+// prepared ray - seven 128-bit shared-memory loads - at the top of a round once `refill_min` lanes are idle.
+// Round 1 refilled lanes in place: ~250 warp-instructions at 1-2 active lanes, which is why it was a net
+// loss on cache-resident scenes; the FIFO splits that into a converged part and a cheap pop.
+//
+// Slot layout, 7 x 16 bytes (a stride of 28 words puts the 128-bit accesses of eight consecutive slots on
+// disjoint banks, so refill stores and pop loads are conflict free):
+//   q0 o.x o.y | q1 o.z d.x | q2 d.y d.z | q3 time tmax | q4 prim0 rank0 item 1/d.x | q5 1/d.y 1/d.z nxl nyl | q6 nzl nxh nyh nzh
+//
+// Measured alternatives (profiles/README.md, round 2): a step-scheduled loop (one node step per round for every
+// lane at an inner node, primitive tests only when `leaf_min` lanes hold a leaf) raised the active lanes from 15
+// to 21 but lost 35 % in time on book2_final - every round pays four warp votes and the reconvergence of three
+// divergent regions, and the tight node loop below is what hides the L1/shared-memory latency.
 //
 // PARK = postponed leaves: a lane that reaches a leaf parks it and keeps descending until every lane of the
 // warp holds one, so the binary64 primitive tests run converged.  Worth it when traversals are long (1M-triangle
-// soup, 106 nodes per ray: 1099 / 392 Mrays/s primary / incoherent with, 907 / 338 without); on the book scenes
-// (11 nodes + 3.7 primitive tests per ray) the extra votes cost more than they save (extend 299 vs 282 ms), so
-// rt_scene_create picks per scene (SceneView::park_leaves).
+// soup, 106 nodes per ray); on the book scenes (11 nodes + 3.7 primitive tests per ray) the extra votes cost more
+// than they save, so rt_scene_create picks per scene (SceneView::park_leaves).
 //
-// IO::load(item, ray, tmin, tmax) -> bool and IO::store(item, hit, t, prim) bind the routine to the
-// path streams (k_extend) or to a plain ray array (k_closest_hit).
+// IO::load(item, ray, tmax, prim0, rank0) -> bool, IO::t_min() and IO::store(item, hit, t, prim) bind the routine
+// to the path streams (k_extend) or to a plain ray array (k_closest_hit).
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t FIFO_SLOT_WORDS = 28;
+constexpr uint32_t FIFO_INVALID_ITEM = 0xFFFFFFFFu;  // a slot of the ragged last group: popped and dropped
 
 // WIDE = traverse the four-wide collapse (sv.nodes4, out-of-cache scenes): four slab tests per fetch, the hit
 // children are ordered by entry distance with a five-exchange network, the nearest is followed and the others
@@ -417,73 +425,149 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
 template <bool COUNT, bool USE_RANK, bool PARK, bool WIDE, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
-                                                 TraceCounters* cnt) {
+                                                 uint32_t* __restrict__ fifo, uint32_t fifo_slots, TraceCounters* cnt) {
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t n_groups = (n + 31u) >> 5;
-    const uint32_t local_n = ((n_groups + G - 1u - b) / G) << 5;  // items dealt to this CTA (the tail may exceed n)
+    const uint32_t local_groups = (n_groups + G - 1u - b) / G;  // groups of 32 items dealt to this CTA
+    const uint32_t q_mask = fifo_slots - 1u;                    // fifo_slots is 32 or 64
+    const uint32_t refill_min = sv.refill_min;
 
-    bool have = false, exhausted = false;
-    bool have_next = false;  // an item is already assigned to this lane and its record is being prefetched
-    uint32_t item = 0, next_item = 0;
+    bool have = false;
+    bool exhausted = false;            // warp-uniform: the CTA's cursor ran past its last group
+    uint32_t head = 0, avail = 0;      // warp-uniform FIFO state: first filled slot, number of filled slots
+    uint32_t item = 0;
     RayD r, lr;
     RayF f;
-    double tmin = 0.0, tbest = 0.0;
-    float tmin_f = 0.f, tmax_f = 0.f;
+    const double tmin = io.t_min();
+    const float tmin_f = __double2float_rd(tmin);
+    double tbest = 0.0;
+    float tmax_f = 0.f;
     uint32_t prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu, cached_xform = 0xFFFFFFFFu;
-    uint32_t cur = INVALID_REF, parked = INVALID_REF;
+    uint32_t cur = INVALID_REF;     // inner node to visit next | a second leaf met while `parked` is taken (PARK) | INVALID_REF
+    uint32_t parked = INVALID_REF;  // the leaf this lane holds
     int sp = 0;
 
-    // lanes without a pending assignment take one from the CTA cursor and start its prefetch
-    auto grab = [&]() {
-        const unsigned need = __ballot_sync(FULL, !have_next);
-        if (exhausted || !need) return;
-        const uint32_t c = __popc(need);
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(s_cursor, c);
-        base = __shfl_sync(FULL, base, 0);
-        if (base + c >= local_n) exhausted = true;
-        if (!have_next) {
-            const uint32_t m = base + __popc(need & ((1u << lane) - 1u));
-            const uint32_t it = ((m >> 5) * G + b) * 32u + (m & 31u);
-            if (m < local_n && it < n) {
-                next_item = it;
-                have_next = true;
-                io.prefetch(it);
-            }
-        }
-    };
+    // the group this warp will load at its next refill: claimed (and prefetched) one refill ahead
+    uint32_t next_group = 0;
+    {
+        if (lane == 0) next_group = atomicAdd(s_cursor, 1u);
+        next_group = __shfl_sync(FULL, next_group, 0);
+        if (next_group < local_groups) io.prefetch((next_group * G + b) * 32u + lane);
+    }
 
     while (true) {
         const unsigned idle = __ballot_sync(FULL, !have);
-        if (idle && (__popc(idle) >= (int)sv.refill_min || idle == FULL) && (!exhausted || __ballot_sync(FULL, have_next))) {
-            if (__ballot_sync(FULL, !have && !have_next)) grab();  // first round, or nothing to promote
-            if (!have && have_next) {  // promote the prefetched assignment
-                have_next = false;
-                double tmax;
-                // prim / prim_rank may start from an incumbent the caller already knows (a medium scatter point)
-                if (io.load(next_item, r, tmin, tmax, prim, prim_rank)) {
-                    item = next_item;
-                    have = true;
-                    tbest = tmax;
-                    tmin_f = __double2float_rd(tmin);
-                    tmax_f = __double2float_ru(tmax);
-                    cached_xform = 0xFFFFFFFFu;
-                    lr = r;
-                    sp = 0;
-                    const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
-                    if (root & LEAF_FLAG) {
-                        parked = root, cur = INVALID_REF;
-                    } else {
-                        parked = INVALID_REF, cur = root;  // INVALID_REF root (empty world) finishes at once
+        // sv.refill_min: idle lanes a warp waits for before it pops (32 = drain the warp completely)
+        if (idle && (fifo_slots ? ((uint32_t)__popc(idle) >= refill_min || idle == FULL) : idle == FULL)) {
+            const uint32_t n_idle = __popc(idle);
+            if (fifo_slots == 0) {
+                // ---- direct mode (no FIFO: the shared memory holds the whole tree instead): the warp has drained,
+                // every lane prepares the ray it will trace itself ----
+                const uint32_t g = next_group;
+                if (g >= local_groups) {
+                    exhausted = true;
+                } else {
+                    if (lane == 0) next_group = atomicAdd(s_cursor, 1u);
+                    next_group = __shfl_sync(FULL, next_group, 0);
+                    if (next_group < local_groups) io.prefetch((next_group * G + b) * 32u + lane);
+                    const uint32_t it = (g * G + b) * 32u + lane;
+                    prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu;
+                    if (it < n && io.load(it, r, tbest, prim, prim_rank)) {
+                        item = it;
                         make_rayf(r, f);
+                        have = true;
+                        tmax_f = __double2float_ru(tbest);
+                        cached_xform = 0xFFFFFFFFu;
+                        lr = r;
+                        sp = 0;
+                        const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
+                        if (root & LEAF_FLAG)
+                            parked = root, cur = INVALID_REF;
+                        else
+                            parked = INVALID_REF, cur = root;
                     }
                 }
+            } else {
+                // ---- refill: every lane of the warp prepares one ray of the claimed group (converged) ----
+                if (avail < n_idle && !exhausted && avail + 32u <= fifo_slots) {
+                    const uint32_t g = next_group;
+                    if (g >= local_groups) {
+                        exhausted = true;
+                    } else {
+                        if (lane == 0) next_group = atomicAdd(s_cursor, 1u);
+                        next_group = __shfl_sync(FULL, next_group, 0);
+                        if (next_group < local_groups) io.prefetch((next_group * G + b) * 32u + lane);
+                        const uint32_t it = (g * G + b) * 32u + lane;
+                        uint32_t* slot = fifo + ((head + avail + lane) & q_mask) * FIFO_SLOT_WORDS;
+                        RayD pr;
+                        RayF pf;
+                        double ptmax = 0.0;
+                        uint32_t p0 = 0xFFFFFFFFu, r0 = 0xFFFFFFFFu;
+                        uint32_t pit = FIFO_INVALID_ITEM;
+                        if (it < n && io.load(it, pr, ptmax, p0, r0)) {
+                            pit = it;
+                            make_rayf(pr, pf);
+                        } else {
+                            pr.o = pr.d = D3{0.0, 0.0, 0.0}, pr.time = 0.0;
+                            pf.idx = pf.idy = pf.idz = pf.nxl = pf.nyl = pf.nzl = pf.nxh = pf.nyh = pf.nzh = 0.f;
+                        }
+                        double2* sd = reinterpret_cast<double2*>(slot);
+                        sd[0] = make_double2(pr.o.x, pr.o.y);
+                        sd[1] = make_double2(pr.o.z, pr.d.x);
+                        sd[2] = make_double2(pr.d.y, pr.d.z);
+                        sd[3] = make_double2(pr.time, ptmax);
+                        float4* sf = reinterpret_cast<float4*>(slot);
+                        sf[4] = make_float4(__uint_as_float(p0), __uint_as_float(r0), __uint_as_float(pit), pf.idx);
+                        sf[5] = make_float4(pf.idy, pf.idz, pf.nxl, pf.nyl);
+                        sf[6] = make_float4(pf.nzl, pf.nxh, pf.nyh, pf.nzh);
+                        avail += 32u;
+                        __syncwarp();  // the slots are read by other lanes below
+                    }
+                }
+                // ---- pop: the k-th idle lane takes the k-th filled slot ----
+                const uint32_t take = min(n_idle, avail);
+                const uint32_t my = __popc(idle & lt_mask);
+                if (!have && my < take) {
+                    const uint32_t* slot = fifo + ((head + my) & q_mask) * FIFO_SLOT_WORDS;
+                    const float4 q4 = reinterpret_cast<const float4*>(slot)[4];
+                    item = __float_as_uint(q4.z);
+                    if (item != FIFO_INVALID_ITEM) {
+                        const double2* sd = reinterpret_cast<const double2*>(slot);
+                        const double2 a0 = sd[0], a1 = sd[1], a2 = sd[2], a3 = sd[3];
+                        const float4 q5 = reinterpret_cast<const float4*>(slot)[5], q6 = reinterpret_cast<const float4*>(slot)[6];
+                        r.o = D3{a0.x, a0.y, a1.x};
+                        r.d = D3{a1.y, a2.x, a2.y};
+                        r.time = a3.x;
+                        tbest = a3.y;
+                        // prim / prim_rank may start from an incumbent the caller already knows (a medium scatter point)
+                        prim = __float_as_uint(q4.x), prim_rank = __float_as_uint(q4.y);
+                        f.idx = q4.w, f.idy = q5.x, f.idz = q5.y;
+                        f.nxl = q5.z, f.nyl = q5.w, f.nzl = q6.x;
+                        f.nxh = q6.y, f.nyh = q6.z, f.nzh = q6.w;
+                        f.sx = f.idx < 0.f, f.sy = f.idy < 0.f, f.sz = f.idz < 0.f;
+                        have = true;
+                        tmax_f = __double2float_ru(tbest);
+                        cached_xform = 0xFFFFFFFFu;
+                        lr = r;
+                        sp = 0;
+                        const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
+                        if (root & LEAF_FLAG)
+                            parked = root, cur = INVALID_REF;
+                        else
+                            parked = INVALID_REF, cur = root;  // INVALID_REF root (empty world) finishes at once
+                    }
+                }
+                head += take, avail -= take;
+                __syncwarp();  // pops are complete before a later refill overwrites the slots
             }
-            grab();  // look one item ahead
         }
-        if (__ballot_sync(FULL, have) == 0) break;
+        if (__ballot_sync(FULL, have) == 0) {
+            if (exhausted && avail == 0) break;
+            continue;  // only dropped slots were popped (ragged tail) or the FIFO still holds rays
+        }
         if (have) {
             // node phase: descend until this lane has parked a leaf and met another, or ran out
             while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
