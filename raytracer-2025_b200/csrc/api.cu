@@ -143,7 +143,7 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
             if (fan.side[i]) cudaStreamDestroy(fan.side[i]);
             if (fan.join[i]) cudaEventDestroy(fan.join[i]);
         }
-        for (int k = 0; k < 2; k++) cudaFree(W.ray_q[k]), cudaFree(W.state_q[k]);
+        for (int k = 0; k < 2; k++) cudaFree(W.ray_q[k]), cudaFree(W.beta_q[k]);
         cudaFree(W.hit_q);
         cudaFree(W.cls_q);
         for (auto& q : W.q_shade) cudaFree(q);
@@ -352,14 +352,11 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         const size_t budget = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024;
         auto fifo_bytes = [](uint32_t slots) { return (size_t)(EXTEND_BLOCK / 32) * slots * 28 * sizeof(uint32_t); };
         v.fifo_slots = stack_bytes + fifo_bytes(64) <= budget ? 64u : 32u;
-        // A tree that fits in shared memory only WITHOUT the FIFOs keeps the round-1 scheme (fifo_slots = 0: a warp
-        // takes 32 rays, drains, takes 32 more): measured on book2_final (3201 nodes = 205 KB), extend 39.8 ms with the
-        // whole tree in shared memory vs 43.5 ms with FIFOs and a third of it; smaller trees (cornell) and trees that
-        // never fit (the 76 k-node mesh scene: 61.8 vs 69.6 ms; the soups: +12..24 %) gain from the FIFO.
-        {
-            const size_t tree = cs.nodes.size() * sizeof(Node);
-            if (cs.nodes4.empty() && stack_bytes + tree <= budget && stack_bytes + fifo_bytes(v.fifo_slots) + tree > budget) v.fifo_slots = 0;
-        }
+        // Cache-resident trees keep the round-1 scheme (fifo_slots = 0: a warp takes 32 rays, drains, takes 32 more; the
+        // shared memory holds the tree instead).  Measured, extend ms per frame, direct vs FIFO: book2_final (3201 nodes)
+        // 40.8 vs 45.9, book1_final 33.5 vs 34.8, cornell 29.0 vs 28.5; trees far beyond shared memory gain from the
+        // per-lane refill: the 76 k-node mesh scene 69.6 (drained) vs 61.8, the 1 M soups +12..24 % in Mrays/s.
+        if (cs.nodes4.empty() && cs.nodes.size() * sizeof(Node) <= 2 * budget) v.fifo_slots = 0;
         if (const char* e = getenv("RT2025_FIFO_SLOTS")) v.fifo_slots = atoi(e) >= 64 ? 64u : (atoi(e) >= 32 ? 32u : 0u);  // tuning knob
         if (stack_bytes + fifo_bytes(v.fifo_slots) > budget) throw CudaFail{"traversal stacks and ray FIFOs do not fit in shared memory"};
         const size_t room = budget - stack_bytes - fifo_bytes(v.fifo_slots);
@@ -523,8 +520,11 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     }
     if (cam->image_width == 0 || cam->image_height == 0 || cam->sqrt_spp == 0)
         return set_err(RT_ERR_INVALID, "camera has an empty image or zero samples");
-    if ((uint64_t)cam->image_width * cam->image_height >= (1ull << 31))
-        return set_err(RT_ERR_UNSUPPORTED, "more than 2^31 pixels (pixel indices are 32-bit)");
+    // the path ids travel packed in the ray record (kernels.h): 28 + 24 + 12 bits
+    if ((uint64_t)cam->image_width * cam->image_height >= (1ull << IDS_PIXEL_BITS))
+        return set_err(RT_ERR_UNSUPPORTED, "more than 2^28 pixels");
+    if ((uint64_t)cam->sqrt_spp * cam->sqrt_spp >= (1ull << IDS_SAMPLE_BITS)) return set_err(RT_ERR_UNSUPPORTED, "more than 2^24 samples per pixel");
+    if (cam->max_depth >= (1u << IDS_SEGMENT_BITS)) return set_err(RT_ERR_UNSUPPORTED, "max_depth above 4095");
     if (cam->background_tex >= s->info.n_textures) return set_err(RT_ERR_INVALID, "camera.background_tex out of range");
     const uint32_t part_count = o.part_count ? o.part_count : 1;
     if (o.part_index >= part_count) return set_err(RT_ERR_INVALID, "part_index >= part_count");
@@ -559,7 +559,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
             WavefrontState& W = ws.W;
             for (int k = 0; k < 2; k++) {
                 CU(cudaMalloc(&W.ray_q[k], (size_t)capacity_alloc * sizeof(RayRec)));
-                CU(cudaMalloc(&W.state_q[k], (size_t)capacity_alloc * sizeof(StateRec)));
+                CU(cudaMalloc(&W.beta_q[k], (size_t)capacity_alloc * sizeof(BetaRec)));
             }
             CU(cudaMalloc(&W.hit_q, (size_t)capacity_alloc * sizeof(HitRec)));
             CU(cudaMalloc(&W.cls_q, (size_t)capacity_alloc));
@@ -582,12 +582,15 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         P.part_index = o.part_index, P.part_count = part_count;
         P.lights_flat = s->lights_flat;
         P.bin_by_class = (o.reserved[0] & 1u) ? 0u : 1u;  // reserved[0] bit 0: disable material binning (A/B evidence)
-        // media-first order (kernels.cu, k_media_bin<PRE>) when every boundary is a single sphere: book2 extend 273 -> 263 ms.
+        // media-first order (kernels.cu, PathIO<MEDIA>: sampled by extend while it prepares the ray) when every boundary is a single sphere.
         // With general boundaries the sampling pass loses its cheapest screen (free flight vs surface distance) and the
         // extra boundary traversals cost more than extend saves (mesh-fog scene 1092 -> 1104 ms), so those keep the
         // classic order.  reserved[0] bit 1 or RT2025_MEDIA_FIRST=0/1 override.
         P.media_first = (s->view.n_media > 0 && !s->generic_media && !(o.reserved[0] & 2u)) ? 1u : 0u;
-        if (const char* e = getenv("RT2025_MEDIA_FIRST")) P.media_first = (s->view.n_media > 0 && atoi(e) != 0) ? 1u : 0u;
+        // 1 = a sampling pass ahead of extend, 2 = sampled by extend while it prepares the ray.  Measured on book2_final (ms per
+        // 800x800x144 frame, extend + media + binning): pass 47.7+2, fused 52.2+2 - the pass runs at 24 warps per SM and streams,
+        // inside extend the same binary64 code runs at 16 warps per SM - so the pass is the default; RT2025_MEDIA_FIRST=0/1/2.
+        if (const char* e = getenv("RT2025_MEDIA_FIRST")) P.media_first = (s->view.n_media > 0 && !s->generic_media) ? (uint32_t)std::max(0, std::min(2, atoi(e))) : 0u;
 
         const bool count = (o.flags & RT_OPT_COUNT) != 0, stage = (o.flags & RT_OPT_STAGE_TIMES) != 0;
         const int grid_e = s->sm_count * s->extend_blocks_per_sm, grid_s = s->sm_count * s->shade_blocks_per_sm;
@@ -613,17 +616,13 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 0), st));
                     launch_generate(P, W, grid_g, st);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 1), st));
-                    if (P.media_first) {  // sample the media, then look for surfaces only up to the scatter point, then bin
-                        launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 1);
-                        if (stage) CU(cudaEventRecord(ws.event(6 * iters + 5), st));
-                        launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
-                        if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
-                        launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 2);
-                    } else {
-                        launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
-                        if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
-                        launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 0);
-                    }
+                    // media_first: extend samples the sphere-bounded media itself and writes the class bytes, only the binning
+                    // pass follows; otherwise the media pass (if the scene has media) runs between extend and the binning
+                    if (P.media_first == 1) launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 1);
+                    if (stage) CU(cudaEventRecord(ws.event(6 * iters + 5), st));
+                    launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
+                    if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
+                    launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, P.media_first ? 2 : 0);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 3), st));
                     launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan());  // generate, k_step, extend + shade
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 4), st));
@@ -637,16 +636,11 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                 for (size_t i = 0; i < iters; i++) {
                     float a, b, c, d;
                     CU(cudaEventElapsedTime(&a, ws.events[6 * i], ws.events[6 * i + 1]));
-                    if (P.media_first) {  // generate | media sampling | extend | binning | shade
-                        float m1;
-                        CU(cudaEventElapsedTime(&m1, ws.events[6 * i + 1], ws.events[6 * i + 5]));
-                        CU(cudaEventElapsedTime(&b, ws.events[6 * i + 5], ws.events[6 * i + 2]));
-                        CU(cudaEventElapsedTime(&c, ws.events[6 * i + 2], ws.events[6 * i + 3]));
-                        c += m1;
-                    } else {
-                        CU(cudaEventElapsedTime(&b, ws.events[6 * i + 1], ws.events[6 * i + 2]));
-                        CU(cudaEventElapsedTime(&c, ws.events[6 * i + 2], ws.events[6 * i + 3]));
-                    }
+                    float m1;  // generate | media sampling pass (if any) | extend | media pass (if any) + binning | shade
+                    CU(cudaEventElapsedTime(&m1, ws.events[6 * i + 1], ws.events[6 * i + 5]));
+                    CU(cudaEventElapsedTime(&b, ws.events[6 * i + 5], ws.events[6 * i + 2]));
+                    CU(cudaEventElapsedTime(&c, ws.events[6 * i + 2], ws.events[6 * i + 3]));
+                    c += m1;
                     CU(cudaEventElapsedTime(&d, ws.events[6 * i + 3], ws.events[6 * i + 4]));
                     ms_gen += a, ms_ext += b, ms_med += c, ms_shd += d;
                 }

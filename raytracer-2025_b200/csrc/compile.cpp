@@ -171,6 +171,7 @@ struct Compiler {
         if (d.version != RT_ABI_VERSION) return fail(RT_ERR_VERSION, "rt_scene_desc.version mismatch");
         if (d.struct_size != sizeof(rt_scene_desc)) return fail(RT_ERR_VERSION, "rt_scene_desc.struct_size mismatch");
         if (d.world_root >= d.n_objects) return fail(RT_ERR_INVALID, "world_root out of range");
+        if (d.n_materials > META_MAT_MASK) return fail(RT_ERR_UNSUPPORTED, "more than 2^26 materials");
         if (d.lights_root != RT_NONE && d.lights_root >= d.n_objects) return fail(RT_ERR_INVALID, "lights_root out of range");
         auto need = [&](const void* p, uint64_t n, const char* what) {
             if (n && !p) return fail(RT_ERR_INVALID, std::string(what) + " is null");
@@ -601,7 +602,7 @@ struct Compiler {
                 ok = false;
                 continue;
             }
-            fp.m.kind_mat = (kind << 30) | d.objects[obj].material;
+            fp.m.kind_mat = (kind << 30) | (out.materials[d.objects[obj].material].shade_class << META_CLASS_SHIFT) | d.objects[obj].material;
             fp.m.object = obj;
             fp.m.rank = in_medium ? 0 : rank0 + (uint32_t)i;
             fp.m.xform = chain.xform;
@@ -629,7 +630,7 @@ struct Compiler {
                 FlatPrim fp;
                 uint32_t kind;
                 if (!leaf(obj, chain, fp.g, kind, fp.lo, fp.hi, nullptr)) return;
-                fp.m.kind_mat = (kind << 30) | o.material;
+                fp.m.kind_mat = (kind << 30) | (out.materials[o.material].shade_class << META_CLASS_SHIFT) | o.material;
                 fp.m.object = obj;
                 fp.m.rank = in_medium ? 0 : next_rank++;
                 if (!in_medium) out.ranks[obj] = fp.m.rank;

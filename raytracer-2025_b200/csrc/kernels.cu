@@ -117,25 +117,33 @@ void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, d
 // ------------------------------------------------------------------------------------------
 // wavefront state
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_ray(const RayRec* __restrict__ rec, RayD& r) {
+__device__ __forceinline__ uint64_t pack_ids(uint32_t pixel, uint32_t sample, uint32_t segment) {
+    return (uint64_t)pixel | ((uint64_t)sample << IDS_PIXEL_BITS) | ((uint64_t)segment << (IDS_PIXEL_BITS + IDS_SAMPLE_BITS));
+}
+__device__ __forceinline__ void unpack_ids(uint64_t ids, uint32_t& pixel, uint32_t& sample, uint32_t& segment) {
+    pixel = (uint32_t)(ids & ((1ull << IDS_PIXEL_BITS) - 1ull));
+    sample = (uint32_t)((ids >> IDS_PIXEL_BITS) & ((1ull << IDS_SAMPLE_BITS) - 1ull));
+    segment = (uint32_t)(ids >> (IDS_PIXEL_BITS + IDS_SAMPLE_BITS));
+}
+__device__ __forceinline__ void load_ray(const RayRec* __restrict__ rec, RayD& r, uint64_t& ids) {
     const double2* p = reinterpret_cast<const double2*>(rec);
     double2 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
     r.o = D3{a0.x, a0.y, a1.x};
     r.d = D3{a1.y, a2.x, a2.y};
     r.time = a3.x;
+    ids = (uint64_t)__double_as_longlong(a3.y);
 }
-__device__ __forceinline__ void store_ray(RayRec* __restrict__ rec, const RayD& r) {
+__device__ __forceinline__ void store_ray(RayRec* __restrict__ rec, const RayD& r, uint64_t ids) {
     double2* p = reinterpret_cast<double2*>(rec);
     p[0] = make_double2(r.o.x, r.o.y);
     p[1] = make_double2(r.o.z, r.d.x);
     p[2] = make_double2(r.d.y, r.d.z);
-    p[3] = make_double2(r.time, 0.0);
+    p[3] = make_double2(r.time, __longlong_as_double((long long)ids));
 }
-__device__ __forceinline__ void store_state(StateRec* __restrict__ rec, D3 beta, uint32_t pixel, uint32_t sample, uint32_t segment) {
+__device__ __forceinline__ void store_beta(BetaRec* __restrict__ rec, D3 beta) {
     double2* p = reinterpret_cast<double2*>(rec);
     p[0] = make_double2(beta.x, beta.y);
     p[1] = make_double2(beta.z, 0.0);
-    reinterpret_cast<uint4*>(p)[2] = make_uint4(pixel, sample, segment, 0u);
 }
 
 // warp-aggregated reservation of one entry in queue `q` (lanes with q < 0 reserve nothing);
@@ -224,8 +232,8 @@ __global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState
         }
         r.d = pixel_sample - r.o;
         r.time = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_TIME).a;
-        store_ray(W.ray_q[W.parity] + extend_base + j, r);
-        store_state(W.state_q[W.parity] + extend_base + j, D3{1.0, 1.0, 1.0}, pixel, sidx, 0u);
+        store_ray(W.ray_q[W.parity] + extend_base + j, r, pack_ids(pixel, sidx, 0u));
+        store_beta(W.beta_q[W.parity] + extend_base + j, D3{1.0, 1.0, 1.0});
     }
 }
 
@@ -250,40 +258,109 @@ __global__ void k_step(WavefrontState W, int phase) {
 // extend
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t MEDIUM_INCUMBENT = 0x80000000u;  // `prim` of a traversal whose incumbent is a medium scatter point: flag | medium index
+
+// ConstantMedium::hit (volume.rs:37-73) for a medium whose boundary is a single Sphere, on the caller's interval
+// [1e-8, inf): true and the scatter distance when the path scatters inside.  XF: the medium or its sphere may sit
+// under a Transform.
+template <bool COUNT, bool XF>
+__device__ __forceinline__ bool sample_sphere_medium(const SceneView& sv, const Medium& med, const RayD& r, double xi, double& tm, TraceCounters* cnt) {
+    RayD lr = r;
+    if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
+    RayD br = lr;
+    if (XF) {
+        const uint32_t bx = sv.meta[med.single_sphere].xform;
+        if (bx != med.xform) br = bx == RT_NONE ? r : ray_to_local(sv, bx, r);
+    }
+    double t1, t2;
+    if (COUNT) cnt->prims += 2;
+    if (!sphere_entry_exit(sv.geom[med.single_sphere].d, br, t1, t2)) return false;
+    if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
+    if (t1 >= t2) return false;
+    if (t1 < 0.0) t1 = 0.0;
+    const double ray_length = length(lr.d);
+    const double distance_inside_boundary = (t2 - t1) * ray_length;
+    // binary32 screen: when even a pessimistic free-flight estimate clears the segment inside the boundary by a wide
+    // margin the path does not scatter here and the binary64 ln is not needed (the exact comparison below is unchanged)
+    const float hf = (float)med.neg_inv_density * logf((float)xi);
+    const float hf_err = 4e-7f * fabsf((float)med.neg_inv_density);
+    if (hf > (float)distance_inside_boundary * 1.001f + hf_err) return false;
+    const double hit_distance = med.neg_inv_density * log(xi);
+    if (hit_distance > distance_inside_boundary) return false;
+    tm = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// MEDIA: 0 = the ray load does not look at media (none, or they are sampled by k_media after extend);
+// 3 = a k_media<PRE> pass ahead of extend left the nearest scatter point of every ray in the hit stream;
+// 1 / 2 = every ConstantMedium boundary is a single Sphere and the media are sampled HERE, while the ray is being
+// prepared (2: some of them under a Transform).  The nearest scatter point becomes the incumbent of the traversal -
+// its distance bounds the search, its tie rank decides an exact tie - so a path scattering inside a dense medium
+// (book2's trapped paths bounce there up to max_depth times) costs a traversal of a few units instead of the whole
+// scene, and no separate pass re-reads the ray stream.  The winner is the same as with Hittables::hit's order
+// (hits.rs:39-46 takes the minimum t over all children, media included).
+template <bool COUNT, int MEDIA>
 struct PathIO {  // k_extend: rays come from the current ray stream, hits go to the hit stream
+    const SceneView& sv;
     const RayRec* __restrict__ rays;
     HitRec* __restrict__ hits;
-    const Medium* __restrict__ media;
-    bool media_first;  // the hit stream already holds the nearest medium scatter point of every ray (k_media_bin<PRE>)
+    uint8_t* __restrict__ cls;  // nullptr: a media pass follows and writes the class bytes
+    uint64_t seed;
+    bool bin_by_class;
+    TraceCounters* cnt;
     __device__ __forceinline__ double t_min() const { return 1e-8; }  // camera.rs:286
     __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t1, uint32_t& prim0, uint32_t& rank0) const {
-        load_ray(rays + j, r);
+        uint64_t ids;
+        load_ray(rays + j, r, ids);
         t1 = INFINITY;
         prim0 = 0xFFFFFFFFu, rank0 = 0xFFFFFFFFu;
-        if (media_first) {
+        if (MEDIA == 3) {
             const double2 hw = *reinterpret_cast<const double2*>(hits + j);
             if ((uint32_t)__double2loint(hw.y) == HIT_MEDIUM) {  // a surface must beat this point (or tie it with a lower rank)
                 const uint32_t m = (uint32_t)__double2hiint(hw.y);
                 t1 = hw.x;
                 prim0 = MEDIUM_INCUMBENT | m;
-                rank0 = media[m].rank;
+                rank0 = sv.media[m].rank;
+            }
+        } else if (MEDIA) {
+            uint32_t pixel, sample, segment;
+            unpack_ids(ids, pixel, sample, segment);
+            for (uint32_t m = 0; m < sv.n_media; m++) {
+                const Medium& med = sv.media[m];
+                const double xi = philox_pair(seed, pixel, sample, segment, RT_SLOT_MEDIUM0 + med.medium_index).a;
+                double tm;
+                if (!sample_sphere_medium<COUNT, MEDIA == 2>(sv, med, r, xi, tm, cnt)) continue;
+                // the media compete with each other like any children of a container: nearest, then lower rank
+                if (prim0 == 0xFFFFFFFFu || tm < t1 || (tm == t1 && med.rank < rank0)) {
+                    t1 = tm;
+                    prim0 = MEDIUM_INCUMBENT | m;
+                    rank0 = med.rank;
+                }
             }
         }
         return true;
     }
     __device__ __forceinline__ void prefetch(uint32_t j) const {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + j));
-        if (media_first) asm volatile("prefetch.global.L2 [%0];" ::"l"(hits + j));
+        if (MEDIA == 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(hits + j));
     }
     __device__ __forceinline__ void store(uint32_t j, bool hit, double t, uint32_t prim) const {
-        if (hit && (prim & MEDIUM_INCUMBENT)) return;  // the medium kept its place: the record is already right
-        *reinterpret_cast<double2*>(hits + j) =
-            make_double2(hit ? t : INFINITY, __hiloint2double((int)prim, (int)(hit ? HIT_SURFACE : HIT_MISS)));
+        uint32_t kind = HIT_MISS, c = SC_MISS;
+        if (hit) {
+            if (MEDIA && (prim & MEDIUM_INCUMBENT)) {  // the scatter point kept its place
+                kind = HIT_MEDIUM, prim &= ~MEDIUM_INCUMBENT;
+                c = SC_ISOTROPIC;  // the phase function of a ConstantMedium is an Isotropic (validated by the scene compiler)
+            } else {
+                kind = HIT_SURFACE;
+                if (cls) c = (__ldg(&sv.meta[prim].kind_mat) >> META_CLASS_SHIFT) & 15u;
+            }
+        }
+        *reinterpret_cast<double2*>(hits + j) = make_double2(hit ? t : INFINITY, __hiloint2double((int)prim, (int)kind));
+        if (cls) cls[j] = (uint8_t)(bin_by_class || c == SC_MISS ? c : SC_DIFFUSE);
     }
 };
 
-// closest surface hit of every path in the extend queue (world.hit without the media, camera.rs:286)
-template <bool COUNT, bool PARK, bool WIDE>
+// closest hit of every path in the extend queue: world.hit (camera.rs:286) over the surfaces and, with MEDIA, the media
+template <bool COUNT, bool PARK, bool WIDE, int MEDIA>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
@@ -295,7 +372,9 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     if (threadIdx.x == 0) s_cursor = 0;
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
-    PathIO io{W.ray_q[W.parity], W.hit_q, sv.media, P.media_first != 0};
+    // a media pass after extend (classic order, or boundaries that are not spheres) owns the class bytes
+    const bool media_pass_follows = sv.n_media != 0 && MEDIA == 0;  // (P.media_first == 0)
+    PathIO<COUNT, MEDIA> io{sv, W.ray_q[W.parity], W.hit_q, media_pass_follows ? nullptr : W.cls_q, P.seed, P.bin_by_class != 0, &cnt};
     trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
@@ -303,149 +382,124 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     }
 }
 
-// ConstantMedium::hit for every medium (volume.rs:37-73) against the surface hit found by k_extend,
-// then the warp-aggregated append to the shade queue of the winner's material class.  Runs fully
-// converged: one thread per extend-queue entry.
-// GENERIC = some boundary is not a single Sphere and needs the BVH traversal (kept out of the common
-// instantiation: it doubles the register footprint of this otherwise small streaming kernel).
-// MODE 0: the scene has no media, this pass only bins the hits (a lean, memory-bound instantiation);
-// MODE 1: every boundary is a single Sphere; MODE 2: general boundaries (BVH traversal per lane);
-// MODE 3: second phase of 1 and 2 - bins the class bytes they left in cls_q.
-// XF = some medium (or its sphere boundary) sits under a Transform.  Without the detransform code the single-sphere
-// pass needs 81 registers instead of 126 and runs three CTAs per SM (book2: 111 -> 85 ms per step).
-// PRE = the media pass runs BEFORE extend: it samples every medium along the ray without knowing the surface hit and
-// leaves the nearest scatter point (or a miss) in the hit stream; extend then looks for a surface hit only up to that
-// distance (with the medium's tie rank as the incumbent), so a path scattering inside a dense medium - book2's trapped
-// paths bounce there up to max_depth times - costs a traversal of a few units instead of the whole scene.  The winner
-// is the same: a surface beyond the scatter point could never have won (hits.rs:39-46 takes the minimum t).
+// Media pass AFTER extend (the order of Hittables::hit): ConstantMedium::hit for every medium (volume.rs:37-73)
+// against the surface hit k_extend found, one thread per extend-queue entry.  Used when some boundary is not a
+// single Sphere (GENERIC: the boundary needs a BVH traversal per lane, kept out of the common instantiation because
+// it doubles the register footprint) and for the classic-order A/B switch; sphere-bounded media are otherwise sampled
+// by k_extend itself (PathIO<MEDIA>).  Writes the winner back to the hit stream and the class byte of every entry.
+//   MODE 1: every boundary is a single Sphere; MODE 2: general boundaries.
+//   XF = some medium (or its sphere boundary) sits under a Transform (without the detransform code the single-sphere
+//   pass needs 81 registers instead of 126 and runs three CTAs per SM).
+//   PRE = the pass runs BEFORE extend (sphere boundaries only): it knows no surface hit and leaves the nearest scatter
+//   point (or a miss) in the hit stream; extend takes it as the incumbent (PathIO<3>) and writes the class bytes.
 template <bool COUNT, int MODE, bool XF, bool PRE>
-__global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_BLOCKS : (MODE == 0 || MODE == 3 ? 4 : (XF ? RT_MEDIA_MIN_BLOCKS : RT_MEDIA_MIN_BLOCKS_NOXF)))
-    k_media_bin(SceneView sv, RenderParams P, WavefrontState W) {
+__global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_BLOCKS : (XF ? RT_MEDIA_MIN_BLOCKS : RT_MEDIA_MIN_BLOCKS_NOXF))
+    k_media(SceneView sv, RenderParams P, WavefrontState W) {
     constexpr bool GENERIC = MODE == 2;
     extern __shared__ float4 s_mem[];  // traversal stacks for boundaries that are not a single sphere
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
     TraceCounters cnt{0, 0};
     const uint32_t n = W.counters->n_extend[W.parity];
-    // the append to the class queues is aggregated per CTA where the per-thread work is uniform (one global
-    // atomic per class per 256 hits: same-address atomics were what bounded the lean instantiation) and per
-    // warp where lanes run a traversal of their own and a CTA-wide barrier would idle the fast warps
-    constexpr bool BLOCK_AGG = MODE == 0 || MODE == 3 || (MODE == 1 && RT_MEDIA_BLOCK_AGG);
-    constexpr bool DEFER = (MODE == 1 || MODE == 2) && (RT_MEDIA_TWO_PHASE || PRE);  // leave the append to a later pass
-    __shared__ uint32_t s_cnt[2][SC_COUNT], s_base[SC_COUNT];
-    if (BLOCK_AGG) {
-        if (threadIdx.x < 2 * SC_COUNT) (&s_cnt[0][0])[threadIdx.x] = 0;
-        __syncthreads();
-    }
-    uint32_t it = 0;
-    const uint32_t n_round = BLOCK_AGG ? (n + MEDIA_BLOCK - 1u) / MEDIA_BLOCK * MEDIA_BLOCK : (n + 31u) & ~31u;  // whole warps / CTAs iterate together
+    const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together
     const RayRec* __restrict__ rays = W.ray_q[W.parity];
-    const StateRec* __restrict__ states = W.state_q[W.parity];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
-        int q = -1;
-        {  // pull the next iteration's records towards L2/L1 while this one computes
+        {  // pull the next iteration's records towards L1 while this one computes
             const uint32_t jn = j + gridDim.x * blockDim.x;
             if (jn < n) {
-                if (MODE == 1 || MODE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + jn));
-                if (MODE != 3 && !PRE) asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
-                if (MODE == 1 || MODE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(states + jn) + 32));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rays + jn));
+                if (!PRE) asm volatile("prefetch.global.L1 [%0];" ::"l"(W.hit_q + jn));
             }
         }
-        if (MODE == 3) {
-            if (j < n) q = W.cls_q[j];
-        } else if (j < n) {
-            double t = INFINITY;
-            uint32_t prim = 0xFFFFFFFFu, kind = HIT_MISS;
-            if (!PRE) {
-                const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
-                t = hw.x;
-                prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
-            }
-            if ((MODE == 1 || MODE == 2) && sv.n_media) {
-                RayD r;
-                load_ray(rays + j, r);
-                const uint4 ids = reinterpret_cast<const uint4*>(states + j)[2];
-                uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
-                for (uint32_t m = 0; m < sv.n_media; m++) {
-                    const Medium& med = sv.media[m];
-                    RayD lr = r;
-                    if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
-                    const double xi = philox_pair(P.seed, ids.x, ids.y, ids.z, RT_SLOT_MEDIUM0 + med.medium_index).a;
-                    // binary32 screens: hf is the free-flight distance in binary32, pessimistic by the margins below.
-                    // (1) the scatter point lies at t1 + dist/len with t1 >= 0, so a free flight that clearly
-                    // overshoots the surface hit cannot win whatever the boundary does: skip the boundary test.
-                    const float hf = (float)med.neg_inv_density * logf((float)xi);
-                    const float hf_err = 4e-7f * fabsf((float)med.neg_inv_density);  // absolute error of hf ((float)xi near 1)
-                    const float len_f = sqrtf((float)lr.d.x * (float)lr.d.x + (float)lr.d.y * (float)lr.d.y + (float)lr.d.z * (float)lr.d.z);
-                    if (RT_MEDIA_EARLY_SCREEN && kind != HIT_MISS && hf > (float)t * len_f * 1.001f + hf_err) continue;
-                    double t1, t2;
-                    if (med.single_sphere != RT_NONE) {
-                        RayD br = lr;
-                        if (XF) {
-                            const uint32_t bx = sv.meta[med.single_sphere].xform;
-                            if (bx != med.xform) br = bx == RT_NONE ? r : ray_to_local(sv, bx, r);
-                        }
-                        if (COUNT) cnt.prims += 2;
-                        if (!sphere_entry_exit(sv.geom[med.single_sphere].d, br, t1, t2)) continue;
-                    } else if (GENERIC) {
-                        uint32_t bp;
-                        if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, s_mem, stack, MEDIA_BLOCK, t1, bp, &cnt)) continue;
-                        if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, s_mem, stack, MEDIA_BLOCK, t2, bp, &cnt)) continue;
-                    } else {
-                        continue;  // unreachable: the host launches the GENERIC instantiation for such scenes
-                    }
-                    if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
-                    if (t1 >= t2) continue;
-                    if (t1 < 0.0) t1 = 0.0;
-                    double ray_length = length(lr.d);
-                    double distance_inside_boundary = (t2 - t1) * ray_length;
-                    // (2) when even the pessimistic estimate clears the segment inside the boundary by a wide margin the
-                    // path does not scatter here and the binary64 ln is not needed (the exact comparison below is
-                    // unchanged; only clear misses skip it)
-                    if (hf > (float)distance_inside_boundary * 1.001f + hf_err) continue;
-                    double hit_distance = med.neg_inv_density * log(xi);
-                    if (hit_distance > distance_inside_boundary) continue;
-                    double tm = t1 + hit_distance / ray_length;
-                    // the medium competes with the other children of its container like any hit
-                    if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
-                        t = tm;
-                        prim = m;
-                        kind = HIT_MEDIUM;
-                        rank = med.rank;
-                    }
-                }
-                if (PRE || kind == HIT_MEDIUM) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
-            }
-            if (PRE) continue;  // classes are binned after extend
-            if (kind == HIT_MISS)
-                q = SC_MISS;
-            else if (kind == HIT_MEDIUM)
-                q = (int)sv.materials[sv.media[prim].material].shade_class;
-            else
-                q = (int)sv.materials[sv.meta[prim].kind_mat & 0x3FFFFFFFu].shade_class;
-            if (!P.bin_by_class) q = q == SC_MISS ? SC_MISS : SC_DIFFUSE;
-            if (DEFER) W.cls_q[j] = (uint8_t)q;
+        if (j >= n) continue;
+        double t = INFINITY;
+        uint32_t prim = 0xFFFFFFFFu, kind = HIT_MISS;
+        if (!PRE) {
+            const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + j);
+            t = hw.x;
+            prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
         }
-        if (DEFER) continue;
-        if (BLOCK_AGG) {
-            uint32_t* cntb = s_cnt[it & 1];
-            const uint32_t local = queue_reserve(cntb, q);
-            __syncthreads();
-            if (threadIdx.x < SC_COUNT) {
-                const uint32_t c = cntb[threadIdx.x];
-                if (c) s_base[threadIdx.x] = atomicAdd(&W.counters->n_shade[threadIdx.x], c);
-                s_cnt[(it & 1) ^ 1][threadIdx.x] = 0;
+        RayD r;
+        uint64_t ids64;
+        load_ray(rays + j, r, ids64);
+        uint32_t pixel, sample, segment;
+        unpack_ids(ids64, pixel, sample, segment);
+        const uint32_t surface_meta = kind == HIT_SURFACE ? __ldg(&sv.meta[prim].kind_mat) : 0u;
+        uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
+        bool changed = false;
+        for (uint32_t m = 0; m < sv.n_media; m++) {
+            const Medium& med = sv.media[m];
+            const double xi = philox_pair(P.seed, pixel, sample, segment, RT_SLOT_MEDIUM0 + med.medium_index).a;
+            double tm;
+            RayD lr = r;
+            if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
+            // binary32 screen: the scatter point lies at t1 + dist/len with t1 >= 0, so a free flight that clearly
+            // overshoots the known hit cannot win whatever the boundary does: skip the boundary test
+            if (RT_MEDIA_EARLY_SCREEN && kind != HIT_MISS) {
+                const float hf = (float)med.neg_inv_density * logf((float)xi);
+                const float hf_err = 4e-7f * fabsf((float)med.neg_inv_density);
+                const float len_f = sqrtf((float)lr.d.x * (float)lr.d.x + (float)lr.d.y * (float)lr.d.y + (float)lr.d.z * (float)lr.d.z);
+                if (hf > (float)t * len_f * 1.001f + hf_err) continue;
             }
-            __syncthreads();
-            if (q >= 0) W.q_shade[q][s_base[q] + local] = j;
-            it++;
-        } else {
-            const uint32_t pos = queue_reserve(W.counters->n_shade, q);
-            if (q >= 0) W.q_shade[q][pos] = j;
+            if (med.single_sphere != RT_NONE) {
+                if (!sample_sphere_medium<COUNT, XF>(sv, med, r, xi, tm, &cnt)) continue;
+            } else if (GENERIC) {
+                double t1, t2;
+                uint32_t bp;
+                if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, s_mem, stack, MEDIA_BLOCK, t1, bp, &cnt)) continue;
+                if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, s_mem, stack, MEDIA_BLOCK, t2, bp, &cnt)) continue;
+                if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
+                if (t1 >= t2) continue;
+                if (t1 < 0.0) t1 = 0.0;
+                const double ray_length = length(lr.d);
+                const double distance_inside_boundary = (t2 - t1) * ray_length;
+                const double hit_distance = med.neg_inv_density * log(xi);
+                if (hit_distance > distance_inside_boundary) continue;
+                tm = t1 + hit_distance / ray_length;
+            } else {
+                continue;  // unreachable: the host launches the GENERIC instantiation for such scenes
+            }
+            // the medium competes with the other children of its container like any hit
+            if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
+                t = tm;
+                prim = m;
+                kind = HIT_MEDIUM;
+                rank = med.rank;
+                changed = true;
+            }
         }
+        if (PRE || changed) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
+        if (PRE) continue;  // extend writes the class bytes
+        uint32_t c = kind == HIT_MISS ? (uint32_t)SC_MISS : (kind == HIT_MEDIUM ? (uint32_t)SC_ISOTROPIC : ((surface_meta >> META_CLASS_SHIFT) & 15u));
+        if (!P.bin_by_class && c != SC_MISS) c = SC_DIFFUSE;
+        W.cls_q[j] = (uint8_t)c;
     }
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
         atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
+    }
+}
+
+// Binning: the append of every queue position to the shade queue of its class byte.  A memory-bound pass (1 byte in,
+// 4 bytes out per entry) with one global atomic per class per 256 entries: same-address atomics are what bounds it.
+__global__ void __launch_bounds__(MEDIA_BLOCK, 4) k_bin(WavefrontState W) {
+    __shared__ uint32_t s_cnt[2][SC_COUNT], s_base[SC_COUNT];
+    if (threadIdx.x < 2 * SC_COUNT) (&s_cnt[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = W.counters->n_extend[W.parity];
+    const uint32_t n_round = (n + MEDIA_BLOCK - 1u) / MEDIA_BLOCK * MEDIA_BLOCK;  // whole CTAs iterate together
+    uint32_t it = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x, it++) {
+        const int q = j < n ? (int)W.cls_q[j] : -1;
+        uint32_t* cntb = s_cnt[it & 1];
+        const uint32_t local = queue_reserve(cntb, q);
+        __syncthreads();
+        if (threadIdx.x < SC_COUNT) {
+            const uint32_t c = cntb[threadIdx.x];
+            if (c) s_base[threadIdx.x] = atomicAdd(&W.counters->n_shade[threadIdx.x], c);
+            s_cnt[(it & 1) ^ 1][threadIdx.x] = 0;
+        }
+        __syncthreads();
+        if (q >= 0) W.q_shade[q][s_base[q] + local] = j;
     }
 }
 
@@ -481,7 +535,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
     __shared__ uint32_t s_base;
     const uint32_t n = W.counters->n_shade[queue];
     const RayRec* __restrict__ rays = W.ray_q[W.parity];
-    const StateRec* __restrict__ states = W.state_q[W.parity];
+    const BetaRec* __restrict__ betas = W.beta_q[W.parity];
     // the loop bound is uniform over the block: the survivor append is aggregated per block
     for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
         const uint32_t j = j0 + threadIdx.x;
@@ -492,12 +546,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
         if (j < n) {
             const uint32_t pos = W.q_shade[queue][j];
             RayD r;
-            load_ray(rays + pos, r);
-            const double2* sp2 = reinterpret_cast<const double2*>(states + pos);
+            uint64_t ids64;
+            load_ray(rays + pos, r, ids64);
+            unpack_ids(ids64, pixel, sidx, segment);
+            const double2* sp2 = reinterpret_cast<const double2*>(betas + pos);
             const double2 b0 = sp2[0], b1 = sp2[1];
             D3 beta = D3{b0.x, b0.y, b1.x};
-            const uint4 ids = reinterpret_cast<const uint4*>(sp2)[2];
-            pixel = ids.x, sidx = ids.y, segment = ids.z;
             const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + pos);
             const double t = hw.x;
             const uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
@@ -525,7 +579,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
                     h.material = med.material;
                     if (med.xform != RT_NONE) hit_ok = hit_to_world(sv, med.xform, h);
                 } else {
-                    uint32_t mat = sv.meta[prim].kind_mat & 0x3FFFFFFFu;
+                    uint32_t mat = sv.meta[prim].kind_mat & META_MAT_MASK;
                     hit_ok = surface_hit_info(sv, prim, t, r, sv.materials[mat].needs_uv != 0, h);
                 }
                 if (!hit_ok) error = true;
@@ -738,8 +792,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
         for (uint32_t w = 0; w < warp; w++) npos += s_warp_count[w];
         __syncthreads();  // s_warp_count / s_base are reused by the next iteration
         if (q == 0) {
-            store_ray(W.ray_q[W.parity ^ 1u] + npos, nr);
-            store_state(W.state_q[W.parity ^ 1u] + npos, nbeta, pixel, sidx, segment + 1);
+            store_ray(W.ray_q[W.parity ^ 1u] + npos, nr, pack_ids(pixel, sidx, segment + 1));
+            store_beta(W.beta_q[W.parity ^ 1u] + npos, nbeta);
         }
     }
 }
@@ -803,51 +857,45 @@ void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, c
     k_generate<<<grid, 256, 0, s>>>(P, W);
     k_step<<<1, 1, 0, s>>>(W, 0);
 }
-void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
-    auto k = sv.nodes4 ? (count ? k_extend<true, true, true> : k_extend<false, true, true>)
-             : count   ? (sv.park_leaves ? k_extend<true, true, false> : k_extend<true, false, false>)
-                       : (sv.park_leaves ? k_extend<false, true, false> : k_extend<false, false, false>);
+template <int MEDIA>
+static void launch_extend_media(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
+    auto k = sv.nodes4 ? (count ? k_extend<true, true, true, MEDIA> : k_extend<false, true, true, MEDIA>)
+             : count   ? (sv.park_leaves ? k_extend<true, true, false, MEDIA> : k_extend<true, false, false, MEDIA>)
+                       : (sv.park_leaves ? k_extend<false, true, false, MEDIA> : k_extend<false, false, false, MEDIA>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, s, sv, P, W);
 }
+void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
+    if (P.media_first == 2 && sv.n_media)
+        sv.media_xform ? launch_extend_media<2>(sv, P, W, count, grid, stack_bytes, s) : launch_extend_media<1>(sv, P, W, count, grid, stack_bytes, s);
+    else if (P.media_first == 1 && sv.n_media)
+        launch_extend_media<3>(sv, P, W, count, grid, stack_bytes, s);
+    else
+        launch_extend_media<0>(sv, P, W, count, grid, stack_bytes, s);
+}
 int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s, int phase) {
-    // media + binning: global-memory nodes only (its shared memory holds just the stacks)
-    SceneView mv = sv;
-    mv.n_cached_nodes = 0;
-    const size_t media_smem = generic ? (size_t)sv.media_stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;  // <= 64 KB, opted in by kernel_setup
-    const int mode = sv.n_media == 0 ? 0 : (generic ? 2 : 1);
-    const bool xf = sv.media_xform != 0;
-    if (phase == 2) {  // media-first order: classes are binned from the final hit stream after extend
-        k_media_bin<false, 0, false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
+    if (phase == 1) {  // media-first order: the sampling pass ahead of extend (sphere boundaries)
+        const bool xf = sv.media_xform != 0;
+        auto k = count ? (xf ? k_media<true, 1, true, true> : k_media<true, 1, false, true>) : (xf ? k_media<false, 1, true, true> : k_media<false, 1, false, true>);
+        k<<<grid, MEDIA_BLOCK, 0, s>>>(sv, P, W);
         return 1;
     }
-    if (phase == 1) {  // media-first order: the sampling pass ahead of extend
-        if (mode == 2) {
-            auto k = count ? (xf ? k_media_bin<true, 2, true, true> : k_media_bin<true, 2, false, true>)
-                           : (xf ? k_media_bin<false, 2, true, true> : k_media_bin<false, 2, false, true>);
+    int launches = 1;
+    if (phase == 0 && sv.n_media) {  // the media pass after extend: global-memory nodes only (its shared memory holds just the stacks)
+        SceneView mv = sv;
+        mv.n_cached_nodes = 0;
+        const size_t media_smem = generic ? (size_t)sv.media_stack_entries * MEDIA_BLOCK * sizeof(uint32_t) : 0;  // <= 64 KB, opted in by kernel_setup
+        const bool xf = sv.media_xform != 0;
+        if (generic) {
+            auto k = count ? (xf ? k_media<true, 2, true, false> : k_media<true, 2, false, false>) : (xf ? k_media<false, 2, true, false> : k_media<false, 2, false, false>);
             k<<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
         } else {
-            auto k = count ? (xf ? k_media_bin<true, 1, true, true> : k_media_bin<true, 1, false, true>)
-                           : (xf ? k_media_bin<false, 1, true, true> : k_media_bin<false, 1, false, true>);
+            auto k = count ? (xf ? k_media<true, 1, true, false> : k_media<true, 1, false, false>) : (xf ? k_media<false, 1, true, false> : k_media<false, 1, false, false>);
             k<<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
         }
-        return 1;
+        launches++;
     }
-    if (mode == 2) {
-        auto k = count ? (xf ? k_media_bin<true, 2, true, false> : k_media_bin<true, 2, false, false>)
-                       : (xf ? k_media_bin<false, 2, true, false> : k_media_bin<false, 2, false, false>);
-        k<<<grid, MEDIA_BLOCK, media_smem, s>>>(mv, P, W);
-    } else if (mode == 1) {
-        auto k = count ? (xf ? k_media_bin<true, 1, true, false> : k_media_bin<true, 1, false, false>)
-                       : (xf ? k_media_bin<false, 1, true, false> : k_media_bin<false, 1, false, false>);
-        k<<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
-    } else {
-        k_media_bin<false, 0, false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
-    }
-    if (mode != 0 && RT_MEDIA_TWO_PHASE) {
-        k_media_bin<false, 3, false, false><<<grid, MEDIA_BLOCK, 0, s>>>(mv, P, W);
-        return 2;
-    }
-    return 1;
+    k_bin<<<grid, MEDIA_BLOCK, 0, s>>>(W);
+    return launches;
 }
 template <uint32_t CLS>
 static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t queue, int grid, cudaStream_t s) {
@@ -901,20 +949,22 @@ void launch_finalize(const double* accum, uint64_t n, double scale, void* out, b
 int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
     // dynamic shared memory above 48 KB is opt-in
     cudaError_t e = cudaSuccess;
-    const void* big_smem[] = {(const void*)k_extend<false, false, false>,      (const void*)k_extend<false, true, false>,      (const void*)k_extend<false, true, true>,
-                              (const void*)k_extend<true, false, false>,       (const void*)k_extend<true, true, false>,       (const void*)k_extend<true, true, true>,
-                              (const void*)k_closest_hit<false, false, false>, (const void*)k_closest_hit<false, true, false>, (const void*)k_closest_hit<false, true, true>,
-                              (const void*)k_closest_hit<true, false, false>,  (const void*)k_closest_hit<true, true, false>,  (const void*)k_closest_hit<true, true, true>};
+    const void* big_smem[] = {
+#define RT_EXTEND_VARIANTS(M)                                                                                                             \
+    (const void*)k_extend<false, false, false, M>, (const void*)k_extend<false, true, false, M>, (const void*)k_extend<false, true, true, M>, \
+        (const void*)k_extend<true, false, false, M>, (const void*)k_extend<true, true, false, M>, (const void*)k_extend<true, true, true, M>
+        RT_EXTEND_VARIANTS(0), RT_EXTEND_VARIANTS(1), RT_EXTEND_VARIANTS(2), RT_EXTEND_VARIANTS(3),
+#undef RT_EXTEND_VARIANTS
+        (const void*)k_closest_hit<false, false, false>, (const void*)k_closest_hit<false, true, false>, (const void*)k_closest_hit<false, true, true>,
+        (const void*)k_closest_hit<true, false, false>,  (const void*)k_closest_hit<true, true, false>,  (const void*)k_closest_hit<true, true, true>};
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB
-    const void* media_smem[] = {(const void*)k_media_bin<false, 2, false, false>, (const void*)k_media_bin<false, 2, true, false>,
-                                (const void*)k_media_bin<true, 2, false, false>,  (const void*)k_media_bin<true, 2, true, false>,
-                                (const void*)k_media_bin<false, 2, false, true>,  (const void*)k_media_bin<false, 2, true, true>,
-                                (const void*)k_media_bin<true, 2, false, true>,   (const void*)k_media_bin<true, 2, true, true>};
+    const void* media_smem[] = {(const void*)k_media<false, 2, false, false>, (const void*)k_media<false, 2, true, false>,
+                                (const void*)k_media<true, 2, false, false>, (const void*)k_media<true, 2, true, false>};
     for (const void* f : media_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * MEDIA_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false>, EXTEND_BLOCK, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false, 0>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_OTHER>, SHADE_BLOCK, 0);  // a class never compiled for three
     return 0;
 }

@@ -61,26 +61,31 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 enum HitKind : uint32_t { HIT_MISS = 0, HIT_SURFACE = 1, HIT_MEDIUM = 2 };
 
 // The wavefront state is a set of dense streams indexed by QUEUE POSITION (no per-path slots):
-//   ray_q[2]   64 B  o(3) d(3) time + 8 spare bytes      read by extend/media/shade, written by shade/generate
-//   state_q[2] 48 B  throughput(3), pixel, sample, segment read by media/shade, written by shade/generate
-//   hit_q      16 B  t, kind, primitive                    written by extend, updated by media, read by shade
-// The two copies of ray_q/state_q alternate every iteration (`parity`): shade reads position p of the
+//   ray_q[2]   64 B  o(3) d(3) time + the packed path ids    read by extend/media/shade, written by shade/generate
+//   beta_q[2]  32 B  throughput(3) + 8 spare bytes           read by shade, written by shade/generate
+//   hit_q      16 B  t, kind, primitive                      written by extend, updated by the media pass, read by shade
+//   cls_q       1 B  shade class of the winner               written by extend (or the media pass), read by the binning pass
+// The two copies of ray_q/beta_q alternate every iteration (`parity`): shade reads position p of the
 // current copy and appends survivors to the other one, generate tops that one up with camera rays.
-// Every access by extend and media is coalesced and its address is known from the position alone,
-// so the next item can be prefetched.
+// Round 1 kept the ids in a 48-byte state record next to the throughput: the media pass and extend then read
+// 48 (64 with sector granularity) bytes for 12 bytes of ids, and every stage re-read the ray record.  With the ids
+// in the ray record's spare 8 bytes, extend - which now also samples the media while it prepares the ray - reads
+// 64 bytes per segment and writes 17; the throughput is touched by shade alone.
 struct alignas(16) RayRec {
-    double w[8];
+    double w[7];
+    uint64_t ids;  // pack_ids(pixel, sample, segment)
 };
-struct alignas(16) StateRec {
+struct alignas(16) BetaRec {
     double beta[3];
-    uint32_t pixel, sample, segment, flags;
     double spare;
 };
 struct alignas(16) HitRec {
     double t;
     uint32_t kind, prim;
 };
-static_assert(sizeof(RayRec) == 64 && sizeof(StateRec) == 48 && sizeof(HitRec) == 16, "stream record sizes");
+static_assert(sizeof(RayRec) == 64 && sizeof(BetaRec) == 32 && sizeof(HitRec) == 16, "stream record sizes");
+// path ids: pixel (28 bits) | sample (24 bits) | segment (12 bits); rt_render_device rejects frames beyond these
+constexpr uint32_t IDS_PIXEL_BITS = 28, IDS_SAMPLE_BITS = 24, IDS_SEGMENT_BITS = 12;
 
 struct Counters {
     uint32_t n_extend[2];  // entries in ray_q/state_q of each parity
@@ -91,9 +96,9 @@ struct Counters {
 
 struct WavefrontState {
     RayRec* ray_q[2];
-    StateRec* state_q[2];
+    BetaRec* beta_q[2];
     HitRec* hit_q;
-    uint8_t* cls_q;  // shade class of every hit (written by the media pass when it leaves the append to a second pass)
+    uint8_t* cls_q;  // shade class of every hit
     uint32_t* q_shade[SC_COUNT];
     uint32_t* pixel_list;
     double* accum;  // W*H*3 binary64 sums
@@ -108,7 +113,8 @@ struct RenderParams {
     uint64_t seed;
     uint32_t sample_begin, part_index, part_count;
     uint32_t lights_flat, bin_by_class;
-    uint32_t media_first;  // the media are sampled before extend, which then only looks for surfaces up to the scatter point
+    uint32_t media_first;  // 0: media sampled after extend (order of Hittables::hit); 1: by a pass ahead of extend, 2: by extend itself while it
+                           // prepares the ray - extend then only looks for surfaces up to the scatter point
 };
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
@@ -116,7 +122,8 @@ void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, d
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s);
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t smem_bytes, cudaStream_t s);
-// phase 0: media sampling + binning after extend; 1 / 2: the sampling pass ahead of extend / the binning pass after it (RenderParams::media_first)
+// phase 0: media sampling after extend (classic order / general boundaries) + binning; phase 1: the sampling pass ahead of extend;
+// phase 2: binning only (extend wrote the class bytes)
 int launch_media_bin(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, bool generic, int grid, cudaStream_t s, int phase);
 struct ShadeFan {  // side streams for the per-class shade kernels (owned by the workspace)
     int n_side = 0;

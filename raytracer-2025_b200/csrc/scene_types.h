@@ -19,6 +19,8 @@ constexpr uint32_t LEAF_FLAG = 0x80000000u;
 constexpr uint32_t INVALID_REF = 0x7FFFFFFFu;  // empty child / empty group
 constexpr int MAX_LEAF_PRIMS = 8;
 constexpr int TRAVERSAL_STACK = 64;
+constexpr uint32_t META_MAT_MASK = 0x03FFFFFFu;  // PrimMeta::kind_mat
+constexpr uint32_t META_CLASS_SHIFT = 26;
 
 // child reference: interior -> node index; leaf -> LEAF_FLAG | first_prim << 3 | (count - 1)
 struct alignas(32) Node {
@@ -47,7 +49,7 @@ struct alignas(32) PrimGeom {
 static_assert(sizeof(PrimGeom) == 128, "primitive record must be 128 bytes");
 
 struct alignas(16) PrimMeta {
-    uint32_t kind_mat;  // kind in bits 30..31, material index in bits 0..29
+    uint32_t kind_mat;  // kind in bits 30..31, shade class of the material in bits 26..29, material index in bits 0..25
     uint32_t rank;      // lower rank wins an exact t tie (hits.rs:42, bvh.rs:78-84)
     uint32_t object;    // index of the leaf shape in rt_scene_desc.objects
     uint32_t xform;     // index into xforms[] (innermost enclosing Transform) or RT_NONE

@@ -148,7 +148,7 @@ __device__ inline bool hit_to_world(const SceneView& sv, uint32_t xform, HitInfo
 __device__ inline bool surface_hit_info(const SceneView& sv, uint32_t prim, double t, const RayD& world_ray, bool want_uv, HitInfo& h) {
     const PrimMeta m = sv.meta[prim];
     const uint32_t kind = m.kind_mat >> 30;
-    h.material = m.kind_mat & 0x3FFFFFFFu;
+    h.material = m.kind_mat & META_MAT_MASK;
     const double* g = sv.geom[prim].d;
     const RayD r = m.xform == RT_NONE ? world_ray : ray_to_local(sv, m.xform, world_ray);
     D3 outward;
