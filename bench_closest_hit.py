@@ -50,52 +50,36 @@ def make_rays(torch, n, kind, seed):
     return rays
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--sizes", type=int, nargs="+", default=[1_000_000, 10_000_000])
-    ap.add_argument("--shapes", nargs="+", default=["tri_soup", "sphere_soup"])
-    ap.add_argument("--rays", type=int, default=1 << 24)
-    ap.add_argument("--oracle-rays", type=int, default=200_000)
-    ap.add_argument("--no-oracle", action="store_true")
-    ap.add_argument("--device-lbvh", action="store_true", help="build the tree with the device LBVH builder (RT_BUILD_DEVICE_LBVH)")
-    args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:  # the scene compile step is OpenMP: share the host cores between the ranks (torchrun presets 1 thread)
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
-    import torch
-    if not torch.cuda.is_available():
-        raise SystemExit("no CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    peaks = {}
+def load_traffic():
+    """ncu DRAM bytes per launch of k_closest_hit, captured once per round (profiles/closest_hit_traffic.json), keyed by workload."""
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return json.load(open(os.path.join(ROOT, "profiles", "closest_hit_traffic.json")))
     except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    for shape in args.shapes:
-        for n in args.sizes:
+        return {}
+
+
+def sweep(torch, sizes, shapes, n_rays, oracle_rays, oracle_max_prims, device_lbvh, world, rank, local_rank, peak, emit, dist=None):
+    """Every (shape, size, ray set) case; `emit(line)` receives one dict per case on rank 0."""
+    traffic = load_traffic()
+    for shape in shapes:
+        for n in sizes:
             t0 = time.perf_counter()
             hs = rt.named_scene(shape, seed=5, params=[n])
             t_host = time.perf_counter() - t0
             t0 = time.perf_counter()
-            sc = rt.Scene(hs, device=local_rank, flags=rt.RT_BUILD_DEVICE_LBVH if args.device_lbvh else 0)
+            sc = rt.Scene(hs, device=local_rank, flags=rt.RT_BUILD_DEVICE_LBVH if device_lbvh else 0)
             t_build = time.perf_counter() - t0
             info = sc.info()
             osc = None
-            if not args.no_oracle and rank == 0:
+            if oracle_rays and n <= oracle_max_prims and rank == 0:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import orc
                 t0 = time.perf_counter()
                 osc = orc.OracleScene(hs)
                 t_orc_build = time.perf_counter() - t0
             for kind in ("primary", "incoherent"):
-                rays_all = make_rays(torch, args.rays, kind, 11)  # same batch on every rank (seeded)
-                per = args.rays // world
+                rays_all = make_rays(torch, n_rays, kind, 11)  # same batch on every rank (seeded)
+                per = n_rays // world
                 rays = rays_all[rank * per:(rank + 1) * per].contiguous() if world > 1 else rays_all
                 n_mine = rays.shape[0]
                 out = torch.empty((n_mine, 3), dtype=torch.float64, device="cuda")  # 24-byte rt_hit records
@@ -121,14 +105,26 @@ def main():
                 P = 128 if shape == "tri_soup" else 64
                 bytes_per_ray = 56 + 24 + nodes * info.node_bytes + prims * P
                 mrays = per * world / best / 1e3
+                workload = f"{shape} N={n} rays={n_rays} {kind}"
                 line = {"metric": "closest_hit_mrays_per_sec", "value": mrays, "unit": "Mrays/s", "n_gpus": world, "dtype": "f64", "scaling": "strong",
-                        "config": {"workload": f"{shape} N={n} rays={args.rays} {kind}", "builder": "device LBVH" if args.device_lbvh else "host binned SAH", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth, "node_bytes": info.node_bytes,
+                        "config": {"workload": workload, "builder": "device LBVH" if device_lbvh else "host binned SAH", "bvh_nodes": info.n_nodes, "bvh_depth": info.bvh_depth, "node_bytes": info.node_bytes,
                                    "device_bytes": info.device_bytes, "host_scene_s": t_host, "scene_create_s": t_build},
                         "ms": best, "nodes_per_ray": nodes, "prims_per_ray": prims,
+                        # `frac` is the no-cache algorithmic figure SURVEY.md 8(d) defines (every node and primitive fetch counted as
+                        # HBM bytes); `dram_frac` is what actually crossed the HBM interface (ncu dram__bytes of this workload, one GPU)
                         "roofline": {"bound": "hbm", "achieved": mrays * 1e6 * bytes_per_ray / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": mrays * 1e6 * bytes_per_ray / 1e9 / peak / world, "bytes_per_ray": bytes_per_ray}}
+                tr = traffic.get(f"{shape} N={n} {kind}")
+                if tr and world == 1:
+                    dram_bytes = tr["dram_bytes_per_launch"] * (n_rays / tr["rays_per_launch"])
+                    line["roofline"]["traffic"] = dram_bytes
+                    line["roofline"]["dram_gbs"] = dram_bytes / (best * 1e-3) / 1e9
+                    line["roofline"]["dram_frac"] = dram_bytes / (best * 1e-3) / 1e9 / peak
+                    line["roofline"]["traffic_source"] = tr.get("source")
+                else:
+                    line["roofline"]["traffic"] = None
                 if osc is not None:
-                    m = min(args.oracle_rays, n_mine)
+                    m = min(oracle_rays, n_mine)
                     pick = torch.arange(m, device="cuda") * (n_mine // m)  # a strided sample of this rank's slice
                     sub = rays[pick].cpu().numpy().view(rt.rt_ray_dtype).reshape(-1)
                     t0 = time.perf_counter()
@@ -141,12 +137,43 @@ def main():
                     line["cpu_baseline"] = {"value": m / dt / 1e6, "unit": "Mrays/s", "cores": orc.lib().orc_num_threads(), "kind": "port",
                                             "sample": f"{m} rays strided through the batch, reference-semantics traversal (median-split BVH built in {t_orc_build:.1f} s)"}
                     line["parity"] = {"rays": int(m), "hits": int(hit.sum()), "ids_bit_exact": ids_ok, "t_bit_exact": t_ok}
-                print(json.dumps(line), flush=True)
+                emit(line)
                 del rays, out, rays_all
             sc.close()
             del sc, hs, osc
 
 
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", type=int, nargs="+", default=[1_000_000, 10_000_000])
+    ap.add_argument("--shapes", nargs="+", default=["tri_soup", "sphere_soup"])
+    ap.add_argument("--rays", type=int, default=1 << 24)
+    ap.add_argument("--oracle-rays", type=int, default=200_000)
+    ap.add_argument("--oracle-max-prims", type=int, default=10_000_000, help="skip the oracle (parity + CPU figure) above this size")
+    ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--device-lbvh", action="store_true", help="build the tree with the device LBVH builder (RT_BUILD_DEVICE_LBVH)")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # the scene compile step is OpenMP: share the host cores between the ranks (torchrun presets 1 thread)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    sweep(torch, args.sizes, args.shapes, args.rays, 0 if args.no_oracle else args.oracle_rays, args.oracle_max_prims, args.device_lbvh,
+          world, rank, local_rank, peak, lambda line: print(json.dumps(line), flush=True), dist)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -49,6 +49,12 @@ def lib():
         L.orc_kat_philox.argtypes = [U, U, U]
         L.orc_kat_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, D]
         L.orc_texture_value.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, D, D]
+        L.orc_kat_world_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, D, D]
+        L.orc_kat_scatter.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, D, D, D]
+        L.orc_kat_cosine_pdf.argtypes = [D, D, D, D, D]
+        L.orc_kat_lights_pdf_value.restype = C.c_double
+        L.orc_kat_lights_pdf_value.argtypes = [C.c_void_p, D, D]
+        L.orc_kat_lights_random.argtypes = [C.c_void_p, D, C.c_uint32, C.c_double, C.c_double, D]
         L.orc_camera_ray.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
@@ -98,6 +104,32 @@ class OracleScene:
         self.L.orc_render(self.h, C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st), threads)
         return img, st
 
+    # ---- known-answer hooks (tests/test_oracle_kat_hand.py) ----
+    def world_hit(self, o, dvec, time=0.0, t_min=1e-8, t_max=float("inf"), xi=None):
+        """world.hit with every random draw forced to xi (None: media disabled) -> dict or None."""
+        ray = rt.make_rays([o], [dvec], [time])
+        out = (C.c_double * 12)()
+        x = d(*xi) if xi is not None else None
+        if not self.L.orc_kat_world_hit(self.h, ray.ctypes.data, t_min, t_max, x, out):
+            return None
+        o12 = list(out)
+        return dict(t=o12[0], p=o12[1:4], normal=o12[4:7], u=o12[7], v=o12[8], front_face=bool(o12[9]), prim_id=int(o12[10]), inst_id=int(o12[11]))
+
+    def scatter(self, mat, o, dvec, p, normal, front_face, u=0.0, v=0.0, xi=(0.5, 0.5), time=0.0):
+        """materials[mat].scatter on a hand-made hit record -> (kind, attenuation, direction, error)."""
+        ray = rt.make_rays([o], [dvec], [time])
+        out = (C.c_double * 7)()
+        kind = self.L.orc_kat_scatter(self.h, mat, ray.ctypes.data, d(*p, *normal, u, v, 1.0 if front_face else 0.0), d(*xi), out)
+        return kind, list(out)[0:3], list(out)[3:6], bool(out[6])
+
+    def lights_pdf_value(self, origin, direction):
+        return self.L.orc_kat_lights_pdf_value(self.h, d(*origin), d(*direction))
+
+    def lights_random(self, origin, leaf, r1, r2):
+        out = (C.c_double * 3)()
+        ok = self.L.orc_kat_lights_random(self.h, d(*origin), leaf, r1, r2, out)
+        return list(out) if ok else None
+
     def texture_value(self, tex, u, v, p):
         out = (C.c_double * 3)()
         self.L.orc_texture_value(self.h, tex, u, v, d(*p), out)
@@ -111,6 +143,15 @@ def camera_rays(camera, seed, pixels_ij, sample):
     for k, (i, j) in enumerate(pixels_ij):
         L.orc_camera_ray(C.byref(camera), seed, int(i), int(j), int(sample), out[k:k + 1].ctypes.data)
     return out
+
+
+def cosine_pdf(albedo, normal, direction, xi=(0.5, 0.5)):
+    """CosinePDF::new(albedo, normal): (value(direction) -> brdf, pdf), generate() with forced draws; None where it would panic."""
+    out = (C.c_double * 7)()
+    if not lib().orc_kat_cosine_pdf(d(*albedo), d(*normal), d(*direction), d(*xi), out):
+        return None
+    o = list(out)
+    return o[0:3], o[3], o[4:7]
 
 
 def tonemap(accum, toon_map=0):

@@ -569,3 +569,64 @@ def test_independent_seeds_are_statistically_consistent(gpu, rt, orc):
     high = rt.tonemap(np.mean(gpu[:8], axis=0))
     assert _psnr8(high, converged) >= 40.0
     assert _psnr8(rt.tonemap(ref_other_seed), converged) >= 30.0
+    # (2') against the ORACLE's converged render (tests/golden/make_converged.py: 32 x 961 spp, seeds of its own): the GPU's
+    # 40 x 961 spp mean must agree to >= 40 dB after the 8-bit encode
+    fx = np.load(os.path.join(GOLDEN, "cornell_glass_converged.npz"))
+    assert int(fx["errors"]) == 0 and not set(fx["seeds"].tolist()) & set(range(1, 41))
+    assert _psnr8(rt.tonemap(np.mean(gpu, axis=0)), rt.tonemap(fx["image"])) >= 40.0
+    assert abs(np.mean(gpu) - fx["image"].mean()) < 0.01 * fx["image"].mean()
+
+
+def test_hand_derived_hit_vectors(gpu, rt):
+    """The paper-derived vectors of tests/test_oracle_kat_hand.py (Sphere / Quad / Triangle / Transform::hit) on the device:
+    t, u, v exact, misses are misses - no oracle in the loop."""
+    from test_oracle_kat_hand import HIT_VECTORS
+    for name, (make, vectors) in sorted(HIT_VECTORS.items()):
+        sc = rt.Scene(make(rt))
+        for o, d, time, t_min, t_max, want in vectors:
+            got, _ = sc.closest_hit(rt.make_rays([o], [d], [time]), t_min=t_min, t_max=t_max)
+            if want is None:
+                assert got["prim_id"][0] == rt.RT_NONE and np.isinf(got["t"][0]), (name, o, d)
+            else:
+                assert got["prim_id"][0] != rt.RT_NONE, (name, o, d)
+                assert got["t"][0] == want["t"] and got["u"][0] == np.float32(want["u"]) and got["v"][0] == np.float32(want["v"]), (name, o, d)
+
+
+@pytest.mark.parametrize("name,params,strata", [("book1_final", [1200, 10, 50], 2), ("book2_final", [800, 1000, 40], 2),
+                                                ("cornell_glass", [600, 1000, 50], 2)])
+def test_baseline_resolution_strata_match_oracle(gpu, rt, orc, name, params, strata):
+    """Configs 1-3 at BASELINE.json's own resolution and sampling grid (1200x675 / 3x3, 800x800 / 31x31, 600x600 / 31x31):
+    strata [0, 2) of the real frame, same seed, against the oracle (about a second of CPU each)."""
+    hs = rt.named_scene(name, seed=7, params=params)
+    cam = hs.camera
+    assert (cam.image_width, cam.image_height, cam.sqrt_spp) == {"book1_final": (1200, 675, 3), "book2_final": (800, 800, 31),
+                                                                 "cornell_glass": (600, 600, 31)}[name]
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    img, st = sc.render(seed=33, sample_begin=0, sample_end=strata)
+    ref, ost = osc.render(seed=33, sample_begin=0, sample_end=strata)
+    assert st.paths == ost.paths == cam.image_width * cam.image_height * strata and int(st.errors) <= int(ost.errors)
+    image_close(img, ref)
+
+
+def test_medium_inside_bvh_and_transform(gpu, rt, orc):
+    """ConstantMedium below a BVH (the reference clamps the exit to the interval the BVH has already shrunk, volume.rs:46-47 with
+    bvh.rs:78-84) and below Transform(BVH): same winners as taking the minimum over all children on [1e-8, inf)."""
+    b = rt.Builder(6)
+    white = b.lambertian(b.solid(0.7, 0.7, 0.7))
+    fog1 = b.medium(b.sphere([-1.5, 0, 0], 1.2, b.empty()), 1.1, b.solid(0.9, 0.5, 0.3))
+    fog2 = b.medium(b.box([-0.8, -0.8, -0.8], [0.8, 0.8, 0.8], b.empty()), 0.7, b.solid(0.3, 0.6, 0.9))
+    inner = b.bvh([b.sphere([-1.5, 0, 0], 0.5, white), fog1, b.quad([-3, -1.3, -2], [6, 0, 0], [0, 0, 4], white),
+                   b.sphere([-1.5, 0.2, 1.6], 0.4, b.metal([0.9, 0.9, 0.9], 0.1))])
+    moved = b.transform(b.bvh([fog2, b.sphere([0, 0, 0], 0.3, white), b.triangle([-1, -1, -1.2], [2, 0, 0], [0, 2, 0], white)]),
+                        offset=[1.8, 0.2, 0.0], quat=b.quat_axis_angle([0, 1, 0], 25.0), scale=[1.2, 1.2, 1.2])
+    light = b.quad([-1, 3.5, -1], [2, 0, 0], [0, 0, 2], b.diffuse_light(b.solid(12, 12, 12)))
+    world = b.list([b.bvh([inner, moved, light])])
+    lights = b.list([b.quad([-1, 3.5, -1], [2, 0, 0], [0, 0, 2], b.empty())])
+    hs = b.finish(world, lights, width=56, spp=16, max_depth=12, vfov=40, look_from=(0, 1.5, 8), look_at=(0, 0, 0), background=b.solid(0.05, 0.06, 0.1))
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    assert sc.info().n_media == 2 and np.array_equal(sc.ranks(), osc.ranks())
+    for classic in (False, True):
+        img, st = sc.render(seed=12, classic_media_order=classic)
+        ref, ost = osc.render(seed=12)
+        assert st.paths == ost.paths and int(st.errors) <= int(ost.errors)
+        image_close(img, ref, frac_bad=5e-3)
