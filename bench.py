@@ -14,6 +14,7 @@ this box's host cores, bounded sample), `e2e` (flatten + upload + render + read-
 per step, i.e. what Camera::render does), `clocks`, `gpu_launches`.
 """
 import argparse
+import ctypes
 import importlib.util
 import json
 import os
@@ -34,9 +35,12 @@ _spec.loader.exec_module(rt)
 SCENE = ("book2_final", 7, [800, 1000, 40])  # name, scene seed, [width, spp, max_depth]
 RENDER_SEED = 2025
 # algorithmic HBM bytes of the dominant kernel (extend) per unit (= one path segment), DESIGN.md §5:
-# ray stream record read (64) + hit stream record read (16: the medium scatter point the sampling pass left as the
-# incumbent; book2_final has media, so that pass runs first) + hit stream record written (16)
-EXTEND_BYTES_PER_SEGMENT = 64 + 16 + 16
+# ray stream record read (64, path ids included) + hit stream record read (16: the medium scatter point the sampling pass
+# left as the incumbent; book2_final has media, so that pass runs first) + hit stream record written (16) + class byte (1)
+EXTEND_BYTES_PER_SEGMENT = 64 + 16 + 16 + 1
+# SURVEY.md §8(d), whole step: 2 x 64 (path state read + written once) + 2 x 16 (hit record written by extend, read by shade)
+# per segment, + 12 per path for the framebuffer add
+STEP_BYTES_PER_SEGMENT, STEP_BYTES_PER_PATH = 160, 12
 
 
 def partition_for_rank(rank, world):
@@ -120,31 +124,22 @@ def cpu_baseline(host_scene, target_seconds=12.0):
                     "the Rust crate itself cannot be built here (no rustc/cargo)"}
 
 
-def closest_hit_metric(torch, n_prims=1_000_000, n_rays=1 << 24):
-    """The second BASELINE metric, on rank 0 at N=1: BVH closest-hit Mrays/s on the 1M-triangle soup of config 5 with
-    2^24 incoherent rays resident in HBM (bench_closest_hit.py has the full sweep and the oracle parity check)."""
-    hs = rt.named_scene("tri_soup", seed=5, params=[n_prims])
-    sc = rt.Scene(hs)
-    g = torch.Generator(device="cuda").manual_seed(11)
-    rays = torch.zeros((n_rays, 7), dtype=torch.float64, device="cuda")
-    rays[:, 0:3] = torch.rand((n_rays, 3), generator=g, device="cuda", dtype=torch.float64)
-    d = torch.randn((n_rays, 3), generator=g, device="cuda", dtype=torch.float64)
-    rays[:, 3:6] = d / d.norm(dim=1, keepdim=True)
-    out = torch.empty((n_rays, 3), dtype=torch.float64, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-    best = None
-    for k in range(6):
-        st = sc.closest_hit_device(rays.data_ptr(), n_rays, out.data_ptr(), stream=stream)
-        if k >= 2 and (best is None or st.ms_total < best):
-            best = st.ms_total
-    cst = sc.closest_hit_device(rays.data_ptr(), n_rays, out.data_ptr(), flags=rt.RT_OPT_COUNT, stream=stream)
-    nodes, prims = cst.node_visits / n_rays, cst.prim_tests / n_rays
-    bytes_per_ray = 56 + 24 + nodes * sc.info().node_bytes + prims * 128
-    mrays = n_rays / best / 1e3
-    sc.close()
-    return {"value": mrays, "unit": "Mrays/s", "workload": f"tri_soup N={n_prims}, {n_rays} incoherent rays, binary64 primitive tests",
-            "ms": best, "nodes_per_ray": nodes, "prims_per_ray": prims, "algorithmic_bytes_per_ray": bytes_per_ray,
-            "achieved_gbs": mrays * 1e6 * bytes_per_ray / 1e9}
+def closest_hit_metric(torch, peak, sizes=(1_000_000, 10_000_000), n_rays=1 << 24):
+    """The second BASELINE metric (config 5), on rank 0 at N=1: BVH closest-hit Mrays/s on the triangle and sphere soups,
+    primary and incoherent rays, 2^24 rays resident in HBM, with an id / t parity check against the oracle on a strided
+    sample of each batch (bench_closest_hit.py is the same sweep as a program of its own, with more sizes and N > 1)."""
+    spec = importlib.util.spec_from_file_location("bench_closest_hit", os.path.join(ROOT, "bench_closest_hit.py"))
+    bch = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bch)
+    cases = []
+    bch.sweep(torch, list(sizes), ["tri_soup", "sphere_soup"], n_rays, 100_000, 1_000_000, False, 1, 0, torch.cuda.current_device(), peak, cases.append)
+    head = next(c for c in cases if c["config"]["workload"].startswith("tri_soup N=1000000") and c["config"]["workload"].endswith("incoherent"))
+    return {"value": head["value"], "unit": "Mrays/s", "workload": head["config"]["workload"] + ", binary64 primitive tests",
+            "note": "`frac` counts every node / primitive fetch as HBM bytes (SURVEY.md 8d, no cache credit); `dram_frac` is the ncu DRAM traffic of the same "
+                    "workload over the measured time; parity = ids and t bit-exact against the oracle on a strided sample (sizes the oracle builds in seconds)",
+            "cases": [{"workload": c["config"]["workload"], "mrays_per_s": c["value"], "ms": c["ms"], "nodes_per_ray": c["nodes_per_ray"],
+                       "prims_per_ray": c["prims_per_ray"], "node_bytes": c["config"]["node_bytes"], "scene_create_s": c["config"]["scene_create_s"],
+                       "roofline": c["roofline"], "parity": c.get("parity"), "cpu_baseline": c.get("cpu_baseline")} for c in cases]}
 
 
 def run_reference(args, rank):
@@ -179,6 +174,63 @@ def run_reference(args, rank):
     }))
 
 
+def run_single_process(args):
+    """--single-process: ONE process, N GPUs, through the library's own multi-GPU entry (rt_render_multi_rgb8): one host thread
+    per GPU inside the library, partial frames summed on GPU 0 by a kernel that reads the peers' memory over NVLink, 8-bit
+    encode on GPU 0, the RgbImage bytes land in a host buffer.  `value`: scenes resident, wall clock around the call (it
+    returns when the bytes are on the host); `e2e`: rt_scene_create on every GPU inside the timed region as well."""
+    import numpy as np
+    import torch
+    n = args.gpus
+    if torch.cuda.device_count() < n:
+        raise SystemExit(f"bench.py --single-process: {n} GPUs requested, {torch.cuda.device_count()} visible")
+    name, seed, params = SCENE
+    params = [params[0], args.spp, params[2]]
+    hs = rt.named_scene(name, seed=seed, params=params)
+    cam = hs.camera
+    W, H = cam.image_width, cam.image_height
+    scenes = [rt.Scene(hs, device=k) for k in range(n)]
+    for _ in range(args.warmup):
+        rt.render_multi_rgb8(scenes, seed=RENDER_SEED)
+    sampler = ClockSampler(0)
+    sampler.start()
+    for k in range(n):
+        torch.cuda.synchronize(k)
+    t0 = time.perf_counter()
+    paths = launches = 0
+    for _ in range(args.steps):
+        img, st = rt.render_multi_rgb8(scenes, seed=RENDER_SEED)
+        paths += st.paths
+        launches += st.kernel_launches
+    dt = time.perf_counter() - t0
+    sampler.stop_flag = True
+    for sc in scenes:
+        sc.close()
+    t0 = time.perf_counter()
+    e2e_paths = 0
+    for _ in range(args.steps):
+        sc2 = [rt.Scene(hs, device=k) for k in range(n)]
+        img, st = rt.render_multi_rgb8(sc2, seed=RENDER_SEED)
+        e2e_paths += st.paths
+        for sc in sc2:
+            sc.close()
+    e2e_dt = time.perf_counter() - t0
+    d = hs.desc.contents
+    h2d = n * (d.n_objects * 72 + d.n_children * 4 + d.n_spheres * 64 + d.n_planars * 144 + d.n_transforms * 80 + d.n_media * 16 +
+               d.n_materials * 176 + d.n_textures * 80 + d.n_perlins * 9216 + d.n_texels * 4)
+    print(json.dumps({
+        "metric": "paths_per_sec", "value": paths / dt, "unit": "paths/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"book2_final {W}x{H} spp={args.spp} ({cam.sqrt_spp ** 2} effective) depth={cam.max_depth}", "scene_seed": seed,
+                   "parallelism": f"single process, rt_render_multi_rgb8 over {n} GPUs (interleaved 8x8 tiles, peer-memory reduce on GPU 0)",
+                   "timing": "host wall clock around the call: it returns when the RgbImage bytes are in the host buffer"},
+        "clocks": sampler.summary(), "gpu_launches": int(launches),
+        "e2e": {"value": e2e_paths / e2e_dt, "unit": "paths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(W * H * 3),
+                "includes": "rt_scene_create on every GPU + rt_render_multi_rgb8"},
+        "image_mean_8bit": float(np.mean(img)),
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +239,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spp", type=int, default=1000, help="samples_per_pixel field (default = the config's 1000)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process drives --gpus N through rt_render_multi_rgb8 (the library's own multi-GPU path: peer-memory reduce on GPU 0) "
+                         "instead of one torchrun rank per GPU with an NCCL reduce")
+    ap.add_argument("--no-closest-hit", action="store_true", help="skip the config-5 closest-hit cases (N=1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -194,6 +250,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.single_process:
+        run_single_process(args)
         return
 
     import numpy as np
@@ -266,7 +325,7 @@ def main():
     # frame back to the host, 8-bit encode.  Host buffers in, host image out.
     d = hs.desc.contents
     h2d = (d.n_objects * 72 + d.n_children * 4 + d.n_spheres * 64 + d.n_planars * 144 + d.n_transforms * 80 + d.n_media * 16 +
-           d.n_materials * 120 + d.n_textures * 80 + d.n_perlins * 9216 + d.n_texels * 4)
+           d.n_materials * 176 + d.n_textures * 80 + d.n_perlins * 9216 + d.n_texels * 4)
     d2h = W * H * 3  # the RgbImage bytes
     host_rgb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
     rgb_dev = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
@@ -275,14 +334,21 @@ def main():
     e2e_paths = 0
     for _ in range(args.steps):
         sc2 = rt.Scene(hs, device=local_rank)  # rt_scene_create: compile + BVH build + H2D of the scene
-        st = sc2.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32,
-                               part_index=part_index, part_count=part_count)
-        e2e_paths += reduce_framebuffer_and_paths(fb, st.paths, dst=0)
-        if rank == 0:
-            # Color::to_rgb where the reduced frame lies, then the D2H of the 8-bit image
-            rt.tonemap_device(fb.data_ptr(), W * H, rgb_dev.data_ptr(), cam.toon_map, rt.RT_ACCUM_F32, stream)
-            host_rgb.copy_(rgb_dev, non_blocking=False)
-            assert host_rgb.shape == (H, W, 3)
+        if world == 1:
+            # the host-buffer entry a client of Camera::render calls: render, Color::to_rgb on the device, D2H of the bytes
+            o = sc2.render_opts(seed=RENDER_SEED)
+            st = rt.rt_stats()
+            rc = sc2.L.rt_render_rgb8(sc2.h, ctypes.byref(cam), ctypes.byref(o), host_rgb.data_ptr(), ctypes.byref(st))
+            assert rc == 0, sc2.L.rt_last_error()
+            e2e_paths += st.paths
+        else:
+            st = sc2.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32,
+                                   part_index=part_index, part_count=part_count)
+            e2e_paths += reduce_framebuffer_and_paths(fb, st.paths, dst=0)
+            if rank == 0:
+                # Color::to_rgb where the reduced frame lies, then the D2H of the 8-bit image
+                rt.tonemap_device(fb.data_ptr(), W * H, rgb_dev.data_ptr(), cam.toon_map, rt.RT_ACCUM_F32, stream)
+                host_rgb.copy_(rgb_dev, non_blocking=False)
         sc2.close()
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -309,7 +375,7 @@ def main():
             traffic = prof.get("dram_bytes_per_launch")
             # the figures that describe an issue-bound kernel, from the same ncu capture (not measured live)
             ncu_issue = {"issue_active_pct": prof.get("issue_active_pct"), "active_lanes_per_instruction": prof.get("active_lanes_per_instruction"),
-                         "warps_active_pct": prof.get("warps_active_pct"), "source": "profiles/r01_v8_ncu_full_summary.csv"}
+                         "warps_active_pct": prof.get("warps_active_pct"), "source": prof.get("source"), "captured_on_commit": prof.get("commit")}
         except Exception:
             pass
         line = {
@@ -323,12 +389,19 @@ def main():
                        "l2": "flushed between steps (256 MiB fill); the ray/state/hit streams of 2^24 paths in flight (4.5 GB) exceed the 126 MB L2, the 0.7 MB scene is cache-resident by design"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "includes": "rt_scene_create (flatten+SAH build+upload), render, reduce, 8-bit encode on the device (rt_tonemap_device), D2H of the RgbImage bytes"},
+                    "includes": ("rt_scene_create (compile + SAH build + upload of the host description) then rt_render_rgb8 into a host buffer (render, 8-bit encode on the device, D2H)"
+                                 if world == 1 else
+                                 "per rank rt_scene_create + rt_render_device, one NCCL reduce, rt_tonemap_device + D2H of the RgbImage bytes on rank 0")},
             "gpu_launches": int(extra[1].item()),
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_segment": EXTEND_BYTES_PER_SEGMENT, "segments_per_launch": seg_rank0 / n_ext_launches,
                          "ms_per_launch": ext_ms_per_launch, "ncu": ncu_issue,
+                         # the whole step by SURVEY.md 8(d)'s formula (all stages, loose by design for a cache-resident scene)
+                         "step": {"bytes_per_segment": STEP_BYTES_PER_SEGMENT, "bytes_per_path": STEP_BYTES_PER_PATH,
+                                  "achieved": (float(extra[0].item()) * STEP_BYTES_PER_SEGMENT + paths * STEP_BYTES_PER_PATH) / (ms_total * 1e-3) / 1e9 / world,
+                                  "frac": (float(extra[0].item()) * STEP_BYTES_PER_SEGMENT + paths * STEP_BYTES_PER_PATH) / (ms_total * 1e-3) / 1e9 / world / peak,
+                                  "unit": "GB/s per GPU"},
                          "stage_ms_per_step": {"generate": ms_gen / args.steps, "extend": ms_extend / args.steps,
                                                "media_bin": ms_media / args.steps, "shade": ms_shade / args.steps},
                          "note": "configs 1-3 keep the scene in L1/L2: the binding limit is SM issue rate under divergence, "
@@ -336,11 +409,14 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(hs)
-            try:
-                line["closest_hit"] = closest_hit_metric(torch)
-                line["closest_hit"]["hbm_frac"] = line["closest_hit"]["achieved_gbs"] / peak
-            except Exception as e:  # the headline line must not depend on the secondary metric
-                line["closest_hit"] = {"error": str(e)}
+            if not args.no_closest_hit:
+                try:
+                    scene.close()
+                    del fb, flush
+                    torch.cuda.empty_cache()
+                    line["closest_hit"] = closest_hit_metric(torch, peak)
+                except Exception as e:  # the headline line must not depend on the secondary metric
+                    line["closest_hit"] = {"error": repr(e)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

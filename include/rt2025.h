@@ -333,11 +333,17 @@ int rt_render_rgb8(const rt_scene* scene, const rt_camera* camera, const rt_rend
                    rt_stats* stats);
 
 /* One process, several GPUs: scenes[i] must be the same description created on distinct devices.
- * GPU i renders partition i of n (interleaved 8x8 tiles) from its own host thread; the partial
- * framebuffers are disjoint and are summed on the host.  `accum` as in rt_render.  opts->part_index /
- * part_count must be 0: the partitioning is done here.  stats are totals (ms_total = slowest GPU). */
+ * GPU i renders partition i of n (interleaved 8x8 tiles) from its own host thread into a framebuffer in its own
+ * memory; GPU scenes[0]->device then sums the partial frames with one kernel that loads the other GPUs' buffers
+ * through peer mappings (NVLink / NVSwitch; staged peer copies where two devices cannot map each other) and only the
+ * finished frame crosses PCIe.  This is the in-library form of the reference's single `par_bridge` over pixels
+ * (camera.rs:179-181) spread over GPUs.  `accum` as in rt_render.  opts->part_index / part_count must be 0: the
+ * partitioning is done here.  stats are totals (times = slowest GPU). */
 int rt_render_multi(rt_scene* const* scenes, uint32_t n_scenes, const rt_camera* camera, const rt_render_opts* opts,
                     void* accum, rt_stats* stats);
+/* The same, ending like Camera::render (camera.rs:193-194): Color::to_rgb on GPU 0, `rgb` receives the RgbImage bytes. */
+int rt_render_multi_rgb8(rt_scene* const* scenes, uint32_t n_scenes, const rt_camera* camera, const rt_render_opts* opts,
+                         uint8_t* rgb, rt_stats* stats);
 
 /* Color::to_rgb — utils/color.rs:27-36: optional ACES, then linear -> sRGB 8 bit.
  * `accum` holds mean linear radiance (host pointer), `rgb` receives n_pixels*3 bytes. */

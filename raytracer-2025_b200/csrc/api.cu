@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -109,7 +110,8 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
     WavefrontState W{};
     uint32_t capacity = 0;
     uint64_t n_pixels_alloc = 0;
-    Counters* h_counters = nullptr;  // pinned
+    Counters* h_counters = nullptr;  // pinned, two copies (pipelined read-back)
+    cudaEvent_t check_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> events;  // stage-timing pool: 4 per iteration, read back after the render
     ShadeFan fan;                     // side streams of the shade stage
     bool fan_ready = false;
@@ -127,6 +129,10 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
         }
         return &fan;
     }
+    cudaEvent_t check_event(int slot) {
+        if (!check_ev[slot]) cudaEventCreateWithFlags(&check_ev[slot], cudaEventDisableTiming);
+        return check_ev[slot];
+    }
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) {
             cudaEvent_t e;
@@ -138,6 +144,8 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
     void release() {
         for (auto e : events) cudaEventDestroy(e);
         events.clear();
+        for (auto& e : check_ev)
+            if (e) cudaEventDestroy(e);
         if (fan.fork) cudaEventDestroy(fan.fork);
         for (int i = 0; i < 3; i++) {
             if (fan.side[i]) cudaStreamDestroy(fan.side[i]);
@@ -157,17 +165,39 @@ struct Workspace {  // wavefront buffers, cached on the scene between renders
 
 }  // namespace
 
-// One wavefront workspace per device, shared by all scenes of the process (a render holds its lock):
-// re-creating a scene (what Camera::render does on every call) must not re-allocate half a gigabyte.
+// Wavefront workspaces are pooled per device and shared by all scenes of the process: re-creating a scene (what
+// Camera::render does on every call) must not re-allocate half a gigabyte.  A render borrows a free workspace for its
+// duration; a second render on the same GPU at the same time (another scene, another host thread) gets one of its own
+// instead of queueing behind the first.
 namespace {
 struct DeviceWorkspace {
     std::mutex mu;
-    Workspace ws;
+    std::vector<std::unique_ptr<Workspace>> all;
+    std::vector<Workspace*> free_list;
 };
 DeviceWorkspace& device_workspace(int device) {
     static DeviceWorkspace pool[64];
     return pool[device & 63];
 }
+struct WorkspaceLease {
+    DeviceWorkspace& d;
+    Workspace* ws = nullptr;
+    explicit WorkspaceLease(DeviceWorkspace& dws) : d(dws) {
+        std::lock_guard<std::mutex> lock(d.mu);
+        if (d.free_list.empty()) {
+            d.all.emplace_back(new Workspace());
+            ws = d.all.back().get();
+        } else {  // the largest one first: it is the least likely to need growing
+            auto it = std::max_element(d.free_list.begin(), d.free_list.end(), [](Workspace* a, Workspace* b) { return a->capacity < b->capacity; });
+            ws = *it;
+            d.free_list.erase(it);
+        }
+    }
+    ~WorkspaceLease() {
+        std::lock_guard<std::mutex> lock(d.mu);
+        d.free_list.push_back(ws);
+    }
+};
 }  // namespace
 
 struct rt_scene {
@@ -304,7 +334,8 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.n_nodes = (uint32_t)cs.nodes.size();
         // the binary tree pushes one reference per level, the four-wide one up to three (compile.cpp keeps it within the limit)
         v.stack_entries = std::min<uint32_t>(std::max(cs.bvh_depth + 2, cs.nodes4.empty() ? 0u : 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK);
-        v.media_stack_entries = std::min<uint32_t>(cs.media_bvh_depth + 2, TRAVERSAL_STACK);  // the media kernel walks boundary groups only
+        v.media_stack_entries = std::min<uint32_t>(cs.media_bvh_depth + 2, TRAVERSAL_STACK);
+        v.tail_stack_entries = std::min<uint32_t>(std::max(cs.bvh_depth, cs.media_bvh_depth) + 2, TRAVERSAL_STACK);  // the media kernel walks boundary groups only
         const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t);
         // persistent traversal: a warp whose BVH lives in L1/shared memory is issue-bound and runs best when it
         // drains completely before taking 32 new rays; once node fetches go to L2/HBM the idle lanes are worth
@@ -534,12 +565,13 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     if (s_begin > s_end || s_end > spp) return set_err(RT_ERR_INVALID, "bad sample range");
     if (stats) std::memset(stats, 0, sizeof(*stats));
 
-    DeviceWorkspace& dws = device_workspace(s->device);
-    std::lock_guard<std::mutex> lock(dws.mu);
+    WorkspaceLease lease(device_workspace(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t n_px_img = (uint64_t)cam->image_width * cam->image_height;
     const uint64_t n_pixels = count_partition_pixels(cam->image_width, cam->image_height, o.part_index, part_count);
-    const uint64_t total_paths = n_pixels * (uint64_t)(s_end - s_begin);
+    const uint64_t nominal_paths = n_pixels * (uint64_t)(s_end - s_begin);
+    // max_depth == 0: ray_color returns black before it looks at the world (camera.rs:282) - no path is traced
+    const uint64_t total_paths = cam->max_depth == 0 ? 0 : nominal_paths;
     // paths in flight: large enough that the ~10 launches of an iteration are amortised over millions of
     // segments (profiles/README.md: 2^21 -> 2^24 is +23 %), never more than the job needs
     uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 24);
@@ -549,7 +581,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     int rc = RT_OK;
     try {
         CU(cudaSetDevice(s->device));
-        Workspace& ws = dws.ws;
+        Workspace& ws = *lease.ws;
         if (ws.capacity < capacity || ws.n_pixels_alloc < n_px_img) {  // grow-only
             const uint32_t keep_cap = std::max(ws.capacity, capacity);
             const uint64_t keep_px = std::max<uint64_t>(ws.n_pixels_alloc, n_px_img);
@@ -567,7 +599,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
             CU(cudaMalloc(&W.pixel_list, n_px_alloc * 4));
             CU(cudaMalloc(&W.accum, n_px_alloc * 3 * sizeof(double)));
             CU(cudaMalloc(&W.counters, sizeof(Counters)));
-            CU(cudaMallocHost(&ws.h_counters, sizeof(Counters)));
+            CU(cudaMallocHost(&ws.h_counters, 2 * sizeof(Counters)));
             ws.capacity = capacity_alloc;
             ws.n_pixels_alloc = n_px_alloc;
         }
@@ -602,22 +634,25 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         CU(cudaMemcpyAsync(W.counters, &init, sizeof(init), cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(W.accum, 0, n_px_img * 3 * sizeof(double), st));
         uint64_t launches = 2;
+        const Counters* final_counters = nullptr;
         double ms_gen = 0, ms_ext = 0, ms_med = 0, ms_shd = 0;
         if (total_paths > 0) {
             launch_init(W, P, grid_g, st);
             launches += 1;
-            const int burst = 8;  // iterations between host checks of the counters
+            // k_tail: below this many live paths (and no camera path left to generate) one launch finishes the frame
+            uint32_t tail_threshold = 1u << 16;
+            if (const char* e = getenv("RT2025_TAIL_PATHS")) tail_threshold = (uint32_t)std::max(0l, atol(e));  // tuning knob (0 disables)
             size_t iters = 0;
-            while (true) {
-                for (int b = 0; b < burst; b++, iters++) {
+            auto enqueue_iterations = [&](size_t n_iter) {
+                for (size_t b = 0; b < n_iter; b++, iters++) {
                     W.parity = (uint32_t)(iters & 1);
                     // stage times: events are only recorded here and read after the render, so the
                     // measurement does not add a host synchronisation to the timed region
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 0), st));
                     launch_generate(P, W, grid_g, st);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 1), st));
-                    // media_first: extend samples the sphere-bounded media itself and writes the class bytes, only the binning
-                    // pass follows; otherwise the media pass (if the scene has media) runs between extend and the binning
+                    // media_first 1: a sampling pass ahead of extend leaves the nearest scatter point as the incumbent; 2: extend
+                    // samples the sphere-bounded media itself; 0: the media pass runs between extend and the binning
                     if (P.media_first == 1) launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, 1);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 5), st));
                     launch_extend(s->view, P, W, count, grid_e, s->stack_bytes, st);
@@ -625,13 +660,35 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, P.media_first ? 2 : 0);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 3), st));
                     launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan());  // generate, k_step, extend + shade
+                    if (tail_threshold) {
+                        launch_tail(s->view, P, W, tail_threshold, s->sm_count, st);
+                        launches += 1;
+                    }
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 4), st));
                 }
-                CU(cudaMemcpyAsync(ws.h_counters, W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                CU(cudaGetLastError());
-                if (ws.h_counters->next_path >= total_paths && ws.h_counters->n_extend[0] == 0 && ws.h_counters->n_extend[1] == 0) break;
+            };
+            auto read_back = [&](int slot) {
+                CU(cudaMemcpyAsync(&ws.h_counters[slot], W.counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+                CU(cudaEventRecord(ws.check_event(slot), st));
+            };
+            // The host never idles the GPU to learn whether the frame is finished.  Generation alone takes at least
+            // total_paths / capacity iterations: those are enqueued without a look at the counters.  After that the counters of
+            // burst k are read while burst k+1 is already queued (two pinned copies, two events); the burst that runs past the
+            // last live path is a list of kernels that find empty queues and return (~3 us each).
+            enqueue_iterations(std::max<size_t>(1, (size_t)((total_paths + capacity - 1) / capacity)));
+            int slot = 0;
+            read_back(slot);
+            const size_t burst = 2;
+            while (true) {
+                enqueue_iterations(burst);
+                read_back(slot ^ 1);
+                CU(cudaEventSynchronize(ws.check_event(slot)));
+                const Counters& hc = ws.h_counters[slot];
+                if (hc.next_path >= total_paths && hc.n_extend[0] == 0 && hc.n_extend[1] == 0) break;  // (the speculative burst adds nothing to it)
+                slot ^= 1;
             }
+            final_counters = &ws.h_counters[slot];
+            CU(cudaGetLastError());
             if (stage) {
                 for (size_t i = 0; i < iters; i++) {
                     float a, b, c, d;
@@ -644,6 +701,11 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     CU(cudaEventElapsedTime(&d, ws.events[6 * i + 3], ws.events[6 * i + 4]));
                     ms_gen += a, ms_ext += b, ms_med += c, ms_shd += d;
                 }
+                // the timing pool grows with the longest render: keep a few hundred iterations' worth
+                while (ws.events.size() > 6 * 512) {
+                    cudaEventDestroy(ws.events.back());
+                    ws.events.pop_back();
+                }
             }
         }
         launch_finalize(W.accum, n_px_img * 3, cam->pixel_sample_scale, d_accum, o.accum_type == RT_ACCUM_F64, grid_g, st);
@@ -654,8 +716,9 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         if (stats) {
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, ev[0], ev[1]));
-            const Counters& c = *ws.h_counters;
-            stats->paths = total_paths;
+            const Counters zero{};
+            const Counters& c = final_counters ? *final_counters : zero;
+            stats->paths = nominal_paths;
             stats->segments = total_paths ? c.segments : 0;
             stats->node_visits = total_paths ? c.node_visits : 0;
             stats->prim_tests = total_paths ? c.prim_tests : 0;
@@ -680,6 +743,7 @@ int rt_render(const rt_scene* s, const rt_camera* cam, const rt_render_opts* opt
     const size_t bytes = (size_t)cam->image_width * cam->image_height * 3 * elem;
     void* d = nullptr;
     int rc = RT_OK;
+    DeviceGuard guard;
     try {
         CU(cudaSetDevice(s->device));
         scratch_alloc(&d, bytes);
@@ -703,6 +767,7 @@ int rt_render_rgb8(const rt_scene* s, const rt_camera* cam, const rt_render_opts
     uint8_t* d_rgb = nullptr;
     int* d_flag = nullptr;
     int rc = RT_OK;
+    DeviceGuard guard;
     try {
         CU(cudaSetDevice(s->device));
         scratch_alloc(&d_accum, n_px * 3 * sizeof(double));
@@ -728,14 +793,41 @@ int rt_render_rgb8(const rt_scene* s, const rt_camera* cam, const rt_render_opts
     return rc;
 }
 
-int rt_render_multi(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, const rt_render_opts* opts, void* accum, rt_stats* stats) {
-    if (!scenes || !n || !cam || !accum) return set_err(RT_ERR_INVALID, "null argument");
+namespace {
+
+// The multi-GPU render behind rt_render_multi / rt_render_multi_rgb8: GPU i renders partition i of n from a host thread of
+// its own into a framebuffer in ITS memory; GPU 0 then sums the partial frames with one kernel that reads the other GPUs'
+// buffers through peer mappings (NVLink loads; a staged cudaMemcpyPeer where two devices cannot map each other).  The
+// partitions are disjoint pixel sets, so the sum is also the gather.  On return `parts[0]` (device scenes[0]->device)
+// holds the complete frame; the caller reads it back - or encodes it first - and frees every buffer with free_parts().
+struct MultiFrame {
+    std::vector<void*> parts;   // parts[i] lives on scenes[i]->device
+    std::vector<int> devices;
+    void* staged = nullptr;     // scratch on device 0 for peers that cannot be mapped
+    ~MultiFrame() {
+        for (size_t i = 0; i < parts.size(); i++)
+            if (parts[i]) {
+                cudaSetDevice(devices[i]);
+                cudaFreeAsync(parts[i], cudaStreamPerThread);
+            }
+        if (staged) {
+            cudaSetDevice(devices[0]);
+            cudaFreeAsync(staged, cudaStreamPerThread);
+        }
+    }
+};
+
+int render_multi_to_device0(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, const rt_render_opts* opts, bool force_f64, MultiFrame& mf,
+                            rt_stats* stats) {
+    if (!scenes || !n || !cam) return set_err(RT_ERR_INVALID, "null argument");
+    if (n > MAX_PARTS) return set_err(RT_ERR_UNSUPPORTED, "more than 16 GPUs");
     rt_render_opts base{};
     if (opts) {
         if (opts->struct_size != sizeof(rt_render_opts)) return set_err(RT_ERR_VERSION, "rt_render_opts.struct_size mismatch");
         base = *opts;
     }
     base.struct_size = sizeof(base);
+    if (force_f64) base.accum_type = RT_ACCUM_F64;
     if (base.part_count > 1 || base.part_index != 0) return set_err(RT_ERR_INVALID, "rt_render_multi partitions the image itself");
     for (uint32_t i = 0; i < n; i++) {
         if (!scenes[i]) return set_err(RT_ERR_INVALID, "null scene");
@@ -744,7 +836,10 @@ int rt_render_multi(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, c
     }
     const size_t n_val = (size_t)cam->image_width * cam->image_height * 3;
     const bool f64 = base.accum_type == RT_ACCUM_F64;
-    std::vector<std::vector<char>> part(n);
+    const size_t bytes = n_val * (f64 ? 8 : 4);
+    mf.parts.assign(n, nullptr);
+    mf.devices.resize(n);
+    for (uint32_t i = 0; i < n; i++) mf.devices[i] = scenes[i]->device;
     std::vector<rt_stats> st(n);
     std::vector<int> rcs(n, RT_OK);
     std::vector<std::string> errs(n);
@@ -754,40 +849,112 @@ int rt_render_multi(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, c
             rt_render_opts o = base;
             o.part_index = i;
             o.part_count = n;
-            part[i].resize(n_val * (f64 ? 8 : 4));
-            rcs[i] = rt_render(scenes[i], cam, &o, part[i].data(), &st[i]);
+            if (cudaSetDevice(scenes[i]->device) != cudaSuccess || cudaMallocAsync(&mf.parts[i], bytes, cudaStreamPerThread) != cudaSuccess) {
+                rcs[i] = RT_ERR_CUDA, errs[i] = "cudaMallocAsync of a partial framebuffer failed";
+                cudaGetLastError();
+                return;
+            }
+            rcs[i] = rt_render_device(scenes[i], cam, &o, mf.parts[i], cudaStreamPerThread, &st[i]);  // returns when the frame is complete
             if (rcs[i] != RT_OK) errs[i] = rt_last_error();  // thread-local: carry it to the caller's thread
         });
     }
     for (auto& t : threads) t.join();
     for (uint32_t i = 0; i < n; i++)
         if (rcs[i] != RT_OK) return set_err(rcs[i], errs[i]);
-    // partitions are disjoint pixel sets: the sum is also the gather
-    if (f64) {
-        double* out = (double*)accum;
-        std::fill(out, out + n_val, 0.0);
-        for (uint32_t i = 0; i < n; i++) {
-            const double* p = (const double*)part[i].data();
-            for (size_t k = 0; k < n_val; k++) out[k] += p[k];
+    try {
+        const int dev0 = scenes[0]->device;
+        CU(cudaSetDevice(dev0));
+        cudaStream_t st0 = cudaStreamPerThread;
+        int launches = 0;
+        if (n > 1) {
+            PartList mapped{};  // partial frames GPU 0 can load from directly
+            mapped.p[mapped.n++] = mf.parts[0];
+            for (uint32_t i = 1; i < n; i++) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, dev0, scenes[i]->device);
+                if (can) {
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(scenes[i]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+                    cudaGetLastError();
+                }
+                if (can) {
+                    mapped.p[mapped.n++] = mf.parts[i];
+                } else {  // no mapping between the two: stage the partial frame on GPU 0 and add it at once
+                    if (!mf.staged) CU(cudaMallocAsync(&mf.staged, bytes, st0));
+                    CU(cudaMemcpyPeerAsync(mf.staged, dev0, mf.parts[i], scenes[i]->device, bytes, st0));
+                    PartList two{};
+                    two.p[0] = mf.parts[0], two.p[1] = mf.staged, two.n = 2;
+                    launch_sum_parts(two, mf.parts[0], n_val, f64, scenes[0]->sm_count * 4, st0);
+                    launches++;
+                }
+            }
+            if (mapped.n > 1) {
+                launch_sum_parts(mapped, mf.parts[0], n_val, f64, scenes[0]->sm_count * 4, st0);
+                launches++;
+            }
+            CU(cudaGetLastError());
         }
-    } else {
-        float* out = (float*)accum;
-        std::fill(out, out + n_val, 0.0f);
-        for (uint32_t i = 0; i < n; i++) {
-            const float* p = (const float*)part[i].data();
-            for (size_t k = 0; k < n_val; k++) out[k] += p[k];
+        CU(cudaStreamSynchronize(st0));
+        if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
+            for (uint32_t i = 0; i < n; i++) {
+                stats->paths += st[i].paths, stats->segments += st[i].segments, stats->errors += st[i].errors;
+                stats->node_visits += st[i].node_visits, stats->prim_tests += st[i].prim_tests;
+                stats->kernel_launches += st[i].kernel_launches, stats->iterations += st[i].iterations;
+                stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
+                stats->ms_raygen = std::max(stats->ms_raygen, st[i].ms_raygen), stats->ms_extend = std::max(stats->ms_extend, st[i].ms_extend);
+                stats->ms_shade = std::max(stats->ms_shade, st[i].ms_shade), stats->ms_other = std::max(stats->ms_other, st[i].ms_other);
+            }
+            stats->kernel_launches += launches;
         }
-    }
-    if (stats) {
-        std::memset(stats, 0, sizeof(*stats));
-        for (uint32_t i = 0; i < n; i++) {
-            stats->paths += st[i].paths, stats->segments += st[i].segments, stats->errors += st[i].errors;
-            stats->node_visits += st[i].node_visits, stats->prim_tests += st[i].prim_tests;
-            stats->kernel_launches += st[i].kernel_launches, stats->iterations += st[i].iterations;
-            stats->ms_total = std::max(stats->ms_total, st[i].ms_total);
-        }
+    } catch (const CudaFail& f) {
+        return set_err(RT_ERR_CUDA, f.what);
     }
     return RT_OK;
+}
+
+}  // namespace
+
+int rt_render_multi(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, const rt_render_opts* opts, void* accum, rt_stats* stats) {
+    if (!accum) return set_err(RT_ERR_INVALID, "null argument");
+    DeviceGuard guard;
+    MultiFrame mf;
+    int rc = render_multi_to_device0(scenes, n, cam, opts, false, mf, stats);
+    if (rc != RT_OK) return rc;
+    const size_t bytes = (size_t)cam->image_width * cam->image_height * 3 * ((opts && opts->accum_type == RT_ACCUM_F64) ? 8 : 4);
+    if (cudaSetDevice(scenes[0]->device) != cudaSuccess || cudaMemcpy(accum, mf.parts[0], bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return set_err(RT_ERR_CUDA, std::string("read-back of the reduced frame: ") + cudaGetErrorString(cudaGetLastError()));
+    return RT_OK;
+}
+
+int rt_render_multi_rgb8(rt_scene* const* scenes, uint32_t n, const rt_camera* cam, const rt_render_opts* opts, uint8_t* rgb, rt_stats* stats) {
+    if (!rgb) return set_err(RT_ERR_INVALID, "null argument");
+    DeviceGuard guard;
+    MultiFrame mf;
+    int rc = render_multi_to_device0(scenes, n, cam, opts, true, mf, stats);
+    if (rc != RT_OK) return rc;
+    const uint64_t n_px = (uint64_t)cam->image_width * cam->image_height;
+    char* d = nullptr;
+    cudaStream_t st0 = cudaStreamPerThread;
+    try {
+        CU(cudaSetDevice(scenes[0]->device));
+        const size_t out_bytes = ((size_t)n_px * 3 + 255) & ~size_t(255);
+        CU(cudaMallocAsync((void**)&d, out_bytes + 256, st0));
+        int* d_flag = reinterpret_cast<int*>(d + out_bytes);
+        CU(cudaMemsetAsync(d_flag, 0, sizeof(int), st0));
+        launch_tonemap(mf.parts[0], true, n_px, cam->toon_map, reinterpret_cast<uint8_t*>(d), d_flag, st0);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(rgb, d, (size_t)n_px * 3, cudaMemcpyDeviceToHost, st0));
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st0));
+        CU(cudaStreamSynchronize(st0));
+        if (flag) rc = set_err(RT_ERR_INVALID, "NaN radiance in the image (utils/color.rs:28 asserts)");
+        if (stats) stats->kernel_launches += 1;
+    } catch (const CudaFail& f) {
+        rc = set_err(RT_ERR_CUDA, f.what);
+    }
+    if (d) cudaFreeAsync(d, st0);
+    return rc;
 }
 
 int rt_tonemap(const void* accum, uint32_t accum_type, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb) {

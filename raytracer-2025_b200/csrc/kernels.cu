@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "shade.cuh"
 
@@ -382,6 +384,57 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     }
 }
 
+// ConstantMedium::hit of every medium against the hit known so far (t, prim, kind; kind == HIT_MISS: none): the nearest scatter
+// point replaces it when it wins (nearer, or an exact tie with the lower rank).  Returns whether it did.
+template <bool COUNT, bool GENERIC, bool XF>
+__device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed, const RayD& r, uint32_t pixel, uint32_t sample, uint32_t segment, double& t,
+                                             uint32_t& prim, uint32_t& kind, const float4* s_mem, uint32_t* stack, int stride, TraceCounters* cntp) {
+    uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
+    bool changed = false;
+        for (uint32_t m = 0; m < sv.n_media; m++) {
+            const Medium& med = sv.media[m];
+            const double xi = philox_pair(seed, pixel, sample, segment, RT_SLOT_MEDIUM0 + med.medium_index).a;
+            double tm;
+            RayD lr = r;
+            if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
+            // binary32 screen: the scatter point lies at t1 + dist/len with t1 >= 0, so a free flight that clearly
+            // overshoots the known hit cannot win whatever the boundary does: skip the boundary test
+            if (RT_MEDIA_EARLY_SCREEN && kind != HIT_MISS) {
+                const float hf = (float)med.neg_inv_density * logf((float)xi);
+                const float hf_err = 4e-7f * fabsf((float)med.neg_inv_density);
+                const float len_f = sqrtf((float)lr.d.x * (float)lr.d.x + (float)lr.d.y * (float)lr.d.y + (float)lr.d.z * (float)lr.d.z);
+                if (hf > (float)t * len_f * 1.001f + hf_err) continue;
+            }
+            if (med.single_sphere != RT_NONE) {
+                if (!sample_sphere_medium<COUNT, XF>(sv, med, r, xi, tm, cntp)) continue;
+            } else if (GENERIC) {
+                double t1, t2;
+                uint32_t bp;
+                if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, s_mem, stack, stride, t1, bp, cntp)) continue;
+                if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, s_mem, stack, stride, t2, bp, cntp)) continue;
+                if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
+                if (t1 >= t2) continue;
+                if (t1 < 0.0) t1 = 0.0;
+                const double ray_length = length(lr.d);
+                const double distance_inside_boundary = (t2 - t1) * ray_length;
+                const double hit_distance = med.neg_inv_density * log(xi);
+                if (hit_distance > distance_inside_boundary) continue;
+                tm = t1 + hit_distance / ray_length;
+            } else {
+                continue;  // unreachable: the host launches the GENERIC instantiation for such scenes
+            }
+            // the medium competes with the other children of its container like any hit
+            if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
+                t = tm;
+                prim = m;
+                kind = HIT_MEDIUM;
+                rank = med.rank;
+                changed = true;
+            }
+        }
+    return changed;
+}
+
 // Media pass AFTER extend (the order of Hittables::hit): ConstantMedium::hit for every medium (volume.rs:37-73)
 // against the surface hit k_extend found, one thread per extend-queue entry.  Used when some boundary is not a
 // single Sphere (GENERIC: the boundary needs a BVH traversal per lane, kept out of the common instantiation because
@@ -424,49 +477,7 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
         uint32_t pixel, sample, segment;
         unpack_ids(ids64, pixel, sample, segment);
         const uint32_t surface_meta = kind == HIT_SURFACE ? __ldg(&sv.meta[prim].kind_mat) : 0u;
-        uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
-        bool changed = false;
-        for (uint32_t m = 0; m < sv.n_media; m++) {
-            const Medium& med = sv.media[m];
-            const double xi = philox_pair(P.seed, pixel, sample, segment, RT_SLOT_MEDIUM0 + med.medium_index).a;
-            double tm;
-            RayD lr = r;
-            if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
-            // binary32 screen: the scatter point lies at t1 + dist/len with t1 >= 0, so a free flight that clearly
-            // overshoots the known hit cannot win whatever the boundary does: skip the boundary test
-            if (RT_MEDIA_EARLY_SCREEN && kind != HIT_MISS) {
-                const float hf = (float)med.neg_inv_density * logf((float)xi);
-                const float hf_err = 4e-7f * fabsf((float)med.neg_inv_density);
-                const float len_f = sqrtf((float)lr.d.x * (float)lr.d.x + (float)lr.d.y * (float)lr.d.y + (float)lr.d.z * (float)lr.d.z);
-                if (hf > (float)t * len_f * 1.001f + hf_err) continue;
-            }
-            if (med.single_sphere != RT_NONE) {
-                if (!sample_sphere_medium<COUNT, XF>(sv, med, r, xi, tm, &cnt)) continue;
-            } else if (GENERIC) {
-                double t1, t2;
-                uint32_t bp;
-                if (!closest_hit<COUNT, false>(sv, med.root, r, -INFINITY, INFINITY, s_mem, stack, MEDIA_BLOCK, t1, bp, &cnt)) continue;
-                if (!closest_hit<COUNT, false>(sv, med.root, r, t1 + 0.0001, INFINITY, s_mem, stack, MEDIA_BLOCK, t2, bp, &cnt)) continue;
-                if (t1 < 1e-8) t1 = 1e-8;  // clamp to the caller's interval [1e-8, inf)
-                if (t1 >= t2) continue;
-                if (t1 < 0.0) t1 = 0.0;
-                const double ray_length = length(lr.d);
-                const double distance_inside_boundary = (t2 - t1) * ray_length;
-                const double hit_distance = med.neg_inv_density * log(xi);
-                if (hit_distance > distance_inside_boundary) continue;
-                tm = t1 + hit_distance / ray_length;
-            } else {
-                continue;  // unreachable: the host launches the GENERIC instantiation for such scenes
-            }
-            // the medium competes with the other children of its container like any hit
-            if (kind == HIT_MISS || tm < t || (tm == t && med.rank < rank)) {
-                t = tm;
-                prim = m;
-                kind = HIT_MEDIUM;
-                rank = med.rank;
-                changed = true;
-            }
-        }
+        const bool changed = sample_media<COUNT, GENERIC, XF>(sv, P.seed, r, pixel, sample, segment, t, prim, kind, s_mem, stack, MEDIA_BLOCK, &cnt);
         if (PRE || changed) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
         if (PRE) continue;  // extend writes the class bytes
         uint32_t c = kind == HIT_MISS ? (uint32_t)SC_MISS : (kind == HIT_MEDIUM ? (uint32_t)SC_ISOTROPIC : ((surface_meta >> META_CLASS_SHIFT) & 15u));
@@ -517,12 +528,12 @@ __device__ __forceinline__ void contribute(const RenderParams& P, const Wavefron
     if (c.z != 0.0) atomicAdd(a + 2, c.z);
 }
 
-// One instantiation per shade class (scene_types.h ShadeClass): the queue it reads only holds hits
-// of that class, so everything another class would need is compiled out and the kernel keeps few
-// registers.  CLS == SC_OTHER is the fully general version (Mix, Portal, Transparent, lights that
-// wrap a material) and is also what runs when binning is switched off.
+// emitted + scatter + mixture-pdf light sampling for ONE hit (camera.rs:288-321).  Returns whether the path goes on, with the
+// next ray and throughput in nr / nbeta.  One instantiation per shade class: everything another class would need is compiled
+// out; CLS == SC_OTHER is the fully general version (Mix, Portal, Transparent, lights that wrap a material, misses, media).
 template <uint32_t CLS>
-__global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 1u) ? 3 : RT_SHADE_MIN_BLOCKS) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
+__device__ __forceinline__ bool shade_one(const SceneView& sv, const RenderParams& P, const WavefrontState& W, const RayD& r, D3 beta, uint32_t pixel,
+                                          uint32_t sidx, uint32_t segment, double t, uint32_t prim, uint32_t kind, RayD& nr, D3& nbeta) {
     constexpr bool GENERIC = CLS == SC_OTHER;
     constexpr bool DO_MISS = CLS == SC_MISS;
     constexpr bool DO_MEDIUM = GENERIC || CLS == SC_ISOTROPIC;
@@ -531,30 +542,6 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
     constexpr bool DO_REMAP = GENERIC || CLS == SC_DISNEY;
     constexpr bool DO_METAL = GENERIC || CLS == SC_METAL;
     constexpr bool DO_DIELECTRIC = GENERIC || CLS == SC_DIELECTRIC;
-    __shared__ uint32_t s_warp_count[SHADE_BLOCK / 32];
-    __shared__ uint32_t s_base;
-    const uint32_t n = W.counters->n_shade[queue];
-    const RayRec* __restrict__ rays = W.ray_q[W.parity];
-    const BetaRec* __restrict__ betas = W.beta_q[W.parity];
-    // the loop bound is uniform over the block: the survivor append is aggregated per block
-    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
-        const uint32_t j = j0 + threadIdx.x;
-        int q = -1;
-        RayD nr;
-        D3 nbeta;
-        uint32_t pixel = 0, sidx = 0, segment = 0;
-        if (j < n) {
-            const uint32_t pos = W.q_shade[queue][j];
-            RayD r;
-            uint64_t ids64;
-            load_ray(rays + pos, r, ids64);
-            unpack_ids(ids64, pixel, sidx, segment);
-            const double2* sp2 = reinterpret_cast<const double2*>(betas + pos);
-            const double2 b0 = sp2[0], b1 = sp2[1];
-            D3 beta = D3{b0.x, b0.y, b1.x};
-            const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + pos);
-            const double t = hw.x;
-            const uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
             bool alive = false, error = false;
             nr = r;
             nbeta = beta;
@@ -774,6 +761,40 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
             }
             // a zero throughput can never contribute again; depth == 0 returns black (camera.rs:282)
             if (alive && (segment + 1 >= P.cam.max_depth || (nbeta.x == 0.0 && nbeta.y == 0.0 && nbeta.z == 0.0))) alive = false;
+            return alive;
+}
+
+// One instantiation per shade class (scene_types.h ShadeClass): the queue it reads only holds hits
+// of that class, so everything another class would need is compiled out and the kernel keeps few
+// registers.  CLS == SC_OTHER is the fully general version (Mix, Portal, Transparent, lights that
+// wrap a material) and is also what runs when binning is switched off.
+template <uint32_t CLS>
+__global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 1u) ? 3 : RT_SHADE_MIN_BLOCKS) k_shade(SceneView sv, RenderParams P, WavefrontState W, uint32_t queue) {
+    __shared__ uint32_t s_warp_count[SHADE_BLOCK / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t n = W.counters->n_shade[queue];
+    const RayRec* __restrict__ rays = W.ray_q[W.parity];
+    const BetaRec* __restrict__ betas = W.beta_q[W.parity];
+    // the loop bound is uniform over the block: the survivor append is aggregated per block
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
+        const uint32_t j = j0 + threadIdx.x;
+        int q = -1;
+        RayD nr;
+        D3 nbeta;
+        uint32_t pixel = 0, sidx = 0, segment = 0;
+        if (j < n) {
+            const uint32_t pos = W.q_shade[queue][j];
+            RayD r;
+            uint64_t ids64;
+            load_ray(rays + pos, r, ids64);
+            unpack_ids(ids64, pixel, sidx, segment);
+            const double2* sp2 = reinterpret_cast<const double2*>(betas + pos);
+            const double2 b0 = sp2[0], b1 = sp2[1];
+            D3 beta = D3{b0.x, b0.y, b1.x};
+            const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + pos);
+            const double t = hw.x;
+            const uint32_t prim = (uint32_t)__double2hiint(hw.y), kind = (uint32_t)__double2loint(hw.y);
+            const bool alive = shade_one<CLS>(sv, P, W, r, beta, pixel, sidx, segment, t, prim, kind, nr, nbeta);
             q = alive ? 0 : -1;
         }
         // survivors are appended to the other copy of the streams: one atomic per block
@@ -798,6 +819,67 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// tail: the last few thousand paths of a frame, traced to completion by one launch
+// ------------------------------------------------------------------------------------------
+// Once every camera path has been generated the wavefront only drains: depth-40 stragglers keep it alive for dozens of
+// iterations of ~14 launches each that move a few hundred paths - a fixed cost per frame that does not shrink when the frame
+// is split over GPUs (round 1: 5.6 % of the 8-GPU step).  k_tail is launched after every iteration and returns at once unless
+// generation is over and at most `threshold` paths are left; then one thread takes one path and runs generate-less
+// extend -> media -> shade in a loop until the path ends.  The draws are addressed by (pixel, sample, segment, slot), so the
+// radiance is the very sum the wavefront would have produced.  The last CTA to finish marks the queue empty.
+constexpr int TAIL_BLOCK = MEDIA_BLOCK;
+__global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(SceneView sv, RenderParams P, WavefrontState W, uint32_t threshold) {
+    extern __shared__ float4 s_mem[];  // traversal stacks (global-memory nodes only)
+    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
+    Counters* c = W.counters;
+    const uint32_t np = W.parity ^ 1u;  // shade has just appended the survivors to the other copy of the streams
+    const uint32_t n = c->n_extend[np];
+    if (n == 0 || n > threshold || c->next_path < W.total_paths) return;
+    const RayRec* __restrict__ rays = W.ray_q[np];
+    const BetaRec* __restrict__ betas = W.beta_q[np];
+    TraceCounters cnt{0, 0};
+    unsigned long long my_segments = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        RayD r;
+        uint64_t ids64;
+        load_ray(rays + j, r, ids64);
+        uint32_t pixel, sidx, segment;
+        unpack_ids(ids64, pixel, sidx, segment);
+        const double2* sp2 = reinterpret_cast<const double2*>(betas + j);
+        const double2 b0 = sp2[0], b1 = sp2[1];
+        D3 beta = D3{b0.x, b0.y, b1.x};
+        while (true) {
+            my_segments++;
+            double t = INFINITY;
+            uint32_t prim = 0xFFFFFFFFu, kind = HIT_MISS;
+            if (closest_hit<false, true>(sv, sv.world_root, r, 1e-8, INFINITY, s_mem, stack, TAIL_BLOCK, t, prim, &cnt)) kind = HIT_SURFACE;
+            if (sv.n_media) sample_media<false, true, true>(sv, P.seed, r, pixel, sidx, segment, t, prim, kind, s_mem, stack, TAIL_BLOCK, &cnt);
+            RayD nr;
+            D3 nbeta;
+            if (!shade_one<SC_OTHER>(sv, P, W, r, beta, pixel, sidx, segment, t, prim, kind, nr, nbeta)) break;
+            r = nr, beta = nbeta, segment++;
+        }
+    }
+    if (my_segments) atomicAdd(&c->segments, my_segments);
+    // every CTA read `n` before it got here, and the last one to arrive does so after all the others have finished
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&c->pad, 1u) == gridDim.x - 1u) {
+            c->n_extend[np] = 0;
+            c->pad = 0;
+            c->iterations += 1;
+        }
+    }
+}
+void launch_tail(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t threshold, int grid, cudaStream_t s) {
+    SceneView tv = sv;
+    tv.n_cached_nodes = 0;  // the non-persistent closest_hit() reads the binary tree from global memory
+    const size_t smem = (size_t)std::max(sv.tail_stack_entries, 4u) * TAIL_BLOCK * sizeof(uint32_t);
+    k_tail<<<grid, TAIL_BLOCK, smem, s>>>(tv, P, W, threshold);
+}
+
 __global__ void k_finalize(const double* __restrict__ accum, uint64_t n, double scale, void* out, int out_f64) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         double v = accum[i] * scale;
@@ -808,6 +890,24 @@ __global__ void k_finalize(const double* __restrict__ accum, uint64_t n, double 
     }
 }
 
+
+// The multi-GPU reduce: GPU 0 sums the partial framebuffers where they lie.  parts.p[k] for k > 0 are PEER pointers (memory of
+// the other GPUs mapped through cudaDeviceEnablePeerAccess), so the loads below cross NVLink / NVSwitch; every value is read once
+// and only GPU 0 writes.  The partitions are disjoint pixel tiles, so most addends are zero and the sum is also the gather.
+template <class T>
+__global__ void __launch_bounds__(256) k_sum_parts(PartList parts, T* __restrict__ out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        T acc = reinterpret_cast<const T*>(parts.p[0])[i];
+        for (uint32_t k = 1; k < parts.n; k++) acc += reinterpret_cast<const T*>(parts.p[k])[i];
+        out[i] = acc;
+    }
+}
+void launch_sum_parts(const PartList& parts, void* out, uint64_t n_values, bool f64, int grid, cudaStream_t s) {
+    if (f64)
+        k_sum_parts<double><<<grid, 256, 0, s>>>(parts, reinterpret_cast<double*>(out), n_values);
+    else
+        k_sum_parts<float><<<grid, 256, 0, s>>>(parts, reinterpret_cast<float*>(out), n_values);
+}
 
 // Color::to_rgb, utils/color.rs:14-36: optional ACES fit, then linear -> sRGB 8 bit.  palette's
 // encoder is not vendored with the reference; this is the standard piecewise curve rounded to
@@ -960,6 +1060,7 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB
+    if ((e = cudaFuncSetAttribute((const void*)k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * TAIL_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
     const void* media_smem[] = {(const void*)k_media<false, 2, false, false>, (const void*)k_media<false, 2, true, false>,
                                 (const void*)k_media<true, 2, false, false>, (const void*)k_media<true, 2, true, false>};
     for (const void* f : media_smem)

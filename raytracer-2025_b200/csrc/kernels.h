@@ -132,6 +132,16 @@ struct ShadeFan {  // side streams for the per-class shade kernels (owned by the
 };
 int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
                  const ShadeFan* fan);
+// partial framebuffers of a multi-GPU render, as GPU 0 sees them (peer-mapped pointers for the other GPUs)
+constexpr uint32_t MAX_PARTS = 16;
+struct PartList {
+    const void* p[MAX_PARTS];
+    uint32_t n;
+};
+// out[i] = sum over parts of p[k][i] (out may be parts.p[0])
+void launch_sum_parts(const PartList& parts, void* out, uint64_t n_values, bool f64, int grid, cudaStream_t s);
+// finishes the frame in one launch once generation is over and at most `threshold` paths are left (kernels.cu, k_tail); a no-op otherwise
+void launch_tail(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t threshold, int grid, cudaStream_t s);
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s);
 void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb, int* error_flag, cudaStream_t s);
 int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm);

@@ -24,7 +24,7 @@ RT_BUILD_DEVICE_LBVH = 2
 # every symbol include/rt2025.h declares (tests check that the library exports them all)
 ABI_SYMBOLS = [
     "rt_scene_create", "rt_scene_destroy", "rt_closest_hit", "rt_closest_hit_device", "rt_render",
-    "rt_render_device", "rt_render_rgb8", "rt_render_multi", "rt_tonemap", "rt_tonemap_device", "rt_scene_get_info", "rt_scene_get_ranks", "rt_last_error",
+    "rt_render_device", "rt_render_rgb8", "rt_render_multi", "rt_render_multi_rgb8", "rt_tonemap", "rt_tonemap_device", "rt_scene_get_info", "rt_scene_get_ranks", "rt_last_error",
     "rt_abi_version", "rt_device_count",
 ]
 
@@ -206,6 +206,9 @@ def product_lib(required=True):
         L.rt_render_rgb8.argtypes = [C.c_void_p, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p, C.POINTER(rt_stats)]
         L.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p,
                                       C.POINTER(rt_stats)]
+        if hasattr(L, "rt_render_multi_rgb8"):  # absent from older builds selected with RT2025_LIB for A/B runs
+            L.rt_render_multi_rgb8.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(rt_camera), C.POINTER(rt_render_opts), C.c_void_p,
+                                               C.POINTER(rt_stats)]
         L.rt_tonemap.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p]
         L.rt_tonemap_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         L.rt_scene_get_info.argtypes = [C.c_void_p, C.POINTER(rt_scene_info)]
@@ -459,8 +462,20 @@ class Scene:
         return st
 
 
+def render_multi_rgb8(scenes, camera=None, **kw):
+    """rt_render_multi_rgb8: Camera::render on several GPUs of one process -> RgbImage bytes (H, W, 3)."""
+    L = product_lib()
+    cam = camera if camera is not None else scenes[0].host.camera
+    o = scenes[0].render_opts(**kw)
+    img = np.zeros((cam.image_height, cam.image_width, 3), dtype=np.uint8)
+    handles = (C.c_void_p * len(scenes))(*[s.h for s in scenes])
+    st = rt_stats()
+    _check(L.rt_render_multi_rgb8(handles, len(scenes), C.byref(cam), C.byref(o), img.ctypes.data, C.byref(st)), L)
+    return img, st
+
+
 def render_multi(scenes, camera=None, **kw):
-    """rt_render_multi: one process, scenes[i] on distinct GPUs, interleaved-tile partitions summed on the host."""
+    """rt_render_multi: one process, scenes[i] on distinct GPUs; GPU 0 sums the partial frames through peer mappings."""
     L = product_lib()
     cam = camera if camera is not None else scenes[0].host.camera
     o = scenes[0].render_opts(**kw)

@@ -535,8 +535,37 @@ def test_render_multi_in_one_process(gpu, rt):
     ref, rst = scenes[0].render(seed=3)
     assert st.paths == rst.paths and st.segments == rst.segments
     assert np.allclose(img, ref, rtol=1e-12, atol=1e-14)
+    # ... ending like Camera::render: the reduced frame is encoded on GPU 0 and only the bytes come back
+    rgb, st8 = rt.render_multi_rgb8(scenes, seed=3)
+    assert np.array_equal(rgb, rt.tonemap(ref, 0)) and st8.paths == rst.paths
+    f32, _ = rt.render_multi(scenes, seed=3, accum_type=rt.RT_ACCUM_F32)
+    assert f32.dtype == np.float32 and np.allclose(f32, ref, rtol=1e-6, atol=1e-7)
     with pytest.raises(rt.RtError):
         rt.render_multi([scenes[0], scenes[0]], seed=3)  # two handles on one device
+
+
+def test_two_renders_share_a_gpu(gpu, rt):
+    """Two scenes rendered from two host threads on one GPU at the same time: each borrows a workspace of its own."""
+    import threading
+    a = rt.Scene(rt.named_scene("cornell_glass", seed=3, params=[48, 9, 12]))
+    b = rt.Scene(rt.named_scene("book1_final", seed=3, params=[64, 4, 12]))
+    want = [a.render(seed=5)[0], b.render(seed=6)[0]]
+    got = [None, None]
+
+    def work(k, sc, seed):
+        for _ in range(3):
+            got[k] = sc.render(seed=seed)[0]
+    th = [threading.Thread(target=work, args=(0, a, 5)), threading.Thread(target=work, args=(1, b, 6))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert np.allclose(got[0], want[0], rtol=1e-12, atol=1e-14) and np.allclose(got[1], want[1], rtol=1e-12, atol=1e-14)
+
+
+def test_zero_depth_is_black(gpu, rt):
+    # ray_color returns black at depth 0 before it looks at the world (camera.rs:282)
+    hs = rt.named_scene("cornell_glass", seed=3, params=[16, 4, 0])
+    img, st = rt.Scene(hs).render(seed=1)
+    assert not img.any() and st.segments == 0 and st.paths == 16 * 16 * 4
 
 
 def _psnr8(a, b):
