@@ -873,8 +873,14 @@ int render_multi_to_device0(rt_scene* const* scenes, uint32_t n, const rt_camera
                 int can = 0;
                 cudaDeviceCanAccessPeer(&can, dev0, scenes[i]->device);
                 if (can) {
-                    const cudaError_t e = cudaDeviceEnablePeerAccess(scenes[i]->device, 0);
-                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+                    // the partial frames are stream-ordered allocations: their visibility to a peer is a property of the owning
+                    // device's memory pool (cudaDeviceEnablePeerAccess only covers cudaMalloc memory)
+                    cudaMemPool_t pool = nullptr;
+                    cudaMemAccessDesc desc{};
+                    desc.location.type = cudaMemLocationTypeDevice;
+                    desc.location.id = dev0;
+                    desc.flags = cudaMemAccessFlagsProtReadWrite;
+                    if (cudaDeviceGetDefaultMemPool(&pool, scenes[i]->device) != cudaSuccess || cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) can = 0;
                     cudaGetLastError();
                 }
                 if (can) {
