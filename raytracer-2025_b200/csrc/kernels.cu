@@ -43,7 +43,7 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
         return true;
     }
     __device__ __forceinline__ void prefetch(uint32_t i) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + i)); }
-    __device__ __forceinline__ void store(uint32_t i, bool hit, double t, uint32_t prim) const {
+    __device__ __forceinline__ void store(uint32_t i, bool hit, double t, uint32_t prim, uint32_t) const {
         rt_hit h;
         if (hit) {
             RayD r;
@@ -345,7 +345,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + j));
         if (MEDIA == 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(hits + j));
     }
-    __device__ __forceinline__ void store(uint32_t j, bool hit, double t, uint32_t prim) const {
+    __device__ __forceinline__ void store(uint32_t j, bool hit, double t, uint32_t prim, uint32_t prim_meta) const {
         uint32_t kind = HIT_MISS, c = SC_MISS;
         if (hit) {
             if (MEDIA && (prim & MEDIUM_INCUMBENT)) {  // the scatter point kept its place
@@ -353,7 +353,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
                 c = SC_ISOTROPIC;  // the phase function of a ConstantMedium is an Isotropic (validated by the scene compiler)
             } else {
                 kind = HIT_SURFACE;
-                if (cls) c = (__ldg(&sv.meta[prim].kind_mat) >> META_CLASS_SHIFT) & 15u;
+                c = (prim_meta >> META_CLASS_SHIFT) & 15u;  // PrimMeta::kind_mat of the winner, kept by the traversal
             }
         }
         *reinterpret_cast<double2*>(hits + j) = make_double2(hit ? t : INFINITY, __hiloint2double((int)prim, (int)kind));
@@ -537,7 +537,7 @@ __device__ __forceinline__ bool shade_one(const SceneView& sv, const RenderParam
     constexpr bool GENERIC = CLS == SC_OTHER;
     constexpr bool DO_MISS = CLS == SC_MISS;
     constexpr bool DO_MEDIUM = GENERIC || CLS == SC_ISOTROPIC;
-    constexpr bool DO_EMIT = GENERIC || CLS == SC_EMISSIVE;
+    constexpr bool DO_EMIT = GENERIC || CLS == SC_EMISSIVE || CLS == SC_DISNEY;  // Disney below DiffuseLight wrappers (the OBJ loader's `Ke`)
     constexpr bool DO_PDF = GENERIC || CLS == SC_DIFFUSE || CLS == SC_TEXTURED || CLS == SC_ISOTROPIC || CLS == SC_DISNEY;
     constexpr bool DO_REMAP = GENERIC || CLS == SC_DISNEY;
     constexpr bool DO_METAL = GENERIC || CLS == SC_METAL;
@@ -782,6 +782,17 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
         RayD nr;
         D3 nbeta;
         uint32_t pixel = 0, sidx = 0, segment = 0;
+#if RT_SHADE_PREFETCH
+        {  // the records are gathered through the class queue: start pulling the next round's towards L2/L1 now
+            const uint32_t jn = j + gridDim.x * blockDim.x;
+            if (jn < n) {
+                const uint32_t pn = W.q_shade[queue][jn];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + pn));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(betas + pn));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(W.hit_q + pn));
+            }
+        }
+#endif
         if (j < n) {
             const uint32_t pos = W.q_shade[queue][j];
             RayD r;

@@ -130,7 +130,7 @@ enum ShadeClass : uint32_t {
     SC_METAL = 4,
     SC_DIELECTRIC = 5,
     SC_EMISSIVE = 6,  // DiffuseLight without inner material: path ends
-    SC_DISNEY = 7,    // Disney BSDF, bare or below the OBJ loader's RemappedMaterial
+    SC_DISNEY = 7,    // Disney BSDF, bare or below the OBJ loader's RemappedMaterial / DiffuseLight wrappers
     SC_OTHER = 8,     // Mix, Portal, Transparent, DiffuseLight with inner, anything nested
     SC_COUNT = 9
 };

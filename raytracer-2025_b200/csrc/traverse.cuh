@@ -446,6 +446,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
     double tbest = 0.0;
     float tmax_f = 0.f;
     uint32_t prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu, cached_xform = 0xFFFFFFFFu;
+    uint32_t prim_meta = 0;         // PrimMeta::kind_mat of the incumbent (kind, shade class, material)
     uint32_t cur = INVALID_REF;     // inner node to visit next | a second leaf met while `parked` is taken (PARK) | INVALID_REF
     uint32_t parked = INVALID_REF;  // the leaf this lane holds
     int sp = 0;
@@ -670,6 +671,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                         tbest = t;
                         prim = pi;
                         prim_rank = km.y;
+                        prim_meta = km.x;
                         tmax_f = __double2float_ru(t);
                     }
                 }
@@ -680,7 +682,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                 }
             }
             if (cur == INVALID_REF) {  // traversal finished
-                io.store(item, prim != 0xFFFFFFFFu, tbest, prim);
+                io.store(item, prim != 0xFFFFFFFFu, tbest, prim, prim_meta);
                 have = false;
             }
         }
