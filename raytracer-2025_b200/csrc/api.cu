@@ -572,9 +572,12 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     const uint64_t nominal_paths = n_pixels * (uint64_t)(s_end - s_begin);
     // max_depth == 0: ray_color returns black before it looks at the world (camera.rs:282) - no path is traced
     const uint64_t total_paths = cam->max_depth == 0 ? 0 : nominal_paths;
-    // paths in flight: large enough that the ~10 launches of an iteration are amortised over millions of
-    // segments (profiles/README.md: 2^21 -> 2^24 is +23 %), never more than the job needs
-    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 24);
+    // paths in flight: large enough that the ~14 launches of an iteration and the under-filled start and end of every
+    // persistent kernel are amortised over many segments, never more than the job needs.  Measured, 800x800x144 book2 frame:
+    // 2^23 / 2^24 / 2^25 / 2^26 paths: 90.9 / 87.9 / 86.6 / 85.5 ms (the 1920x1080 mesh scene: 105.0 -> 97.9 ms from 2^24 to 2^25);
+    // 2^26 paths are 16 GB of streams (245 B per path), 9 % of a B200's memory.
+    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 26);
+    if (const char* e = getenv("RT2025_PATHS_IN_FLIGHT")) capacity = (uint32_t)std::max(1024l, atol(e));  // tuning knob
     capacity = (uint32_t)std::min<uint64_t>(capacity, ((total_paths + 1023) / 1024) * 1024);
     capacity = std::max(capacity, 1024u);
     cudaEvent_t ev[8] = {nullptr};

@@ -1,18 +1,20 @@
-"""Throughput of every BASELINE.json config that can be built here (1, 2, 3, synthetic stand-in for 4), 1 GPU."""
+"""Throughput of every BASELINE.json config that can be built here (1, 2, 3, 4 on the shipped assets, a synthetic stand-in for 4), 1 GPU."""
 import os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import orc
-from scenes_util import write_synthetic_assets, synthetic_obj_scene
+from scenes_util import final_reduced_scene, write_synthetic_assets, synthetic_obj_scene
 rt = orc.rt
 cfgs = [("cfg1 book1_final 1200x675 spp 10->9 depth 50", lambda: rt.named_scene("book1_final", seed=7, params=[1200, 10, 50]), 1),
         ("cfg2 book2_final 800x800 spp 1000->961 depth 40", lambda: rt.named_scene("book2_final", seed=7, params=[800, 1000, 40]), 4),
         ("cfg3 cornell_glass 600x600 spp 1000->961 depth 50", lambda: rt.named_scene("cornell_glass", seed=7, params=[600, 1000, 50]), 4),
+        ("cfg4 assets/Final reduced (13 of 15 meshes, 38 234 triangles, generated HDR environment) 1920x1080 spp 256 of 3000 depth 30",
+         lambda: final_reduced_scene(rt, width=1920, spp=256, depth=30), 1),
         ("cfg4-synthetic obj scene 1920x1080 spp 256 depth 30 (11.5k faces, Disney, fog mesh, portal)",
          lambda: synthetic_obj_scene(rt, write_synthetic_assets(tempfile.mkdtemp(), n=72), width=1920, spp=256, depth=30), 1)]
 pick = os.environ.get("CFGS")  # e.g. CFGS=3,4; NO_ORACLE=1 skips the CPU side
 for name, make, strata in cfgs:
-    if pick and name[3] not in pick.split(","):
+    if pick and name.split()[0][3:] not in pick.split(","):
         continue
     hs = make()
     sc = rt.Scene(hs)
