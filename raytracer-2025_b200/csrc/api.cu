@@ -662,7 +662,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
                     launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, P.media_first ? 2 : 0);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 3), st));
-                    launches += 3 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan());  // generate, k_step, extend + shade
+                    launches += 2 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan(), tail_threshold != 0);  // generate, extend + shade
                     if (tail_threshold) {
                         launch_tail(s->view, P, W, tail_threshold, s->sm_count, st);
                         launches += 1;

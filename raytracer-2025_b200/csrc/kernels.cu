@@ -237,24 +237,30 @@ __global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState
         store_ray(W.ray_q[W.parity] + extend_base + j, r, pack_ids(pixel, sidx, 0u));
         store_beta(W.beta_q[W.parity] + extend_base + j, D3{1.0, 1.0, 1.0});
     }
-}
-
-// single-thread bookkeeping between the stages
-__global__ void k_step(WavefrontState W, int phase) {
-    Counters* c = W.counters;
-    if (phase == 0) {  // after generate
-        uint64_t remaining = W.total_paths - c->next_path;
-        uint32_t room = W.capacity - c->n_extend[W.parity];
-        uint32_t n_new = (uint32_t)(remaining < (uint64_t)room ? remaining : (uint64_t)room);
-        c->next_path += n_new;
-        c->n_extend[W.parity] += n_new;
-        c->segments += c->n_extend[W.parity];
-        c->iterations += (c->n_extend[W.parity] > 0);
-    } else if (phase == 2) {  // after shade: the current stream is consumed
-        c->n_extend[W.parity] = 0;
-        for (int k = 0; k < SC_COUNT; k++) c->n_shade[k] = 0;
+    // Bookkeeping of the stage (it used to be a launch of its own): every block read the counters above before it got here,
+    // so the LAST block to arrive may advance them - the next kernel of the stream sees the topped-up queue length.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Counters* c = W.counters;
+        __threadfence();
+        if (atomicAdd(&c->gen_done, 1u) == gridDim.x - 1u) {
+            c->gen_done = 0;
+            c->next_path += n_new;
+            c->n_extend[W.parity] = extend_base + n_new;
+            c->segments += extend_base + n_new;
+            c->iterations += (extend_base + n_new > 0);
+            __threadfence();
+        }
     }
 }
+
+// after shade the current stream is consumed: its length and the class queues are reset (one thread)
+__device__ __forceinline__ void reset_consumed_queues(const WavefrontState& W) {
+    Counters* c = W.counters;
+    c->n_extend[W.parity] = 0;
+    for (int k = 0; k < SC_COUNT; k++) c->n_shade[k] = 0;
+}
+__global__ void k_step(WavefrontState W) { reset_consumed_queues(W); }
 
 // ------------------------------------------------------------------------------------------
 // extend
@@ -844,6 +850,8 @@ __global__ void __launch_bounds__(TAIL_BLOCK, 1) k_tail(SceneView sv, RenderPara
     extern __shared__ float4 s_mem[];  // traversal stacks (global-memory nodes only)
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
     Counters* c = W.counters;
+    // the bookkeeping after shade (nobody in this kernel reads what it resets: the consumed stream's length and the class queues)
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_consumed_queues(W);
     const uint32_t np = W.parity ^ 1u;  // shade has just appended the survivors to the other copy of the streams
     const uint32_t n = c->n_extend[np];
     if (n == 0 || n > threshold || c->next_path < W.total_paths) return;
@@ -966,7 +974,6 @@ void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaS
 }
 void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
     k_generate<<<grid, 256, 0, s>>>(P, W);
-    k_step<<<1, 1, 0, s>>>(W, 0);
 }
 template <int MEDIA>
 static void launch_extend_media(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
@@ -1018,8 +1025,8 @@ static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const W
 // The class kernels are independent (own queue each, atomics on the shared outputs): with `fan` they are dealt
 // over side streams between a fork and a join event so that the tail of one overlaps the start of the next.
 int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
-                 const ShadeFan* fan) {
-    int launches = 2;  // the miss kernel and k_step
+                 const ShadeFan* fan, bool tail_follows) {
+    int launches = tail_follows ? 1 : 2;  // the miss kernel (and k_step)
     if (!P.bin_by_class) {  // everything but misses sits in the SC_DIFFUSE queue: general kernel
         launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, s);
         launch_shade_cls<SC_OTHER>(sv, P, W, SC_DIFFUSE, grid, s);
@@ -1050,7 +1057,7 @@ int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontStat
             cudaStreamWaitEvent(s, fan->join[i], 0);
         }
     }
-    k_step<<<1, 1, 0, s>>>(W, 2);
+    if (!tail_follows) k_step<<<1, 1, 0, s>>>(W);  // otherwise k_tail, launched next, resets the consumed queues
     return launches;
 }
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s) {

@@ -93,7 +93,8 @@ constexpr uint32_t IDS_PIXEL_BITS = 28, IDS_SAMPLE_BITS = 24, IDS_SEGMENT_BITS =
 struct Counters {
     uint32_t n_extend[2];  // entries in ray_q/state_q of each parity
     uint32_t n_shade[SC_COUNT];
-    uint32_t n_pixels, pad;
+    uint32_t n_pixels, pad;  // pad: arrival counter of k_tail's CTAs
+    uint32_t gen_done, pad2;  // arrival counter of k_generate's CTAs
     unsigned long long next_path, segments, iterations, errors, node_visits, prim_tests;
 };
 
@@ -134,7 +135,7 @@ struct ShadeFan {  // side streams for the per-class shade kernels (owned by the
     cudaEvent_t fork = nullptr, join[3] = {};
 };
 int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
-                 const ShadeFan* fan);
+                 const ShadeFan* fan, bool tail_follows);
 // partial framebuffers of a multi-GPU render, as GPU 0 sees them (peer-mapped pointers for the other GPUs)
 constexpr uint32_t MAX_PARTS = 16;
 struct PartList {
