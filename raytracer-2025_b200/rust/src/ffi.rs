@@ -36,6 +36,20 @@ pub const RT_IMG_LINEAR: u32 = 1;
 pub const RT_IMG_INTERP: u32 = 2;
 pub const RT_ACCUM_F32: u32 = 0;
 pub const RT_ACCUM_F64: u32 = 1;
+// order of the DisneyParameters scalars in rt_material.v (rt2025.h)
+pub const RT_DISNEY_ROUGHNESS: usize = 0;
+pub const RT_DISNEY_ANISOTROPIC: usize = 1;
+pub const RT_DISNEY_SHEEN: usize = 2;
+pub const RT_DISNEY_SHEEN_TINT: usize = 3;
+pub const RT_DISNEY_CLEARCOAT: usize = 4;
+pub const RT_DISNEY_CLEARCOAT_GLOSS: usize = 5;
+pub const RT_DISNEY_SPECULAR_TINT: usize = 6;
+pub const RT_DISNEY_METALLIC: usize = 7;
+pub const RT_DISNEY_IOR: usize = 8;
+pub const RT_DISNEY_FLATNESS: usize = 9;
+pub const RT_DISNEY_SPEC_TRANS: usize = 10;
+pub const RT_DISNEY_DIFF_TRANS: usize = 11;
+pub const RT_DISNEY_THIN: usize = 12;
 
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct rt_object { pub kind: u32, pub material: u32, pub first_child: u32, pub child_count: u32, pub data: u32, pub reserved: u32, pub bbox: [f64; 6] }
@@ -99,6 +113,10 @@ extern "C" {
     pub fn rt_scene_destroy(scene: *mut rt_scene) -> i32;
     pub fn rt_closest_hit(scene: *const rt_scene, rays: *const rt_ray, n: u64, t_min: f64, t_max: f64, flags: u32, out: *mut rt_hit, stats: *mut rt_stats) -> i32;
     pub fn rt_render(scene: *const rt_scene, cam: *const rt_camera, opts: *const rt_render_opts, accum: *mut c_void, stats: *mut rt_stats) -> i32;
+    pub fn rt_render_device(scene: *const rt_scene, cam: *const rt_camera, opts: *const rt_render_opts, d_accum: *mut c_void, stream: *mut c_void, stats: *mut rt_stats) -> i32;
+    pub fn rt_render_rgb8(scene: *const rt_scene, cam: *const rt_camera, opts: *const rt_render_opts, rgb: *mut u8, stats: *mut rt_stats) -> i32;
+    pub fn rt_render_multi(scenes: *const *mut rt_scene, n_scenes: u32, cam: *const rt_camera, opts: *const rt_render_opts, accum: *mut c_void, stats: *mut rt_stats) -> i32;
+    pub fn rt_render_multi_rgb8(scenes: *const *mut rt_scene, n_scenes: u32, cam: *const rt_camera, opts: *const rt_render_opts, rgb: *mut u8, stats: *mut rt_stats) -> i32;
     pub fn rt_tonemap(accum: *const c_void, accum_type: u32, n_pixels: u64, toon_map: u32, rgb: *mut u8) -> i32;
     pub fn rt_tonemap_device(d_accum: *const c_void, accum_type: u32, n_pixels: u64, toon_map: u32, d_rgb: *mut u8, stream: *mut c_void) -> i32;
     pub fn rt_last_error() -> *const c_char;
