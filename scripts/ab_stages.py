@@ -1,6 +1,6 @@
 """A/B of library builds and tuning knobs on the stage times of a render (runs every variant in a process of its own).
 
-usage: python scripts/ab_stages.py [--scene book2|book1|cornell|final] [--spp N] variant ...
+usage: python scripts/ab_stages.py [--scene book2|book1|cornell|final|synth] [--spp N] variant ...
   variant = name[:lib=<path under raytracer-2025_b200/>][:ENV=value]...      e.g.  r1:lib=librt2025_r1.so  new  new64:RT2025_FIFO_SLOTS=64
 """
 import os, subprocess, sys
@@ -15,6 +15,10 @@ scene, spp = %(scene)r, %(spp)d
 if scene == "book2": hs = rt.named_scene("book2_final", seed=7, params=[800, spp, 40])
 elif scene == "book1": hs = rt.named_scene("book1_final", seed=7, params=[1200, spp, 50])
 elif scene == "cornell": hs = rt.named_scene("cornell_glass", seed=7, params=[600, spp, 50])
+elif scene == "synth":
+    import tempfile
+    from scenes_util import write_synthetic_assets, synthetic_obj_scene
+    hs = synthetic_obj_scene(rt, write_synthetic_assets(tempfile.mkdtemp(), n=72), width=1920, spp=spp, depth=30)
 else:
     from scenes_util import final_reduced_scene
     hs = final_reduced_scene(rt, width=1920, spp=spp, depth=30)
