@@ -589,26 +589,38 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         CU(cudaSetDevice(s->device));
         Workspace& ws = *lease.ws;
         if (ws.capacity < capacity || ws.n_pixels_alloc < n_px_img) {  // grow-only
-            const uint32_t keep_cap = std::max(ws.capacity, capacity);
-            const uint64_t keep_px = std::max<uint64_t>(ws.n_pixels_alloc, n_px_img);
-            ws.release();
-            const uint32_t capacity_alloc = keep_cap;
-            const uint64_t n_px_alloc = keep_px;
-            WavefrontState& W = ws.W;
-            for (int k = 0; k < 2; k++) {
-                CU(cudaMalloc(&W.ray_q[k], (size_t)capacity_alloc * sizeof(RayRec)));
-                CU(cudaMalloc(&W.beta_q[k], (size_t)capacity_alloc * sizeof(BetaRec)));
+            uint32_t capacity_alloc = std::max(ws.capacity, capacity);
+            const uint64_t n_px_alloc = std::max<uint64_t>(ws.n_pixels_alloc, n_px_img);
+            // the streams are 245 bytes per path in flight (16 GB at the default 2^26): when the device cannot give that much
+            // - other tenants, a smaller part - halve the capacity instead of failing; the image does not depend on it
+            while (true) {
+                ws.release();
+                WavefrontState& W = ws.W;
+                bool ok = true;
+                auto alloc = [&](auto** p, size_t bytes) { ok = ok && cudaMalloc((void**)p, bytes) == cudaSuccess; };
+                for (int k = 0; k < 2; k++) {
+                    alloc(&W.ray_q[k], (size_t)capacity_alloc * sizeof(RayRec));
+                    alloc(&W.beta_q[k], (size_t)capacity_alloc * sizeof(BetaRec));
+                }
+                alloc(&W.hit_q, (size_t)capacity_alloc * sizeof(HitRec));
+                alloc(&W.cls_q, (size_t)capacity_alloc);
+                for (auto& q : W.q_shade) alloc(&q, (size_t)capacity_alloc * 4);
+                alloc(&W.pixel_list, n_px_alloc * 4);
+                alloc(&W.accum, n_px_alloc * 3 * sizeof(double));
+                alloc(&W.counters, sizeof(Counters));
+                if (ok) break;
+                cudaGetLastError();
+                if (capacity_alloc <= (1u << 20)) {
+                    ws.release();
+                    throw CudaFail{"out of device memory for the wavefront streams (even at 2^20 paths in flight)"};
+                }
+                capacity_alloc >>= 1;
             }
-            CU(cudaMalloc(&W.hit_q, (size_t)capacity_alloc * sizeof(HitRec)));
-            CU(cudaMalloc(&W.cls_q, (size_t)capacity_alloc));
-            for (auto& q : W.q_shade) CU(cudaMalloc(&q, (size_t)capacity_alloc * 4));
-            CU(cudaMalloc(&W.pixel_list, n_px_alloc * 4));
-            CU(cudaMalloc(&W.accum, n_px_alloc * 3 * sizeof(double)));
-            CU(cudaMalloc(&W.counters, sizeof(Counters)));
             CU(cudaMallocHost(&ws.h_counters, 2 * sizeof(Counters)));
             ws.capacity = capacity_alloc;
             ws.n_pixels_alloc = n_px_alloc;
         }
+        capacity = std::min(capacity, ws.capacity);
         WavefrontState W = ws.W;
         W.capacity = capacity;
         W.n_pixels = (uint32_t)n_pixels;
