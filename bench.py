@@ -243,6 +243,9 @@ def main():
                     help="one process drives --gpus N through rt_render_multi_rgb8 (the library's own multi-GPU path: peer-memory reduce on GPU 0) "
                          "instead of one torchrun rank per GPU with an NCCL reduce")
     ap.add_argument("--no-closest-hit", action="store_true", help="skip the config-5 closest-hit cases (N=1 only)")
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "strata"],
+                    help="how N > 1 ranks share the frame: interleaved 8x8 pixel tiles (default) or contiguous stratum ranges of every pixel")
+    ap.add_argument("--rank-times", action="store_true", help="print every rank's device time per step to stderr (load-balance diagnosis)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -275,14 +278,19 @@ def main():
     scene = rt.Scene(hs, device=local_rank)
     info = scene.info()
     part_index, part_count = partition_for_rank(rank, world)
+    spp_eff = cam.sqrt_spp ** 2
+    part_kw = dict(part_index=part_index, part_count=part_count)
+    if args.partition == "strata" and world > 1:  # every rank renders all pixels, strata [begin, end) of the sampling grid
+        part_kw = dict(sample_begin=rank * spp_eff // world, sample_end=(rank + 1) * spp_eff // world)
     fb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(flags=rt.RT_OPT_STAGE_TIMES):
         flush.zero_()
-        st = scene.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32,
-                                 part_index=part_index, part_count=part_count, flags=flags)
+        st = scene.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32, flags=flags, **part_kw)
+        if args.rank_times:
+            print(f"[rank {rank}] render {st.ms_total:.2f} ms, {st.paths} paths, {st.iterations} iterations", file=sys.stderr, flush=True)
         total = reduce_framebuffer_and_paths(fb, st.paths, dst=0)
         return st, total
 
@@ -342,8 +350,7 @@ def main():
             assert rc == 0, sc2.L.rt_last_error()
             e2e_paths += st.paths
         else:
-            st = sc2.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32,
-                                   part_index=part_index, part_count=part_count)
+            st = sc2.render_device(fb.data_ptr(), stream=stream, seed=RENDER_SEED, accum_type=rt.RT_ACCUM_F32, **part_kw)
             e2e_paths += reduce_framebuffer_and_paths(fb, st.paths, dst=0)
             if rank == 0:
                 # Color::to_rgb where the reduced frame lies, then the D2H of the 8-bit image
@@ -385,7 +392,7 @@ def main():
             "config": {"workload": f"book2_final {W}x{H} spp={args.spp} ({cam.sqrt_spp ** 2} effective) depth={cam.max_depth}",
                        "scene_seed": seed, "prims": info.n_prims, "bvh_nodes": info.n_nodes, "media": info.n_media,
                        "paths_per_step": paths // max(1, args.steps), "segments_per_path": float(extra[0].item()) / max(1, paths),
-                       "parallelism": f"tiles{world}" if world > 1 else "single",
+                       "parallelism": f"{args.partition}{world}" if world > 1 else "single",
                        "l2": "flushed between steps (256 MiB fill); the ray/state/hit streams of 2^24 paths in flight (4.5 GB) exceed the 126 MB L2, the 0.7 MB scene is cache-resident by design"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

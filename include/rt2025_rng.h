@@ -43,8 +43,9 @@
 #define RT_SLOT_DISNEY 7u      /* a = lobe pick (disney.rs:674), b = the lobe's own extra decision:     */
                                /*     diff_trans flip (disney.rs:607) or Fresnel pick (disney.rs:651);   */
                                /*     the lobe's r0,r1 are RT_SLOT_DIRECTION                             */
-#define RT_SLOT_MEDIUM0 16u    /* a = free-flight draw of medium m (volume.rs:58): slot 16 + m,  */
-                               /*     m = index into rt_scene_desc.media                        */
+#define RT_SLOT_MEDIUM0 16u    /* free-flight draw of medium m (volume.rs:58), m = index into rt_scene_desc.media:          */
+                               /*     slot 16 + m/2, component a for even m, b for odd m - one Philox call serves two media */
+#define RT_MEDIUM_SLOT(m) (RT_SLOT_MEDIUM0 + ((m) >> 1))
 
 /* light leaf pick: the lights tree is flattened depth first; leaf i carries the probability
  * w_i = product over its ancestors of 1/len (hits.rs:69-75 picks uniformly at every level) and

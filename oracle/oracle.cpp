@@ -1209,7 +1209,8 @@ struct ConstantMedium : Hittable {  // volume.rs
         if (rec1.t < 0.0) rec1.t = 0.0;
         double ray_length = length(r.dir);
         double distance_inside_boundary = (rec2.t - rec1.t) * ray_length;
-        double hit_distance = neg_inv_density * std::log(ctx.draw(RT_SLOT_MEDIUM0 + medium_index).a);
+        const Rand2 draw = ctx.draw(RT_MEDIUM_SLOT(medium_index));  // rt2025_rng.h: a for even media, b for odd ones
+        double hit_distance = neg_inv_density * std::log((medium_index & 1u) ? draw.b : draw.a);
         if (hit_distance > distance_inside_boundary) return false;
         double t = rec1.t + hit_distance / ray_length;
         Vec3 p = r.at(t);

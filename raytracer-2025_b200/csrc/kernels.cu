@@ -265,6 +265,21 @@ __global__ void k_step(WavefrontState W) { reset_consumed_queues(W); }
 // ------------------------------------------------------------------------------------------
 // extend
 // ------------------------------------------------------------------------------------------
+// the free-flight draw of one medium (rt2025_rng.h: one Philox call serves two media; `cache` keeps the pair between the
+// iterations of a loop over the media)
+struct MediumDraws {
+    Rand2 pair;
+    uint32_t slot = 0xFFFFFFFFu;
+    __device__ __forceinline__ double get(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t segment, uint32_t medium_index) {
+        const uint32_t s = RT_MEDIUM_SLOT(medium_index);
+        if (s != slot) {
+            pair = philox_pair(seed, pixel, sample, segment, s);
+            slot = s;
+        }
+        return (medium_index & 1u) ? pair.b : pair.a;
+    }
+};
+
 constexpr uint32_t MEDIUM_INCUMBENT = 0x80000000u;  // `prim` of a traversal whose incumbent is a medium scatter point: flag | medium index
 
 // ConstantMedium::hit (volume.rs:37-73) for a medium whose boundary is a single Sphere, on the caller's interval
@@ -332,9 +347,10 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
         } else if (MEDIA) {
             uint32_t pixel, sample, segment;
             unpack_ids(ids, pixel, sample, segment);
+            MediumDraws draws;
             for (uint32_t m = 0; m < sv.n_media; m++) {
                 const Medium& med = sv.media[m];
-                const double xi = philox_pair(seed, pixel, sample, segment, RT_SLOT_MEDIUM0 + med.medium_index).a;
+                const double xi = draws.get(seed, pixel, sample, segment, med.medium_index);
                 double tm;
                 if (!sample_sphere_medium<COUNT, MEDIA == 2>(sv, med, r, xi, tm, cnt)) continue;
                 // the media compete with each other like any children of a container: nearest, then lower rank
@@ -397,9 +413,10 @@ __device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed,
                                              uint32_t& prim, uint32_t& kind, const float4* s_mem, uint32_t* stack, int stride, TraceCounters* cntp) {
     uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
     bool changed = false;
+    MediumDraws draws;
         for (uint32_t m = 0; m < sv.n_media; m++) {
             const Medium& med = sv.media[m];
-            const double xi = philox_pair(seed, pixel, sample, segment, RT_SLOT_MEDIUM0 + med.medium_index).a;
+            const double xi = draws.get(seed, pixel, sample, segment, med.medium_index);
             double tm;
             RayD lr = r;
             if (XF && med.xform != RT_NONE) lr = ray_to_local(sv, med.xform, r);
