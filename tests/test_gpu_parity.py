@@ -659,3 +659,35 @@ def test_medium_inside_bvh_and_transform(gpu, rt, orc):
         ref, ost = osc.render(seed=12)
         assert st.paths == ost.paths and int(st.errors) <= int(ost.errors)
         image_close(img, ref, frac_bad=5e-3)
+
+
+@pytest.mark.parametrize("knobs", [
+    {"RT2025_FIFO_SLOTS": "64", "RT2025_REFILL_MIN": "1"}, {"RT2025_FIFO_SLOTS": "32", "RT2025_REFILL_MIN": "16"}, {"RT2025_FIFO_SLOTS": "0"},
+    {"RT2025_MEDIA_FIRST": "2"}, {"RT2025_MEDIA_FIRST": "0"}, {"RT2025_TAIL_PATHS": "0"}, {"RT2025_TAIL_PATHS": "1000000"},
+    {"RT2025_PATHS_IN_FLIGHT": "8192", "RT2025_TAIL_PATHS": "100"}, {"RT2025_PARK_LEAVES": "1", "RT2025_FIFO_SLOTS": "64"},
+])
+def test_every_traversal_and_scheduling_mode_gives_the_same_answer(gpu, rt, orc, monkeypatch, knobs):
+    """The tuning knobs pick between code paths that must not change results: prepared-ray FIFO vs direct refill, postponed leaves,
+    media sampled after / ahead of / inside extend, the tail kernel, the wavefront capacity.  Ids and t bit-exact, images equal."""
+    scenes = [rt.named_scene("book2_final", seed=7, params=[48, 9, 20]),
+              random_graph_scene(rt, 13, n_prims=90, with_media=True, width=32, spp=9, depth=8)]
+    base = []
+    rng = np.random.default_rng(5)
+    o, d, t = random_rays(rng, 20000)
+    rays = rt.make_rays(o * 40 + 250, d, t)  # through the book-2 box and the random graph alike
+    for hs in scenes:
+        sc = rt.Scene(hs)
+        base.append((sc.closest_hit(rays)[0], sc.render(seed=11)))
+        sc.close()
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    for hs, (hits0, (img0, st0)) in zip(scenes, base):
+        sc = rt.Scene(hs)
+        hits = sc.closest_hit(rays)[0]
+        assert np.array_equal(hits["prim_id"], hits0["prim_id"]) and np.array_equal(hits["t"], hits0["t"])
+        img, st = sc.render(seed=11)
+        assert st.paths == st0.paths and st.segments == st0.segments and st.errors == st0.errors
+        assert np.allclose(img, img0, rtol=1e-11, atol=1e-13)
+        ref, _ = orc.OracleScene(hs).render(seed=11)
+        image_close(img, ref, frac_bad=5e-3)
+        sc.close()
