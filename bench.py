@@ -306,12 +306,13 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    paths = segs = launches = iters = 0
+    paths = segs = walk_segs = launches = iters = 0
     ms_extend = ms_shade = ms_gen = ms_media = 0.0
     for _ in range(args.steps):
         st, total = step()
         paths += total
         segs += st.segments
+        walk_segs += st.walk_segments  # evaluated in registers by k_walk: they never pass through k_extend
         launches += st.kernel_launches + 1  # + the L2 flush fill
         iters += st.iterations
         ms_extend += st.ms_extend
@@ -372,7 +373,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         n_ext_launches = max(1, iters)
-        seg_rank0 = segs
+        seg_rank0 = segs - walk_segs  # the segments k_extend processed on this rank
         ext_bytes_per_launch = seg_rank0 * EXTEND_BYTES_PER_SEGMENT / n_ext_launches
         ext_ms_per_launch = ms_extend / n_ext_launches
         achieved = ext_bytes_per_launch / (ext_ms_per_launch * 1e-3) / 1e9 if ext_ms_per_launch > 0 else 0.0
@@ -403,6 +404,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_segment": EXTEND_BYTES_PER_SEGMENT, "segments_per_launch": seg_rank0 / n_ext_launches,
+                         "walk_segment_share": walk_segs / max(1, segs),
                          "ms_per_launch": ext_ms_per_launch, "ncu": ncu_issue,
                          # the whole step by SURVEY.md 8(d)'s formula (all stages, loose by design for a cache-resident scene)
                          "step": {"bytes_per_segment": STEP_BYTES_PER_SEGMENT, "bytes_per_path": STEP_BYTES_PER_PATH,

@@ -284,7 +284,8 @@ typedef struct rt_stats {
     double ms_total;       /* device time of the call, CUDA events on its stream             */
     double ms_raygen, ms_extend, ms_shade, ms_other; /* filled when RT_OPT_STAGE_TIMES is set */
     uint64_t iterations;   /* wavefront iterations                                          */
-    uint64_t reserved[4];
+    uint64_t reserved[4];  /* reserved[0]: of `segments`, those evaluated inside the random-walk kernel of an optically
+                              thick ConstantMedium (they never passed through extend)               */
 } rt_stats;
 
 /* Closest surface hit for a batch of rays over `world` (media excluded: they are stochastic,

@@ -210,7 +210,7 @@ struct rt_scene {
     uint32_t lights_flat = 1;
     uint32_t class_mask = 0;     // shade classes the scene's materials can produce
     bool generic_media = false;  // some ConstantMedium boundary is not a single Sphere
-    int extend_blocks_per_sm = 4, shade_blocks_per_sm = 4;
+    int extend_blocks_per_sm = 4, shade_blocks_per_sm = 4, walk_blocks_per_sm = 1;
     size_t stack_bytes = 0;  // dynamic shared memory of the traversal kernels: cached nodes + stacks
 };
 
@@ -318,6 +318,8 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         for (auto& m : cs.media)
             if (m.xform != RT_NONE || (m.single_sphere != RT_NONE && cs.meta[m.single_sphere].xform != RT_NONE)) v.media_xform = 1;
         for (auto& m : cs.materials) s->class_mask |= 1u << m.shade_class;
+        for (auto& m : cs.media)
+            if (m.flags & MEDIUM_THICK) s->class_mask |= 1u << SC_WALK;  // scatter points of thick media go to the random-walk kernel
         // lights is "flat" when every leaf has the same weight 1/n (a single-level list)
         s->lights_flat = 1;
         for (auto& l : cs.lights)
@@ -398,10 +400,11 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // (measured: synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s)
         if (!cs.nodes4.empty() && !getenv("RT2025_SMEM_NODES_KB")) v.n_cached_nodes = 0;
         s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (size_t)v.n_cached_nodes * sizeof(Node);
-        if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm) != 0)
+        if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm, &s->walk_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
         if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;
         if (s->shade_blocks_per_sm < 1) s->shade_blocks_per_sm = 1;
+        if (s->walk_blocks_per_sm < 1) s->walk_blocks_per_sm = 1;
         CU(cudaDeviceSynchronize());
         *out = s;
         return RT_OK;
@@ -677,7 +680,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 2), st));
                     launches += launch_media_bin(s->view, P, W, count, s->generic_media, grid_m, st, P.media_first ? 2 : 0);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 3), st));
-                    launches += 2 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan(), tail_threshold != 0);  // generate, extend + shade
+                    launches += 2 + launch_shade(s->view, P, W, s->class_mask, grid_s, st, ws.shade_fan(), tail_threshold != 0, s->sm_count * s->walk_blocks_per_sm);  // generate, extend + shade
                     if (tail_threshold) {
                         launch_tail(s->view, P, W, tail_threshold, s->sm_count, st);
                         launches += 1;
@@ -742,6 +745,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
             stats->prim_tests = total_paths ? c.prim_tests : 0;
             stats->errors = total_paths ? c.errors : 0;
             stats->iterations = total_paths ? c.iterations : 0;
+            stats->reserved[0] = total_paths ? c.walk_segments : 0;  // rt_stats.walk_segments
             stats->kernel_launches = launches;
             stats->ms_total = ms;
             stats->ms_raygen = ms_gen, stats->ms_extend = ms_ext, stats->ms_shade = ms_shd;

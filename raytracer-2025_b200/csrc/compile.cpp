@@ -729,6 +729,40 @@ struct Compiler {
         }
     };
 
+    struct GroupBox {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    };
+    std::vector<GroupBox> group_boxes;
+    bool is_world_group(const RawVec<FlatPrim>* g) const { return g == &groups[0]; }
+
+    // leaves of the world tree whose box overlaps `b` (padded): the only primitives a segment inside `b` can meet
+    // (sphere != nullptr: the boundary is that static, untransformed sphere {cx, cy, cz, r} - boxes are tested against the ball)
+    bool overlapping_leaves(const GroupBox& b, const double* sphere, uint32_t ref, uint32_t* entry, uint32_t& n) const {
+        if (ref == INVALID_REF) return true;
+        if (ref & LEAF_FLAG) {
+            if (n == MEDIUM_MAX_ENTRIES) return false;
+            entry[n++] = ref;
+            return true;
+        }
+        const Node& nd = out.nodes[ref];
+        auto overlaps = [&](const float* lo, const float* hi) {
+            for (int k = 0; k < 3; k++)
+                if (!(lo[k] <= b.hi[k] && hi[k] >= b.lo[k])) return false;
+            if (sphere) {
+                double d2 = 0.0;
+                for (int k = 0; k < 3; k++) {
+                    const double c = sphere[k], dk = c < (double)lo[k] ? (double)lo[k] - c : (c > (double)hi[k] ? c - (double)hi[k] : 0.0);
+                    d2 += dk * dk;
+                }
+                if (d2 > sphere[3] * sphere[3]) return false;
+            }
+            return true;
+        };
+        if (overlaps(nd.lo0, nd.hi0) && !overlapping_leaves(b, sphere, nd.child0, entry, n)) return false;
+        if (overlaps(nd.lo1, nd.hi1) && !overlapping_leaves(b, sphere, nd.child1, entry, n)) return false;
+        return true;
+    }
+
     PhaseTimer timer;
     int run() {
         if (!validate()) return status;
@@ -764,6 +798,12 @@ struct Compiler {
 #pragma omp parallel for schedule(static) if (g.size() > 65536)
             for (size_t i = 0; i < g.size(); i++)
                 for (int k = 0; k < 3; k++) boxes[i].lo[k] = round_down(g[i].lo[k]), boxes[i].hi[k] = round_up(g[i].hi[k]);
+            {  // world box of the group (the boundary of a medium: MEDIUM_THICK entry leaves below)
+                GroupBox gb;
+                for (size_t i = 0; i < g.size(); i++)
+                    for (int k = 0; k < 3; k++) gb.lo[k] = std::min(gb.lo[k], boxes[i].lo[k]), gb.hi[k] = std::max(gb.hi[k], boxes[i].hi[k]);
+                if (!is_world_group(&g)) group_boxes.resize(groups.size()), group_boxes[&g - &groups[0]] = gb;
+            }
             RawVec<uint32_t> order;
             timer.lap("build boxes");
             uint32_t root = INVALID_REF;
@@ -843,6 +883,34 @@ struct Compiler {
                 uint32_t pi = (med.root & ~LEAF_FLAG) >> 3;
                 if ((out.meta[pi].kind_mat >> 30) == PRIM_SPHERE) med.single_sphere = pi;
             }
+        }
+        // optically thick media (scene_types.h, MEDIUM_THICK): only when the sampling of EVERY medium is the closed-form
+        // sphere test, because the random walk looks one segment ahead over all of them
+        bool all_spheres = true;
+        for (const Medium& med : out.media) all_spheres = all_spheres && med.single_sphere != RT_NONE;
+        double min_depth = 1.0;
+        if (const char* e = getenv("RT2025_WALK_MIN_DEPTH")) min_depth = atof(e);  // tuning knob; <= 0 switches the walk off
+        for (Medium& med : out.media) {
+            med.flags = 0;
+            if (!all_spheres || !(min_depth > 0.0)) continue;
+            const double radius = std::fabs(out.geom[med.single_sphere].d[6]);
+            if (radius * std::fabs(1.0 / med.neg_inv_density) >= min_depth) med.flags |= MEDIUM_THICK;
+        }
+        for (size_t m = 0; m < out.media.size(); m++) {
+            Medium& med = out.media[m];
+            med.n_entry = MEDIUM_NO_ENTRIES;
+            if (!(med.flags & MEDIUM_THICK) || getenv("RT2025_WALK_NO_ENTRIES")) continue;
+            GroupBox b = group_boxes[group_of_medium[m]];
+            for (int k = 0; k < 3; k++) {  // the scatter points are inside the boundary up to rounding
+                const float pad = 1e-4f * std::max(1.0f, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+                b.lo[k] -= pad, b.hi[k] += pad;
+            }
+            uint32_t n = 0;
+            const double* g = out.geom[med.single_sphere].d;
+            const bool plain = med.xform == RT_NONE && out.meta[med.single_sphere].xform == RT_NONE && g[3] == 0.0 && g[4] == 0.0 && g[5] == 0.0;
+            const double ball[4] = {g[0], g[1], g[2], std::fabs(g[6]) * (1.0 + 1e-4) + 1e-4};
+            if (overlapping_leaves(b, plain ? ball : nullptr, out.world_root, med.entry, n)) med.n_entry = n;
+            if (timer.on) fprintf(stderr, "[rt2025 compile] medium %zu is optically thick: %d entry leaves\n", m, (int)med.n_entry);
         }
         return RT_OK;
     }

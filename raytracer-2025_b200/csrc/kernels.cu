@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState
 __device__ __forceinline__ void reset_consumed_queues(const WavefrontState& W) {
     Counters* c = W.counters;
     c->n_extend[W.parity] = 0;
+    c->walk_cursor = 0;
     for (int k = 0; k < SC_COUNT; k++) c->n_shade[k] = 0;
 }
 __global__ void k_step(WavefrontState W) { reset_consumed_queues(W); }
@@ -372,7 +373,8 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
         if (hit) {
             if (MEDIA && (prim & MEDIUM_INCUMBENT)) {  // the scatter point kept its place
                 kind = HIT_MEDIUM, prim &= ~MEDIUM_INCUMBENT;
-                c = SC_ISOTROPIC;  // the phase function of a ConstantMedium is an Isotropic (validated by the scene compiler)
+                // the phase function of a ConstantMedium is an Isotropic (validated by the scene compiler)
+                c = (sv.media[prim].flags & MEDIUM_THICK) ? SC_WALK : SC_ISOTROPIC;
             } else {
                 kind = HIT_SURFACE;
                 c = (prim_meta >> META_CLASS_SHIFT) & 15u;  // PrimMeta::kind_mat of the winner, kept by the traversal
@@ -408,13 +410,19 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
 
 // ConstantMedium::hit of every medium against the hit known so far (t, prim, kind; kind == HIT_MISS: none): the nearest scatter
 // point replaces it when it wins (nearer, or an exact tie with the lower rank).  Returns whether it did.
-template <bool COUNT, bool GENERIC, bool XF>
+// `first`: the medium tried first (the winner is the minimum of (t, rank) and does not depend on the order; the one the path
+// is most likely to scatter in goes first so that its scatter point screens the others).  FILTER: 0 = every medium,
+// 1 = only MEDIUM_THICK ones, 2 = only the others (k_walk asks in two steps and shares the draws between them).
+template <bool COUNT, bool GENERIC, bool XF, int FILTER = 0>
 __device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed, const RayD& r, uint32_t pixel, uint32_t sample, uint32_t segment, double& t,
-                                             uint32_t& prim, uint32_t& kind, const float4* s_mem, uint32_t* stack, int stride, TraceCounters* cntp) {
-    uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : 0xFFFFFFFFu;
+                                             uint32_t& prim, uint32_t& kind, const float4* s_mem, uint32_t* stack, int stride, TraceCounters* cntp,
+                                             uint32_t first, MediumDraws& draws) {
+    uint32_t rank = kind == HIT_SURFACE ? sv.meta[prim].rank : (kind == HIT_MEDIUM ? sv.media[prim].rank : 0xFFFFFFFFu);
     bool changed = false;
-    MediumDraws draws;
-        for (uint32_t m = 0; m < sv.n_media; m++) {
+        for (uint32_t k = 0; k < sv.n_media; k++) {
+            uint32_t m = first + k;
+            if (m >= sv.n_media) m -= sv.n_media;
+            if (FILTER && ((sv.media[m].flags & MEDIUM_THICK) != 0u) != (FILTER == 1)) continue;
             const Medium& med = sv.media[m];
             const double xi = draws.get(seed, pixel, sample, segment, med.medium_index);
             double tm;
@@ -456,6 +464,13 @@ __device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed,
             }
         }
     return changed;
+}
+
+template <bool COUNT, bool GENERIC, bool XF>
+__device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed, const RayD& r, uint32_t pixel, uint32_t sample, uint32_t segment, double& t,
+                                             uint32_t& prim, uint32_t& kind, const float4* s_mem, uint32_t* stack, int stride, TraceCounters* cntp) {
+    MediumDraws draws;
+    return sample_media<COUNT, GENERIC, XF, 0>(sv, seed, r, pixel, sample, segment, t, prim, kind, s_mem, stack, stride, cntp, 0u, draws);
 }
 
 // Media pass AFTER extend (the order of Hittables::hit): ConstantMedium::hit for every medium (volume.rs:37-73)
@@ -503,7 +518,9 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
         const bool changed = sample_media<COUNT, GENERIC, XF>(sv, P.seed, r, pixel, sample, segment, t, prim, kind, s_mem, stack, MEDIA_BLOCK, &cnt);
         if (PRE || changed) *reinterpret_cast<double2*>(W.hit_q + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
         if (PRE) continue;  // extend writes the class bytes
-        uint32_t c = kind == HIT_MISS ? (uint32_t)SC_MISS : (kind == HIT_MEDIUM ? (uint32_t)SC_ISOTROPIC : ((surface_meta >> META_CLASS_SHIFT) & 15u));
+        uint32_t c = kind == HIT_MISS     ? (uint32_t)SC_MISS
+                     : kind == HIT_MEDIUM ? ((sv.media[prim].flags & MEDIUM_THICK) ? (uint32_t)SC_WALK : (uint32_t)SC_ISOTROPIC)
+                                          : ((surface_meta >> META_CLASS_SHIFT) & 15u);
         if (!P.bin_by_class && c != SC_MISS) c = SC_DIFFUSE;
         W.cls_q[j] = (uint8_t)c;
     }
@@ -854,6 +871,145 @@ __global__ void __launch_bounds__(SHADE_BLOCK, ((RT_SHADE_3BLOCK_MASK >> CLS) & 
 }
 
 // ------------------------------------------------------------------------------------------
+// random walk inside an optically thick medium
+// ------------------------------------------------------------------------------------------
+// A path that scatters inside a dense ConstantMedium (book2's blue subsurface sphere: mean free path 5 in a sphere of radius 70)
+// scatters there again and again until max_depth ends it: on book2_final a third of ALL segments are such scatter points, and
+// each went through the sampling pass, extend, the binning and the isotropic shade kernel - four trips through HBM and a
+// traversal at extend's 15 active lanes for a segment that is a few units long.  k_walk takes the queue of scatter points inside
+// MEDIUM_THICK media and keeps every path in registers from one scatter point to the next: Isotropic::scatter + the mixture pdf
+// (the SC_ISOTROPIC code of shade_one), then world.hit of the NEXT segment in place - the free-flight draw of every medium
+// (volume.rs:37-73, the medium the path is in first, so that its scatter point screens the others) and a traversal bounded by
+// the nearest scatter point, with the tie rule of the wavefront (a surface wins with a smaller t, or the same t and a lower
+// rank).  While a thick medium wins again the loop goes on; otherwise the new ray is appended to the ray stream like any
+// survivor of a shade kernel and the wavefront evaluates that segment itself (one look-ahead per walk is computed twice).
+// Every draw is addressed by (pixel, sample, segment, slot), so the radiance is the very sum the wavefront alone produces.
+// A lane whose walk ends takes the next queue entry at once (static striding, no atomics): the loop body is the same for every
+// lane, so the warp stays converged however long the individual walks are.
+#ifndef RT_WALK_BLOCK
+#define RT_WALK_BLOCK 128
+#endif
+constexpr int WALK_BLOCK = RT_WALK_BLOCK;
+#ifndef RT_WALK_MIN_BLOCKS
+#define RT_WALK_MIN_BLOCKS 4
+#endif
+template <bool XF>
+__global__ void __launch_bounds__(WALK_BLOCK, RT_WALK_MIN_BLOCKS) k_walk(SceneView sv, RenderParams P, WavefrontState W) {
+    extern __shared__ float4 s_mem[];  // traversal stacks (global-memory nodes only)
+    uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
+    const uint32_t n = W.counters->n_shade[SC_WALK];
+    const RayRec* __restrict__ rays = W.ray_q[W.parity];
+    const BetaRec* __restrict__ betas = W.beta_q[W.parity];
+    const uint32_t* __restrict__ queue = W.q_shade[SC_WALK];
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xFFFFFFFFu, lt_mask = (1u << lane) - 1u;
+    TraceCounters cnt{0, 0};
+    unsigned long long walked = 0;
+    bool have = false;
+    RayD r;
+    D3 beta;
+    uint32_t pixel = 0, sidx = 0, segment = 0, medium = 0;
+    double t = 0.0;
+    // queue entries are claimed 32 at a time per warp (one atomic, records prefetched) and handed to the lanes as their walks end
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
+    bool exhausted = false;                // warp-uniform: the cursor ran past the queue
+    while (true) {
+        unsigned need = __ballot_sync(FULL, !have);
+        while (need && !(exhausted && pool_next == pool_end)) {
+            if (pool_next == pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&W.counters->walk_cursor, 32u);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) {
+                    exhausted = true;
+                    break;
+                }
+                pool_next = base, pool_end = min(base + 32u, n);
+                if (base + lane < pool_end) {
+                    const uint32_t pos = queue[base + lane];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + pos));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(betas + pos));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(W.hit_q + pos));
+                }
+            }
+            const uint32_t take = min((uint32_t)__popc(need), pool_end - pool_next);
+            const uint32_t my = __popc(need & lt_mask);
+            if (!have && my < take) {
+                const uint32_t pos = queue[pool_next + my];
+                uint64_t ids64;
+                load_ray(rays + pos, r, ids64);
+                unpack_ids(ids64, pixel, sidx, segment);
+                const double2* sp2 = reinterpret_cast<const double2*>(betas + pos);
+                const double2 b0 = sp2[0], b1 = sp2[1];
+                beta = D3{b0.x, b0.y, b1.x};
+                const double2 hw = *reinterpret_cast<const double2*>(W.hit_q + pos);
+                t = hw.x;
+                medium = (uint32_t)__double2hiint(hw.y);
+                have = true;
+            }
+            pool_next += take;
+            need = __ballot_sync(FULL, !have);
+        }
+        if (need == FULL) break;  // nothing left to claim and every walk of the warp has ended
+        if (have) {
+            RayD nr;
+            D3 nbeta;
+            if (!shade_one<SC_ISOTROPIC>(sv, P, W, r, beta, pixel, sidx, segment, t, medium, HIT_MEDIUM, nr, nbeta)) {
+                have = false;
+            } else {
+                // world.hit of the next segment: the thick media first (the one the path is in leads); when none of them scatters
+                // the walk is over whatever the thin ones do, otherwise they are screened by the scatter point found
+                double tn = INFINITY;
+                uint32_t pn = 0xFFFFFFFFu, kn = HIT_MISS;
+                MediumDraws draws;
+                sample_media<false, false, XF, 1>(sv, P.seed, nr, pixel, sidx, segment + 1u, tn, pn, kn, s_mem, stack, WALK_BLOCK, &cnt, medium, draws);
+                bool stay = kn == HIT_MEDIUM;
+                if (stay) {
+                    sample_media<false, false, XF, 2>(sv, P.seed, nr, pixel, sidx, segment + 1u, tn, pn, kn, s_mem, stack, WALK_BLOCK, &cnt, 0u, draws);
+                    stay = (sv.media[pn].flags & MEDIUM_THICK) != 0u;
+                }
+                if (stay) {
+                    const Medium& mn = sv.media[pn];
+                    const uint32_t med_rank = mn.rank;
+                    double ts;
+                    uint32_t ps;
+                    if (pn == medium && mn.n_entry != MEDIUM_NO_ENTRIES) {
+                        // both ends of the segment lie inside the same boundary: only the world leaves that overlap it can be met
+                        for (uint32_t e = 0; e < mn.n_entry && stay; e++)
+                            if (closest_hit<false, true>(sv, mn.entry[e], nr, 1e-8, tn, s_mem, stack, WALK_BLOCK, ts, ps, &cnt))
+                                stay = !(ts < tn || sv.meta[ps].rank < med_rank);  // ts <= tn here
+                    } else if (closest_hit<false, true>(sv, sv.world_root, nr, 1e-8, tn, s_mem, stack, WALK_BLOCK, ts, ps, &cnt)) {
+                        stay = !(ts < tn || sv.meta[ps].rank < med_rank);
+                    }
+                }
+                if (stay) {
+                    r = nr, beta = nbeta, segment++, t = tn, medium = pn;
+                    walked++;
+                } else {
+                    const uint32_t npos = queue_reserve(&W.counters->n_extend[W.parity ^ 1u], 0);
+                    store_ray(W.ray_q[W.parity ^ 1u] + npos, nr, pack_ids(pixel, sidx, segment + 1u));
+                    store_beta(W.beta_q[W.parity ^ 1u] + npos, nbeta);
+                    have = false;
+                }
+            }
+        }
+    }
+    if (walked) {
+        atomicAdd(&W.counters->segments, walked);
+        atomicAdd(&W.counters->walk_segments, walked);
+    }
+}
+static void launch_walk(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
+    SceneView wv = sv;
+    wv.n_cached_nodes = 0;  // the non-persistent closest_hit() reads the binary tree from global memory
+    const size_t smem = (size_t)std::max(sv.tail_stack_entries, 4u) * WALK_BLOCK * sizeof(uint32_t);
+    if (sv.media_xform)
+        k_walk<true><<<grid, WALK_BLOCK, smem, s>>>(wv, P, W);
+    else
+        k_walk<false><<<grid, WALK_BLOCK, smem, s>>>(wv, P, W);
+}
+
+// ------------------------------------------------------------------------------------------
 // tail: the last few thousand paths of a frame, traced to completion by one launch
 // ------------------------------------------------------------------------------------------
 // Once every camera path has been generated the wavefront only drains: depth-40 stragglers keep it alive for dozens of
@@ -1042,7 +1198,7 @@ static void launch_shade_cls(const SceneView& sv, const RenderParams& P, const W
 // The class kernels are independent (own queue each, atomics on the shared outputs): with `fan` they are dealt
 // over side streams between a fork and a join event so that the tail of one overlaps the start of the next.
 int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
-                 const ShadeFan* fan, bool tail_follows) {
+                 const ShadeFan* fan, bool tail_follows, int walk_grid) {
     int launches = tail_follows ? 1 : 2;  // the miss kernel (and k_step)
     if (!P.bin_by_class) {  // everything but misses sits in the SC_DIFFUSE queue: general kernel
         launch_shade_cls<SC_MISS>(sv, P, W, SC_MISS, grid, s);
@@ -1059,6 +1215,8 @@ int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontStat
             const int k = next++ % (n_side + 1);
             return k == 0 ? s : fan->side[k - 1];
         };
+        // the random walk runs longest (one launch takes its paths through dozens of segments): start it first
+        if (class_mask & (1u << SC_WALK)) launch_walk(sv, P, W, walk_grid, lane()), launches++;
         // the classes that usually hold most hits first, so they start on different streams
         if (class_mask & (1u << SC_DIFFUSE)) launch_shade_cls<SC_DIFFUSE>(sv, P, W, SC_DIFFUSE, grid, lane()), launches++;
         if (class_mask & (1u << SC_ISOTROPIC)) launch_shade_cls<SC_ISOTROPIC>(sv, P, W, SC_ISOTROPIC, grid, lane()), launches++;
@@ -1081,7 +1239,7 @@ void launch_finalize(const double* accum, uint64_t n, double scale, void* out, b
     k_finalize<<<grid, 256, 0, s>>>(accum, n, scale, out, out_f64 ? 1 : 0);
 }
 
-int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm) {
+int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm, int* walk_blocks_per_sm) {
     // dynamic shared memory above 48 KB is opt-in
     cudaError_t e = cudaSuccess;
     const void* big_smem[] = {
@@ -1096,12 +1254,15 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB
     if ((e = cudaFuncSetAttribute((const void*)k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * TAIL_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
+    for (const void* f : {(const void*)k_walk<false>, (const void*)k_walk<true>})
+        if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * WALK_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
     const void* media_smem[] = {(const void*)k_media<false, 2, false, false>, (const void*)k_media<false, 2, true, false>,
                                 (const void*)k_media<true, 2, false, false>, (const void*)k_media<true, 2, true, false>};
     for (const void* f : media_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * MEDIA_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false, 0>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_OTHER>, SHADE_BLOCK, 0);  // a class never compiled for three
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(walk_blocks_per_sm, k_walk<true>, WALK_BLOCK, 24 * WALK_BLOCK * sizeof(uint32_t));
     return 0;
 }
 

@@ -94,8 +94,9 @@ struct Counters {
     uint32_t n_extend[2];  // entries in ray_q/state_q of each parity
     uint32_t n_shade[SC_COUNT];
     uint32_t n_pixels, pad;  // pad: arrival counter of k_tail's CTAs
-    uint32_t gen_done, pad2;  // arrival counter of k_generate's CTAs
+    uint32_t gen_done, walk_cursor;  // arrival counter of k_generate's CTAs; next entry of the SC_WALK queue to be claimed (k_walk)
     unsigned long long next_path, segments, iterations, errors, node_visits, prim_tests;
+    unsigned long long walk_segments;  // of `segments`: evaluated inside k_walk (they never went through the streams)
 };
 
 struct WavefrontState {
@@ -135,7 +136,7 @@ struct ShadeFan {  // side streams for the per-class shade kernels (owned by the
     cudaEvent_t fork = nullptr, join[3] = {};
 };
 int launch_shade(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t class_mask, int grid, cudaStream_t s,
-                 const ShadeFan* fan, bool tail_follows);
+                 const ShadeFan* fan, bool tail_follows, int walk_grid);
 // partial framebuffers of a multi-GPU render, as GPU 0 sees them (peer-mapped pointers for the other GPUs)
 constexpr uint32_t MAX_PARTS = 16;
 struct PartList {
@@ -148,6 +149,6 @@ void launch_sum_parts(const PartList& parts, void* out, uint64_t n_values, bool 
 void launch_tail(const SceneView& sv, const RenderParams& P, const WavefrontState& W, uint32_t threshold, int grid, cudaStream_t s);
 void launch_finalize(const double* accum, uint64_t n, double scale, void* out, bool out_f64, int grid, cudaStream_t s);
 void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t toon_map, uint8_t* rgb, int* error_flag, cudaStream_t s);
-int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm);
+int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks_per_sm, int* walk_blocks_per_sm);
 
 }  // namespace rt

@@ -101,6 +101,7 @@ struct Perlin {
     uint32_t perm_x[256], perm_y[256], perm_z[256];
 };
 
+constexpr uint32_t MEDIUM_MAX_ENTRIES = 6, MEDIUM_NO_ENTRIES = 0xFFFFFFFFu;
 struct Medium {
     uint32_t root;      // boundary group root reference
     uint32_t material;  // its Isotropic
@@ -110,8 +111,18 @@ struct Medium {
     uint32_t xform;     // Transform chain above the medium (ray_length is local, volume.rs:55) or RT_NONE
     uint32_t medium_index;
     uint32_t single_sphere;  // primitive index when the boundary is exactly one Sphere, else RT_NONE
+    uint32_t flags;          // MEDIUM_THICK
+    // MEDIUM_THICK: every world primitive that can be met by a segment lying inside the boundary sits in one of these
+    // leaves of the world tree (leaf references; found by the scene compiler with a box-overlap walk).  n_entry ==
+    // MEDIUM_NO_ENTRIES: too many, traverse from the world root.
+    uint32_t n_entry;
+    uint32_t entry[MEDIUM_MAX_ENTRIES];
     uint32_t pad;
 };
+// An optically thick medium (boundary radius x density >= 1, every boundary of the scene a single Sphere): a path that
+// scatters inside most likely scatters there again, so its scatter points go to the random-walk kernel (k_walk), which
+// keeps the path in registers from one scatter point to the next instead of sending it through the streams.
+constexpr uint32_t MEDIUM_THICK = 1u;
 
 // One leaf of the lights tree (hits.rs:52-75), geometry in the local space of its Transform chain
 struct Light {
@@ -132,7 +143,8 @@ enum ShadeClass : uint32_t {
     SC_EMISSIVE = 6,  // DiffuseLight without inner material: path ends
     SC_DISNEY = 7,    // Disney BSDF, bare or below the OBJ loader's RemappedMaterial / DiffuseLight wrappers
     SC_OTHER = 8,     // Mix, Portal, Transparent, DiffuseLight with inner, anything nested
-    SC_COUNT = 9
+    SC_WALK = 9,      // scatter point inside an optically thick ConstantMedium (MEDIUM_THICK): k_walk
+    SC_COUNT = 10
 };
 
 struct SceneView {

@@ -70,6 +70,11 @@ class rt_stats(C.Structure):
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
+    @property
+    def walk_segments(self):
+        """of `segments`: evaluated inside the random-walk kernel of an optically thick medium (rt2025.h, reserved[0])"""
+        return int(self.reserved[0])
+
 
 class rt_scene_info(C.Structure):
     _fields_ = [

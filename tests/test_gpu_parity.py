@@ -301,6 +301,57 @@ def test_media_order_does_not_change_the_image(gpu, rt, orc):
     assert sa.segments == sc_.segments
 
 
+def _walk_scene(rt, variant):
+    """An optically thick medium (radius x density >= 1) whose scatter points go to the random-walk kernel."""
+    b = rt.Builder(11)
+    floor = b.quad([-6, -1.5, -6], [12, 0, 0], [0, 0, 12], b.lambertian(b.solid(0.6, 0.6, 0.6)))
+    lamp = b.quad([-1.5, 4, -1.5], [3, 0, 0], [0, 0, 3], b.diffuse_light(b.solid(12, 12, 12)))
+    lights = b.list([b.quad([-1.5, 4, -1.5], [3, 0, 0], [0, 0, 3], b.empty())])
+    things = [floor, lamp]
+    if variant == "surfaces_inside":  # a metal ball and a quad INSIDE the boundary: the walk must see them (entry leaves)
+        things += [b.medium(b.sphere([0, 0, 0], 1.2, b.empty()), 4.0, b.solid(0.3, 0.5, 0.9)),
+                   b.sphere([0.3, 0.1, 0.0], 0.35, b.metal([0.9, 0.8, 0.7], 0.05)),
+                   b.quad([-0.9, -0.4, -0.5], [0.6, 0, 0], [0, 0.5, 0.3], b.lambertian(b.solid(0.8, 0.2, 0.2))),
+                   b.sphere([0, 0, 0], 1.2, b.dielectric(b.solid(1, 1, 1), 1.5))]
+    elif variant == "overlapping":  # two thick media that overlap, and a thin fog around everything
+        things += [b.medium(b.sphere([-0.5, 0, 0], 1.0, b.empty()), 3.0, b.solid(0.9, 0.4, 0.3)),
+                   b.medium(b.sphere([0.5, 0, 0], 1.0, b.empty()), 5.0, b.solid(0.3, 0.9, 0.4)),
+                   b.medium(b.sphere([0, 0, 0], 40.0, b.empty()), 0.01, b.solid(1, 1, 1))]
+    elif variant == "many_neighbours":  # more overlapping leaves than entry slots: traversal from the world root
+        things += [b.medium(b.sphere([0, 0, 0], 1.2, b.empty()), 4.0, b.solid(0.3, 0.5, 0.9))]
+        for k in range(24):
+            things.append(b.sphere([0.8 * np.cos(k), 0.5 * np.sin(2.0 * k), 0.8 * np.sin(k)], 0.12, b.lambertian(b.solid(0.2 + 0.03 * k, 0.5, 0.5))))
+    else:  # "moving_transformed": a moving boundary below a rotated, scaled Transform
+        things += [b.transform(b.medium(b.sphere_moving([0, 0, 0], [0.3, 0.1, 0], 1.0, b.empty()), 3.0, b.solid(0.7, 0.7, 0.2)),
+                               offset=[0.2, 0, 0], quat=b.quat_axis_angle([0, 1, 1], 25.0), scale=[1.2, 1.2, 1.2]),
+                   b.sphere([0.2, 0, 0], 0.3, b.lambertian(b.solid(0.2, 0.8, 0.8)))]
+    return b.finish(b.list(things), lights, width=40, spp=16, max_depth=24, vfov=35, look_from=(0, 1.5, 6), background=b.solid(0.5, 0.6, 0.8))
+
+
+@pytest.mark.parametrize("variant", ["surfaces_inside", "overlapping", "many_neighbours", "moving_transformed"])
+def test_random_walk_kernel_vs_wavefront_and_oracle(gpu, rt, orc, variant, monkeypatch):
+    """k_walk keeps a path inside an optically thick medium in registers from scatter point to scatter point.  The draws are
+    addressed, so the image, the segment count and the error count must be those of the plain wavefront (walk switched
+    off), with and without the entry-leaf shortcut, and the image must match the oracle."""
+    hs = _walk_scene(rt, variant)
+    sc = rt.Scene(hs)
+    a, sa = sc.render(seed=9)
+    assert sa.walk_segments > 0
+    monkeypatch.setenv("RT2025_WALK_NO_ENTRIES", "1")
+    b_, sb = rt.Scene(hs).render(seed=9)
+    monkeypatch.delenv("RT2025_WALK_NO_ENTRIES")
+    monkeypatch.setenv("RT2025_WALK_MIN_DEPTH", "0")
+    c, sc_ = rt.Scene(hs).render(seed=9)
+    monkeypatch.delenv("RT2025_WALK_MIN_DEPTH")
+    assert sc_.walk_segments == 0 and sb.walk_segments == sa.walk_segments
+    assert sa.segments == sb.segments == sc_.segments and sa.errors == sb.errors == sc_.errors
+    assert sc_.iterations >= sa.iterations
+    image_close(a, c, frac_bad=0.0, rel=1e-9)
+    image_close(b_, c, frac_bad=0.0, rel=1e-9)
+    ref, ost = orc.OracleScene(hs).render(seed=9)
+    image_close(a, ref)
+
+
 def test_binning_does_not_change_the_image(gpu, rt):
     import ctypes as C
     hs = rt.named_scene("book2_final", seed=5, params=[64, 4, 20])
