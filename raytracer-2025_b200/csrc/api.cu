@@ -405,6 +405,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;
         if (s->shade_blocks_per_sm < 1) s->shade_blocks_per_sm = 1;
         if (s->walk_blocks_per_sm < 1) s->walk_blocks_per_sm = 1;
+        if (const char* e = getenv("RT2025_WALK_BLOCKS")) s->walk_blocks_per_sm = std::max(1, std::min(s->walk_blocks_per_sm, atoi(e)));  // tuning knob
         CU(cudaDeviceSynchronize());
         *out = s;
         return RT_OK;
@@ -645,7 +646,10 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         // inside extend the same binary64 code runs at 16 warps per SM - so the pass is the default; RT2025_MEDIA_FIRST=0/1/2.
         if (const char* e = getenv("RT2025_MEDIA_FIRST")) P.media_first = (s->view.n_media > 0 && !s->generic_media) ? (uint32_t)std::max(0, std::min(2, atoi(e))) : 0u;
 
+        P.sample_in_generate = 1;
+        if (const char* e = getenv("RT2025_GEN_MEDIA")) P.sample_in_generate = atoi(e) != 0;  // tuning knob
         const bool count = (o.flags & RT_OPT_COUNT) != 0, stage = (o.flags & RT_OPT_STAGE_TIMES) != 0;
+        if (count) P.sample_in_generate = 0;  // the counting instantiation of the sampling pass sees every segment
         const int grid_e = s->sm_count * s->extend_blocks_per_sm, grid_s = s->sm_count * s->shade_blocks_per_sm;
         const int grid_g = s->sm_count * 4;
         const int grid_m = s->sm_count * 8;
@@ -670,7 +674,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
                     // stage times: events are only recorded here and read after the render, so the
                     // measurement does not add a host synchronisation to the timed region
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 0), st));
-                    launch_generate(P, W, grid_g, st);
+                    launch_generate(s->view, P, W, grid_g, st);
                     if (stage) CU(cudaEventRecord(ws.event(6 * iters + 1), st));
                     // media_first 1: a sampling pass ahead of extend leaves the nearest scatter point as the incumbent; 2: extend
                     // samples the sphere-bounded media itself; 0: the media pass runs between extend and the binning

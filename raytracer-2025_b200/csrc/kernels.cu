@@ -202,58 +202,6 @@ __global__ void k_pixel_list(uint32_t W, uint32_t H, uint32_t part_index, uint32
     }
 }
 
-// Camera::get_ray, camera.rs:247-273: tops the current ray stream up to capacity with camera rays
-__global__ void __launch_bounds__(256) k_generate(RenderParams P, WavefrontState W) {
-    const uint64_t remaining = W.total_paths - W.counters->next_path;
-    const uint32_t extend_base = W.counters->n_extend[W.parity];
-    const uint32_t room = W.capacity - extend_base;
-    const uint32_t n_new = (uint32_t)(remaining < (uint64_t)room ? remaining : (uint64_t)room);
-    const uint64_t first = W.counters->next_path;
-    const rt_camera& cam = P.cam;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
-        uint64_t g = first + j;
-        uint32_t sidx = P.sample_begin + (uint32_t)(g / W.n_pixels);
-        uint32_t pixel = W.pixel_list[g % W.n_pixels];
-        uint32_t i = pixel % cam.image_width, jj = pixel / cam.image_width;
-        uint32_t s_i = sidx / cam.sqrt_spp, s_j = sidx % cam.sqrt_spp;
-        Rand2 jit = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_JITTER);
-        double px = (((double)s_i + jit.a) * cam.recip_sqrt_spp) - 0.5;
-        double py = (((double)s_j + jit.b) * cam.recip_sqrt_spp) - 0.5;
-        D3 pixel_sample = ld3(cam.pixel00_loc) + (((double)i + px) * ld3(cam.pixel_delta_u)) + (((double)jj + py) * ld3(cam.pixel_delta_v));
-        RayD r;
-        if (cam.defocus_angle_in_degrees <= 0.0) {
-            r.o = ld3(cam.center);
-        } else {  // defocus_disk_sample, vec3.rs:63-69
-            Rand2 dk = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_DISK);
-            double theta = (2.0 * RT_PI) * dk.a;
-            double rr = sqrt(dk.b);
-            double s, c;
-            sincos(theta, &s, &c);
-            double p0 = rr * c, p1 = rr * s;
-            r.o = ld3(cam.center) + (p0 * ld3(cam.defocus_disk_u)) + (p1 * ld3(cam.defocus_disk_v));
-        }
-        r.d = pixel_sample - r.o;
-        r.time = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_TIME).a;
-        store_ray(W.ray_q[W.parity] + extend_base + j, r, pack_ids(pixel, sidx, 0u));
-        store_beta(W.beta_q[W.parity] + extend_base + j, D3{1.0, 1.0, 1.0});
-    }
-    // Bookkeeping of the stage (it used to be a launch of its own): every block read the counters above before it got here,
-    // so the LAST block to arrive may advance them - the next kernel of the stream sees the topped-up queue length.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Counters* c = W.counters;
-        __threadfence();
-        if (atomicAdd(&c->gen_done, 1u) == gridDim.x - 1u) {
-            c->gen_done = 0;
-            c->next_path += n_new;
-            c->n_extend[W.parity] = extend_base + n_new;
-            c->segments += extend_base + n_new;
-            c->iterations += (extend_base + n_new > 0);
-            __threadfence();
-        }
-    }
-}
-
 // after shade the current stream is consumed: its length and the class queues are reset (one thread)
 __device__ __forceinline__ void reset_consumed_queues(const WavefrontState& W) {
     Counters* c = W.counters;
@@ -473,6 +421,71 @@ __device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed,
     return sample_media<COUNT, GENERIC, XF, 0>(sv, seed, r, pixel, sample, segment, t, prim, kind, s_mem, stack, stride, cntp, 0u, draws);
 }
 
+// Camera::get_ray, camera.rs:247-273: tops the current ray stream up to capacity with camera rays
+// MEDIA: the scene's media all have sphere boundaries and are sampled ahead of extend (RenderParams::media_first == 1): the
+// free-flight draws of segment 0 are taken here, while the ray is in registers, and the nearest scatter point goes to the hit
+// stream as extend's incumbent - the sampling pass then only reads the survivors of the last shade stage (a camera ray is a
+// quarter to a third of all segments, and this kernel is bound by its stores).  XF as in k_media.
+template <bool MEDIA, bool XF>
+__global__ void __launch_bounds__(256) k_generate(SceneView sv, RenderParams P, WavefrontState W) {
+    const uint64_t remaining = W.total_paths - W.counters->next_path;
+    const uint32_t extend_base = W.counters->n_extend[W.parity];
+    const uint32_t room = W.capacity - extend_base;
+    const uint32_t n_new = (uint32_t)(remaining < (uint64_t)room ? remaining : (uint64_t)room);
+    const uint64_t first = W.counters->next_path;
+    const rt_camera& cam = P.cam;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_new; j += gridDim.x * blockDim.x) {
+        uint64_t g = first + j;
+        uint32_t sidx = P.sample_begin + (uint32_t)(g / W.n_pixels);
+        uint32_t pixel = W.pixel_list[g % W.n_pixels];
+        uint32_t i = pixel % cam.image_width, jj = pixel / cam.image_width;
+        uint32_t s_i = sidx / cam.sqrt_spp, s_j = sidx % cam.sqrt_spp;
+        Rand2 jit = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_JITTER);
+        double px = (((double)s_i + jit.a) * cam.recip_sqrt_spp) - 0.5;
+        double py = (((double)s_j + jit.b) * cam.recip_sqrt_spp) - 0.5;
+        D3 pixel_sample = ld3(cam.pixel00_loc) + (((double)i + px) * ld3(cam.pixel_delta_u)) + (((double)jj + py) * ld3(cam.pixel_delta_v));
+        RayD r;
+        if (cam.defocus_angle_in_degrees <= 0.0) {
+            r.o = ld3(cam.center);
+        } else {  // defocus_disk_sample, vec3.rs:63-69
+            Rand2 dk = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_DISK);
+            double theta = (2.0 * RT_PI) * dk.a;
+            double rr = sqrt(dk.b);
+            double s, c;
+            sincos(theta, &s, &c);
+            double p0 = rr * c, p1 = rr * s;
+            r.o = ld3(cam.center) + (p0 * ld3(cam.defocus_disk_u)) + (p1 * ld3(cam.defocus_disk_v));
+        }
+        r.d = pixel_sample - r.o;
+        r.time = philox_pair(P.seed, pixel, sidx, 0, RT_SLOT_CAM_TIME).a;
+        store_ray(W.ray_q[W.parity] + extend_base + j, r, pack_ids(pixel, sidx, 0u));
+        store_beta(W.beta_q[W.parity] + extend_base + j, D3{1.0, 1.0, 1.0});
+        if (MEDIA) {
+            double t = INFINITY;
+            uint32_t prim = 0xFFFFFFFFu, kind = HIT_MISS;
+            TraceCounters cnt{0, 0};
+            sample_media<false, false, XF>(sv, P.seed, r, pixel, sidx, 0u, t, prim, kind, nullptr, nullptr, 0, &cnt);
+            *reinterpret_cast<double2*>(W.hit_q + extend_base + j) = make_double2(t, __hiloint2double((int)prim, (int)kind));
+        }
+    }
+    // Bookkeeping of the stage (it used to be a launch of its own): every block read the counters above before it got here,
+    // so the LAST block to arrive may advance them - the next kernel of the stream sees the topped-up queue length.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Counters* c = W.counters;
+        __threadfence();
+        if (atomicAdd(&c->gen_done, 1u) == gridDim.x - 1u) {
+            c->gen_done = 0;
+            c->next_path += n_new;
+            c->n_extend[W.parity] = extend_base + n_new;
+            c->n_unsampled = MEDIA ? extend_base : extend_base + n_new;
+            c->segments += extend_base + n_new;
+            c->iterations += (extend_base + n_new > 0);
+            __threadfence();
+        }
+    }
+}
+
 // Media pass AFTER extend (the order of Hittables::hit): ConstantMedium::hit for every medium (volume.rs:37-73)
 // against the surface hit k_extend found, one thread per extend-queue entry.  Used when some boundary is not a
 // single Sphere (GENERIC: the boundary needs a BVH traversal per lane, kept out of the common instantiation because
@@ -490,7 +503,7 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
     extern __shared__ float4 s_mem[];  // traversal stacks for boundaries that are not a single sphere
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
     TraceCounters cnt{0, 0};
-    const uint32_t n = W.counters->n_extend[W.parity];
+    const uint32_t n = PRE ? W.counters->n_unsampled : W.counters->n_extend[W.parity];
     const uint32_t n_round = (n + 31u) & ~31u;  // whole warps iterate together
     const RayRec* __restrict__ rays = W.ray_q[W.parity];
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
@@ -1145,8 +1158,11 @@ void launch_tonemap(const void* accum, bool f64, uint64_t n_pixels, uint32_t too
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s) {
     k_pixel_list<<<grid, 256, 0, s>>>(P.cam.image_width, P.cam.image_height, P.part_index, P.part_count, W.pixel_list, &W.counters->n_pixels);
 }
-void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
-    k_generate<<<grid, 256, 0, s>>>(P, W);
+void launch_generate(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
+    if (P.media_first == 1 && sv.n_media && P.sample_in_generate)
+        sv.media_xform ? k_generate<true, true><<<grid, 256, 0, s>>>(sv, P, W) : k_generate<true, false><<<grid, 256, 0, s>>>(sv, P, W);
+    else
+        k_generate<false, false><<<grid, 256, 0, s>>>(sv, P, W);
 }
 template <int MEDIA>
 static void launch_extend_media(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {

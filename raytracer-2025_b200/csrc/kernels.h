@@ -27,6 +27,9 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_SLAB_SIGNSEL
 #define RT_SLAB_SIGNSEL 1  // slab test: near/far planes picked by the sign of 1/d, error bound folded into the addend
 #endif
+#ifndef RT_PARK_VOTE
+#define RT_PARK_VOTE 1  // postponed leaves: leave the node loop as soon as every lane of the warp holds a leaf (0: only at a second leaf)
+#endif
 #ifndef RT_LDG256
 #define RT_LDG256 1  // 256-bit global loads for nodes and primitive records
 #endif
@@ -94,6 +97,8 @@ struct Counters {
     uint32_t n_extend[2];  // entries in ray_q/state_q of each parity
     uint32_t n_shade[SC_COUNT];
     uint32_t n_pixels, pad;  // pad: arrival counter of k_tail's CTAs
+    uint32_t n_unsampled, pad3;  // entries [0, n_unsampled) of the current ray stream still need the media sampling pass (the camera
+                                 // rays behind them were sampled by k_generate while it had them in registers)
     uint32_t gen_done, walk_cursor;  // arrival counter of k_generate's CTAs; next entry of the SC_WALK queue to be claimed (k_walk)
     unsigned long long next_path, segments, iterations, errors, node_visits, prim_tests;
     unsigned long long walk_segments;  // of `segments`: evaluated inside k_walk (they never went through the streams)
@@ -118,6 +123,7 @@ struct RenderParams {
     uint64_t seed;
     uint32_t sample_begin, part_index, part_count;
     uint32_t lights_flat, bin_by_class;
+    uint32_t sample_in_generate;  // media_first == 1: k_generate samples the media for the camera rays it writes (A/B knob RT2025_GEN_MEDIA=0)
     uint32_t media_first;  // 0: media sampled after extend (order of Hittables::hit); 1: by a pass ahead of extend, 2: by extend itself while it
                            // prepares the ray - extend then only looks for surfaces up to the scatter point
 };
@@ -125,7 +131,7 @@ struct RenderParams {
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t smem_bytes, cudaStream_t stream);
 void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaStream_t s);
-void launch_generate(const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
+void launch_generate(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s);
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t smem_bytes, cudaStream_t s);
 // phase 0: media sampling after extend (classic order / general boundaries) + binning; phase 1: the sampling pass ahead of extend;
 // phase 2: binning only (extend wrote the class bytes)

@@ -645,7 +645,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                         parked = cur;
                         cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
                     }
+#if RT_PARK_VOTE
                     if (!__any_sync(__activemask(), parked == INVALID_REF)) break;
+#endif
                 } else if (cur & LEAF_FLAG) {  // plain while-while: leave the node loop with the leaf
                     parked = cur;
                     cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
