@@ -289,6 +289,17 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
             rc = check_device(opts ? opts->device : -1, device, sms);
             if (rc != RT_OK) return rc;
         }
+        {
+            // a small scene's four-wide collapse is only used when all of it fits in a traversal CTA's shared memory next to the
+            // stacks (compile.cpp); otherwise its binary tree is traversed, which then fits
+            const size_t budget = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024;
+            const size_t stacks = (size_t)std::min<uint32_t>(std::max(cs.bvh_depth + 2, 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK) * EXTEND_BLOCK * sizeof(uint32_t);
+            if (!cs.nodes4.empty() && cs.nodes.size() * sizeof(Node) <= 2 * budget && stacks + cs.nodes4.size() * sizeof(Node4) > budget &&
+                !getenv("RT2025_WIDE_BVH")) {
+                RawVec<Node4>().swap(cs.nodes4);
+                cs.world_root4 = INVALID_REF;
+            }
+        }
         s = new rt_scene();
         s->device = device;
         s->sm_count = sms;
@@ -389,17 +400,21 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // shared memory holds the tree instead).  Measured, extend ms per frame, direct vs FIFO: book2_final (3201 nodes)
         // 40.8 vs 45.9, book1_final 33.5 vs 34.8, cornell 29.0 vs 28.5; trees far beyond shared memory gain from the
         // per-lane refill: the 76 k-node mesh scene 69.6 (drained) vs 61.8, the 1 M soups +12..24 % in Mrays/s.
-        if (cs.nodes4.empty() && cs.nodes.size() * sizeof(Node) <= 2 * budget) v.fifo_slots = 0;
+        if (cs.nodes.size() * sizeof(Node) <= 2 * budget) v.fifo_slots = 0;
         if (const char* e = getenv("RT2025_FIFO_SLOTS")) v.fifo_slots = atoi(e) >= 64 ? 64u : (atoi(e) >= 32 ? 32u : 0u);  // tuning knob
         if (stack_bytes + fifo_bytes(v.fifo_slots) > budget) throw CudaFail{"traversal stacks and ray FIFOs do not fit in shared memory"};
         const size_t room = budget - stack_bytes - fifo_bytes(v.fifo_slots);
         size_t cache_bytes = room;
         if (const char* e = getenv("RT2025_SMEM_NODES_KB")) cache_bytes = std::min<size_t>(room, (size_t)atol(e) * 1024);  // tuning knob
-        v.n_cached_nodes = (uint32_t)std::min<size_t>(cs.nodes.size(), cache_bytes / sizeof(Node));
-        // the four-wide traversal never reads the binary nodes: staging them only takes the shared memory away from the L1
-        // (measured: synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s)
-        if (!cs.nodes4.empty() && !getenv("RT2025_SMEM_NODES_KB")) v.n_cached_nodes = 0;
-        s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (size_t)v.n_cached_nodes * sizeof(Node);
+        // the persistent traversal reads ONE tree: the four-wide collapse when there is one (n_cached_nodes then counts Node4)
+        const size_t node_size = cs.nodes4.empty() ? sizeof(Node) : sizeof(Node4);
+        const size_t tree_nodes = cs.nodes4.empty() ? cs.nodes.size() : cs.nodes4.size();
+        v.n_cached_nodes = (uint32_t)std::min<size_t>(tree_nodes, cache_bytes / node_size);
+        // A four-wide tree is only staged when ALL of it fits (RT2025_WIDE_BVH=1 on a book-sized scene): staging the top of a tree
+        // that lives in L2 takes the shared memory away from the L1 and buys nothing (measured with the binary top in round 2:
+        // synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s without it)
+        if (!cs.nodes4.empty() && v.n_cached_nodes < tree_nodes && !getenv("RT2025_SMEM_NODES_KB")) v.n_cached_nodes = 0;
+        s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (size_t)v.n_cached_nodes * node_size;
         if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm, &s->walk_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
         if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;

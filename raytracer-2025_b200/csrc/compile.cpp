@@ -827,7 +827,11 @@ struct Compiler {
         }
         // Scenes that cannot stay in the caches are traversed through a four-wide collapse of the world tree (half
         // the dependent node fetches); RT2025_WIDE_BVH=0/1 overrides the size rule (tests force it on small scenes).
-        bool wide = out.nodes.size() > 8192;  // book-sized trees stay binary: their top lives in shared memory (book2 extend 276 vs 299 ms; an 11.5 k-face mesh scene 477 vs 459 ms the other way)
+        // Small trees too, when the whole collapse fits in a traversal CTA's shared memory (api.cu checks, and falls back to the
+        // binary nodes, which then fit as well): half the node visits at shared-memory latency - cornell extend 28.7 -> 25.9 ms,
+        // book1 2.21 -> 2.03 ms.  In between (book2: 3201 nodes, the binary tree fills the shared memory) both are equal
+        // and the tree stays binary.
+        bool wide = out.nodes.size() > 8192 || out.nodes.size() * sizeof(Node) <= 170 * 1024;
         if (const char* e = getenv("RT2025_WIDE_BVH")) wide = atoi(e) != 0;
         // Renumber the nodes breadth first from the world root (then the media groups): any prefix of
         // the array is then the top of the tree, which the kernels stage in shared memory.  Skipped when the

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
-    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes);
+    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + (sv.nodes4 ? 8 : 4) * sv.n_cached_nodes);
     uint32_t* stack = stack_base + threadIdx.x;
     uint32_t* fifo = stack_base + sv.stack_entries * EXTEND_BLOCK + (threadIdx.x >> 5) * sv.fifo_slots * FIFO_SLOT_WORDS;
     if (threadIdx.x == 0) s_cursor = 0;
@@ -338,7 +338,7 @@ template <bool COUNT, bool PARK, bool WIDE, int MEDIA>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
-    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + 4 * sv.n_cached_nodes);
+    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + (sv.nodes4 ? 8 : 4) * sv.n_cached_nodes);
     uint32_t* stack = stack_base + threadIdx.x;
     uint32_t* fifo = stack_base + sv.stack_entries * EXTEND_BLOCK + (threadIdx.x >> 5) * sv.fifo_slots * FIFO_SLOT_WORDS;
     const uint32_t n = W.counters->n_extend[W.parity];
@@ -426,8 +426,11 @@ __device__ __forceinline__ bool sample_media(const SceneView& sv, uint64_t seed,
 // free-flight draws of segment 0 are taken here, while the ray is in registers, and the nearest scatter point goes to the hit
 // stream as extend's incumbent - the sampling pass then only reads the survivors of the last shade stage (a camera ray is a
 // quarter to a third of all segments, and this kernel is bound by its stores).  XF as in k_media.
+#ifndef RT_GEN_MEDIA_MIN_BLOCKS
+#define RT_GEN_MEDIA_MIN_BLOCKS 4
+#endif
 template <bool MEDIA, bool XF>
-__global__ void __launch_bounds__(256) k_generate(SceneView sv, RenderParams P, WavefrontState W) {
+__global__ void __launch_bounds__(256, MEDIA ? RT_GEN_MEDIA_MIN_BLOCKS : 4) k_generate(SceneView sv, RenderParams P, WavefrontState W) {
     const uint64_t remaining = W.total_paths - W.counters->next_path;
     const uint32_t extend_base = W.counters->n_extend[W.parity];
     const uint32_t room = W.capacity - extend_base;
@@ -1159,9 +1162,10 @@ void launch_init(const WavefrontState& W, const RenderParams& P, int grid, cudaS
     k_pixel_list<<<grid, 256, 0, s>>>(P.cam.image_width, P.cam.image_height, P.part_index, P.part_count, W.pixel_list, &W.counters->n_pixels);
 }
 void launch_generate(const SceneView& sv, const RenderParams& P, const WavefrontState& W, int grid, cudaStream_t s) {
-    if (P.media_first == 1 && sv.n_media && P.sample_in_generate)
+    if (P.media_first == 1 && sv.n_media && P.sample_in_generate) {
+        grid = grid / 4 * RT_GEN_MEDIA_MIN_BLOCKS;  // api.cu sizes the grid for four resident CTAs per SM
         sv.media_xform ? k_generate<true, true><<<grid, 256, 0, s>>>(sv, P, W) : k_generate<true, false><<<grid, 256, 0, s>>>(sv, P, W);
-    else
+    } else
         k_generate<false, false><<<grid, 256, 0, s>>>(sv, P, W);
 }
 template <int MEDIA>

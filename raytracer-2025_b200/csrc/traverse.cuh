@@ -251,7 +251,8 @@ struct TraceCounters {
 // is spent on the copy, and it overlaps with the rest of the CTA's prologue.
 __device__ __forceinline__ void stage_nodes(const SceneView& sv, float4* smem_nodes) {
     __shared__ alignas(8) unsigned long long s_bar;
-    const uint32_t bytes = sv.n_cached_nodes * (uint32_t)sizeof(Node);
+    // (the four-wide tree when the scene is traversed through it: n_cached_nodes then counts Node4)
+    const uint32_t bytes = sv.n_cached_nodes * (uint32_t)(sv.nodes4 ? sizeof(Node4) : sizeof(Node));
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -261,7 +262,7 @@ __device__ __forceinline__ void stage_nodes(const SceneView& sv, float4* smem_no
     if (bytes == 0) return;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        const char* src = reinterpret_cast<const char*>(sv.nodes);
+        const char* src = sv.nodes4 ? reinterpret_cast<const char*>(sv.nodes4) : reinterpret_cast<const char*>(sv.nodes);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_nodes);
         for (uint32_t off = 0; off < bytes; off += 32768u) {
             const uint32_t n = min(32768u, bytes - off);
@@ -573,12 +574,19 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
             // node phase: descend until this lane has parked a leaf and met another, or ran out
             while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
                 if (WIDE) {
-                    const float4* np = reinterpret_cast<const float4*>(sv.nodes4 + cur);
                     float4 a0, a1, a2, a3, a4, a5;
-                    ldg256(np, a0, a1);
-                    ldg256(np + 2, a2, a3);
-                    ldg256(np + 4, a4, a5);
-                    const uint4 cr = __ldg(reinterpret_cast<const uint4*>(np + 6));
+                    uint4 cr;
+                    if (cur < sv.n_cached_nodes) {  // top of the (or the whole) four-wide tree: shared memory
+                        const float4* np = smem_nodes + 8 * cur;
+                        a0 = np[0], a1 = np[1], a2 = np[2], a3 = np[3], a4 = np[4], a5 = np[5];
+                        cr = *reinterpret_cast<const uint4*>(np + 6);
+                    } else {
+                        const float4* np = reinterpret_cast<const float4*>(sv.nodes4 + cur);
+                        ldg256(np, a0, a1);
+                        ldg256(np + 2, a2, a3);
+                        ldg256(np + 4, a4, a5);
+                        cr = __ldg(reinterpret_cast<const uint4*>(np + 6));
+                    }
                     if (COUNT) cnt->nodes++;
                     const float l0[3] = {a0.x, a0.y, a0.z}, u0[3] = {a0.w, a1.x, a1.y};
                     const float l1[3] = {a1.z, a1.w, a2.x}, u1[3] = {a2.y, a2.z, a2.w};

@@ -12,13 +12,16 @@ from scenes_util import compare_hits, final_reduced_scene, random_graph_scene, r
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["by_size", "four_wide"])
+@pytest.fixture(autouse=True, params=["by_size", "four_wide", "binary"])
 def tree_variant(request, monkeypatch):
-    """Every test of this module runs twice: with the tree rt_scene_create picks by scene size (binary for these
-    small scenes, four-wide for the soups) and with the four-wide collapse forced, so that empty worlds, single
-    primitives, ties, Transforms, media and degenerate rays are all checked on both traversal kernels."""
+    """Every test of this module runs three times: with the tree rt_scene_create picks by scene size (the four-wide collapse
+    in shared memory for the smallest scenes, the binary tree in shared memory for book-sized ones, the four-wide tree in
+    global memory for the soups), with the four-wide collapse forced and with the binary tree forced, so that empty worlds,
+    single primitives, ties, Transforms, media and degenerate rays are all checked on every traversal variant."""
     if request.param == "four_wide":
         monkeypatch.setenv("RT2025_WIDE_BVH", "1")
+    elif request.param == "binary":
+        monkeypatch.setenv("RT2025_WIDE_BVH", "0")
     return request.param
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
