@@ -293,7 +293,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
             // a small scene's four-wide collapse is only used when all of it fits in a traversal CTA's shared memory next to the
             // stacks (compile.cpp); otherwise its binary tree is traversed, which then fits
             const size_t budget = EXTEND_SMEM_MAX / EXTEND_MIN_BLOCKS - 1024;
-            const size_t stacks = (size_t)std::min<uint32_t>(std::max(cs.bvh_depth + 2, 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK) * EXTEND_BLOCK * sizeof(uint32_t);
+            const size_t stacks = (size_t)std::min<uint32_t>(std::max(cs.bvh_depth + 2, 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK) * EXTEND_BLOCK * sizeof(uint32_t) + EXTEND_RAY_SMEM_BYTES;
             if (!cs.nodes4.empty() && cs.nodes.size() * sizeof(Node) <= 2 * budget && stacks + cs.nodes4.size() * sizeof(Node4) > budget &&
                 !getenv("RT2025_WIDE_BVH")) {
                 RawVec<Node4>().swap(cs.nodes4);
@@ -349,7 +349,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         v.stack_entries = std::min<uint32_t>(std::max(cs.bvh_depth + 2, cs.nodes4.empty() ? 0u : 3 * cs.bvh4_depth + 2), TRAVERSAL_STACK);
         v.media_stack_entries = std::min<uint32_t>(cs.media_bvh_depth + 2, TRAVERSAL_STACK);
         v.tail_stack_entries = std::min<uint32_t>(std::max(cs.bvh_depth, cs.media_bvh_depth) + 2, TRAVERSAL_STACK);  // the media kernel walks boundary groups only
-        const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t);
+        const size_t stack_bytes = (size_t)v.stack_entries * EXTEND_BLOCK * sizeof(uint32_t) + EXTEND_RAY_SMEM_BYTES;  // (+ the rays, behind the FIFOs)
         // persistent traversal: a warp whose BVH lives in L1/shared memory is issue-bound and runs best when it
         // drains completely before taking 32 new rays; once node fetches go to L2/HBM the idle lanes are worth
         // more as loads in flight and every finished lane is refilled at once (profiles/README.md: 1M-triangle
@@ -407,14 +407,14 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         size_t cache_bytes = room;
         if (const char* e = getenv("RT2025_SMEM_NODES_KB")) cache_bytes = std::min<size_t>(room, (size_t)atol(e) * 1024);  // tuning knob
         // the persistent traversal reads ONE tree: the four-wide collapse when there is one (n_cached_nodes then counts Node4)
-        const size_t node_size = cs.nodes4.empty() ? sizeof(Node) : sizeof(Node4);
+        const size_t node_size = cs.nodes4.empty() ? 56 : sizeof(Node4);  // traverse.cuh: binary nodes are stored compact (SMEM_NODE_BYTES)
         const size_t tree_nodes = cs.nodes4.empty() ? cs.nodes.size() : cs.nodes4.size();
-        v.n_cached_nodes = (uint32_t)std::min<size_t>(tree_nodes, cache_bytes / node_size);
+        v.n_cached_nodes = (uint32_t)std::min<size_t>(tree_nodes, (cache_bytes >= 16 ? cache_bytes - 16 : 0) / node_size);  // (the region is rounded up to 16 bytes)
         // A four-wide tree is only staged when ALL of it fits (RT2025_WIDE_BVH=1 on a book-sized scene): staging the top of a tree
         // that lives in L2 takes the shared memory away from the L1 and buys nothing (measured with the binary top in round 2:
         // synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s without it)
         if (!cs.nodes4.empty() && v.n_cached_nodes < tree_nodes && !getenv("RT2025_SMEM_NODES_KB")) v.n_cached_nodes = 0;
-        s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (size_t)v.n_cached_nodes * node_size;
+        s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (((size_t)v.n_cached_nodes * node_size + 15) & ~(size_t)15);
         if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm, &s->walk_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
         if (s->extend_blocks_per_sm < 1) s->extend_blocks_per_sm = 1;

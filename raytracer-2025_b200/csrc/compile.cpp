@@ -888,6 +888,7 @@ struct Compiler {
                 if ((out.meta[pi].kind_mat >> 30) == PRIM_SPHERE) med.single_sphere = pi;
             }
         }
+        if (timer.on) fprintf(stderr, "[rt2025 compile] %zu binary nodes (depth %u), %zu four-wide nodes (depth %u), %zu primitives\n", out.nodes.size(), out.bvh_depth, out.nodes4.size(), out.bvh4_depth, out.geom.size());
         // optically thick media (scene_types.h, MEDIUM_THICK): only when the sampling of EVERY medium is the closed-form
         // sphere test, because the random walk looks one segment ahead over all of them
         bool all_spheres = true;

@@ -71,14 +71,15 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
-    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + (sv.nodes4 ? 8 : 4) * sv.n_cached_nodes);
+    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + cached_tree_float4(sv));
     uint32_t* stack = stack_base + threadIdx.x;
     uint32_t* fifo = stack_base + sv.stack_entries * EXTEND_BLOCK + (threadIdx.x >> 5) * sv.fifo_slots * FIFO_SLOT_WORDS;
     if (threadIdx.x == 0) s_cursor = 0;
     stage_nodes(sv, s_mem);
     TraceCounters cnt{0, 0};
     RayArrayIO io{sv, rays, out, tmin, tmax};
-    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt);
+    double* ray_s = reinterpret_cast<double*>(stack_base + sv.stack_entries * EXTEND_BLOCK + (EXTEND_BLOCK / 32) * sv.fifo_slots * FIFO_SLOT_WORDS) + threadIdx.x;
+    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
         atomicAdd(&counters[1], (unsigned long long)cnt.prims);
@@ -338,7 +339,7 @@ template <bool COUNT, bool PARK, bool WIDE, int MEDIA>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
-    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + (sv.nodes4 ? 8 : 4) * sv.n_cached_nodes);
+    uint32_t* stack_base = reinterpret_cast<uint32_t*>(s_mem + cached_tree_float4(sv));
     uint32_t* stack = stack_base + threadIdx.x;
     uint32_t* fifo = stack_base + sv.stack_entries * EXTEND_BLOCK + (threadIdx.x >> 5) * sv.fifo_slots * FIFO_SLOT_WORDS;
     const uint32_t n = W.counters->n_extend[W.parity];
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     // a media pass after extend (classic order, or boundaries that are not spheres) owns the class bytes
     const bool media_pass_follows = sv.n_media != 0 && MEDIA == 0;  // (P.media_first == 0)
     PathIO<COUNT, MEDIA> io{sv, W.ray_q[W.parity], W.hit_q, media_pass_follows ? nullptr : W.cls_q, P.seed, P.bin_by_class != 0, &cnt};
-    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt);
+    double* ray_s = reinterpret_cast<double*>(stack_base + sv.stack_entries * EXTEND_BLOCK + (EXTEND_BLOCK / 32) * sv.fifo_slots * FIFO_SLOT_WORDS) + threadIdx.x;
+    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
         atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);

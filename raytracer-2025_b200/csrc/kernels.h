@@ -27,6 +27,10 @@ constexpr int REFILL_MIN = RT_REFILL_MIN;
 #ifndef RT_SLAB_SIGNSEL
 #define RT_SLAB_SIGNSEL 1  // slab test: near/far planes picked by the sign of 1/d, error bound folded into the addend
 #endif
+#ifndef RT_RAY_SMEM
+#define RT_RAY_SMEM 0  // persistent traversal: the binary64 ray lives in shared memory instead of 28 registers (traverse.cuh)
+#endif
+constexpr size_t EXTEND_RAY_SMEM_BYTES = RT_RAY_SMEM ? (size_t)14 * sizeof(double) * RT_EXTEND_BLOCK : 0;
 #ifndef RT_PARK_VOTE
 #define RT_PARK_VOTE 1  // postponed leaves: leave the node loop as soon as every lane of the warp holds a leaf (0: only at a second leaf)
 #endif

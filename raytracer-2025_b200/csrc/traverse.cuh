@@ -245,24 +245,46 @@ struct TraceCounters {
     uint32_t nodes, prims;
 };
 
-// Stage the breadth-first top of the BVH in shared memory with the TMA bulk-copy engine: one elected
-// thread arms an mbarrier with the byte count and issues cp.async.bulk (global -> shared, UBLKCP in
-// SASS) in 32 KB pieces; every thread then waits on the barrier's phase.  No register or LSU traffic
-// is spent on the copy, and it overlaps with the rest of the CTA's prologue.
+// Shared-memory copy of the breadth-first top of the traversed tree (all of it for book-sized scenes).
+//
+// Four-wide nodes are staged with the TMA bulk-copy engine: one elected thread arms an mbarrier with the byte count and issues
+// cp.async.bulk (global -> shared, UBLKCP in SASS) in 32 KB pieces; every thread then waits on the barrier's phase.  No register
+// or LSU traffic is spent on the copy, and it overlaps with the rest of the CTA's prologue.
+//
+// Binary nodes are stored COMPACT: the 48 bytes of boxes of node i at float4[3 i .. 3 i + 2], its two child references in a
+// uint2 array behind the boxes - 56 bytes per node instead of the 64 of the global layout (8 are padding), so that book2_final's
+// 3201 nodes fit next to the stacks (188 KB) and the node loop never takes its global-memory path: with 6 % of the nodes left
+// in global memory almost every warp-wide visit executed both paths.  All threads copy (4 x LDG.128 -> 3 x STS.128 + STS.64).
+constexpr uint32_t SMEM_NODE_BYTES = 56;
+__device__ __forceinline__ uint32_t cached_tree_float4(const SceneView& sv) {  // size of the node region in float4 units
+    return sv.nodes4 ? 8u * sv.n_cached_nodes : (sv.n_cached_nodes * SMEM_NODE_BYTES + 15u) / 16u;
+}
 __device__ __forceinline__ void stage_nodes(const SceneView& sv, float4* smem_nodes) {
     __shared__ alignas(8) unsigned long long s_bar;
-    // (the four-wide tree when the scene is traversed through it: n_cached_nodes then counts Node4)
-    const uint32_t bytes = sv.n_cached_nodes * (uint32_t)(sv.nodes4 ? sizeof(Node4) : sizeof(Node));
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (bytes == 0) return;
+    if (sv.n_cached_nodes == 0) return;
+    if (!sv.nodes4) {
+        uint2* children = reinterpret_cast<uint2*>(smem_nodes + 3 * sv.n_cached_nodes);
+        for (uint32_t i = threadIdx.x; i < sv.n_cached_nodes; i += blockDim.x) {
+            const float4* np = reinterpret_cast<const float4*>(sv.nodes + i);
+            float4 n0, n1, n2, n3;
+            ldg256(np, n0, n1);
+            ldg256(np + 2, n2, n3);
+            smem_nodes[3 * i] = n0, smem_nodes[3 * i + 1] = n1, smem_nodes[3 * i + 2] = n2;
+            children[i] = make_uint2(__float_as_uint(n3.x), __float_as_uint(n3.y));
+        }
+        __syncthreads();
+        return;
+    }
+    const uint32_t bytes = sv.n_cached_nodes * (uint32_t)sizeof(Node4);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        const char* src = sv.nodes4 ? reinterpret_cast<const char*>(sv.nodes4) : reinterpret_cast<const char*>(sv.nodes);
+        const char* src = reinterpret_cast<const char*>(sv.nodes4);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_nodes);
         for (uint32_t off = 0; off < bytes; off += 32768u) {
             const uint32_t n = min(32768u, bytes - off);
@@ -342,11 +364,8 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
         uint32_t parked = INVALID_REF;  // postponed leaf
         while (cur != INVALID_REF) {
             while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
-                float4 n0, n1, n2, n3;
-                if (cur < sv.n_cached_nodes) {  // top of the tree: shared memory
-                    const float4* np = smem_nodes + 4 * cur;
-                    n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
-                } else {
+                float4 n0, n1, n2, n3;  // (global memory: the callers - k_tail, k_walk, the media pass - stage no nodes)
+                {
                     const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
                     ldg256(np, n0, n1);
                     ldg256(np + 2, n2, n3);
@@ -426,9 +445,25 @@ constexpr uint32_t FIFO_INVALID_ITEM = 0xFFFFFFFFu;  // a slot of the ragged las
 template <bool COUNT, bool USE_RANK, bool PARK, bool WIDE, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
-                                                 uint32_t* __restrict__ fifo, uint32_t fifo_slots, TraceCounters* cnt) {
+                                                 uint32_t* __restrict__ fifo, uint32_t fifo_slots, TraceCounters* cnt, double* __restrict__ ray_s = nullptr) {
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t lane = threadIdx.x & 31u;
+#if RT_RAY_SMEM
+    // The binary64 ray (and its image in the local space of the last Transform met) lives in shared memory, component k of this
+    // thread at ray_s[k * stride]: only the leaf tests read it, and 28 registers fewer per thread are four more warps per SM.
+    auto put_ray = [&](int base, const RayD& q) {
+        ray_s[(base + 0) * stride] = q.o.x, ray_s[(base + 1) * stride] = q.o.y, ray_s[(base + 2) * stride] = q.o.z;
+        ray_s[(base + 3) * stride] = q.d.x, ray_s[(base + 4) * stride] = q.d.y, ray_s[(base + 5) * stride] = q.d.z;
+        ray_s[(base + 6) * stride] = q.time;
+    };
+    auto get_ray = [&](int base) {
+        RayD q;
+        q.o = D3{ray_s[(base + 0) * stride], ray_s[(base + 1) * stride], ray_s[(base + 2) * stride]};
+        q.d = D3{ray_s[(base + 3) * stride], ray_s[(base + 4) * stride], ray_s[(base + 5) * stride]};
+        q.time = ray_s[(base + 6) * stride];
+        return q;
+    };
+#endif
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t G = gridDim.x, b = blockIdx.x;
     const uint32_t n_groups = (n + 31u) >> 5;
@@ -440,7 +475,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
     bool exhausted = false;            // warp-uniform: the CTA's cursor ran past its last group
     uint32_t head = 0, avail = 0;      // warp-uniform FIFO state: first filled slot, number of filled slots
     uint32_t item = 0;
+#if !RT_RAY_SMEM
     RayD r, lr;
+#endif
     RayF f;
     const double tmin = io.t_min();
     const float tmin_f = __double2float_rd(tmin);
@@ -477,13 +514,20 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                     if (next_group < local_groups) io.prefetch((next_group * G + b) * 32u + lane);
                     const uint32_t it = (g * G + b) * 32u + lane;
                     prim = 0xFFFFFFFFu, prim_rank = 0xFFFFFFFFu;
+#if RT_RAY_SMEM
+                    RayD r;
+#endif
                     if (it < n && io.load(it, r, tbest, prim, prim_rank)) {
                         item = it;
                         make_rayf(r, f);
                         have = true;
                         tmax_f = __double2float_ru(tbest);
                         cached_xform = 0xFFFFFFFFu;
+#if RT_RAY_SMEM
+                        put_ray(0, r);
+#else
                         lr = r;
+#endif
                         sp = 0;
                         const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
                         if (root & LEAF_FLAG)
@@ -540,6 +584,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                         const double2* sd = reinterpret_cast<const double2*>(slot);
                         const double2 a0 = sd[0], a1 = sd[1], a2 = sd[2], a3 = sd[3];
                         const float4 q5 = reinterpret_cast<const float4*>(slot)[5], q6 = reinterpret_cast<const float4*>(slot)[6];
+#if RT_RAY_SMEM
+                        RayD r;
+#endif
                         r.o = D3{a0.x, a0.y, a1.x};
                         r.d = D3{a1.y, a2.x, a2.y};
                         r.time = a3.x;
@@ -553,7 +600,11 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                         have = true;
                         tmax_f = __double2float_ru(tbest);
                         cached_xform = 0xFFFFFFFFu;
+#if RT_RAY_SMEM
+                        put_ray(0, r);
+#else
                         lr = r;
+#endif
                         sp = 0;
                         const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
                         if (root & LEAF_FLAG)
@@ -622,19 +673,23 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                     else
                         cur = sp > 0 ? stack[(--sp) * stride] : INVALID_REF;
                 } else {
-                    float4 n0, n1, n2, n3;
-                    if (cur < sv.n_cached_nodes) {
-                        const float4* np = smem_nodes + 4 * cur;
-                        n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+                    float4 n0, n1, n2;
+                    uint32_t c0, c1;
+                    if (cur < sv.n_cached_nodes) {  // compact shared-memory layout (stage_nodes)
+                        const float4* np = smem_nodes + 3 * cur;
+                        n0 = np[0], n1 = np[1], n2 = np[2];
+                        const uint2 cc = reinterpret_cast<const uint2*>(smem_nodes + 3 * sv.n_cached_nodes)[cur];
+                        c0 = cc.x, c1 = cc.y;
                     } else {
                         const float4* np = reinterpret_cast<const float4*>(sv.nodes + cur);
+                        float4 n3;
                         ldg256(np, n0, n1);
                         ldg256(np + 2, n2, n3);
+                        c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
                     }
                     if (COUNT) cnt->nodes++;
                     float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
                     float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
-                    uint32_t c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
                     float t0, t1;
                     bool h0 = slab(f, lo0, hi0, tmin_f, tmax_f, t0);
                     bool h1 = slab(f, lo1, hi1, tmin_f, tmax_f, t1);
@@ -669,10 +724,18 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                     const uint32_t pi = first + i;
                     const uint4 km = __ldg(reinterpret_cast<const uint4*>(&sv.meta[pi]));
                     const uint32_t kind = km.x >> 30;
+#if RT_RAY_SMEM
+                    if (km.w != 0xFFFFFFFFu && km.w != cached_xform) {
+                        put_ray(7, ray_to_local(sv, km.w, get_ray(0)));
+                        cached_xform = km.w;
+                    }
+                    const RayD lr = get_ray(km.w == 0xFFFFFFFFu ? 0 : 7);
+#else
                     if (km.w != cached_xform) {
                         lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
                         cached_xform = km.w;
                     }
+#endif
                     const double* g = sv.geom[pi].d;
                     double t;
                     bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, tbest, t);
