@@ -928,6 +928,12 @@ __global__ void __launch_bounds__(WALK_BLOCK, RT_WALK_MIN_BLOCKS) k_walk(SceneVi
     D3 beta;
     uint32_t pixel = 0, sidx = 0, segment = 0, medium = 0;
     double t = 0.0;
+    // A walk is a serial chain (about 8 us per segment for a warp that has the SM to itself): once the queue is too short to fill the
+    // GPU - the drain of a frame, where every iteration would wait some 300 us for the handful of paths that have just entered the
+    // medium - a walk is cut after `drain_steps` segments and its path goes back to the ray stream; the wavefront evaluates the
+    // next segment, finds the same scatter point and queues the path for the walk of the next iteration.
+    const uint32_t max_steps = n <= P.walk_drain_queue ? P.walk_drain_steps : 0xFFFFFFFFu;
+    uint32_t steps = 0;
     // queue entries are claimed 32 at a time per warp (one atomic, records prefetched) and handed to the lanes as their walks end
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform
     bool exhausted = false;                // warp-uniform: the cursor ran past the queue
@@ -964,6 +970,7 @@ __global__ void __launch_bounds__(WALK_BLOCK, RT_WALK_MIN_BLOCKS) k_walk(SceneVi
                 t = hw.x;
                 medium = (uint32_t)__double2hiint(hw.y);
                 have = true;
+                steps = 0;
             }
             pool_next += take;
             need = __ballot_sync(FULL, !have);
@@ -981,7 +988,7 @@ __global__ void __launch_bounds__(WALK_BLOCK, RT_WALK_MIN_BLOCKS) k_walk(SceneVi
                 uint32_t pn = 0xFFFFFFFFu, kn = HIT_MISS;
                 MediumDraws draws;
                 sample_media<false, false, XF, 1>(sv, P.seed, nr, pixel, sidx, segment + 1u, tn, pn, kn, s_mem, stack, WALK_BLOCK, &cnt, medium, draws);
-                bool stay = kn == HIT_MEDIUM;
+                bool stay = kn == HIT_MEDIUM && ++steps < max_steps;
                 if (stay) {
                     sample_media<false, false, XF, 2>(sv, P.seed, nr, pixel, sidx, segment + 1u, tn, pn, kn, s_mem, stack, WALK_BLOCK, &cnt, 0u, draws);
                     stay = (sv.media[pn].flags & MEDIUM_THICK) != 0u;

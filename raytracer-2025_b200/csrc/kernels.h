@@ -127,6 +127,7 @@ struct RenderParams {
     uint64_t seed;
     uint32_t sample_begin, part_index, part_count;
     uint32_t lights_flat, bin_by_class;
+    uint32_t walk_drain_queue, walk_drain_steps;  // k_walk: queues of at most walk_drain_queue entries cut every walk after walk_drain_steps segments
     uint32_t sample_in_generate;  // media_first == 1: k_generate samples the media for the camera rays it writes (A/B knob RT2025_GEN_MEDIA=0)
     uint32_t media_first;  // 0: media sampled after extend (order of Hittables::hit); 1: by a pass ahead of extend, 2: by extend itself while it
                            // prepares the ray - extend then only looks for surfaces up to the scatter point

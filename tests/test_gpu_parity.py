@@ -339,15 +339,19 @@ def test_random_walk_kernel_vs_wavefront_and_oracle(gpu, rt, orc, variant, monke
     hs = _walk_scene(rt, variant)
     monkeypatch.setenv("RT2025_TAIL_PATHS", "0")  # these frames are small enough for k_tail to finish them after one iteration
     sc = rt.Scene(hs)
-    a, sa = sc.render(seed=9)
+    a, sa = sc.render(seed=9)  # (a queue this short cuts every walk after four segments: the drain rule of k_walk)
     assert sa.walk_segments > 0
+    monkeypatch.setenv("RT2025_WALK_DRAIN_QUEUE", "0")  # walks of any length
+    a2, sa2 = sc.render(seed=9)
+    assert sa2.walk_segments > sa.walk_segments and sa2.segments == sa.segments and sa2.errors == sa.errors
+    image_close(a2, a, frac_bad=0.0, rel=1e-9)
     monkeypatch.setenv("RT2025_WALK_NO_ENTRIES", "1")
     b_, sb = rt.Scene(hs).render(seed=9)
     monkeypatch.delenv("RT2025_WALK_NO_ENTRIES")
     monkeypatch.setenv("RT2025_WALK_MIN_DEPTH", "0")
     c, sc_ = rt.Scene(hs).render(seed=9)
     monkeypatch.delenv("RT2025_WALK_MIN_DEPTH")
-    assert sc_.walk_segments == 0 and sb.walk_segments == sa.walk_segments
+    assert sc_.walk_segments == 0 and sb.walk_segments == sa2.walk_segments
     assert sa.segments == sb.segments == sc_.segments and sa.errors == sb.errors == sc_.errors
     assert sc_.iterations >= sa.iterations
     image_close(a, c, frac_bad=0.0, rel=1e-9)
