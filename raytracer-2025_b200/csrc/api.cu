@@ -413,7 +413,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // A four-wide tree is only staged when ALL of it fits (RT2025_WIDE_BVH=1 on a book-sized scene): staging the top of a tree
         // that lives in L2 takes the shared memory away from the L1 and buys nothing (measured with the binary top in round 2:
         // synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s without it)
-        if (!cs.nodes4.empty() && v.n_cached_nodes < tree_nodes && !getenv("RT2025_SMEM_NODES_KB")) v.n_cached_nodes = 0;
+        if (!cs.nodes4.empty() && v.n_cached_nodes < tree_nodes) v.n_cached_nodes = 0;  // (all or nothing: the kernels have no mixed variant)
         s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (((size_t)v.n_cached_nodes * node_size + 15) & ~(size_t)15);
         if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm, &s->walk_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};

@@ -66,7 +66,7 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
     }
 };
 
-template <bool COUNT, bool PARK, bool WIDE>
+template <bool COUNT, bool PARK, int WIDE>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint32_t n, double tmin,
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
@@ -111,9 +111,10 @@ static void launch_with_l2_window(K kernel, const SceneView& sv, int grid, int b
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
-    auto k = sv.nodes4 ? (count ? k_closest_hit<true, true, true> : k_closest_hit<false, true, true>)
-             : count   ? (sv.park_leaves ? k_closest_hit<true, true, false> : k_closest_hit<true, false, false>)
-                       : (sv.park_leaves ? k_closest_hit<false, true, false> : k_closest_hit<false, false, false>);
+    auto k = sv.nodes4 ? (sv.n_cached_nodes ? (count ? k_closest_hit<true, true, 2> : k_closest_hit<false, true, 2>)
+                                            : (count ? k_closest_hit<true, true, 1> : k_closest_hit<false, true, 1>))
+             : count   ? (sv.park_leaves ? k_closest_hit<true, true, 0> : k_closest_hit<true, false, 0>)
+                       : (sv.park_leaves ? k_closest_hit<false, true, 0> : k_closest_hit<false, false, 0>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, stream, sv, d_rays, n, tmin, tmax, d_out, d_counters);
 }
 
@@ -335,7 +336,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
 };
 
 // closest hit of every path in the extend queue: world.hit (camera.rs:286) over the surfaces and, with MEDIA, the media
-template <bool COUNT, bool PARK, bool WIDE, int MEDIA>
+template <bool COUNT, bool PARK, int WIDE, int MEDIA>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
     __shared__ uint32_t s_cursor;
@@ -1179,9 +1180,10 @@ void launch_generate(const SceneView& sv, const RenderParams& P, const Wavefront
 }
 template <int MEDIA>
 static void launch_extend_media(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
-    auto k = sv.nodes4 ? (count ? k_extend<true, true, true, MEDIA> : k_extend<false, true, true, MEDIA>)
-             : count   ? (sv.park_leaves ? k_extend<true, true, false, MEDIA> : k_extend<true, false, false, MEDIA>)
-                       : (sv.park_leaves ? k_extend<false, true, false, MEDIA> : k_extend<false, false, false, MEDIA>);
+    auto k = sv.nodes4 ? (sv.n_cached_nodes ? (count ? k_extend<true, true, 2, MEDIA> : k_extend<false, true, 2, MEDIA>)
+                                            : (count ? k_extend<true, true, 1, MEDIA> : k_extend<false, true, 1, MEDIA>))
+             : count   ? (sv.park_leaves ? k_extend<true, true, 0, MEDIA> : k_extend<true, false, 0, MEDIA>)
+                       : (sv.park_leaves ? k_extend<false, true, 0, MEDIA> : k_extend<false, false, 0, MEDIA>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, s, sv, P, W);
 }
 void launch_extend(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
@@ -1272,13 +1274,15 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
     // dynamic shared memory above 48 KB is opt-in
     cudaError_t e = cudaSuccess;
     const void* big_smem[] = {
-#define RT_EXTEND_VARIANTS(M)                                                                                                             \
-    (const void*)k_extend<false, false, false, M>, (const void*)k_extend<false, true, false, M>, (const void*)k_extend<false, true, true, M>, \
-        (const void*)k_extend<true, false, false, M>, (const void*)k_extend<true, true, false, M>, (const void*)k_extend<true, true, true, M>
+#define RT_EXTEND_VARIANTS(M)                                                                                                     \
+    (const void*)k_extend<false, false, 0, M>, (const void*)k_extend<false, true, 0, M>, (const void*)k_extend<false, true, 1, M>, \
+        (const void*)k_extend<false, true, 2, M>, (const void*)k_extend<true, false, 0, M>, (const void*)k_extend<true, true, 0, M>, \
+        (const void*)k_extend<true, true, 1, M>, (const void*)k_extend<true, true, 2, M>
         RT_EXTEND_VARIANTS(0), RT_EXTEND_VARIANTS(1), RT_EXTEND_VARIANTS(2), RT_EXTEND_VARIANTS(3),
 #undef RT_EXTEND_VARIANTS
-        (const void*)k_closest_hit<false, false, false>, (const void*)k_closest_hit<false, true, false>, (const void*)k_closest_hit<false, true, true>,
-        (const void*)k_closest_hit<true, false, false>,  (const void*)k_closest_hit<true, true, false>,  (const void*)k_closest_hit<true, true, true>};
+        (const void*)k_closest_hit<false, false, 0>, (const void*)k_closest_hit<false, true, 0>, (const void*)k_closest_hit<false, true, 1>,
+        (const void*)k_closest_hit<false, true, 2>,  (const void*)k_closest_hit<true, false, 0>, (const void*)k_closest_hit<true, true, 0>,
+        (const void*)k_closest_hit<true, true, 1>,   (const void*)k_closest_hit<true, true, 2>};
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB
@@ -1289,7 +1293,7 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
                                 (const void*)k_media<true, 2, false, false>, (const void*)k_media<true, 2, true, false>};
     for (const void* f : media_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * MEDIA_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, false, 0>, EXTEND_BLOCK, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, 0, 0>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_OTHER>, SHADE_BLOCK, 0);  // a class never compiled for three
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(walk_blocks_per_sm, k_walk<true>, WALK_BLOCK, 24 * WALK_BLOCK * sizeof(uint32_t));
     return 0;

@@ -442,7 +442,9 @@ constexpr uint32_t FIFO_INVALID_ITEM = 0xFFFFFFFFu;  // a slot of the ragged las
 // WIDE = traverse the four-wide collapse (sv.nodes4, out-of-cache scenes): four slab tests per fetch, the hit
 // children are ordered by entry distance with a five-exchange network, the nearest is followed and the others
 // are pushed farthest first.
-template <bool COUNT, bool USE_RANK, bool PARK, bool WIDE, class IO>
+// (WIDE == 2: the whole four-wide tree is in shared memory - a variant of its own, because a per-visit choice between the two
+// node sources costs the global-memory traversal of the big scenes 7 % in Mrays/s)
+template <bool COUNT, bool USE_RANK, bool PARK, int WIDE, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
                                                  uint32_t* __restrict__ fifo, uint32_t fifo_slots, TraceCounters* cnt, double* __restrict__ ray_s = nullptr) {
@@ -627,7 +629,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                 if (WIDE) {
                     float4 a0, a1, a2, a3, a4, a5;
                     uint4 cr;
-                    if (cur < sv.n_cached_nodes) {  // top of the (or the whole) four-wide tree: shared memory
+                    if (WIDE == 2) {
                         const float4* np = smem_nodes + 8 * cur;
                         a0 = np[0], a1 = np[1], a2 = np[2], a3 = np[3], a4 = np[4], a5 = np[5];
                         cr = *reinterpret_cast<const uint4*>(np + 6);
