@@ -329,8 +329,10 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         for (auto& m : cs.media)
             if (m.xform != RT_NONE || (m.single_sphere != RT_NONE && cs.meta[m.single_sphere].xform != RT_NONE)) v.media_xform = 1;
         for (auto& m : cs.materials) s->class_mask |= 1u << m.shade_class;
+        uint32_t n_thick = 0, n_thick_entries = 0;
         for (auto& m : cs.media)
-            if (m.flags & MEDIUM_THICK) s->class_mask |= 1u << SC_WALK;  // scatter points of thick media go to the random-walk kernel
+            if (m.flags & MEDIUM_THICK) s->class_mask |= 1u << SC_WALK, n_thick++, n_thick_entries += m.n_entry != MEDIUM_NO_ENTRIES;
+        v.walk_entries_only = n_thick == 1 && n_thick_entries == 1;  // scatter points of thick media go to the random-walk kernel
         // lights is "flat" when every leaf has the same weight 1/n (a single-level list)
         s->lights_flat = 1;
         for (auto& l : cs.lights)
@@ -413,7 +415,8 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // A four-wide tree is only staged when ALL of it fits (RT2025_WIDE_BVH=1 on a book-sized scene): staging the top of a tree
         // that lives in L2 takes the shared memory away from the L1 and buys nothing (measured with the binary top in round 2:
         // synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s without it)
-        if (!cs.nodes4.empty() && v.n_cached_nodes < tree_nodes) v.n_cached_nodes = 0;  // (all or nothing: the kernels have no mixed variant)
+        // (all or nothing, and in direct mode only: the kernels have no mixed four-wide variant)
+        if (!cs.nodes4.empty() && (v.n_cached_nodes < tree_nodes || v.fifo_slots)) v.n_cached_nodes = 0;
         s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (((size_t)v.n_cached_nodes * node_size + 15) & ~(size_t)15);
         if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm, &s->walk_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};

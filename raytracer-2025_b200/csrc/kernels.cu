@@ -111,8 +111,9 @@ static void launch_with_l2_window(K kernel, const SceneView& sv, int grid, int b
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
-    auto k = sv.nodes4 ? (sv.n_cached_nodes ? (count ? k_closest_hit<true, true, 2> : k_closest_hit<false, true, 2>)
+    auto k = sv.nodes4 ? (sv.n_cached_nodes && !sv.fifo_slots ? (count ? k_closest_hit<true, true, 2> : k_closest_hit<false, true, 2>)
                                             : (count ? k_closest_hit<true, true, 1> : k_closest_hit<false, true, 1>))
+             : (!sv.park_leaves && !sv.fifo_slots && sv.n_cached_nodes == sv.n_nodes) ? (count ? k_closest_hit<true, false, 3> : k_closest_hit<false, false, 3>)
              : count   ? (sv.park_leaves ? k_closest_hit<true, true, 0> : k_closest_hit<true, false, 0>)
                        : (sv.park_leaves ? k_closest_hit<false, true, 0> : k_closest_hit<false, false, 0>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, stream, sv, d_rays, n, tmin, tmax, d_out, d_counters);
@@ -912,7 +913,9 @@ constexpr int WALK_BLOCK = RT_WALK_BLOCK;
 #ifndef RT_WALK_MIN_BLOCKS
 #define RT_WALK_MIN_BLOCKS 4
 #endif
-template <bool XF>
+// ENTRIES: every thick medium of the scene has its entry leaves and there is only one of them, so the traversal from the world
+// root (another medium's scatter point, more leaves than slots) is never needed and is compiled out.
+template <bool XF, bool ENTRIES>
 __global__ void __launch_bounds__(WALK_BLOCK, RT_WALK_MIN_BLOCKS) k_walk(SceneView sv, RenderParams P, WavefrontState W) {
     extern __shared__ float4 s_mem[];  // traversal stacks (global-memory nodes only)
     uint32_t* stack = reinterpret_cast<uint32_t*>(s_mem) + threadIdx.x;
@@ -999,11 +1002,9 @@ __global__ void __launch_bounds__(WALK_BLOCK, RT_WALK_MIN_BLOCKS) k_walk(SceneVi
                     const uint32_t med_rank = mn.rank;
                     double ts;
                     uint32_t ps;
-                    if (pn == medium && mn.n_entry != MEDIUM_NO_ENTRIES) {
+                    if (ENTRIES || (pn == medium && mn.n_entry != MEDIUM_NO_ENTRIES)) {
                         // both ends of the segment lie inside the same boundary: only the world leaves that overlap it can be met
-                        for (uint32_t e = 0; e < mn.n_entry && stay; e++)
-                            if (closest_hit<false, true>(sv, mn.entry[e], nr, 1e-8, tn, s_mem, stack, WALK_BLOCK, ts, ps, &cnt))
-                                stay = !(ts < tn || sv.meta[ps].rank < med_rank);  // ts <= tn here
+                        for (uint32_t e = 0; e < mn.n_entry && stay; e++) stay = !leaf_beats_scatter(sv, mn.entry[e], nr, 1e-8, tn, med_rank);
                     } else if (closest_hit<false, true>(sv, sv.world_root, nr, 1e-8, tn, s_mem, stack, WALK_BLOCK, ts, ps, &cnt)) {
                         stay = !(ts < tn || sv.meta[ps].rank < med_rank);
                     }
@@ -1029,10 +1030,8 @@ static void launch_walk(const SceneView& sv, const RenderParams& P, const Wavefr
     SceneView wv = sv;
     wv.n_cached_nodes = 0;  // the non-persistent closest_hit() reads the binary tree from global memory
     const size_t smem = (size_t)std::max(sv.tail_stack_entries, 4u) * WALK_BLOCK * sizeof(uint32_t);
-    if (sv.media_xform)
-        k_walk<true><<<grid, WALK_BLOCK, smem, s>>>(wv, P, W);
-    else
-        k_walk<false><<<grid, WALK_BLOCK, smem, s>>>(wv, P, W);
+    auto k = sv.media_xform ? (sv.walk_entries_only ? k_walk<true, true> : k_walk<true, false>) : (sv.walk_entries_only ? k_walk<false, true> : k_walk<false, false>);
+    k<<<grid, WALK_BLOCK, smem, s>>>(wv, P, W);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1180,8 +1179,9 @@ void launch_generate(const SceneView& sv, const RenderParams& P, const Wavefront
 }
 template <int MEDIA>
 static void launch_extend_media(const SceneView& sv, const RenderParams& P, const WavefrontState& W, bool count, int grid, size_t stack_bytes, cudaStream_t s) {
-    auto k = sv.nodes4 ? (sv.n_cached_nodes ? (count ? k_extend<true, true, 2, MEDIA> : k_extend<false, true, 2, MEDIA>)
+    auto k = sv.nodes4 ? (sv.n_cached_nodes && !sv.fifo_slots ? (count ? k_extend<true, true, 2, MEDIA> : k_extend<false, true, 2, MEDIA>)
                                             : (count ? k_extend<true, true, 1, MEDIA> : k_extend<false, true, 1, MEDIA>))
+             : (!sv.park_leaves && !sv.fifo_slots && sv.n_cached_nodes == sv.n_nodes) ? (count ? k_extend<true, false, 3, MEDIA> : k_extend<false, false, 3, MEDIA>)
              : count   ? (sv.park_leaves ? k_extend<true, true, 0, MEDIA> : k_extend<true, false, 0, MEDIA>)
                        : (sv.park_leaves ? k_extend<false, true, 0, MEDIA> : k_extend<false, false, 0, MEDIA>);
     launch_with_l2_window(k, sv, grid, EXTEND_BLOCK, stack_bytes, s, sv, P, W);
@@ -1277,17 +1277,19 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
 #define RT_EXTEND_VARIANTS(M)                                                                                                     \
     (const void*)k_extend<false, false, 0, M>, (const void*)k_extend<false, true, 0, M>, (const void*)k_extend<false, true, 1, M>, \
         (const void*)k_extend<false, true, 2, M>, (const void*)k_extend<true, false, 0, M>, (const void*)k_extend<true, true, 0, M>, \
-        (const void*)k_extend<true, true, 1, M>, (const void*)k_extend<true, true, 2, M>
+        (const void*)k_extend<true, true, 1, M>, (const void*)k_extend<true, true, 2, M>, (const void*)k_extend<false, false, 3, M>, \
+        (const void*)k_extend<true, false, 3, M>
         RT_EXTEND_VARIANTS(0), RT_EXTEND_VARIANTS(1), RT_EXTEND_VARIANTS(2), RT_EXTEND_VARIANTS(3),
 #undef RT_EXTEND_VARIANTS
         (const void*)k_closest_hit<false, false, 0>, (const void*)k_closest_hit<false, true, 0>, (const void*)k_closest_hit<false, true, 1>,
         (const void*)k_closest_hit<false, true, 2>,  (const void*)k_closest_hit<true, false, 0>, (const void*)k_closest_hit<true, true, 0>,
-        (const void*)k_closest_hit<true, true, 1>,   (const void*)k_closest_hit<true, true, 2>};
+        (const void*)k_closest_hit<true, true, 1>,   (const void*)k_closest_hit<true, true, 2>,  (const void*)k_closest_hit<false, false, 3>,
+        (const void*)k_closest_hit<true, false, 3>};
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB
     if ((e = cudaFuncSetAttribute((const void*)k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * TAIL_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
-    for (const void* f : {(const void*)k_walk<false>, (const void*)k_walk<true>})
+    for (const void* f : {(const void*)k_walk<false, false>, (const void*)k_walk<true, false>, (const void*)k_walk<false, true>, (const void*)k_walk<true, true>})
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * WALK_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
     const void* media_smem[] = {(const void*)k_media<false, 2, false, false>, (const void*)k_media<false, 2, true, false>,
                                 (const void*)k_media<true, 2, false, false>, (const void*)k_media<true, 2, true, false>};
@@ -1295,7 +1297,7 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TRAVERSAL_STACK * MEDIA_BLOCK * (int)sizeof(uint32_t))) != cudaSuccess) return (int)e;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend<false, false, 0, 0>, EXTEND_BLOCK, smem_bytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<SC_OTHER>, SHADE_BLOCK, 0);  // a class never compiled for three
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(walk_blocks_per_sm, k_walk<true>, WALK_BLOCK, 24 * WALK_BLOCK * sizeof(uint32_t));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(walk_blocks_per_sm, k_walk<true, false>, WALK_BLOCK, 24 * WALK_BLOCK * sizeof(uint32_t));
     return 0;
 }
 

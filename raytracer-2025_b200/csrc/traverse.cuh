@@ -408,6 +408,30 @@ __device__ __forceinline__ bool closest_hit(const SceneView& sv, uint32_t root, 
     return true;
 }
 
+// Does a primitive of `leaf` (a leaf reference) beat a scatter point at distance t_scatter with tie rank `rank` - a hit in
+// [tmin, t_scatter] that is nearer, or at the same distance with a lower rank (the rule of closest_hit)?  k_walk's test of the
+// entry leaves of a medium: no boxes, no stack.
+__device__ __forceinline__ bool leaf_beats_scatter(const SceneView& sv, uint32_t leaf, const RayD& r, double tmin, double t_scatter, uint32_t rank) {
+    const uint32_t first = (leaf & ~LEAF_FLAG) >> 3, count = (leaf & 7u) + 1;
+    uint32_t cached_xform = 0xFFFFFFFFu;
+    RayD lr = r;
+    bool beaten = false;
+    for (uint32_t i = 0; i < count; i++) {
+        const uint32_t pi = first + i;
+        const uint4 km = __ldg(reinterpret_cast<const uint4*>(&sv.meta[pi]));  // kind_mat, rank, object, xform
+        if (km.w != cached_xform) {
+            lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
+            cached_xform = km.w;
+        }
+        const double* g = sv.geom[pi].d;
+        const uint32_t kind = km.x >> 30;
+        double t;
+        const bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, t_scatter, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, t_scatter, t);
+        beaten = beaten || (hit && (t < t_scatter || km.y < rank));  // t <= t_scatter here
+    }
+    return beaten;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent "while-while" traversal fed from a per-warp FIFO of PREPARED rays.
 //
@@ -443,11 +467,14 @@ constexpr uint32_t FIFO_INVALID_ITEM = 0xFFFFFFFFu;  // a slot of the ragged las
 // children are ordered by entry distance with a five-exchange network, the nearest is followed and the others
 // are pushed farthest first.
 // (WIDE == 2: the whole four-wide tree is in shared memory - a variant of its own, because a per-visit choice between the two
-// node sources costs the global-memory traversal of the big scenes 7 % in Mrays/s)
+// node sources costs the global-memory traversal of the big scenes 7 % in Mrays/s; WIDE == 3: the BINARY tree, all of it in
+// shared memory, likewise without the global-memory path)
 template <bool COUNT, bool USE_RANK, bool PARK, int WIDE, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
-                                                 uint32_t* __restrict__ fifo, uint32_t fifo_slots, TraceCounters* cnt, double* __restrict__ ray_s = nullptr) {
+                                                 uint32_t* __restrict__ fifo, uint32_t fifo_slots_arg, TraceCounters* cnt, double* __restrict__ ray_s = nullptr) {
+    // the all-in-shared-memory variants run in direct mode only (the shared memory holds the tree, not FIFOs): no FIFO code in them
+    const uint32_t fifo_slots = WIDE >= 2 ? 0u : fifo_slots_arg;
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t lane = threadIdx.x & 31u;
 #if RT_RAY_SMEM
@@ -531,7 +558,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                         lr = r;
 #endif
                         sp = 0;
-                        const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
+                        const uint32_t root = (WIDE == 1 || WIDE == 2) ? sv.world_root4 : sv.world_root;
                         if (root & LEAF_FLAG)
                             parked = root, cur = INVALID_REF;
                         else
@@ -608,7 +635,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                         lr = r;
 #endif
                         sp = 0;
-                        const uint32_t root = WIDE ? sv.world_root4 : sv.world_root;
+                        const uint32_t root = (WIDE == 1 || WIDE == 2) ? sv.world_root4 : sv.world_root;
                         if (root & LEAF_FLAG)
                             parked = root, cur = INVALID_REF;
                         else
@@ -626,7 +653,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
         if (have) {
             // node phase: descend until this lane has parked a leaf and met another, or ran out
             while (!(cur & LEAF_FLAG) && cur != INVALID_REF) {
-                if (WIDE) {
+                if (WIDE == 1 || WIDE == 2) {
                     float4 a0, a1, a2, a3, a4, a5;
                     uint4 cr;
                     if (WIDE == 2) {
@@ -677,7 +704,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                 } else {
                     float4 n0, n1, n2;
                     uint32_t c0, c1;
-                    if (cur < sv.n_cached_nodes) {  // compact shared-memory layout (stage_nodes)
+                    if (WIDE == 3 || cur < sv.n_cached_nodes) {  // compact shared-memory layout (stage_nodes); WIDE == 3: every node is there
                         const float4* np = smem_nodes + 3 * cur;
                         n0 = np[0], n1 = np[1], n2 = np[2];
                         const uint2 cc = reinterpret_cast<const uint2*>(smem_nodes + 3 * sv.n_cached_nodes)[cur];
