@@ -404,6 +404,11 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // per-lane refill: the 76 k-node mesh scene 69.6 (drained) vs 61.8, the 1 M soups +12..24 % in Mrays/s.
         if (cs.nodes.size() * sizeof(Node) <= 2 * budget) v.fifo_slots = 0;
         if (const char* e = getenv("RT2025_FIFO_SLOTS")) v.fifo_slots = atoi(e) >= 64 ? 64u : (atoi(e) >= 32 ? 32u : 0u);  // tuning knob
+        // a four-wide tree is either all in shared memory (direct mode) or all in global memory and fed from the FIFOs: the kernels
+        // have no other four-wide variant
+        const bool wide_in_smem = !cs.nodes4.empty() && v.fifo_slots == 0 && stack_bytes + cs.nodes4.size() * sizeof(Node4) + 16 <= budget &&
+                                  !(getenv("RT2025_SMEM_NODES_KB") && (size_t)atol(getenv("RT2025_SMEM_NODES_KB")) * 1024 < cs.nodes4.size() * sizeof(Node4));
+        if (!cs.nodes4.empty() && !wide_in_smem && v.fifo_slots == 0) v.fifo_slots = 32;
         if (stack_bytes + fifo_bytes(v.fifo_slots) > budget) throw CudaFail{"traversal stacks and ray FIFOs do not fit in shared memory"};
         const size_t room = budget - stack_bytes - fifo_bytes(v.fifo_slots);
         size_t cache_bytes = room;
@@ -415,8 +420,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         // A four-wide tree is only staged when ALL of it fits (RT2025_WIDE_BVH=1 on a book-sized scene): staging the top of a tree
         // that lives in L2 takes the shared memory away from the L1 and buys nothing (measured with the binary top in round 2:
         // synthetic mesh scene extend 30.1 -> 26.8 ms, 1 M-triangle soup +3 % Mrays/s without it)
-        // (all or nothing, and in direct mode only: the kernels have no mixed four-wide variant)
-        if (!cs.nodes4.empty() && (v.n_cached_nodes < tree_nodes || v.fifo_slots)) v.n_cached_nodes = 0;
+        if (!cs.nodes4.empty()) v.n_cached_nodes = wide_in_smem ? (uint32_t)tree_nodes : 0u;
         s->stack_bytes = stack_bytes + fifo_bytes(v.fifo_slots) + (((size_t)v.n_cached_nodes * node_size + 15) & ~(size_t)15);
         if (kernel_setup(s->stack_bytes, &s->extend_blocks_per_sm, &s->shade_blocks_per_sm, &s->walk_blocks_per_sm) != 0)
             throw CudaFail{"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};

@@ -473,8 +473,10 @@ template <bool COUNT, bool USE_RANK, bool PARK, int WIDE, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
                                                  uint32_t* __restrict__ fifo, uint32_t fifo_slots_arg, TraceCounters* cnt, double* __restrict__ ray_s = nullptr) {
-    // the all-in-shared-memory variants run in direct mode only (the shared memory holds the tree, not FIFOs): no FIFO code in them
+    // the all-in-shared-memory variants run in direct mode only (the shared memory holds the tree, not FIFOs): no FIFO code in them;
+    // the four-wide tree in global memory is always fed from the FIFOs (api.cu gives it at least 32 slots): no direct-mode code
     const uint32_t fifo_slots = WIDE >= 2 ? 0u : fifo_slots_arg;
+    constexpr bool FIFO_ONLY = WIDE == 1;
     const unsigned FULL = 0xFFFFFFFFu;
     const uint32_t lane = threadIdx.x & 31u;
 #if RT_RAY_SMEM
@@ -529,9 +531,9 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
     while (true) {
         const unsigned idle = __ballot_sync(FULL, !have);
         // sv.refill_min: idle lanes a warp waits for before it pops (32 = drain the warp completely)
-        if (idle && (fifo_slots ? ((uint32_t)__popc(idle) >= refill_min || idle == FULL) : idle == FULL)) {
+        if (idle && ((FIFO_ONLY || fifo_slots) ? ((uint32_t)__popc(idle) >= refill_min || idle == FULL) : idle == FULL)) {
             const uint32_t n_idle = __popc(idle);
-            if (fifo_slots == 0) {
+            if (!FIFO_ONLY && fifo_slots == 0) {
                 // ---- direct mode (no FIFO: the shared memory holds the whole tree instead): the warp has drained,
                 // every lane prepares the ray it will trace itself ----
                 const uint32_t g = next_group;
