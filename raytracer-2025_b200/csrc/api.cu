@@ -321,6 +321,8 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         }
         v.world_root = cs.world_root;
         v.n_media = (uint32_t)cs.media.size();
+        v.n_xforms = (uint32_t)cs.xforms.size();
+        v.kinds = (cs.n_spheres && !cs.n_planars) ? 1u : ((cs.n_planars && !cs.n_spheres) ? 2u : 0u);
         v.n_lights = (uint32_t)cs.lights.size();
         v.n_prims = (uint32_t)cs.geom.size();
         s->ranks = cs.ranks;

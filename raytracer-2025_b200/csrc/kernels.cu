@@ -66,7 +66,7 @@ struct RayArrayIO {  // rt_closest_hit batches: rays in, rt_hit out
     }
 };
 
-template <bool COUNT, bool PARK, int WIDE>
+template <bool COUNT, bool PARK, int WIDE, bool XF = true, int KINDS = 0>
 __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit(SceneView sv, const rt_ray* __restrict__ rays, uint32_t n, double tmin,
                                                                  double tmax, rt_hit* __restrict__ out, unsigned long long* counters) {
     extern __shared__ float4 s_mem[];  // [cached nodes | traversal stacks | per-warp ray FIFOs]
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_closest_hit
     TraceCounters cnt{0, 0};
     RayArrayIO io{sv, rays, out, tmin, tmax};
     double* ray_s = reinterpret_cast<double*>(stack_base + sv.stack_entries * EXTEND_BLOCK + (EXTEND_BLOCK / 32) * sv.fifo_slots * FIFO_SLOT_WORDS) + threadIdx.x;
-    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
+    trace_persistent<COUNT, true, PARK, WIDE, XF, KINDS>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)cnt.nodes);
         atomicAdd(&counters[1], (unsigned long long)cnt.prims);
@@ -111,7 +111,15 @@ static void launch_with_l2_window(K kernel, const SceneView& sv, int grid, int b
 
 void launch_closest_hit(const SceneView& sv, const rt_ray* d_rays, uint32_t n, double tmin, double tmax, bool count, rt_hit* d_out,
                         unsigned long long* d_counters, int grid, size_t stack_bytes, cudaStream_t stream) {  // stack_bytes = whole dynamic smem
-    auto k = sv.nodes4 ? (sv.n_cached_nodes && !sv.fifo_slots ? (count ? k_closest_hit<true, true, 2> : k_closest_hit<false, true, 2>)
+    // scenes without any Transform that hold one kind of primitive (a mesh, the soups) have variants without the detransform and
+    // without the other primitive test
+    auto soup = [&]() {
+        if (sv.kinds == 1) return count ? k_closest_hit<true, true, 1, false, 1> : k_closest_hit<false, true, 1, false, 1>;
+        if (sv.kinds == 2) return count ? k_closest_hit<true, true, 1, false, 2> : k_closest_hit<false, true, 1, false, 2>;
+        return count ? k_closest_hit<true, true, 1, false, 0> : k_closest_hit<false, true, 1, false, 0>;
+    };
+    auto k = (sv.nodes4 && !sv.n_cached_nodes && !sv.n_xforms) ? soup()
+             : sv.nodes4 ? (sv.n_cached_nodes && !sv.fifo_slots ? (count ? k_closest_hit<true, true, 2> : k_closest_hit<false, true, 2>)
                                             : (count ? k_closest_hit<true, true, 1> : k_closest_hit<false, true, 1>))
              : (!sv.park_leaves && !sv.fifo_slots && sv.n_cached_nodes == sv.n_nodes) ? (count ? k_closest_hit<true, false, 3> : k_closest_hit<false, false, 3>)
              : count   ? (sv.park_leaves ? k_closest_hit<true, true, 0> : k_closest_hit<true, false, 0>)
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     const bool media_pass_follows = sv.n_media != 0 && MEDIA == 0;  // (P.media_first == 0)
     PathIO<COUNT, MEDIA> io{sv, W.ray_q[W.parity], W.hit_q, media_pass_follows ? nullptr : W.cls_q, P.seed, P.bin_by_class != 0, &cnt};
     double* ray_s = reinterpret_cast<double*>(stack_base + sv.stack_entries * EXTEND_BLOCK + (EXTEND_BLOCK / 32) * sv.fifo_slots * FIFO_SLOT_WORDS) + threadIdx.x;
-    trace_persistent<COUNT, true, PARK, WIDE>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
+    trace_persistent<COUNT, true, PARK, WIDE, true, 0>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
         atomicAdd(&W.counters->prim_tests, (unsigned long long)cnt.prims);
@@ -1284,7 +1292,9 @@ int kernel_setup(size_t smem_bytes, int* extend_blocks_per_sm, int* shade_blocks
         (const void*)k_closest_hit<false, false, 0>, (const void*)k_closest_hit<false, true, 0>, (const void*)k_closest_hit<false, true, 1>,
         (const void*)k_closest_hit<false, true, 2>,  (const void*)k_closest_hit<true, false, 0>, (const void*)k_closest_hit<true, true, 0>,
         (const void*)k_closest_hit<true, true, 1>,   (const void*)k_closest_hit<true, true, 2>,  (const void*)k_closest_hit<false, false, 3>,
-        (const void*)k_closest_hit<true, false, 3>};
+        (const void*)k_closest_hit<true, false, 3>,  (const void*)k_closest_hit<false, true, 1, false, 0>,  (const void*)k_closest_hit<true, true, 1, false, 0>,
+        (const void*)k_closest_hit<false, true, 1, false, 1>,  (const void*)k_closest_hit<true, true, 1, false, 1>,
+        (const void*)k_closest_hit<false, true, 1, false, 2>,  (const void*)k_closest_hit<true, true, 1, false, 2>};
     for (const void* f : big_smem)
         if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EXTEND_SMEM_MAX - 1024))) != cudaSuccess) return (int)e;
     // the general-boundary media pass: TRAVERSAL_STACK entries per thread is 64 KB

@@ -173,6 +173,8 @@ struct SceneView {
     uint32_t refill_min;      // idle lanes a warp of the persistent traversal waits for before it takes new rays (1..32)
     uint32_t media_stack_entries;  // traversal stack entries per thread of the media kernel (depth of the deepest boundary group)
     uint32_t tail_stack_entries;  // stack entries per thread of k_tail: depth of the deepest binary tree (world or boundary group) + 2
+    uint32_t kinds;              // world primitives: 1 = spheres only, 2 = quads / triangles only, 0 = both (or none)
+    uint32_t n_xforms;           // Transforms in the scene (0: the traversal needs no local-space rays)
     uint32_t walk_entries_only;  // exactly one MEDIUM_THICK medium and it has its entry leaves: k_walk never traverses from the world root
     uint32_t fifo_slots;      // prepared-ray FIFO slots per warp of the persistent traversal: 32 or 64; 0 = no FIFO (traverse.cuh)
 };

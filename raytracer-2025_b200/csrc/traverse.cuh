@@ -469,7 +469,9 @@ constexpr uint32_t FIFO_INVALID_ITEM = 0xFFFFFFFFu;  // a slot of the ragged las
 // (WIDE == 2: the whole four-wide tree is in shared memory - a variant of its own, because a per-visit choice between the two
 // node sources costs the global-memory traversal of the big scenes 7 % in Mrays/s; WIDE == 3: the BINARY tree, all of it in
 // shared memory, likewise without the global-memory path)
-template <bool COUNT, bool USE_RANK, bool PARK, int WIDE, class IO>
+// XF = false: the scene has no Transform at all (the soups): no local-space copy of the ray, no detransform code.
+// KINDS: 0 = any primitives, 1 = the scene holds spheres only, 2 = quads / triangles only (a mesh, the soups): the other test is compiled out.
+template <bool COUNT, bool USE_RANK, bool PARK, int WIDE, bool XF, int KINDS, class IO>
 __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, uint32_t n, uint32_t* s_cursor,
                                                  const float4* __restrict__ smem_nodes, uint32_t* __restrict__ stack, int stride,
                                                  uint32_t* __restrict__ fifo, uint32_t fifo_slots_arg, TraceCounters* cnt, double* __restrict__ ray_s = nullptr) {
@@ -557,7 +559,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
 #if RT_RAY_SMEM
                         put_ray(0, r);
 #else
-                        lr = r;
+                        if (XF) lr = r;
 #endif
                         sp = 0;
                         const uint32_t root = (WIDE == 1 || WIDE == 2) ? sv.world_root4 : sv.world_root;
@@ -634,7 +636,7 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
 #if RT_RAY_SMEM
                         put_ray(0, r);
 #else
-                        lr = r;
+                        if (XF) lr = r;
 #endif
                         sp = 0;
                         const uint32_t root = (WIDE == 1 || WIDE == 2) ? sv.world_root4 : sv.world_root;
@@ -762,14 +764,17 @@ __device__ __forceinline__ void trace_persistent(const SceneView& sv, IO& io, ui
                     }
                     const RayD lr = get_ray(km.w == 0xFFFFFFFFu ? 0 : 7);
 #else
-                    if (km.w != cached_xform) {
+                    if (XF && km.w != cached_xform) {
                         lr = km.w == 0xFFFFFFFFu ? r : ray_to_local(sv, km.w, r);
                         cached_xform = km.w;
                     }
 #endif
                     const double* g = sv.geom[pi].d;
                     double t;
-                    bool hit = kind == PRIM_SPHERE ? sphere_hit(g, lr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, lr, tmin, tbest, t);
+                    const RayD& tr = XF ? lr : r;
+                    bool hit = KINDS == 1   ? sphere_hit(g, tr, tmin, tbest, t)
+                               : KINDS == 2 ? planar_hit(g, kind == PRIM_TRIANGLE, tr, tmin, tbest, t)
+                               : kind == PRIM_SPHERE ? sphere_hit(g, tr, tmin, tbest, t) : planar_hit(g, kind == PRIM_TRIANGLE, tr, tmin, tbest, t);
                     if (COUNT) cnt->prims++;
                     if (hit && (prim == 0xFFFFFFFFu || t < tbest || (USE_RANK && km.y < prim_rank))) {
                         tbest = t;
