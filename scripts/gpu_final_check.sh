@@ -1,6 +1,6 @@
+# the round-end sequence the driver runs, in one gpurun call: GPU tests, smoke(), the default bench line
 set -x
 mkdir -p gpurun_out
-SECONDS=0
-python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; echo "bench default rc=$? wall=${SECONDS}s"
-SECONDS=0
-python bench.py --impl reference > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; echo "bench reference rc=$? wall=${SECONDS}s"; cut -c1-400 gpurun_out/r2_bench_reference.json
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/final_tests.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 | tee gpurun_out/final_smoke.log
+python bench.py 2>gpurun_out/final_bench.err | tee gpurun_out/final_bench.json | python scripts/bench_line.py

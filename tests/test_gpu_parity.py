@@ -84,6 +84,22 @@ def test_closest_hit_matches_oracle_on_random_graphs(gpu, rt, orc, seed):
     compare_hits(rt, got, osc.closest_hit(rays, t_min=0.5, t_max=7.0, mode=0))
 
 
+def test_closest_hit_on_a_tree_larger_than_shared_memory(gpu, rt, orc):
+    """6000 primitives: the binary tree (about 5000 nodes) only partly fits in a traversal CTA's shared memory, so the forced-binary
+    variant of this module walks the mixed shared / global-memory node loop in direct mode (book-sized trees are entirely in
+    shared memory, the soups entirely in global memory), and the by-size variant the four-wide tree fed from the FIFOs."""
+    hs = random_graph_scene(rt, 21, n_prims=6000, with_lights=False)
+    sc, osc = rt.Scene(hs), orc.OracleScene(hs)
+    assert np.array_equal(sc.ranks(), osc.ranks())
+    o, d, t = random_rays(np.random.default_rng(21), 40000)
+    rays = rt.make_rays(o, d, t)
+    got, st = sc.closest_hit(rays, flags=rt.RT_OPT_COUNT)
+    compare_hits(rt, got, osc.closest_hit(rays, mode=0))
+    assert st.node_visits > 0 and st.prim_tests > 0
+    img, _ = sc.render(seed=4)
+    image_close(img, osc.render(seed=4)[0])
+
+
 def test_ellipsoids_and_nested_transforms(gpu, rt, orc):
     # a Sphere under a non-uniform scale is an ellipsoid (shapes.rs:74-84); Transforms nest
     b = rt.Builder(9)
