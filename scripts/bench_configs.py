@@ -24,7 +24,8 @@ for name, make, strata in cfgs:
         if best is None or st.ms_total < best.ms_total:
             best = st
     _, cst = sc.render(seed=1, accum_type=rt.RT_ACCUM_F32, flags=rt.RT_OPT_COUNT)
-    ctxt = f", {cst.node_visits/cst.segments:.1f} nodes + {cst.prim_tests/cst.segments:.1f} prims per segment"
+    ext = max(1, cst.segments - cst.walk_segments)  # the counters see the segments that pass through k_extend / the media passes
+    ctxt = f", {cst.node_visits/ext:.1f} nodes + {cst.prim_tests/ext:.1f} prims per segment through extend"
     otxt = ""
     if not os.environ.get("NO_ORACLE"):
         osc = orc.OracleScene(hs)
