@@ -210,6 +210,7 @@ struct rt_scene {
     uint32_t lights_flat = 1;
     uint32_t class_mask = 0;     // shade classes the scene's materials can produce
     bool generic_media = false;  // some ConstantMedium boundary is not a single Sphere
+    std::vector<uint8_t> black_texture;  // per texture: a solid colour (0, 0, 0) - a miss against such a background contributes nothing
     int extend_blocks_per_sm = 4, shade_blocks_per_sm = 4, walk_blocks_per_sm = 1;
     size_t stack_bytes = 0;  // dynamic shared memory of the traversal kernels: cached nodes + stacks
 };
@@ -331,6 +332,7 @@ int rt_scene_create(const rt_scene_desc* desc, const rt_build_opts* opts, rt_sce
         for (auto& m : cs.media)
             if (m.xform != RT_NONE || (m.single_sphere != RT_NONE && cs.meta[m.single_sphere].xform != RT_NONE)) v.media_xform = 1;
         for (auto& m : cs.materials) s->class_mask |= 1u << m.shade_class;
+        for (auto& t : cs.textures) s->black_texture.push_back(t.kind == RT_TEX_SOLID && t.color[0] == 0.0 && t.color[1] == 0.0 && t.color[2] == 0.0);
         uint32_t n_thick = 0, n_thick_entries = 0;
         for (auto& m : cs.media)
             if (m.flags & MEDIUM_THICK) s->class_mask |= 1u << SC_WALK, n_thick++, n_thick_entries += m.n_entry != MEDIUM_NO_ENTRIES;
@@ -674,6 +676,8 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         P.walk_drain_queue = 262144, P.walk_drain_steps = 4;
         if (const char* e = getenv("RT2025_WALK_DRAIN_QUEUE")) P.walk_drain_queue = (uint32_t)std::max(0l, atol(e));  // tuning knobs
         if (const char* e = getenv("RT2025_WALK_DRAIN_STEPS")) P.walk_drain_steps = (uint32_t)std::max(1l, atol(e));
+        // a miss against a black background adds nothing to the frame: extend drops the path instead of queueing it for the miss kernel
+        P.drop_misses = s->black_texture[cam->background_tex] && !getenv("RT2025_KEEP_MISSES");
         P.sample_in_generate = 1;
         if (const char* e = getenv("RT2025_GEN_MEDIA")) P.sample_in_generate = atoi(e) != 0;  // tuning knob
         const bool count = (o.flags & RT_OPT_COUNT) != 0, stage = (o.flags & RT_OPT_STAGE_TIMES) != 0;

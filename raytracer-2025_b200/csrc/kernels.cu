@@ -288,7 +288,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
     HitRec* __restrict__ hits;
     uint8_t* __restrict__ cls;  // nullptr: a media pass follows and writes the class bytes
     uint64_t seed;
-    bool bin_by_class;
+    bool bin_by_class, drop_misses;
     TraceCounters* cnt;
     __device__ __forceinline__ double t_min() const { return 1e-8; }  // camera.rs:286
     __device__ __forceinline__ bool load(uint32_t j, RayD& r, double& t1, uint32_t& prim0, uint32_t& rank0) const {
@@ -340,7 +340,7 @@ struct PathIO {  // k_extend: rays come from the current ray stream, hits go to 
             }
         }
         *reinterpret_cast<double2*>(hits + j) = make_double2(hit ? t : INFINITY, __hiloint2double((int)prim, (int)kind));
-        if (cls) cls[j] = (uint8_t)(bin_by_class || c == SC_MISS ? c : SC_DIFFUSE);
+        if (cls) cls[j] = (c == SC_MISS && drop_misses) ? CLASS_DROPPED : (uint8_t)(bin_by_class || c == SC_MISS ? c : SC_DIFFUSE);
     }
 };
 
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(EXTEND_BLOCK, EXTEND_MIN_BLOCKS) k_extend(Scen
     TraceCounters cnt{0, 0};
     // a media pass after extend (classic order, or boundaries that are not spheres) owns the class bytes
     const bool media_pass_follows = sv.n_media != 0 && MEDIA == 0;  // (P.media_first == 0)
-    PathIO<COUNT, MEDIA> io{sv, W.ray_q[W.parity], W.hit_q, media_pass_follows ? nullptr : W.cls_q, P.seed, P.bin_by_class != 0, &cnt};
+    PathIO<COUNT, MEDIA> io{sv, W.ray_q[W.parity], W.hit_q, media_pass_follows ? nullptr : W.cls_q, P.seed, P.bin_by_class != 0, P.drop_misses != 0, &cnt};
     double* ray_s = reinterpret_cast<double*>(stack_base + sv.stack_entries * EXTEND_BLOCK + (EXTEND_BLOCK / 32) * sv.fifo_slots * FIFO_SLOT_WORDS) + threadIdx.x;
     trace_persistent<COUNT, true, PARK, WIDE, true, 0>(sv, io, n, &s_cursor, s_mem, stack, EXTEND_BLOCK, fifo, sv.fifo_slots, &cnt, ray_s);
     if (COUNT) {
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, MODE == 2 ? RT_MEDIA_GENERIC_MIN_
                      : kind == HIT_MEDIUM ? ((sv.media[prim].flags & MEDIUM_THICK) ? (uint32_t)SC_WALK : (uint32_t)SC_ISOTROPIC)
                                           : ((surface_meta >> META_CLASS_SHIFT) & 15u);
         if (!P.bin_by_class && c != SC_MISS) c = SC_DIFFUSE;
-        W.cls_q[j] = (uint8_t)c;
+        W.cls_q[j] = (c == SC_MISS && P.drop_misses) ? CLASS_DROPPED : (uint8_t)c;
     }
     if (COUNT) {
         atomicAdd(&W.counters->node_visits, (unsigned long long)cnt.nodes);
@@ -568,7 +568,8 @@ __global__ void __launch_bounds__(MEDIA_BLOCK, 4) k_bin(WavefrontState W) {
     const uint32_t n_round = (n + MEDIA_BLOCK - 1u) / MEDIA_BLOCK * MEDIA_BLOCK;  // whole CTAs iterate together
     uint32_t it = 0;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x, it++) {
-        const int q = j < n ? (int)W.cls_q[j] : -1;
+        int q = j < n ? (int)W.cls_q[j] : -1;
+        if (q == (int)CLASS_DROPPED) q = -1;
         uint32_t* cntb = s_cnt[it & 1];
         const uint32_t local = queue_reserve(cntb, q);
         __syncthreads();

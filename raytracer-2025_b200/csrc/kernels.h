@@ -68,6 +68,7 @@ constexpr size_t EXTEND_RAY_SMEM_BYTES = RT_RAY_SMEM ? (size_t)14 * sizeof(doubl
 #define RT_SHADE_MIN_BLOCKS 2
 #endif
 
+constexpr uint8_t CLASS_DROPPED = 0xFF;  // cls_q: the path ended in extend, no shade kernel reads the entry
 enum HitKind : uint32_t { HIT_MISS = 0, HIT_SURFACE = 1, HIT_MEDIUM = 2 };
 
 // The wavefront state is a set of dense streams indexed by QUEUE POSITION (no per-path slots):
@@ -128,6 +129,7 @@ struct RenderParams {
     uint32_t sample_begin, part_index, part_count;
     uint32_t lights_flat, bin_by_class;
     uint32_t walk_drain_queue, walk_drain_steps;  // k_walk: queues of at most walk_drain_queue entries cut every walk after walk_drain_steps segments
+    uint32_t drop_misses;  // the background is a solid (0, 0, 0): a path that misses everything ends in extend (class byte CLASS_DROPPED)
     uint32_t sample_in_generate;  // media_first == 1: k_generate samples the media for the camera rays it writes (A/B knob RT2025_GEN_MEDIA=0)
     uint32_t media_first;  // 0: media sampled after extend (order of Hittables::hit); 1: by a pass ahead of extend, 2: by extend itself while it
                            // prepares the ray - extend then only looks for surfaces up to the scatter point
