@@ -608,8 +608,9 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
     // paths in flight: large enough that the ~14 launches of an iteration and the under-filled start and end of every
     // persistent kernel are amortised over many segments, never more than the job needs.  Measured, 800x800x144 book2 frame:
     // 2^23 / 2^24 / 2^25 / 2^26 paths: 90.9 / 87.9 / 86.6 / 85.5 ms (the 1920x1080 mesh scene: 105.0 -> 97.9 ms from 2^24 to 2^25);
-    // 2^26 paths are 16 GB of streams (245 B per path), 9 % of a B200's memory.
-    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 26);
+    // 2^27 paths are 33 GB of streams (249 B per path), 18 % of a B200's memory; a device that cannot give that much gets half (below).
+    // (2^27 since the random walk took a third of the segments out of the streams: 455.9 -> 449.8 ms on the bench frame, 45 -> 39 iterations)
+    uint32_t capacity = o.max_paths_in_flight ? o.max_paths_in_flight : (1u << 27);
     if (const char* e = getenv("RT2025_PATHS_IN_FLIGHT")) capacity = (uint32_t)std::max(1024l, atol(e));  // tuning knob
     capacity = (uint32_t)std::min<uint64_t>(capacity, ((total_paths + 1023) / 1024) * 1024);
     capacity = std::max(capacity, 1024u);
@@ -621,7 +622,7 @@ int rt_render_device(const rt_scene* cs, const rt_camera* cam, const rt_render_o
         if (ws.capacity < capacity || ws.n_pixels_alloc < n_px_img) {  // grow-only
             uint32_t capacity_alloc = std::max(ws.capacity, capacity);
             const uint64_t n_px_alloc = std::max<uint64_t>(ws.n_pixels_alloc, n_px_img);
-            // the streams are 245 bytes per path in flight (16 GB at the default 2^26): when the device cannot give that much
+            // the streams are 249 bytes per path in flight (33 GB at the default 2^27): when the device cannot give that much
             // - other tenants, a smaller part - halve the capacity instead of failing; the image does not depend on it
             while (true) {
                 ws.release();
