@@ -42,6 +42,10 @@ build/time_compile: scripts/time_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_ca
 	mkdir -p build && $(CXX) $(CXXFLAGS) -O3 -I$(PKG)/csrc -I$(PKG)/host -I/usr/local/cuda/include -o $@ scripts/time_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp
 check_tie_order: build/check_tie_order
 	build/check_tie_order
+build/check_walk_entries: scripts/check_walk_entries.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp $(PRODUCT_HDR)
+	mkdir -p build && $(CXX) $(CXXFLAGS) -I$(PKG)/csrc -I$(PKG)/host -I/usr/local/cuda/include -o $@ scripts/check_walk_entries.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp
+check_walk_entries: build/check_walk_entries
+	build/check_walk_entries
 build/fuzz_compile: scripts/fuzz_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp $(PRODUCT_HDR)
 	mkdir -p build && $(CXX) -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -fopenmp -std=c++17 -ffp-contract=off -Iinclude -I$(PKG)/csrc -I$(PKG)/host -I/usr/local/cuda/include -o $@ scripts/fuzz_compile.cpp $(HOSTTOOL_SRC) $(PKG)/host/host_capi.cpp
 fuzz_compile: build/fuzz_compile
@@ -50,4 +54,4 @@ fuzz_compile: build/fuzz_compile
 clean:
 	rm -f $(PKG)/librt2025.so $(PKG)/librt2025_host.so oracle/liboracle.so
 
-.PHONY: all product host oracle examples clean check_tie_order fuzz_compile
+.PHONY: all product host oracle examples clean check_tie_order check_walk_entries fuzz_compile

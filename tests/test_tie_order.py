@@ -11,3 +11,12 @@ def test_partition_walk_matches_per_node_stable_sort():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.strip().endswith("OK")
     assert "0 rank mismatches" in r.stdout
+
+
+def test_entry_leaves_of_thick_media_are_complete():
+    """csrc/compile.cpp, Medium::entry: the leaves k_walk tests instead of traversing from the root are all the world leaves
+    whose box meets the boundary ball (flat scan over every node), parents' boxes contain their children's, and only media
+    with an optical radius >= 1 are flagged (book2_final, 12 seeds)."""
+    r = subprocess.run(["make", "-s", "check_walk_entries"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "12 thick media checked, 0 problems" in r.stdout
