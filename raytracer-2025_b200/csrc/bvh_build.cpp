@@ -52,17 +52,51 @@ uint32_t make_leaf(const Ctx& c, uint32_t begin, uint32_t end) {
     return LEAF_FLAG | ((c.base + begin) << 3) | (end - begin - 1);
 }
 
+// Big ranges (the top of a 10^7..10^8-primitive tree) are processed by the whole team: the range is cut into chunks that run as
+// tasks (the caller is already inside the build's task region, so a nested parallel loop would run on one thread), the partial
+// results are merged by the caller.  With one task per node the first four levels ran on 1, 2, 4 and 8 cores.
+constexpr uint32_t PAR_MIN = 1u << 21;
+constexpr int PAR_CHUNKS = 64;
+struct Bins {
+    uint32_t cnt[3][NBINS];
+    Box3 bb[3][NBINS];
+    void reset() {
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < NBINS; k++) cnt[a][k] = 0, bb[a][k].reset();
+    }
+};
+inline int bin_of(float ce, float lo, float scale) { return std::min(NBINS - 1, std::max(0, (int)((ce - lo) * scale))); }
+
 // returns the child reference for [begin,end) and its bounds
 uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth, Box3& bounds) {
     const uint32_t n = end - begin;
+    const bool par = n >= PAR_MIN;
+    auto chunk_at = [&](int k) { return begin + (uint32_t)((uint64_t)n * (uint64_t)k / PAR_CHUNKS); };
     bounds.reset();
     Box3 cb;
     cb.reset();
-    for (uint32_t i = begin; i < end; i++) {
-        const BuildBox& b = c.boxes[c.idx[i]];
-        bounds.grow(b.lo, b.hi);
-        float ce[3] = {centroid(b, 0), centroid(b, 1), centroid(b, 2)};
-        cb.grow(ce, ce);
+    if (par) {
+        std::vector<Box3> pb(PAR_CHUNKS), pc(PAR_CHUNKS);
+#pragma omp taskloop grainsize(1) default(shared)
+        for (int k = 0; k < PAR_CHUNKS; k++) {
+            Box3 b0, c0;
+            b0.reset(), c0.reset();
+            for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) {
+                const BuildBox& b = c.boxes[c.idx[i]];
+                b0.grow(b.lo, b.hi);
+                float ce[3] = {centroid(b, 0), centroid(b, 1), centroid(b, 2)};
+                c0.grow(ce, ce);
+            }
+            pb[k] = b0, pc[k] = c0;
+        }
+        for (int k = 0; k < PAR_CHUNKS; k++) bounds.grow(pb[k].lo, pb[k].hi), cb.grow(pc[k].lo, pc[k].hi);
+    } else {
+        for (uint32_t i = begin; i < end; i++) {
+            const BuildBox& b = c.boxes[c.idx[i]];
+            bounds.grow(b.lo, b.hi);
+            float ce[3] = {centroid(b, 0), centroid(b, 1), centroid(b, 2)};
+            cb.grow(ce, ce);
+        }
     }
     uint32_t d = c.max_depth->load(std::memory_order_relaxed);
     while (depth > d && !c.max_depth->compare_exchange_weak(d, depth)) {
@@ -74,19 +108,39 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
     if (depth < 32) {
         float best_cost = INFINITY;
         int best_axis = -1, best_bin = -1;
-        for (int a = 0; a < 3; a++) {
-            float ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.f)) continue;
-            float scale = NBINS / ext;
-            uint32_t cnt[NBINS] = {0};
-            Box3 bb[NBINS];
-            for (auto& x : bb) x.reset();
-            for (uint32_t i = begin; i < end; i++) {
+        // the three axes are binned in ONE pass over the range (the boxes are read through the index list, i.e. at random)
+        float ext3[3], scale3[3];
+        for (int a = 0; a < 3; a++) ext3[a] = cb.hi[a] - cb.lo[a], scale3[a] = ext3[a] > 0.f ? NBINS / ext3[a] : 0.f;
+        Bins bins;
+        bins.reset();
+        auto bin_range = [&](uint32_t i0, uint32_t i1, Bins& out) {
+            for (uint32_t i = i0; i < i1; i++) {
                 const BuildBox& b = c.boxes[c.idx[i]];
-                int k = std::min(NBINS - 1, std::max(0, (int)((centroid(b, a) - cb.lo[a]) * scale)));
-                cnt[k]++;
-                bb[k].grow(b.lo, b.hi);
+                for (int a = 0; a < 3; a++) {
+                    if (!(ext3[a] > 0.f)) continue;
+                    const int k = bin_of(centroid(b, a), cb.lo[a], scale3[a]);
+                    out.cnt[a][k]++;
+                    out.bb[a][k].grow(b.lo, b.hi);
+                }
             }
+        };
+        if (par) {
+            std::vector<Bins> part(PAR_CHUNKS);
+#pragma omp taskloop grainsize(1) default(shared)
+            for (int k = 0; k < PAR_CHUNKS; k++) {
+                part[k].reset();
+                bin_range(chunk_at(k), chunk_at(k + 1), part[k]);
+            }
+            for (int k = 0; k < PAR_CHUNKS; k++)
+                for (int a = 0; a < 3; a++)
+                    for (int q = 0; q < NBINS; q++) bins.cnt[a][q] += part[k].cnt[a][q], bins.bb[a][q].grow(part[k].bb[a][q].lo, part[k].bb[a][q].hi);
+        } else {
+            bin_range(begin, end, bins);
+        }
+        for (int a = 0; a < 3; a++) {
+            if (!(ext3[a] > 0.f)) continue;
+            const uint32_t* cnt = bins.cnt[a];
+            const Box3* bb = bins.bb[a];
             float right_area[NBINS];
             uint32_t right_cnt[NBINS];
             Box3 acc;
@@ -113,13 +167,37 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
             float split_cost = C_TRAV + (area > 0.f ? best_cost / area : (float)n) * C_PRIM;
             float leaf_cost = (float)n * C_PRIM;
             if (n <= LEAF_TARGET && leaf_cost <= split_cost) return make_leaf(c, begin, end);
-            float ext = cb.hi[best_axis] - cb.lo[best_axis];
-            float scale = NBINS / ext, lo = cb.lo[best_axis];
-            uint32_t* p = std::partition(c.idx + begin, c.idx + end, [&](uint32_t i) {
-                int k = std::min(NBINS - 1, std::max(0, (int)((centroid(c.boxes[i], best_axis) - lo) * scale)));
-                return k <= best_bin;
-            });
-            mid = (uint32_t)(p - c.idx);
+            const float scale = scale3[best_axis], lo = cb.lo[best_axis];
+            auto goes_left = [&](uint32_t i) { return bin_of(centroid(c.boxes[i], best_axis), lo, scale) <= best_bin; };
+            if (par) {
+                // chunked partition through a scratch copy: count per chunk, then every chunk writes its two parts at their offsets
+                std::vector<uint32_t> scratch(c.idx + begin, c.idx + end);
+                const uint32_t* src = scratch.data() - begin;
+                std::vector<uint32_t> n_left(PAR_CHUNKS + 1, 0);
+#pragma omp taskloop grainsize(1) default(shared)
+                for (int k = 0; k < PAR_CHUNKS; k++) {
+                    uint32_t nl = 0;
+                    for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) nl += goes_left(src[i]);
+                    n_left[k + 1] = nl;
+                }
+                for (int k = 0; k < PAR_CHUNKS; k++) n_left[k + 1] += n_left[k];
+                mid = begin + n_left[PAR_CHUNKS];
+#pragma omp taskloop grainsize(1) default(shared)
+                for (int k = 0; k < PAR_CHUNKS; k++) {
+                    uint32_t* l = c.idx + begin + n_left[k];
+                    uint32_t* r = c.idx + mid + (chunk_at(k) - begin - n_left[k]);
+                    for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) {
+                        const uint32_t v = src[i];
+                        if (goes_left(v))
+                            *l++ = v;
+                        else
+                            *r++ = v;
+                    }
+                }
+            } else {
+                uint32_t* p = std::partition(c.idx + begin, c.idx + end, goes_left);
+                mid = (uint32_t)(p - c.idx);
+            }
             have_split = mid > begin && mid < end;
         }
     }

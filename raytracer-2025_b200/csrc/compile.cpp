@@ -14,6 +14,8 @@
 //   6. build one SAH BVH per group and store primitives in leaf order.
 #include "compile.h"
 
+#include <omp.h>
+
 #include <memory>
 #include <parallel/algorithm>
 
@@ -550,6 +552,89 @@ struct Compiler {
             tie_order_node(T, off, mid, buf ^ 1, axis, out + n_right);
         }
     }
+    // One BIG node of the walk above, split by ALL threads (the task recursion gives a node to one thread: on a 10^8-child tree
+    // the first four levels then run on 1, 2, 4 and 8 of the cores and take as long as all the levels below them together).
+    // Same steps as tie_order_node: bounds -> axis, side bytes, stable partition of the two other lists (two passes over
+    // per-thread chunks: count, then write at the chunk's offsets), equal-key runs re-sorted by position.  Returns the axis.
+    int split_node_parallel(const TieOrder& T, size_t off, size_t len, int buf) {
+        AxisEnt* const* cur = T.list[buf];
+        AxisEnt* const* nxt = T.list[buf ^ 1];
+        double s[3];
+        for (int k = 0; k < 3; k++) {
+            double mn = INFINITY, mx = -INFINITY;
+            const AxisEnt* e = cur[k] + off;
+#pragma omp parallel for schedule(static) reduction(min : mn) reduction(max : mx)
+            for (size_t i = 0; i < len; i++) mn = std::fmin(mn, e[i].mn), mx = std::fmax(mx, e[i].mx);
+            s[k] = std::fmax(mx - mn, 0.0);
+        }
+        const int axis = s[0] > s[1] ? (s[0] > s[2] ? 0 : 2) : (s[1] > s[2] ? 1 : 2);  // aabb.rs:80-92
+        const size_t mid = len / 2;
+        {
+            const AxisEnt* e = cur[axis] + off;
+#pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < len; i++) T.side[e[i].id] = i >= mid;
+        }
+        const int n_chunks = std::max(1, omp_get_max_threads());
+        std::vector<size_t> lo_count((size_t)n_chunks + 1);
+        bool ties = false;
+        for (int k = 0; k < 3; k++) {
+            const AxisEnt* e = cur[k] + off;
+            if (k == axis) {
+#pragma omp parallel for schedule(static)
+                for (size_t i = 0; i < len; i++) nxt[k][off + i] = e[i];
+                continue;
+            }
+            auto chunk_begin = [&](int c) { return len * (size_t)c / (size_t)n_chunks; };
+#pragma omp parallel for schedule(static, 1)
+            for (int c = 0; c < n_chunks; c++) {
+                size_t n_lo = 0;
+                for (size_t i = chunk_begin(c); i < chunk_begin(c + 1); i++) n_lo += !T.side[e[i].id];
+                lo_count[(size_t)c + 1] = n_lo;
+            }
+            lo_count[0] = 0;
+            for (int c = 0; c < n_chunks; c++) lo_count[(size_t)c + 1] += lo_count[(size_t)c];  // lows before chunk c
+#pragma omp parallel for schedule(static, 1)
+            for (int c = 0; c < n_chunks; c++) {
+                AxisEnt* lo = nxt[k] + off + lo_count[(size_t)c];
+                AxisEnt* hi = nxt[k] + off + mid + (chunk_begin(c) - lo_count[(size_t)c]);
+                for (size_t i = chunk_begin(c); i < chunk_begin(c + 1); i++) {
+                    if (!T.side[e[i].id])
+                        *lo++ = e[i];
+                    else
+                        *hi++ = e[i];
+                }
+            }
+            // equal keys next to each other inside a half: the run has to be put into this node's order (below)
+            const AxisEnt* o = nxt[k] + off;
+            bool t = false;
+#pragma omp parallel for schedule(static) reduction(|| : t)
+            for (size_t i = 1; i < len; i++)
+                if (i != mid && total_order_key(o[i].mn) == total_order_key(o[i - 1].mn)) t = true;
+            ties = ties || t;
+        }
+        if (ties) {
+            const AxisEnt* e = cur[axis] + off;
+#pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < len; i++) T.pos[e[i].id] = (uint32_t)i;
+            const size_t n_right = len - mid;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+            for (int k = 0; k < 3; k++)
+                for (int h = 0; h < 2; h++) {
+                    if (k == axis) continue;
+                    AxisEnt* half = nxt[k] + off + (h ? mid : 0);
+                    const size_t n = h ? n_right : mid;
+                    for (size_t i = 0; i + 1 < n;) {
+                        size_t j = i + 1;
+                        const uint64_t key = total_order_key(half[i].mn);
+                        while (j < n && total_order_key(half[j].mn) == key) j++;
+                        if (j - i > 1) std::sort(half + i, half + j, [&](const AxisEnt& x, const AxisEnt& y) { return T.pos[x.id] < T.pos[y.id]; });
+                        i = j;
+                    }
+                }
+        }
+        return axis;
+    }
+
     // kids[0..n) -> the same ids in tie order
     void bvh_visit_order(std::vector<uint32_t>& kids) {
         const size_t n = kids.size();
@@ -568,6 +653,7 @@ struct Compiler {
             const double* bb = d.objects[kids[i]].bbox;
             for (int k = 0; k < 3; k++) T.list[0][k][i] = AxisEnt{bb[2 * k], bb[2 * k + 1], (uint32_t)i, 0};
         }
+        if (n > 100000) timer.lap("    tie order: fill");
         // the three stable sorts by box-min: libstdc++'s parallel multiway merge sort for big inputs (it brings its own
         // team, so it runs outside the task region of the walk)
         for (int k = 0; k < 3; k++) {
@@ -576,9 +662,36 @@ struct Compiler {
             else
                 std::stable_sort(T.list[0][k], T.list[0][k] + n, key_less);
         }
+        if (n > 100000) timer.lap("    tie order: three stable sorts");
+        // the big nodes at the top are split one after the other by all threads; what is left goes to the task recursion
+        struct Job {
+            size_t off, len;
+            int buf, p_axis;
+            uint32_t* out;
+        };
+        size_t par_min = 1u << 20;
+        if (const char* e = getenv("RT2025_TIE_PAR_MIN")) par_min = (size_t)std::max(8l, atol(e));  // (the CPU check forces the parallel split on small inputs)
+        std::vector<Job> big{{0, n, 0, -1, out.data()}}, rest;
+        while (!big.empty()) {
+            const Job j = big.back();
+            big.pop_back();
+            if (j.len < par_min || j.len < 8) {
+                rest.push_back(j);
+                continue;
+            }
+            const int axis = split_node_parallel(T, j.off, j.len, j.buf);
+            const size_t mid = j.len / 2, n_right = j.len - mid;
+            big.push_back({j.off + mid, n_right, j.buf ^ 1, axis, j.out});          // right first (bvh.rs:78-84)
+            big.push_back({j.off, mid, j.buf ^ 1, axis, j.out + n_right});
+        }
+        if (n > 100000) timer.lap("    tie order: big nodes, all threads");
 #pragma omp parallel if (n > 32768)  // waking the team costs more than a book-sized tree (a few thousand children) takes
 #pragma omp single
-        tie_order_node(T, 0, n, 0, -1, out.data());
+        for (const Job& j : rest) {
+#pragma omp task default(shared) firstprivate(j)
+            tie_order_node(T, j.off, j.len, j.buf, j.p_axis, j.out);
+        }
+        if (n > 100000) timer.lap("    tie order: subtrees as tasks");
         kids.swap(out);
     }
 

@@ -5,7 +5,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "compile.h"
 
@@ -27,5 +29,41 @@ int main(int argc, char** argv) {
     printf("%s N=%.0f: host scene %.2f s, compile %.2f s (rc %d %s), %zu nodes, depth %u\n", name, n,
            std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(), rc, err.c_str(),
            cs.nodes.size(), cs.bvh_depth);
+    if (rc == 0 && getenv("RT2025_VERIFY_TREE")) {
+        // every world primitive in exactly one leaf, every child box inside its parent's copy of it
+        std::vector<unsigned char> seen(cs.geom.size(), 0);
+        std::vector<uint32_t> todo{cs.world_root};
+        size_t bad = 0, leaves = 0;
+        auto visit_leaf = [&](uint32_t ref) {
+            const uint32_t first = (ref & ~rt::LEAF_FLAG) >> 3, count = (ref & 7u) + 1;
+            for (uint32_t i = first; i < first + count; i++) bad += i >= seen.size() || seen[i]++;
+            leaves++;
+        };
+        while (!todo.empty()) {
+            const uint32_t ref = todo.back();
+            todo.pop_back();
+            if (ref == rt::INVALID_REF) continue;
+            if (ref & rt::LEAF_FLAG) {
+                visit_leaf(ref);
+                continue;
+            }
+            const rt::Node& nd = cs.nodes[ref];
+            const float* lo[2] = {nd.lo0, nd.lo1};
+            const float* hi[2] = {nd.hi0, nd.hi1};
+            const uint32_t child[2] = {nd.child0, nd.child1};
+            for (int c = 0; c < 2; c++) {
+                if (child[c] != rt::INVALID_REF && !(child[c] & rt::LEAF_FLAG)) {
+                    const rt::Node& ch = cs.nodes[child[c]];
+                    for (int k = 0; k < 3; k++)
+                        bad += std::min(ch.lo0[k], ch.lo1[k]) < lo[c][k] || std::max(ch.hi0[k], ch.hi1[k]) > hi[c][k];
+                }
+                todo.push_back(child[c]);
+            }
+        }
+        size_t missing = 0;
+        for (unsigned char v : seen) missing += v != 1;
+        printf("tree check: %zu leaves, %zu primitives not in exactly one leaf, %zu other problems\n", leaves, missing, bad);
+        if (missing || bad) return 3;
+    }
     return rc;
 }

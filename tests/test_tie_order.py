@@ -13,6 +13,16 @@ def test_partition_walk_matches_per_node_stable_sort():
     assert "0 rank mismatches" in r.stdout
 
 
+def test_team_parallel_split_of_big_nodes_gives_the_same_order():
+    """Nodes of a million children and more are split by all threads (compile.cpp, split_node_parallel) instead of one task each;
+    RT2025_TIE_PAR_MIN forces that path on the small, tie-ridden inputs of the check."""
+    env = dict(os.environ, RT2025_TIE_PAR_MIN="8")
+    r = subprocess.run(["build/check_tie_order"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.strip().endswith("OK") and "0 rank mismatches" in r.stdout
+    assert "1 rank mismatches" not in r.stdout
+
+
 def test_entry_leaves_of_thick_media_are_complete():
     """csrc/compile.cpp, Medium::entry: the leaves k_walk tests instead of traversing from the root are all the world leaves
     whose box meets the boundary ball (flat scan over every node), parents' boxes contain their children's, and only media
