@@ -394,7 +394,7 @@ def main():
                        "scene_seed": seed, "prims": info.n_prims, "bvh_nodes": info.n_nodes, "media": info.n_media,
                        "paths_per_step": paths // max(1, args.steps), "segments_per_path": float(extra[0].item()) / max(1, paths),
                        "parallelism": f"{args.partition}{world}" if world > 1 else "single",
-                       "l2": "flushed between steps (256 MiB fill); the ray/state/hit streams of 2^24 paths in flight (4.5 GB) exceed the 126 MB L2, the 0.7 MB scene is cache-resident by design"},
+                       "l2": "flushed between steps (256 MiB fill); the ray/throughput/hit streams of up to 2^27 paths in flight (249 B per path, 33 GB) exceed the 126 MB L2, the 0.7 MB scene is cache-resident by design"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "includes": ("rt_scene_create (compile + SAH build + upload of the host description) then rt_render_rgb8 into a host buffer (render, 8-bit encode on the device, D2H)"

@@ -11,6 +11,8 @@
 //   bin      : the append of every queue position to the shade queue of the winner's material class
 //   shade    : one kernel per class - emitted + scatter + mixture-pdf light sampling (camera.rs:290-321);
 //              survivors are appended to the other copy of the ray/state streams
+//   walk     : the class of scatter points inside optically thick media: the path stays in registers from one scatter point to
+//              the next (Isotropic::scatter, then world.hit of the next segment in place) until it leaves the medium or ends
 //
 // Paths flow through dense, position-indexed streams (kernels.h); terminated paths simply are not
 // re-appended.  Radiance is accumulated with binary64 atomics into a per-pixel framebuffer.
