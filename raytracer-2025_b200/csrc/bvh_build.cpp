@@ -16,9 +16,16 @@ namespace rt {
 
 namespace {
 
+// The builder permutes RECORDS (box + primitive index, 28 bytes), not an index list: every pass over a range then streams through
+// memory instead of gathering 24-byte boxes at random - on 10^7 primitives the passes of the upper levels were bound by the
+// latency of those gathers.
+struct Rec {
+    float lo[3], hi[3];
+    uint32_t id;
+};
 struct Ctx {
-    const BuildBox* boxes;
-    uint32_t* idx;
+    Rec* recs;
+    Rec* scratch;  // as long as recs: the chunked partition of a big range copies through it
     Node* nodes;
     std::atomic<uint32_t>* node_count;
     std::atomic<uint32_t>* max_depth;
@@ -46,7 +53,7 @@ float C_TRAV = 1.0f, C_PRIM = 4.0f;  // a binary64 primitive test costs several 
 uint32_t LEAF_TARGET = 2;  // SAH may stop at <= this many primitives
 constexpr uint32_t TASK_MIN = 8192;
 
-inline float centroid(const BuildBox& b, int a) { return 0.5f * (b.lo[a] + b.hi[a]); }
+inline float centroid(const Rec& b, int a) { return 0.5f * (b.lo[a] + b.hi[a]); }
 
 uint32_t make_leaf(const Ctx& c, uint32_t begin, uint32_t end) {
     return LEAF_FLAG | ((c.base + begin) << 3) | (end - begin - 1);
@@ -82,7 +89,7 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
             Box3 b0, c0;
             b0.reset(), c0.reset();
             for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) {
-                const BuildBox& b = c.boxes[c.idx[i]];
+                const Rec& b = c.recs[i];
                 b0.grow(b.lo, b.hi);
                 float ce[3] = {centroid(b, 0), centroid(b, 1), centroid(b, 2)};
                 c0.grow(ce, ce);
@@ -92,7 +99,7 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
         for (int k = 0; k < PAR_CHUNKS; k++) bounds.grow(pb[k].lo, pb[k].hi), cb.grow(pc[k].lo, pc[k].hi);
     } else {
         for (uint32_t i = begin; i < end; i++) {
-            const BuildBox& b = c.boxes[c.idx[i]];
+            const Rec& b = c.recs[i];
             bounds.grow(b.lo, b.hi);
             float ce[3] = {centroid(b, 0), centroid(b, 1), centroid(b, 2)};
             cb.grow(ce, ce);
@@ -111,11 +118,44 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
         // the three axes are binned in ONE pass over the range (the boxes are read through the index list, i.e. at random)
         float ext3[3], scale3[3];
         for (int a = 0; a < 3; a++) ext3[a] = cb.hi[a] - cb.lo[a], scale3[a] = ext3[a] > 0.f ? NBINS / ext3[a] : 0.f;
+        // Most nodes of a tree hold a handful of primitives, and for those the 3 x 16 bins (1.3 KB to clear and to sweep) cost far more
+        // than the primitives: a small range is sorted by bin index instead and only the boundaries between OCCUPIED bins are
+        // evaluated.  Same candidates, same costs (unions and counts do not depend on the order), same first minimum: same tree.
+        constexpr uint32_t SMALL_N = 12;
+        if (n <= SMALL_N) {
+            for (int a = 0; a < 3; a++) {
+                if (!(ext3[a] > 0.f)) continue;
+                int kb[SMALL_N];
+                uint8_t ord[SMALL_N];
+                for (uint32_t i = 0; i < n; i++) {
+                    kb[i] = bin_of(centroid(c.recs[begin + i], a), cb.lo[a], scale3[a]);
+                    uint32_t j = i;  // insertion sort by bin index
+                    while (j > 0 && kb[ord[j - 1]] > kb[i]) ord[j] = ord[j - 1], j--;
+                    ord[j] = (uint8_t)i;
+                }
+                float right_area[SMALL_N + 1];
+                Box3 acc;
+                acc.reset();
+                for (uint32_t j = n; j-- > 1;) {
+                    const Rec& b = c.recs[begin + ord[j]];
+                    acc.grow(b.lo, b.hi);
+                    right_area[j] = acc.half_area();
+                }
+                acc.reset();
+                for (uint32_t j = 0; j + 1 < n; j++) {
+                    const Rec& b = c.recs[begin + ord[j]];
+                    acc.grow(b.lo, b.hi);
+                    if (kb[ord[j]] == kb[ord[j + 1]]) continue;  // not a bin boundary
+                    const float cost = acc.half_area() * (float)(j + 1) + right_area[j + 1] * (float)(n - j - 1);
+                    if (cost < best_cost) best_cost = cost, best_axis = a, best_bin = kb[ord[j]];
+                }
+            }
+        }
         Bins bins;
-        bins.reset();
+        if (n > SMALL_N) bins.reset();
         auto bin_range = [&](uint32_t i0, uint32_t i1, Bins& out) {
             for (uint32_t i = i0; i < i1; i++) {
-                const BuildBox& b = c.boxes[c.idx[i]];
+                const Rec& b = c.recs[i];
                 for (int a = 0; a < 3; a++) {
                     if (!(ext3[a] > 0.f)) continue;
                     const int k = bin_of(centroid(b, a), cb.lo[a], scale3[a]);
@@ -134,10 +174,10 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
             for (int k = 0; k < PAR_CHUNKS; k++)
                 for (int a = 0; a < 3; a++)
                     for (int q = 0; q < NBINS; q++) bins.cnt[a][q] += part[k].cnt[a][q], bins.bb[a][q].grow(part[k].bb[a][q].lo, part[k].bb[a][q].hi);
-        } else {
+        } else if (n > SMALL_N) {
             bin_range(begin, end, bins);
         }
-        for (int a = 0; a < 3; a++) {
+        for (int a = 0; a < 3 && n > SMALL_N; a++) {
             if (!(ext3[a] > 0.f)) continue;
             const uint32_t* cnt = bins.cnt[a];
             const Box3* bb = bins.bb[a];
@@ -168,35 +208,37 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
             float leaf_cost = (float)n * C_PRIM;
             if (n <= LEAF_TARGET && leaf_cost <= split_cost) return make_leaf(c, begin, end);
             const float scale = scale3[best_axis], lo = cb.lo[best_axis];
-            auto goes_left = [&](uint32_t i) { return bin_of(centroid(c.boxes[i], best_axis), lo, scale) <= best_bin; };
+            auto goes_left = [&](const Rec& b) { return bin_of(centroid(b, best_axis), lo, scale) <= best_bin; };
             if (par) {
-                // chunked partition through a scratch copy: count per chunk, then every chunk writes its two parts at their offsets
-                std::vector<uint32_t> scratch(c.idx + begin, c.idx + end);
-                const uint32_t* src = scratch.data() - begin;
+                // chunked partition through the scratch copy: count per chunk (while copying), then every chunk writes its two parts
+                // at their offsets
+                const Rec* src = c.scratch;
                 std::vector<uint32_t> n_left(PAR_CHUNKS + 1, 0);
 #pragma omp taskloop grainsize(1) default(shared)
                 for (int k = 0; k < PAR_CHUNKS; k++) {
                     uint32_t nl = 0;
-                    for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) nl += goes_left(src[i]);
+                    for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) {
+                        c.scratch[i] = c.recs[i];
+                        nl += goes_left(c.recs[i]);
+                    }
                     n_left[k + 1] = nl;
                 }
                 for (int k = 0; k < PAR_CHUNKS; k++) n_left[k + 1] += n_left[k];
                 mid = begin + n_left[PAR_CHUNKS];
 #pragma omp taskloop grainsize(1) default(shared)
                 for (int k = 0; k < PAR_CHUNKS; k++) {
-                    uint32_t* l = c.idx + begin + n_left[k];
-                    uint32_t* r = c.idx + mid + (chunk_at(k) - begin - n_left[k]);
+                    Rec* l = c.recs + begin + n_left[k];
+                    Rec* r = c.recs + mid + (chunk_at(k) - begin - n_left[k]);
                     for (uint32_t i = chunk_at(k); i < chunk_at(k + 1); i++) {
-                        const uint32_t v = src[i];
-                        if (goes_left(v))
-                            *l++ = v;
+                        if (goes_left(src[i]))
+                            *l++ = src[i];
                         else
-                            *r++ = v;
+                            *r++ = src[i];
                     }
                 }
             } else {
-                uint32_t* p = std::partition(c.idx + begin, c.idx + end, goes_left);
-                mid = (uint32_t)(p - c.idx);
+                Rec* p = std::partition(c.recs + begin, c.recs + end, goes_left);
+                mid = (uint32_t)(p - c.recs);
             }
             have_split = mid > begin && mid < end;
         }
@@ -208,8 +250,7 @@ uint32_t build_range(const Ctx& c, uint32_t begin, uint32_t end, uint32_t depth,
         for (int k = 1; k < 3; k++)
             if (cb.hi[k] - cb.lo[k] > cb.hi[a] - cb.lo[a]) a = k;
         mid = begin + n / 2;
-        std::nth_element(c.idx + begin, c.idx + mid, c.idx + end,
-                         [&](uint32_t x, uint32_t y) { return centroid(c.boxes[x], a) < centroid(c.boxes[y], a); });
+        std::nth_element(c.recs + begin, c.recs + mid, c.recs + end, [&](const Rec& x, const Rec& y) { return centroid(x, a) < centroid(y, a); });
     }
 
     uint32_t me = c.node_count->fetch_add(1);
@@ -240,17 +281,24 @@ uint32_t build_bvh(const RawVec<BuildBox>& boxes, uint32_t first_prim_base, RawV
     if (const char* e = getenv("RT2025_SAH_LEAF")) LEAF_TARGET = (uint32_t)atoi(e);
     const uint32_t n = (uint32_t)boxes.size();
     order.resize(n);
-    for (uint32_t i = 0; i < n; i++) order[i] = i;
     if (n == 0) return INVALID_REF;
+    RawVec<Rec> recs(n), scratch(n >= PAR_MIN ? n : 0);
+#pragma omp parallel for schedule(static) if (n > 65536)
+    for (uint32_t i = 0; i < n; i++) {
+        for (int a = 0; a < 3; a++) recs[i].lo[a] = boxes[i].lo[a], recs[i].hi[a] = boxes[i].hi[a];
+        recs[i].id = i;
+    }
     const uint32_t node_base = (uint32_t)nodes.size();
     nodes.resize(node_base + (n > 1 ? n - 1 : 0));
     std::atomic<uint32_t> count{node_base}, depth{0};
-    Ctx c{boxes.data(), order.data(), nodes.data(), &count, &depth, first_prim_base};
+    Ctx c{recs.data(), scratch.data(), nodes.data(), &count, &depth, first_prim_base};
     Box3 b;
     uint32_t root = 0;
 #pragma omp parallel if (n > 32768)  // no team for book-sized scenes (the build itself is ~1 us per primitive)
 #pragma omp single
     root = build_range(c, 0, n, 1, b);
+#pragma omp parallel for schedule(static) if (n > 65536)
+    for (uint32_t i = 0; i < n; i++) order[i] = recs[i].id;
     nodes.resize(count.load());
     depth_out = std::max(depth_out, depth.load());
     return root;

@@ -29,6 +29,16 @@ int main(int argc, char** argv) {
     printf("%s N=%.0f: host scene %.2f s, compile %.2f s (rc %d %s), %zu nodes, depth %u\n", name, n,
            std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count(), rc, err.c_str(),
            cs.nodes.size(), cs.bvh_depth);
+    if (rc == 0 && getenv("RT2025_TREE_HASH")) {  // FNV-1a over the node array and the primitive order: equal trees, equal hashes
+        auto fnv = [](const void* p, size_t n, uint64_t h) {
+            const unsigned char* b = (const unsigned char*)p;
+            for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+            return h;
+        };
+        uint64_t h = fnv(cs.nodes.data(), cs.nodes.size() * sizeof(rt::Node), 1469598103934665603ull);
+        h = fnv(cs.meta.data(), cs.meta.size() * sizeof(rt::PrimMeta), h);
+        printf("tree hash %016llx\n", (unsigned long long)h);
+    }
     if (rc == 0 && getenv("RT2025_VERIFY_TREE")) {
         // every world primitive in exactly one leaf, every child box inside its parent's copy of it
         std::vector<unsigned char> seen(cs.geom.size(), 0);
