@@ -712,6 +712,15 @@ struct Compiler {
         uint64_t n_sph = 0;
 #pragma omp parallel for schedule(static) reduction(&& : ok) reduction(+ : n_sph)
         for (size_t i = 0; i < n; i++) {
+            // `order` is the tie order, a permutation: the object and its shape record are read at random - ask for them early
+            if (i + 16 < n) __builtin_prefetch(&d.objects[order[i + 16]]);
+            if (i + 8 < n) {
+                const rt_object& po = d.objects[order[i + 8]];
+                if (po.kind == RT_OBJ_SPHERE)
+                    __builtin_prefetch(&d.spheres[po.data]);
+                else
+                    __builtin_prefetch(&d.planars[po.data]), __builtin_prefetch((const char*)&d.planars[po.data] + 64), __builtin_prefetch((const char*)&d.planars[po.data] + 128);
+            }
             const uint32_t obj = order[i];
             FlatPrim& fp = G[base + i];
             uint32_t kind = 0;
