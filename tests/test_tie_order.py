@@ -17,6 +17,8 @@ def test_team_parallel_split_of_big_nodes_gives_the_same_order():
     """Nodes of a million children and more are split by all threads (compile.cpp, split_node_parallel) instead of one task each;
     RT2025_TIE_PAR_MIN forces that path on the small, tie-ridden inputs of the check."""
     env = dict(os.environ, RT2025_TIE_PAR_MIN="8")
+    b = subprocess.run(["make", "-s", "build/check_tie_order"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert b.returncode == 0, b.stdout[-2000:] + b.stderr[-2000:]
     r = subprocess.run(["build/check_tie_order"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.strip().endswith("OK") and "0 rank mismatches" in r.stdout
