@@ -635,6 +635,52 @@ struct Compiler {
         return axis;
     }
 
+    // Stable LSD radix sort of a[0..n) by total_order_key(mn), four 16-bit digits, all threads: every thread counts the digits of
+    // its chunk, the offsets are laid out digit-major / thread-minor (which is what keeps equal keys in input order), every
+    // thread scatters its chunk.  A digit on which all keys agree costs no pass.  `tmp` is scratch of the same length.
+    // (The three lists of 16 M entries on 8 cores: 1.1-1.5 s against 2.2 s for libstdc++'s parallel multiway merge sort.)
+    static void radix_sort_by_min(AxisEnt* a, AxisEnt* tmp, size_t n) {
+        const int T = std::max(1, omp_get_max_threads());
+        std::vector<size_t> hist((size_t)T * 65536);
+        AxisEnt* src = a;
+        AxisEnt* dst = tmp;
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 16 * pass;
+            std::fill(hist.begin(), hist.end(), 0);
+#pragma omp parallel num_threads(T)
+            {
+                const int t = omp_get_thread_num();
+                size_t* h = hist.data() + (size_t)t * 65536;
+                const size_t i0 = n * (size_t)t / (size_t)T, i1 = n * (size_t)(t + 1) / (size_t)T;
+                for (size_t i = i0; i < i1; i++) h[(total_order_key(src[i].mn) >> shift) & 0xFFFFu]++;
+            }
+            size_t run = 0;
+            bool one_bucket = false;
+            for (size_t d = 0; d < 65536; d++) {
+                size_t in_digit = 0;
+                for (int t = 0; t < T; t++) {
+                    const size_t c = hist[(size_t)t * 65536 + d];
+                    hist[(size_t)t * 65536 + d] = run;
+                    run += c, in_digit += c;
+                }
+                one_bucket = one_bucket || in_digit == n;
+            }
+            if (one_bucket) continue;  // all keys share this digit: nothing moves
+#pragma omp parallel num_threads(T)
+            {
+                const int t = omp_get_thread_num();
+                size_t* h = hist.data() + (size_t)t * 65536;
+                const size_t i0 = n * (size_t)t / (size_t)T, i1 = n * (size_t)(t + 1) / (size_t)T;
+                for (size_t i = i0; i < i1; i++) dst[h[(total_order_key(src[i].mn) >> shift) & 0xFFFFu]++] = src[i];
+            }
+            std::swap(src, dst);
+        }
+        if (src != a) {
+#pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < n; i++) a[i] = src[i];
+        }
+    }
+
     // kids[0..n) -> the same ids in tie order
     void bvh_visit_order(std::vector<uint32_t>& kids) {
         const size_t n = kids.size();
@@ -654,10 +700,14 @@ struct Compiler {
             for (int k = 0; k < 3; k++) T.list[0][k][i] = AxisEnt{bb[2 * k], bb[2 * k + 1], (uint32_t)i, 0};
         }
         if (n > 100000) timer.lap("    tie order: fill");
-        // the three stable sorts by box-min: libstdc++'s parallel multiway merge sort for big inputs (it brings its own
-        // team, so it runs outside the task region of the walk)
+        // the three stable sorts by box-min: a radix sort by all threads for big inputs (the second copy of the list is its scratch;
+        // it brings its own team, so it runs outside the task region of the walk)
+        size_t radix_min = 32768;
+        if (const char* e = getenv("RT2025_TIE_RADIX_MIN")) radix_min = (size_t)std::max(2l, atol(e));  // (the CPU check forces it on small inputs)
         for (int k = 0; k < 3; k++) {
-            if (n > 32768)
+            if (n > radix_min)
+                radix_sort_by_min(T.list[0][k], T.list[1][k], n);
+            else if (n > 32768)
                 __gnu_parallel::stable_sort(T.list[0][k], T.list[0][k] + n, key_less);
             else
                 std::stable_sort(T.list[0][k], T.list[0][k] + n, key_less);

@@ -14,9 +14,10 @@ def test_partition_walk_matches_per_node_stable_sort():
 
 
 def test_team_parallel_split_of_big_nodes_gives_the_same_order():
-    """Nodes of a million children and more are split by all threads (compile.cpp, split_node_parallel) instead of one task each;
-    RT2025_TIE_PAR_MIN forces that path on the small, tie-ridden inputs of the check."""
-    env = dict(os.environ, RT2025_TIE_PAR_MIN="8")
+    """Nodes of a million children and more are split by all threads (compile.cpp, split_node_parallel) instead of one task each,
+    and lists of more than 32768 children are sorted by the parallel radix sort; RT2025_TIE_PAR_MIN / RT2025_TIE_RADIX_MIN force
+    both paths on the small, tie-ridden inputs of the check (signed zeros included)."""
+    env = dict(os.environ, RT2025_TIE_PAR_MIN="8", RT2025_TIE_RADIX_MIN="2")  # (and the radix sort of the three lists)
     b = subprocess.run(["make", "-s", "build/check_tie_order"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert b.returncode == 0, b.stdout[-2000:] + b.stderr[-2000:]
     r = subprocess.run(["build/check_tie_order"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
