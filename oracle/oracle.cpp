@@ -1901,6 +1901,23 @@ int orc_kat_cosine_pdf(const double* albedo, const double* normal, const double*
     out7[3] = pdf;
     return err ? 0 : 1;
 }
+// Disney::evaluate_disney (material/disney.rs:289-401) on local-space unit vectors (y = normal).  params15: base_color(3), roughness,
+// anisotropic, sheen, sheen_tint, clearcoat, clearcoat_gloss, specular_tint, metallic, ior, flatness, spec_trans, diff_trans; out4:
+// reflectance(3), forward pdf.  Returns 0 where the reference would panic.
+int orc_kat_disney_evaluate(const double* params15, int thin, const double* v_out, const double* v_in, int front_face, double* out4) {
+    DisneyParameters P;
+    P.base_color = Vec3(params15);
+    P.roughness = params15[3], P.anisotropic = params15[4], P.sheen = params15[5], P.sheen_tint = params15[6], P.clearcoat = params15[7];
+    P.clearcoat_gloss = params15[8], P.specular_tint = params15[9], P.metallic = params15[10], P.ior = params15[11], P.flatness = params15[12];
+    P.spec_trans = params15[13], P.diff_trans = params15[14], P.thin = thin != 0;
+    Vec3 refl;
+    double pdf = 0.0;
+    bool error = false;
+    disney::evaluate_disney(P, Vec3(v_out), Vec3(v_in), front_face != 0, refl, pdf, error);
+    for (int k = 0; k < 3; k++) out4[k] = refl[k];
+    out4[3] = pdf;
+    return error ? 0 : 1;
+}
 // lights.pdf_value(origin, direction) and lights.random(origin) of the scene's lights tree (hits.rs:52-75 and the shapes below it)
 double orc_kat_lights_pdf_value(const void* s, const double* origin, const double* direction) {
     const Scene& sc = *(const Scene*)s;

@@ -52,6 +52,7 @@ def lib():
         L.orc_kat_world_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, D, D]
         L.orc_kat_scatter.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, D, D, D]
         L.orc_kat_cosine_pdf.argtypes = [D, D, D, D, D]
+        L.orc_kat_disney_evaluate.argtypes = [D, C.c_int, D, D, C.c_int, D]
         L.orc_kat_lights_pdf_value.restype = C.c_double
         L.orc_kat_lights_pdf_value.argtypes = [C.c_void_p, D, D]
         L.orc_kat_lights_random.argtypes = [C.c_void_p, D, C.c_uint32, C.c_double, C.c_double, D]
@@ -134,6 +135,14 @@ class OracleScene:
         out = (C.c_double * 3)()
         self.L.orc_texture_value(self.h, tex, u, v, d(*p), out)
         return np.array(out)
+
+
+def disney_evaluate(params15, thin, v_out, v_in, front_face):
+    """Disney::evaluate_disney of the oracle on local-space unit vectors -> (reflectance(3), forward pdf) or None where the reference panics."""
+    out = (C.c_double * 4)()
+    if not lib().orc_kat_disney_evaluate(d(*params15), int(bool(thin)), d(*v_out), d(*v_in), int(bool(front_face)), out):
+        return None
+    return np.array(out[:3]), out[3]
 
 
 def camera_rays(camera, seed, pixels_ij, sample):
