@@ -231,8 +231,15 @@ struct PathCtx {
     uint64_t seed = 0;
     uint32_t pixel = 0, sample = 0, segment = 0;
     bool media_enabled = true;  // orc_closest_hit leaves media out (they are stochastic)
-    const double* forced = nullptr;  // known-answer hooks only: every draw returns (forced[0], forced[1])
-    Rand2 draw(uint32_t slot) const { return forced ? Rand2{forced[0], forced[1]} : philox_pair(seed, pixel, sample, segment, slot); }
+    const double* forced = nullptr;  // known-answer hooks only: every draw returns (forced[0], forced[1]) ...
+    const double* forced_direction = nullptr;  // ... except RT_SLOT_DIRECTION, which returns this pair when it is set
+    Rand2 draw(uint32_t slot) const {
+        if (forced) {
+            const double* f = (slot == RT_SLOT_DIRECTION && forced_direction) ? forced_direction : forced;
+            return Rand2{f[0], f[1]};
+        }
+        return philox_pair(seed, pixel, sample, segment, slot);
+    }
 };
 
 // ---------------------------------------------------------------- sampling helpers, vec3.rs
@@ -1917,6 +1924,31 @@ int orc_kat_disney_evaluate(const double* params15, int thin, const double* v_ou
     for (int k = 0; k < 3; k++) out4[k] = refl[k];
     out4[3] = pdf;
     return error ? 0 : 1;
+}
+// DisneyPDF::generate (disney.rs:542-720) in the local frame (identity basis, y = normal) with the draws forced: pick2 = the RT_SLOT_DISNEY
+// pair (lobe choice, coin of the diffuse-transmission / Fresnel decision), u2 = the RT_SLOT_DIRECTION pair.  Returns 1 and the direction,
+// 0 for None, -1 where the reference would panic.
+int orc_kat_disney_generate(const double* params15, int thin, const double* v_out, int front_face, const double* pick2, const double* u2, double* out3) {
+    ScatterRecord sr;
+    sr.kind = SCATTER_DISNEY;
+    DisneyParameters& P = sr.params;
+    P.base_color = Vec3(params15);
+    P.roughness = params15[3], P.anisotropic = params15[4], P.sheen = params15[5], P.sheen_tint = params15[6], P.clearcoat = params15[7];
+    P.clearcoat_gloss = params15[8], P.specular_tint = params15[9], P.metallic = params15[10], P.ior = params15[11], P.flatness = params15[12];
+    P.spec_trans = params15[13], P.diff_trans = params15[14], P.thin = thin != 0;
+    sr.v_out = Vec3(v_out);
+    sr.front_face = front_face != 0;
+    sr.uvw.axis[0] = Vec3(1, 0, 0), sr.uvw.axis[1] = Vec3(0, 1, 0), sr.uvw.axis[2] = Vec3(0, 0, 1);
+    PathCtx ctx;
+    ctx.forced = pick2;
+    ctx.forced_direction = u2;
+    Vec3 out;
+    bool error = false;
+    const bool some = disney::generate(sr, ctx, out, error);
+    if (error) return -1;
+    if (!some) return 0;
+    for (int k = 0; k < 3; k++) out3[k] = out[k];
+    return 1;
 }
 // lights.pdf_value(origin, direction) and lights.random(origin) of the scene's lights tree (hits.rs:52-75 and the shapes below it)
 double orc_kat_lights_pdf_value(const void* s, const double* origin, const double* direction) {

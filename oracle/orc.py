@@ -53,6 +53,7 @@ def lib():
         L.orc_kat_scatter.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, D, D, D]
         L.orc_kat_cosine_pdf.argtypes = [D, D, D, D, D]
         L.orc_kat_disney_evaluate.argtypes = [D, C.c_int, D, D, C.c_int, D]
+        L.orc_kat_disney_generate.argtypes = [D, C.c_int, D, C.c_int, D, D, D]
         L.orc_kat_lights_pdf_value.restype = C.c_double
         L.orc_kat_lights_pdf_value.argtypes = [C.c_void_p, D, D]
         L.orc_kat_lights_random.argtypes = [C.c_void_p, D, C.c_uint32, C.c_double, C.c_double, D]
@@ -143,6 +144,13 @@ def disney_evaluate(params15, thin, v_out, v_in, front_face):
     if not lib().orc_kat_disney_evaluate(d(*params15), int(bool(thin)), d(*v_out), d(*v_in), int(bool(front_face)), out):
         return None
     return np.array(out[:3]), out[3]
+
+
+def disney_generate(params15, thin, v_out, front_face, pick, u):
+    """DisneyPDF::generate of the oracle in the local frame with forced draws -> direction, None (the reference's None) or "panic"."""
+    out = (C.c_double * 3)()
+    rc = lib().orc_kat_disney_generate(d(*params15), int(bool(thin)), d(*v_out), int(bool(front_face)), d(*pick), d(*u), out)
+    return np.array(out) if rc == 1 else (None if rc == 0 else "panic")
 
 
 def camera_rays(camera, seed, pixels_ij, sample):

@@ -1,4 +1,4 @@
-"""Disney::evaluate_disney of the oracle against an independent restatement in plain Python, written from the reference's source
+"""Disney::evaluate_disney and DisneyPDF::generate of the oracle against an independent restatement in plain Python, written from the reference's source
 (material/disney.rs:102-520, utils/fresnel.rs, the UnitVec3 trigonometry of utils/vec3.rs:376-426 with its quirks: cos_theta2()
 returns y, cos_phi() / sin_phi() are 1 for every unit vector).  The reference holds no vectors for the BSDF; this pins the
 oracle's lobes - clearcoat, diffuse + retro-reflection + sheen, thin-surface subsurface, specular transmission with its Jacobian,
@@ -288,3 +288,113 @@ def test_disney_evaluate_matches_a_plain_restatement(orc, name):
             assert np.allclose(got[0], want_refl, rtol=1e-11, atol=1e-300), (name, v_out, v_in, front, got[0], want_refl)
             checked += 1
     assert checked == 600
+
+
+# ---- DisneyPDF::generate and its samplers, material/disney.rs:542-720; vec3.rs:76-78, 333-343, 357-366 ----------------------
+def reflect2(v, n):
+    k = 2.0 * dot(v, n)
+    return tuple(-a + k * b for a, b in zip(v, n))
+
+
+def refract2(v, n, relative_eta):
+    cos_t = min(dot(v, n), 1.0)
+    perp = tuple(relative_eta * (-a + cos_t * b) for a, b in zip(v, n))
+    arg = 1.0 - dot(perp, perp)
+    if arg < 0.0:
+        return None  # sqrt -> NaN -> None
+    par = math.sqrt(arg)
+    return tuple(a + (-par) * b for a, b in zip(perp, n))
+
+
+def cross(a, b):
+    return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
+
+
+def sample_ggx_vndf_anisotropic(v_out, ax, ay, u1, u2):
+    v = unit((v_out[0] * ax, v_out[1], v_out[2] * ay))
+    t1 = cross(v, (0.0, 1.0, 0.0)) if v[1] < 0.9999999 else (1.0, 0.0, 0.0)
+    t2 = cross(t1, v)
+    a = 1.0 / (1.0 + v[1])
+    r = math.sqrt(u1)
+    phi = (u2 / a) * PI if u2 < a else PI + (u2 - a) / (1.0 - a) * PI
+    p1 = r * math.cos(phi)
+    p2 = r * math.sin(phi) * (1.0 if u2 < a else v[1])
+    s = math.sqrt(max(1.0 - p1 * p1 - p2 * p2, 0.0))
+    n = tuple(p1 * x + p2 * y + s * z for x, y, z in zip(t1, t2, v))
+    return unit((ax * n[0], n[1], ay * n[2]))
+
+
+def disney_generate(p, v_out, front_face, pick, u):
+    """-> local direction or None.  The draws of the reference's thread RNG are the addressed pairs of this implementation: pick.a chooses
+    the lobe, pick.b is the coin of the second decision inside a lobe, u = (r0, r1) of the lobe's sampler (include/rt2025_rng.h)."""
+    p_spec, p_diff, p_clear, p_trans = lobe_pdfs(p)
+    q = pick[0]
+    if q <= p_spec:  # sample_disney_brdf
+        ax, ay = aniso_params(p.roughness, p.anisotropic)
+        h = sample_ggx_vndf_anisotropic(v_out, ax, ay, u[0], u[1])
+        v_in = unit(reflect2(v_out, h))
+        return None if cos_theta(v_in) <= 0.0 else v_in
+    if q <= p_spec + p_clear:  # sample_disney_clearcoat
+        a2 = 0.25 * 0.25
+        ct = math.sqrt(max((1.0 - a2 ** (1.0 - u[0])) / (1.0 - a2), 0.0))
+        st = math.sqrt(max(1.0 - ct * ct, 0.0))
+        phi = 2.0 * PI * u[1]
+        h = (st * math.cos(phi), ct, st * math.sin(phi))
+        if dot(h, v_out) < 0.0:
+            h = tuple(-x for x in h)
+        v_in = reflect2(v_out, h)
+        return None if dot(v_in, v_out) < 0.0 else unit(v_in)
+    if q <= p_spec + p_diff + p_clear:  # sample_disney_diffuse
+        sign = math.copysign(1.0, cos_theta(v_out))
+        phi = 2.0 * PI * u[0]
+        c = (math.sin(phi) * math.sqrt(u[1]), math.sqrt(1.0 - u[1]), math.cos(phi) * math.sqrt(u[1]))  # random_cosine_direction
+        v_in = tuple(sign * x for x in c)
+        if pick[1] <= p.diff_trans:
+            v_in = tuple(-x for x in v_in)
+        return None if cos_theta(v_in) == 0.0 else unit(v_in)
+    assert p_trans >= 0.0  # disney_spec_transmission
+    ior = p.ior if front_face else 1.0 / p.ior
+    if cos_theta(v_out) == 0.0:
+        return None
+    rscaled = thin_transmission_roughness(ior, p.roughness) if p.thin else p.roughness
+    tax, tay = aniso_params(rscaled, p.anisotropic)
+    h = sample_ggx_vndf_anisotropic(v_out, tax, tay, u[0], u[1])
+    dot_vh = dot(v_out, h)
+    if h[1] < 0.0:
+        dot_vh = -dot_vh
+    ni, nt = (1.0, ior) if v_out[1] > 0.0 else (ior, 1.0)
+    f = dielectric(dot_vh, 1.0, p.ior)
+    if pick[1] <= f:
+        v_in = unit(reflect2(v_out, h))
+    elif p.thin:
+        wi = reflect2(v_out, h)
+        v_in = unit((wi[0], -wi[1], wi[2]))
+    else:
+        v_in = refract2(v_out, h, ni / nt)
+        if v_in is None:
+            v_in = unit(reflect2(v_out, h))
+    return None if cos_theta(v_in) == 0.0 else unit(v_in)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_disney_generate_matches_a_plain_restatement(orc, name):
+    p = CASES[name]
+    rng = np.random.default_rng(1000 + sum(map(ord, name)))
+    some = none = 0
+    for _ in range(500):
+        v_out = unit(tuple(rng.normal(size=3)))
+        if abs(v_out[1]) < 1e-3:
+            continue
+        pick, u = tuple(rng.uniform(size=2)), tuple(rng.uniform(size=2))
+        for front in (True, False):
+            got = orc.disney_generate(p.flat(), p.thin, v_out, front, pick, u)
+            want = disney_generate(p, v_out, front, pick, u)
+            assert not isinstance(got, str), "the oracle reports a panic"
+            if want is None:
+                assert got is None, (name, v_out, front, pick, u, got)
+                none += 1
+            else:
+                assert got is not None, (name, v_out, front, pick, u, want)
+                assert np.allclose(got, want, rtol=0.0, atol=1e-11), (name, v_out, front, pick, u, got, want)
+                some += 1
+    assert some > 300
