@@ -1,0 +1,93 @@
+"""CheckerTexture and ImageTexture of the oracle against an independent restatement in Python written from the reference's source
+(texture.rs:38-174, utils/image.rs:63-82): the checker's floor / parity rule with negative coordinates, the nearest lookup with its
+flipped v and the clamp at v == 1, the sRGB decode of non-raw images (palette's Srgba::into_linear is the standard piecewise curve),
+the bilinear lookup of raw images in binary32, and the cyan of a missing image."""
+import math
+
+import numpy as np
+
+f32 = np.float32
+
+
+def srgb_to_linear(c):
+    c = float(c)
+    return c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4
+
+
+def abs_fract(x):
+    return x - math.floor(x)
+
+
+def nearest(img, u, v, raw):  # texture.rs:108-116, image.rs:63-82
+    h, w, _ = img.shape
+    uu, vv = abs_fract(u), 1.0 - abs_fract(v)
+    i, j = min(int(uu * w), w - 1), min(int(vv * h), h - 1)
+    px = img[j, i]
+    return [float(px[k]) if raw else srgb_to_linear(px[k]) for k in range(3)]
+
+
+def bilinear(img, u, v):  # texture.rs:118-148 (raw images: no decode)
+    h, w, _ = img.shape
+    uu, vv = abs_fract(u), 1.0 - abs_fract(v)
+    x, y = uu * w - 0.5, vv * h - 0.5
+    x0, y0 = int(max(math.floor(x), 0.0)), int(max(math.floor(y), 0.0))
+    x1, y1 = min(x0 + 1, w - 1), min(y0 + 1, h - 1)
+    dx, dy = f32(x - x0), f32(y - y0)
+    cx0, cy0 = min(x0, w - 1), min(y0, h - 1)  # pixel_data clamps
+    out = []
+    for k in range(3):
+        p00, p10, p01, p11 = img[cy0, cx0, k], img[cy0, x1, k], img[y1, cx0, k], img[y1, x1, k]
+        v0 = p00 * (f32(1.0) - dx) + p10 * dx
+        v1 = p01 * (f32(1.0) - dx) + p11 * dx
+        out.append(float(v0 * (f32(1.0) - dy) + v1 * dy))
+    return out
+
+
+def test_checker_and_image_textures_match_a_plain_restatement(rt, orc):
+    rng = np.random.default_rng(23)
+    img = rng.uniform(0.0, 1.0, (5, 7, 4)).astype(np.float32)
+    b = rt.Builder(3)
+    even, odd = b.solid(0.9, 0.1, 0.2), b.solid(0.05, 0.6, 0.3)
+    scale = 0.32
+    chk = b.checker(scale, even, odd)
+    t_srgb = b.image(img)                       # ImageTexture::new on a PNG-like image: decoded
+    t_lin = b.image(img, linear_format=True)    # .hdr / .exr: used as stored
+    t_raw = b.image(img, raw=True)              # new_raw_image: bilinear, no decode
+    t_missing = b.image_missing()
+    hs = b.finish(b.list([b.sphere([0, 0, 0], 1.0, b.lambertian(chk)), b.sphere([3, 0, 0], 1.0, b.lambertian(t_srgb)),
+                          b.sphere([6, 0, 0], 1.0, b.lambertian(t_lin)), b.sphere([9, 0, 0], 1.0, b.lambertian(t_raw)),
+                          b.sphere([12, 0, 0], 1.0, b.lambertian(t_missing))]), width=8, spp=1)
+    osc = orc.OracleScene(hs)
+    inv = 1.0 / scale
+    for _ in range(500):
+        p = list(rng.uniform(-9.0, 9.0, 3))
+        s = math.floor(inv * p[0]) + math.floor(inv * p[1]) + math.floor(inv * p[2])
+        want = (0.9, 0.1, 0.2) if s % 2 == 0 else (0.05, 0.6, 0.3)
+        assert tuple(osc.texture_value(chk, 0.3, 0.4, p)) == want
+    uvs = [tuple(rng.uniform(-2.0, 3.0, 2)) for _ in range(400)] + [(0.0, 0.0), (1.0, 1.0), (0.0, 1.0), (-1.0, 2.0), (0.999999, 1e-9), (0.5, -0.0)]
+    for u, v in uvs:
+        assert np.allclose(osc.texture_value(t_srgb, u, v, [0, 0, 0]), nearest(img, u, v, raw=False), rtol=2e-6, atol=1e-7)
+        assert np.allclose(osc.texture_value(t_lin, u, v, [0, 0, 0]), nearest(img, u, v, raw=True), rtol=0, atol=0)
+        assert np.allclose(osc.texture_value(t_raw, u, v, [0, 0, 0]), bilinear(img, u, v), rtol=3e-7, atol=1e-7)
+        assert tuple(osc.texture_value(t_missing, u, v, [0, 0, 0])) == (0.0, 1.0, 1.0)
+
+
+def test_tone_map_matches_a_plain_restatement(orc):
+    """Color::to_rgb (utils/color.rs:14-36): the ACES fit with its constants and clamp, then the sRGB encode.  The `palette` crate is not
+    vendored with the reference, so the encode is the standard piecewise curve rounded to nearest - what this pins is the ACES arithmetic
+    and that both tone-map settings go through the same encode (the 8-bit codes are stated to +-1 against the real crate)."""
+    rng = np.random.default_rng(31)
+    c = np.concatenate([rng.uniform(0.0, 1.5, (300, 3)), rng.uniform(0.0, 30.0, (100, 3)), np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.0031308, 0.5, 100.0]])])
+
+    def encode(x):
+        e = 12.92 * x if x <= 0.0031308 else 1.055 * x ** (1.0 / 2.4) - 0.055
+        return int(math.floor(min(max(e, 0.0), 1.0) * 255.0 + 0.5))
+
+    def aces(x):
+        return min(max((x * (2.51 * x + 0.03)) / (x * (2.43 * x + 0.59) + 0.14), 0.0), 1.0)
+
+    plain = orc.tonemap(c, toon_map=0)
+    mapped = orc.tonemap(c, toon_map=1)
+    for row, p_row, m_row in zip(c, plain, mapped):
+        assert [encode(x) for x in row] == list(p_row)
+        assert [encode(aces(x)) for x in row] == list(m_row)
