@@ -91,3 +91,34 @@ def test_tone_map_matches_a_plain_restatement(orc):
     for row, p_row, m_row in zip(c, plain, mapped):
         assert [encode(x) for x in row] == list(p_row)
         assert [encode(aces(x)) for x in row] == list(m_row)
+
+
+def test_portal_transparent_and_mix_scatter(rt, orc):
+    """Portal::scatter (material/portal.rs:14-30: direction turned by q v q*, quaternion.rs:72-104), Transparent (material.rs:209-218) and
+    Mix (material.rs:249-257: `Random::f64() > ratio` takes mat1) with the draw forced."""
+    def qmul(a, b):
+        return (a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0])
+
+    b = rt.Builder(4)
+    q = b.quat_axis_angle([0.3, 1.0, -0.2], 77.0)
+    portal = b.portal([0.9, 0.8, 0.7], [1.0, -2.0, 0.5], q)
+    clear = b.transparent()
+    red = b.metal([0.8, 0.1, 0.1], 0.0)
+    mix = b.mix(red, clear, 0.25)
+    hs = b.finish(b.list([b.sphere([0, 0, 0], 1.0, portal), b.sphere([3, 0, 0], 1.0, clear), b.sphere([6, 0, 0], 1.0, mix)]), width=8, spp=1)
+    osc = orc.OracleScene(hs)
+    rng = np.random.default_rng(9)
+    RAY = 3  # ScatterKind::SCATTER_RAY of the oracle
+    for _ in range(50):
+        dvec = list(rng.normal(size=3))
+        n = list(rng.normal(size=3))
+        n = [x / math.sqrt(sum(y * y for y in n)) for x in n]
+        kind, att, out, err = osc.scatter(portal, [0, 0, 5], dvec, [0.1, 0.2, 0.3], n, True)
+        r = qmul(qmul(tuple(q), (0.0, *dvec)), (q[0], -q[1], -q[2], -q[3]))
+        assert kind == RAY and not err and att == [0.9, 0.8, 0.7] and out == list(r[1:])
+        kind, att, out, err = osc.scatter(clear, [0, 0, 5], dvec, [0.1, 0.2, 0.3], n, False)
+        assert kind == RAY and att == [1.0, 1.0, 1.0] and out == dvec
+        for xi0 in (0.0, 0.25, 0.2500001, 0.9):
+            kind, att, out, err = osc.scatter(mix, [0, 0, 5], dvec, [0.1, 0.2, 0.3], n, True, xi=(xi0, 0.5))
+            assert kind == RAY and att == ([0.8, 0.1, 0.1] if xi0 > 0.25 else [1.0, 1.0, 1.0])
