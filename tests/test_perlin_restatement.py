@@ -53,6 +53,7 @@ def test_noise_texture_matches_a_plain_restatement(rt, orc):
     for perm in (tab.perm_x, tab.perm_y, tab.perm_z):
         assert sorted(perm) == list(range(256))
     osc = orc.OracleScene(hs)
+    tex = C.c_uint32.from_address(d.materials + 176 * int(hs.objects()[0]["material"]) + 4).value  # the texture's index after flattening
     rng = np.random.default_rng(5)
     pts = [list(rng.uniform(-300.0, 300.0, 3)) for _ in range(400)]
     pts += [[0.5, -0.5, 2.5], [-1e-9, 255.999, -256.0], [1e5 + 0.25, -1e5 - 0.75, 3.125], [-0.0, 0.0, 0.0]]

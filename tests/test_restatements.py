@@ -9,6 +9,15 @@ import numpy as np
 f32 = np.float32
 
 
+def flat_material(hs, obj):
+    """(material index, texture index) of object `obj` in the FLATTENED description - the host mirror numbers materials and textures in
+    the order the flattening meets them, not in the order the builder created them."""
+    import ctypes as C
+    mi = int(hs.objects()[obj]["material"])
+    tex = C.c_uint32.from_address(hs.desc.contents.materials + 176 * mi + 4).value
+    return mi, tex
+
+
 def srgb_to_linear(c):
     c = float(c)
     return c / 12.92 if c <= 0.04045 else ((c + 0.055) / 1.055) ** 2.4
@@ -58,6 +67,7 @@ def test_checker_and_image_textures_match_a_plain_restatement(rt, orc):
                           b.sphere([6, 0, 0], 1.0, b.lambertian(t_lin)), b.sphere([9, 0, 0], 1.0, b.lambertian(t_raw)),
                           b.sphere([12, 0, 0], 1.0, b.lambertian(t_missing))]), width=8, spp=1)
     osc = orc.OracleScene(hs)
+    chk, t_srgb, t_lin, t_raw, t_missing = (flat_material(hs, k)[1] for k in range(5))
     inv = 1.0 / scale
     for _ in range(500):
         p = list(rng.uniform(-9.0, 9.0, 3))
@@ -108,6 +118,7 @@ def test_portal_transparent_and_mix_scatter(rt, orc):
     mix = b.mix(red, clear, 0.25)
     hs = b.finish(b.list([b.sphere([0, 0, 0], 1.0, portal), b.sphere([3, 0, 0], 1.0, clear), b.sphere([6, 0, 0], 1.0, mix)]), width=8, spp=1)
     osc = orc.OracleScene(hs)
+    portal, clear, mix = (flat_material(hs, k)[0] for k in range(3))
     rng = np.random.default_rng(9)
     RAY = 3  # ScatterKind::SCATTER_RAY of the oracle
     for _ in range(50):
@@ -122,3 +133,39 @@ def test_portal_transparent_and_mix_scatter(rt, orc):
         for xi0 in (0.0, 0.25, 0.2500001, 0.9):
             kind, att, out, err = osc.scatter(mix, [0, 0, 5], dvec, [0.1, 0.2, 0.3], n, True, xi=(xi0, 0.5))
             assert kind == RAY and att == ([0.8, 0.1, 0.1] if xi0 > 0.25 else [1.0, 1.0, 1.0])
+
+
+def test_remapped_material_remaps_uv_and_normal(rt, orc):
+    """RemappedMaterial::remap_record (shapes/obj.rs:32-62) without a normal map: the inner material sees the face's texture coordinate
+    tex_ori + u tex_u + v tex_v and the interpolated, normalised vertex normal.  A mirror inside reveals the normal, an image-textured
+    Lambertian the texture coordinate."""
+    rng = np.random.default_rng(41)
+    img = rng.uniform(0.0, 1.0, (6, 5, 4)).astype(np.float32)
+    b = rt.Builder(6)
+    mirror = b.metal([1.0, 1.0, 1.0], 0.0)
+    painted = b.lambertian(b.image(img, linear_format=True))
+    pos = [[0.0, 0.0, 0.0], [2.0, 0.0, 0.0], [0.0, 0.0, -2.0]]
+    uv = [[0.1, 0.2], [0.9, 0.3], [0.2, 0.8]]
+    nrm = [[0.1, 1.0, 0.0], [-0.2, 0.9, 0.3], [0.0, 0.8, -0.4]]
+    m_mirror, m_painted = b.remapped(mirror, pos, uv, nrm), b.remapped(painted, pos, uv, nrm)
+    hs = b.finish(b.list([b.obj_face(mirror, pos, uv, nrm), b.sphere([5, 0, 0], 1.0, m_mirror), b.sphere([8, 0, 0], 1.0, m_painted)]), width=8, spp=1)
+    osc = orc.OracleScene(hs)
+    m_mirror, m_painted = flat_material(hs, 1)[0], flat_material(hs, 2)[0]
+    COSINE, RAY = 1, 3
+    h, w, _ = img.shape
+    for _ in range(100):
+        u = rng.uniform(0.0, 1.0)
+        v = rng.uniform(0.0, 1.0 - u)
+        dvec = rng.normal(size=3)
+        n = (1.0 - u - v) * np.array(nrm[0]) + u * np.array(nrm[1]) + v * np.array(nrm[2])
+        n = n / np.sqrt(n @ n)
+        ud = dvec / np.sqrt(dvec @ dvec)
+        refl = ud - 2.0 * (ud @ n) * n
+        refl = refl / np.sqrt(refl @ refl)
+        kind, att, out, err = osc.scatter(m_mirror, [0, 3, 0], list(dvec), [0.5, 0.0, -0.5], [0.0, 1.0, 0.0], True, u=u, v=v)
+        assert kind == RAY and not err and np.allclose(out, refl, rtol=0, atol=1e-12)
+        tu = uv[0][0] + u * (uv[1][0] - uv[0][0]) + v * (uv[2][0] - uv[0][0])
+        tv = uv[0][1] + u * (uv[1][1] - uv[0][1]) + v * (uv[2][1] - uv[0][1])
+        want = img[min(int((1.0 - (tv - math.floor(tv))) * h), h - 1), min(int((tu - math.floor(tu)) * w), w - 1), :3]
+        kind, att, out, err = osc.scatter(m_painted, [0, 3, 0], list(dvec), [0.5, 0.0, -0.5], [0.0, 1.0, 0.0], True, u=u, v=v)
+        assert kind == COSINE and not err and att == [float(x) for x in want]
