@@ -169,3 +169,61 @@ def test_remapped_material_remaps_uv_and_normal(rt, orc):
         want = img[min(int((1.0 - (tv - math.floor(tv))) * h), h - 1), min(int((tu - math.floor(tu)) * w), w - 1), :3]
         kind, att, out, err = osc.scatter(m_painted, [0, 3, 0], list(dvec), [0.5, 0.0, -0.5], [0.0, 1.0, 0.0], True, u=u, v=v)
         assert kind == COSINE and not err and att == [float(x) for x in want]
+
+
+def test_normal_mapped_remap_and_triangle_light(rt, orc):
+    """The normal-map branch of remap_record with uv_local_to_world (shapes/obj.rs:44-53, 196-210): the mapped normal is
+    unit(u_vec c.x + v_vec c.y + n c.z) with c = 2 texel - 1, revealed by a mirror inside.  Triangle::pdf_value / random
+    (shapes/triangle.rs:104-128: area |u x v| / 2, the fold of the unit square onto the triangle)."""
+    rng = np.random.default_rng(57)
+    nmap = rng.uniform(0.3, 1.0, (4, 4, 4)).astype(np.float32)
+    b = rt.Builder(8)
+    t_n = b.image(nmap, linear_format=True)
+    mirror = b.metal([1.0, 1.0, 1.0], 0.0)
+    pos = [[0.0, 0.0, 0.0], [2.0, 0.5, 0.0], [0.3, 0.0, -2.0]]
+    uv = [[0.1, 0.2], [0.9, 0.3], [0.2, 0.8]]
+    nrm = [[0.1, 1.0, 0.0], [-0.2, 0.9, 0.3], [0.0, 0.8, -0.4]]
+    mm = b.remapped(mirror, pos, uv, nrm, normal_tex=t_n)
+    tri = b.triangle([1.0, 4.0, -1.0], [2.0, 0.0, 0.5], [0.0, 0.5, 2.0], b.diffuse_light(b.solid(5, 5, 5)))
+    lights = b.list([b.triangle([1.0, 4.0, -1.0], [2.0, 0.0, 0.5], [0.0, 0.5, 2.0], b.empty())])
+    hs = b.finish(b.list([b.sphere([5, 0, 0], 1.0, mm), tri]), lights, width=8, spp=1)
+    osc = orc.OracleScene(hs)
+    mm = flat_material(hs, 0)[0]
+    P = [np.array(p) for p in pos]
+    tex_u, tex_v = np.array(uv[1] + [0.0]) - np.array(uv[0] + [0.0]), np.array(uv[2] + [0.0]) - np.array(uv[0] + [0.0])
+    world_u, world_v = P[1] - P[0], P[2] - P[0]
+    ua = tex_v[1] / (-tex_u[1] * tex_v[0] + tex_u[0] * tex_v[1])
+    ub = tex_u[1] / (tex_u[1] * tex_v[0] - tex_u[0] * tex_v[1])
+    va = tex_v[0] / (tex_u[1] * tex_v[0] - tex_u[0] * tex_v[1])
+    vb = tex_u[0] / (-tex_u[1] * tex_v[0] + tex_u[0] * tex_v[1])
+    unit_ = lambda x: x / np.sqrt(x @ x)
+    u_vec, v_vec = unit_(world_u * ua + world_v * ub), unit_(world_u * va + world_v * vb)
+    for _ in range(100):
+        u = rng.uniform(0.0, 1.0)
+        v = rng.uniform(0.0, 1.0 - u)
+        dvec = rng.normal(size=3)
+        n = unit_((1.0 - u - v) * np.array(nrm[0]) + u * np.array(nrm[1]) + v * np.array(nrm[2]))
+        tc = np.array(uv[0] + [0.0]) + u * tex_u + v * tex_v
+        c = np.array(nearest(nmap, tc[0], tc[1], raw=True)) * 2.0 - 1.0
+        n2 = unit_(u_vec * c[0] + v_vec * c[1] + n * c[2])
+        ud = unit_(dvec)
+        refl = unit_(ud - 2.0 * (ud @ n2) * n2)
+        kind, att, out, err = osc.scatter(mm, [0, 3, 0], list(dvec), [0.5, 0.0, -0.5], [0.0, 1.0, 0.0], True, u=u, v=v)
+        assert kind == 3 and not err and np.allclose(out, refl, rtol=0, atol=1e-11)
+    # the triangle light
+    A, U, V = np.array([1.0, 4.0, -1.0]), np.array([2.0, 0.0, 0.5]), np.array([0.0, 0.5, 2.0])
+    nvec = np.cross(U, V)
+    area, normal = np.sqrt(nvec @ nvec) / 2.0, unit_(nvec)
+    origin = np.array([1.5, 0.0, 0.0])
+    for _ in range(100):
+        r1, r2 = rng.uniform(size=2)
+        ul, vl = (1.0 - r2, 1.0 - r1) if r1 + r2 > 1.0 else (r1, r2)
+        want_dir = unit_(A + ul * U + vl * V - origin)
+        got = osc.lights_random(list(origin), 0, r1, r2)
+        assert np.allclose(got, want_dir, rtol=0, atol=1e-12)
+        # a direction through the triangle: pdf = t^2 |d|^2 / (|d . n| / |d| * area), with t from the plane equation
+        d = want_dir * rng.uniform(0.5, 3.0)
+        t = (normal @ A - normal @ origin) / (normal @ d)
+        want_pdf = t * t * (d @ d) / (abs(d @ normal / np.sqrt(d @ d)) * area)
+        assert osc.lights_pdf_value(list(origin), list(d)) == __import__("pytest").approx(want_pdf, rel=1e-12)
+    assert osc.lights_pdf_value(list(origin), [0.0, -1.0, 0.0]) == 0.0  # away from the light
