@@ -15,7 +15,14 @@
 // longest_axis/union/from_points (aabb.rs:199-253), get_sphere_uv (sphere.rs:152-169), Ray::at,
 // Vec3 algebra and quaternion rotation; tests/test_oracle_kat.py checks those through the orc_kat_*
 // entry points below.  Hits, scatter, pdfs, media, textures and the tone map have no vectors
-// in the reference: for them this oracle is "parity unpinned" (SURVEY.md §8c).
+// in the reference and the reference cannot be run here; round 2 pinned them by other means:
+//   * hand-derived exact vectors (inputs whose every intermediate is representable) for Sphere / Quad / Triangle / Transform /
+//     ConstantMedium hits, Dielectric / Metal / Lambertian / Isotropic scatter, CosinePDF and the light pdfs - tests/test_oracle_kat_hand.py;
+//   * independent restatements written from the Rust source in plain Python for Perlin noise and NoiseTexture, Disney::evaluate_disney
+//     and DisneyPDF::generate with all their samplers, Checker / Image textures, the ACES fit, Portal / Transparent / Mix,
+//     RemappedMaterial::remap_record (with and without a normal map) and the Triangle light - tests/test_perlin_restatement.py,
+//     tests/test_disney_restatement.py, tests/test_restatements.py.
+// What is left "parity unpinned" (SURVEY.md 8c): palette's sRGB encoder (crate not vendored; 8-bit codes are stated to +-1).
 //
 // The one deliberate difference: the reference draws from the unseeded thread RNG; here every
 // draw is an addressed Philox4x32-10 sample (include/rt2025_rng.h), which the CUDA core uses too.
