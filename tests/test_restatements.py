@@ -227,3 +227,39 @@ def test_normal_mapped_remap_and_triangle_light(rt, orc):
         want_pdf = t * t * (d @ d) / (abs(d @ normal / np.sqrt(d @ d)) * area)
         assert osc.lights_pdf_value(list(origin), list(d)) == __import__("pytest").approx(want_pdf, rel=1e-12)
     assert osc.lights_pdf_value(list(origin), [0.0, -1.0, 0.0]) == 0.0  # away from the light
+
+
+def test_camera_get_ray_matches_a_plain_restatement(rt, orc):
+    """Camera::get_ray (camera.rs:247-273) with sample_square_stratified and defocus_disk_sample (vec3.rs:63-69): the oracle's rays
+    against the formulas restated on the camera block, the draws taken through the addressed-Philox hook (slots 0, 1, 2 of
+    include/rt2025_rng.h: jitter, defocus disk, time; pixel = j * width + i, segment 0)."""
+    import ctypes as C
+    for name, params in (("book1_final", [120, 25, 5]), ("book2_final", [80, 16, 5])):  # book 1 has a defocus disk, book 2 does not
+        hs = rt.named_scene(name, seed=3, params=params)
+        cam = hs.camera
+        L = orc.lib()
+        v3 = lambda a: np.array(list(a))
+        rng = np.random.default_rng(77)
+        px = [(int(rng.integers(0, cam.image_width)), int(rng.integers(0, cam.image_height))) for _ in range(60)]
+        spp = cam.sqrt_spp * cam.sqrt_spp
+        for sidx in (0, 1, spp // 2, spp - 1):
+            got = orc.camera_rays(cam, 9, px, sidx)
+            for (i, j), ray in zip(px, got):
+                pixel = j * cam.image_width + i
+                pair = (C.c_double * 2)()
+                draw = lambda slot: (L.orc_kat_draw(9, pixel, sidx, 0, slot, pair), (pair[0], pair[1]))[1]
+                s_i, s_j = sidx // cam.sqrt_spp, sidx % cam.sqrt_spp
+                ja, jb = draw(0)
+                ox = ((s_i + ja) * cam.recip_sqrt_spp) - 0.5
+                oy = ((s_j + jb) * cam.recip_sqrt_spp) - 0.5
+                sample = v3(cam.pixel00_loc) + ((i + ox) * v3(cam.pixel_delta_u)) + ((j + oy) * v3(cam.pixel_delta_v))
+                if cam.defocus_angle_in_degrees <= 0.0:
+                    origin = v3(cam.center)
+                else:
+                    da, db = draw(1)
+                    theta, r = (2.0 * math.pi) * da, math.sqrt(db)
+                    origin = v3(cam.center) + ((r * math.cos(theta)) * v3(cam.defocus_disk_u)) + ((r * math.sin(theta)) * v3(cam.defocus_disk_v))
+                assert np.array_equal(ray["origin"], origin)
+                assert np.array_equal(ray["direction"], sample - origin)
+                assert ray["time"] == draw(2)[0]
+        assert (cam.defocus_angle_in_degrees > 0.0) == (name == "book1_final")
